@@ -1,0 +1,283 @@
+"""ctypes binding of the C ABI in include/hakai_b200.h (the Python twin of the Julia `ccall` stub).
+
+`Engine` binds hakai_fem_b200/libhakai_b200.so — the CUDA engine.  There is no CPU fallback:
+if the library is missing or no CUDA device exists the constructor raises.  The generic
+`EngineBase(lib, prefix)` exists so that tests can drive the CPU oracle (prefix ``hko_``)
+through the very same calls; the product never loads the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhakai_b200.so")
+
+c_i64 = C.c_int64
+c_f64 = C.c_double
+P_i64 = C.POINTER(C.c_int64)
+P_f64 = C.POINTER(C.c_double)
+
+
+class HkParams(C.Structure):
+    """struct hk_params (include/hakai_b200.h)."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32),
+        ("d_time", c_f64), ("element_min_size", c_f64), ("element_max_size", c_f64),
+        ("contact_flag", C.c_int32), ("triax_route", C.c_int32),
+        ("contact_d_lim_factor", c_f64), ("contact_myu", c_f64),
+        ("contact_kc_other", c_f64), ("contact_kc_self", c_f64),
+        ("contact_cr_other", c_f64), ("contact_cr_self", c_f64),
+        ("contact_ddiv_other", c_f64), ("contact_ddiv_self", c_f64),
+        ("deterministic", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+EXPORTS = [
+    "default_params", "create", "destroy", "last_error", "set_mesh", "add_material", "add_bc", "add_ic",
+    "add_instance", "add_contact_pair", "finalize", "step", "download", "download_ex", "upload_state",
+    "deleted_ids", "contact_pair_info", "counters", "profile", "profile_read", "set_stream",
+]
+
+
+class HakaiError(RuntimeError):
+    pass
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _pf(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(P_f64)
+
+
+def _pi(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(P_i64)
+
+
+def _csr(lists: Sequence[np.ndarray]):
+    ptr = np.zeros(len(lists) + 1, np.int64)
+    for j, l in enumerate(lists):
+        ptr[j + 1] = ptr[j] + len(l)
+    flat = _i64(np.concatenate([_i64(l) for l in lists])) if len(lists) else np.zeros(0, np.int64)
+    return ptr, flat
+
+
+class EngineBase:
+    """Thin, stateful wrapper: one instance = one hk_engine*."""
+
+    def __init__(self, lib: C.CDLL, prefix: str, **params):
+        self._lib = lib
+        self._pfx = prefix
+        self._h = C.c_void_p()
+        self._fn("last_error").restype = C.c_char_p
+        self._fn("last_error").argtypes = [C.c_void_p]
+        self.params = HkParams()
+        self._chk(self._fn("default_params")(C.byref(self.params)), created=False)
+        for k, v in params.items():
+            if not hasattr(self.params, k):
+                raise AttributeError(f"hk_params has no field {k}")
+            setattr(self.params, k, v)
+        rc = self._fn("create")(C.byref(self._h), C.byref(self.params))
+        self._chk(rc, created=False)
+        self.nNode = 0
+        self.nElement = 0
+
+    # -- plumbing ------------------------------------------------------------------
+    def _fn(self, name):
+        return getattr(self._lib, self._pfx + name)
+
+    def _chk(self, rc: int, created: bool = True):
+        if rc != 0:
+            msg = self._fn("last_error")(self._h if created else None)
+            raise HakaiError(f"{self._pfx}* call failed (code {rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._h:
+            self._fn("destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- set-up ---------------------------------------------------------------------
+    def set_mesh(self, coordmat, elementmat, element_material, element_instance, diag_M):
+        coordmat = np.asarray(coordmat)
+        elementmat = np.asarray(elementmat)
+        self.nNode = coordmat.shape[1]
+        self.nElement = elementmat.shape[1]
+        # (3,nNode) / (8,nElement) column-major == C-order of the transposes
+        cm = _f64(coordmat.T)
+        em = _i64(elementmat.T)
+        emat = _i64(element_material)
+        eins = None if element_instance is None else _i64(element_instance)
+        dm = _f64(diag_M)
+        self._chk(self._fn("set_mesh")(self._h, c_i64(self.nNode), c_i64(self.nElement), _pf(cm), _pi(em),
+                                       _pi(emat), _pi(eins), _pf(dm)))
+
+    def add_material(self, young, poisson, density, plastic=None, Hd=None, ductile=None):
+        npp = 0 if plastic is None else int(np.asarray(plastic).shape[0])
+        nd = 0 if ductile is None else int(np.asarray(ductile).shape[0])
+        pl = _f64(np.asarray(plastic).T) if npp else None          # (npp,2) column-major
+        hd = _f64(Hd) if npp > 1 else None
+        du = _f64(np.asarray(ductile).T) if nd else None
+        self._chk(self._fn("add_material")(self._h, c_f64(young), c_f64(poisson), c_f64(density),
+                                           c_i64(npp), _pf(pl), _pf(hd), c_i64(nd), _pf(du)))
+
+    def add_bc(self, dof_lists, values, amp_time=None, amp_value=None):
+        ptr, flat = _csr(dof_lists)
+        vals = _f64(values)
+        n_amp = 0 if amp_time is None else len(amp_time)
+        at = _f64(amp_time) if n_amp else None
+        av = _f64(amp_value) if n_amp else None
+        self._chk(self._fn("add_bc")(self._h, c_i64(len(dof_lists)), _pi(ptr), _pi(flat), _pf(vals),
+                                     c_i64(n_amp), _pf(at), _pf(av)))
+
+    def add_ic(self, dof_lists, values):
+        ptr, flat = _csr(dof_lists)
+        vals = _f64(values)
+        self._chk(self._fn("add_ic")(self._h, c_i64(len(dof_lists)), _pi(ptr), _pi(flat), _pf(vals)))
+
+    def add_instance(self, node_offset, nNode, element_offset, nElement, surfaces=None, surfaces_eleid=None):
+        sf = None if surfaces is None else _i64(np.asarray(surfaces).T)       # (6nE,4) column-major
+        se = None if surfaces_eleid is None else _i64(surfaces_eleid)
+        self._chk(self._fn("add_instance")(self._h, c_i64(node_offset), c_i64(nNode), c_i64(element_offset),
+                                           c_i64(nElement), _pi(sf), _pi(se)))
+
+    def add_contact_pair(self, i_instance, j_instance, c_nodes_i, c_nodes_j, c_triangles, c_triangles_eleid, young):
+        ni, nj = _i64(c_nodes_i), _i64(c_nodes_j)
+        tri = _i64(np.asarray(c_triangles).reshape(-1, 3).T)                   # (nTri,3) column-major
+        te = _i64(c_triangles_eleid)
+        self._chk(self._fn("add_contact_pair")(self._h, c_i64(i_instance), c_i64(j_instance), c_i64(len(ni)), _pi(ni),
+                                               c_i64(len(nj)), _pi(nj), c_i64(len(te)), _pi(tri), _pi(te),
+                                               c_f64(young)))
+
+    def finalize(self):
+        self._chk(self._fn("finalize")(self._h))
+
+    # -- stepping ---------------------------------------------------------------------
+    def step(self, t_first: int, n_steps: int = 1) -> int:
+        nd = c_i64(0)
+        self._chk(self._fn("step")(self._h, c_i64(t_first), c_i64(n_steps), C.byref(nd)))
+        return nd.value
+
+    # -- taps ---------------------------------------------------------------------------
+    def download(self, fields=("disp", "velo", "integ_stress", "integ_strain", "integ_eq_plastic_strain",
+                               "integ_triax_stress", "element_flag"), out=None):
+        """Returns a dict of arrays in the reference's shapes: (fn,), (6,nip) column-major -> returned as
+        numpy (nip,6) C-order viewed transposed, i.e. out['integ_stress'][c, ip]."""
+        nN, nE = self.nNode, self.nElement
+        fn, nip = 3 * nN, 8 * nE
+        shapes = dict(disp=(fn,), velo=(fn,), integ_stress=(nip, 6), integ_strain=(nip, 6),
+                      integ_eq_plastic_strain=(nip,), integ_triax_stress=(nip,), element_flag=(nE,))
+        bufs = {}
+        for k in shapes:
+            if k in fields:
+                if out is not None and k in out:
+                    bufs[k] = out[k]
+                else:
+                    bufs[k] = np.empty(shapes[k], np.int64 if k == "element_flag" else np.float64)
+            else:
+                bufs[k] = None
+        self._chk(self._fn("download")(self._h, _pf(bufs["disp"]), _pf(bufs["velo"]), _pf(bufs["integ_stress"]),
+                                       _pf(bufs["integ_strain"]), _pf(bufs["integ_eq_plastic_strain"]),
+                                       _pf(bufs["integ_triax_stress"]), _pi(bufs["element_flag"])))
+        res = {}
+        for k, v in bufs.items():
+            if v is None:
+                continue
+            res[k] = v.T if k in ("integ_stress", "integ_strain") else v
+        return res
+
+    def download_ex(self, fields=("disp_pre", "Q", "external_force", "position", "integ_yield_stress",
+                                  "elementVolume")):
+        nN, nE = self.nNode, self.nElement
+        fn, nip = 3 * nN, 8 * nE
+        shapes = dict(disp_pre=(fn,), Q=(fn,), external_force=(fn,), position=(nN, 3),
+                      integ_yield_stress=(nip,), elementVolume=(nE,))
+        bufs = {k: (np.empty(s) if k in fields else None) for k, s in shapes.items()}
+        self._chk(self._fn("download_ex")(self._h, _pf(bufs["disp_pre"]), _pf(bufs["Q"]), _pf(bufs["external_force"]),
+                                          _pf(bufs["position"]), _pf(bufs["integ_yield_stress"]),
+                                          _pf(bufs["elementVolume"])))
+        res = {k: v for k, v in bufs.items() if v is not None}
+        if "position" in res:
+            res["position"] = res["position"].T
+        return res
+
+    def upload_state(self, disp=None, disp_pre=None, velo=None, Q=None, integ_stress=None, integ_strain=None,
+                     integ_eq_plastic_strain=None, integ_yield_stress=None, element_flag=None):
+        def f(a, mat=False):
+            if a is None:
+                return None
+            a = np.asarray(a)
+            return _f64(a.T) if mat else _f64(a)
+        a = [f(disp), f(disp_pre), f(velo), f(Q), f(integ_stress, True), f(integ_strain, True),
+             f(integ_eq_plastic_strain), f(integ_yield_stress)]
+        fl = None if element_flag is None else _i64(element_flag)
+        self._chk(self._fn("upload_state")(self._h, *[_pf(x) for x in a], _pi(fl)))
+
+    def deleted_ids(self) -> np.ndarray:
+        n = c_i64(0)
+        self._chk(self._fn("deleted_ids")(self._h, None, c_i64(0), C.byref(n)))
+        ids = np.zeros(n.value, np.int64)
+        if n.value:
+            self._chk(self._fn("deleted_ids")(self._h, _pi(ids), c_i64(n.value), C.byref(n)))
+        return ids
+
+    def contact_pair(self, c: int):
+        a, b, t = c_i64(0), c_i64(0), c_i64(0)
+        self._chk(self._fn("contact_pair_info")(self._h, c_i64(c), C.byref(a), C.byref(b), C.byref(t),
+                                                None, None, None, None))
+        ni, nj = np.zeros(a.value, np.int64), np.zeros(b.value, np.int64)
+        tri, te = np.zeros((3, t.value), np.int64), np.zeros(t.value, np.int64)
+        self._chk(self._fn("contact_pair_info")(self._h, c_i64(c), None, None, None, _pi(ni), _pi(nj), _pi(tri),
+                                                _pi(te)))
+        return dict(c_nodes_i=ni, c_nodes_j=nj, c_triangles=tri.T.copy(), c_triangles_eleid=te)
+
+    def counters(self) -> np.ndarray:
+        out = np.zeros(8, np.int64)
+        self._chk(self._fn("counters")(self._h, _pi(out)))
+        return out
+
+    def profile(self, enable: bool = True):
+        self._chk(self._fn("profile")(self._h, C.c_int32(1 if enable else 0)))
+
+    def profile_read(self):
+        ms = np.zeros(4)
+        n = np.zeros(4, np.int64)
+        self._chk(self._fn("profile_read")(self._h, _pf(ms), _pi(n)))
+        return ms, n
+
+    def set_stream(self, stream_ptr: int):
+        self._chk(self._fn("set_stream")(self._h, C.c_void_p(stream_ptr)))
+
+
+_lib_cache = {}
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """Loads libhakai_b200.so; raises (never falls back) when it is missing."""
+    if path not in _lib_cache:
+        if not os.path.exists(path):
+            raise HakaiError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)")
+        _lib_cache[path] = C.CDLL(path)
+    return _lib_cache[path]
+
+
+class Engine(EngineBase):
+    """The CUDA engine (libhakai_b200.so)."""
+
+    def __init__(self, **params):
+        super().__init__(load_library(), "hk_", **params)

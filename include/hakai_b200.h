@@ -1,0 +1,187 @@
+/*
+ * hakai_b200.h — C ABI of the B200-native HAKAI time-step engine (libhakai_b200.so).
+ *
+ * The reference (yozoyugen/HAKAI-fem) has no FFI: its per-step hot path is inline Julia in
+ * hakai() (HAKAI-v0.0.2/Julia/HAKAI_j.jl:487-951, cited below as J2:<line>).  This header is the
+ * boundary a maintainer binds with `ccall` to replace that loop body; INTEGRATION.md shows the
+ * Julia stub.  Conventions:
+ *   - plain C, no exceptions; every call returns 0 on success or a negative hk_status code,
+ *     with a message available from hk_last_error().
+ *   - all pointers are HOST pointers owned by the caller, in the reference's own (Julia,
+ *     column-major, 1-based, Int64/Float64) layouts; the library copies and never keeps them.
+ *   - the engine owns all device memory; one host thread drives one engine; not re-entrant.
+ *   - fn = 3*nNode, nip = 8*nElement.  Voigt order xx,yy,zz,xy,yz,xz (engineering shear).
+ *
+ * The same signatures with prefix `hko_` are exported by oracle/libhakai_oracle.so (the CPU
+ * restatement used ONLY by tests/ and bench.py's cpu_baseline) so the parity tests can drive
+ * both through one wrapper.
+ */
+#ifndef HAKAI_B200_H
+#define HAKAI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hk_engine hk_engine;
+
+enum hk_status {
+    HK_OK = 0,
+    HK_ERR_ARG = -1,        /* bad argument / call order                      */
+    HK_ERR_CUDA = -2,       /* CUDA runtime error (message has the detail)    */
+    HK_ERR_NO_DEVICE = -3,  /* no sm_100 device: there is NO CPU fallback     */
+    HK_ERR_STATE = -4,      /* engine not finalised / already finalised       */
+    HK_ERR_UNSUPPORTED = -5
+};
+
+/* Every constant the reference hard-codes in source (SURVEY §5 "Config / flags").
+ * hk_default_params() fills the reference's values. */
+typedef struct hk_params {
+    int32_t struct_size;        /* = sizeof(hk_params), ABI check                               */
+    int32_t device;             /* CUDA device ordinal                                          */
+    double  d_time;             /* MODEL.d_time*sqrt(mass_scaling)                J2:114        */
+    double  element_min_size;   /* elementMinSize                                 J2:418        */
+    double  element_max_size;   /* elementMaxSize                                 J2:420        */
+    int32_t contact_flag;       /* MODEL.contact_flag (0 none, 1 contact, 2 +self) J2:100       */
+    int32_t triax_route;        /* 0 = invariants (I1/3)/sqrt(3 J2); 1 = closed-form 3x3 eigen-
+                                   values as StaticArrays.eigvals (oracle only)    J2:1004-1016 */
+    double  contact_d_lim_factor; /* d_lim = factor*elementMinSize, 0.3           J2:2254       */
+    double  contact_myu;          /* friction coefficient, 0.25                   J2:2255       */
+    double  contact_kc_other;     /* kc_o = 1                                     J2:2256       */
+    double  contact_kc_self;      /* kc_s = 1                                     J2:2257       */
+    double  contact_cr_other;     /* Cr_o = 0                                     J2:2258       */
+    double  contact_cr_self;      /* Cr_s = 0                                     J2:2259       */
+    double  contact_ddiv_other;   /* cell size factor 1.1*elementMaxSize          J2:2331       */
+    double  contact_ddiv_self;    /* 0.6*elementMaxSize for self contact          J2:2333       */
+    int32_t deterministic;        /* 1 (default): reproducible assembly and contact sums        */
+    int32_t reserved;
+} hk_params;
+
+int hk_default_params(hk_params* p);
+
+/* Allocates the engine on p->device.  Fails with HK_ERR_NO_DEVICE when no CUDA device exists. */
+int hk_create(hk_engine** out, const hk_params* p);
+int hk_destroy(hk_engine* e);
+const char* hk_last_error(const hk_engine* e);   /* e may be NULL: last create() error */
+
+/* Mesh (replaces the locals of hakai(), J2:91-98, 186-218).
+ *   coordmat          f64 (3,nNode) column-major                      J2:93
+ *   elementmat        i64 (8,nElement) column-major, 1-based          J2:96
+ *   element_material  i64 (nElement) 1-based material index            J2:97
+ *   element_instance  i64 (nElement) 1-based instance index            J2:98 (may be NULL: all 1)
+ *   diag_M            f64 (fn); the 3 dofs of a node must hold the same mass (J2:205-215)
+ */
+int hk_set_mesh(hk_engine* e, int64_t nNode, int64_t nElement,
+                const double* coordmat, const int64_t* elementmat,
+                const int64_t* element_material, const int64_t* element_instance,
+                const double* diag_M);
+
+/* One call per MODEL.MATERIAL entry, in order (MaterialType, readInpFile_j.jl:84-96).
+ *   plastic  f64 (npp,2) column-major [yield stress | eq. plastic strain]; npp = 0: elastic
+ *   Hd       f64 (npp-1) hardening slopes                readInpFile_j.jl:763-768
+ *   ductile  f64 (nd,3) column-major [eps_f | triax | rate]; nd = 0: no deletion
+ * Dmat and G are rebuilt from young/poisson exactly as J2:143-159. */
+int hk_add_material(hk_engine* e, double young, double poisson, double density,
+                    int64_t npp, const double* plastic, const double* Hd,
+                    int64_t nd, const double* ductile);
+
+/* One call per MODEL.BC entry, in order (later entries override earlier ones, J2:585-617).
+ *   dof_ptr  i64 (n_lists+1) CSR offsets (0-based) into dofs
+ *   dofs     i64 1-based dof ids (BC[i].dof[j])
+ *   values   f64 (n_lists)   BC[i].value[j]
+ *   n_amp = 0: amp = 1; else piecewise-linear table amp_time/amp_value (n_amp >= 2). */
+int hk_add_bc(hk_engine* e, int64_t n_lists, const int64_t* dof_ptr, const int64_t* dofs,
+              const double* values, int64_t n_amp, const double* amp_time, const double* amp_value);
+
+/* Initial velocity (J2:233-239): disp_pre[dof] = -value*d_time, velo[dof] = value.
+ * Call once per MODEL.IC entry, in order. */
+int hk_add_ic(hk_engine* e, int64_t n_lists, const int64_t* dof_ptr, const int64_t* dofs,
+              const double* values);
+
+/* Contact set-up (J2:250-398).  One hk_add_instance per MODEL.INSTANCE (in order) with the
+ * outward-oriented element faces of get_element_face (J2:1946-1992), part-local 1-based node
+ * ids; then one hk_add_contact_pair per ContactTriangle CT[c] (J2:357-398), global 1-based ids. */
+int hk_add_instance(hk_engine* e, int64_t node_offset, int64_t nNode,
+                    int64_t element_offset, int64_t nElement,
+                    const int64_t* surfaces /* (6*nElement,4) col-major */,
+                    const int64_t* surfaces_eleid /* (6*nElement) */);
+int hk_add_contact_pair(hk_engine* e, int64_t i_instance, int64_t j_instance,
+                        int64_t nn_i, const int64_t* c_nodes_i,
+                        int64_t nn_j, const int64_t* c_nodes_j,
+                        int64_t nTri, const int64_t* c_triangles /* (nTri,3) col-major */,
+                        const int64_t* c_triangles_eleid, double young);
+
+/* Freezes the set-up: builds device layouts (SoA state, node->element gather table, BC table,
+ * contact buckets), initialises state as J2:220-230, 447-465 (zero state, yield = plastic[1,1],
+ * element_flag = 1).  Must be called once before hk_step/hk_upload_state/hk_download. */
+int hk_finalize(hk_engine* e);
+
+/* Runs steps t = t_first .. t_first+n_steps-1 of the loop J2:487-951 (t is 1-based;
+ * current_time = t*d_time, J2:589).  Synchronous on return.  *n_deleted_out (may be NULL)
+ * receives the number of elements deleted during these steps (J2:733-736). */
+int hk_step(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_deleted_out);
+
+/* Output taps (A13): fills caller-owned arrays in the reference's layouts; NULL = skip.
+ *   disp, velo                       f64 (fn)
+ *   integ_stress, integ_strain       f64 (6,nip) column-major
+ *   integ_eq_plastic_strain, integ_triax_stress   f64 (nip)
+ *   element_flag                     i64 (nElement) */
+int hk_download(hk_engine* e, double* disp, double* velo,
+                double* integ_stress, double* integ_strain,
+                double* integ_eq_plastic_strain, double* integ_triax_stress,
+                int64_t* element_flag);
+
+/* Remaining loop-carried state, for tests / restart.  NULL = skip.
+ *   disp_pre, Q, external_force f64 (fn); position f64 (3,nNode); integ_yield_stress f64 (nip);
+ *   elementVolume f64 (nElement)  (J2:1169) */
+int hk_download_ex(hk_engine* e, double* disp_pre, double* Q, double* external_force,
+                   double* position, double* integ_yield_stress, double* elementVolume);
+
+/* Overwrite loop-carried state (tests, restart).  NULL = keep.  Layouts as hk_download*. */
+int hk_upload_state(hk_engine* e, const double* disp, const double* disp_pre, const double* velo,
+                    const double* Q, const double* integ_stress, const double* integ_strain,
+                    const double* integ_eq_plastic_strain, const double* integ_yield_stress,
+                    const int64_t* element_flag);
+
+/* Ids (1-based, deletion order: ascending step, ascending id within a step, J2:701-735) of
+ * all elements deleted since hk_finalize.  Copies min(cap, n) ids; *n_out = total count. */
+int hk_deleted_ids(hk_engine* e, int64_t* ids, int64_t cap, int64_t* n_out);
+
+/* Current contact surface of pair c (0-based), after A10 updates (J2:767-804): sizes, or
+ * arrays when non-NULL (caller sizes them from a first call). */
+int hk_contact_pair_info(hk_engine* e, int64_t c, int64_t* nn_i, int64_t* nn_j, int64_t* nTri,
+                         int64_t* c_nodes_i, int64_t* c_nodes_j,
+                         int64_t* c_triangles, int64_t* c_triangles_eleid);
+
+/* Counters since finalize: [0] negative-Jacobian warnings (J2:1736-1739), [1] contact hits,
+ * [2] contact candidate tests, [3] kernel launches, [4] steps run. */
+int hk_counters(hk_engine* e, int64_t out[8]);
+
+/* Per-kernel device timing with CUDA events on the engine's stream.
+ *   kind: 0 contact, 1 nodal update (+assembly gather, BC, kinematics), 2 element, 3 other.
+ * hk_profile(e, 1) enables/reset; hk_profile_read returns total ms and launch count per kind. */
+int hk_profile(hk_engine* e, int32_t enable);
+int hk_profile_read(hk_engine* e, double ms[4], int64_t launches[4]);
+
+/* Use an externally created CUDA stream (cudaStream_t as void*) for all work; NULL = own. */
+int hk_set_stream(hk_engine* e, void* cuda_stream);
+
+/* ---- multi-GPU (one engine per rank) -------------------------------------------
+ * Shared-interface nodes: list of LOCAL 1-based node ids whose internal force must be summed
+ * with a neighbour rank's partial.  The engine packs/unpacks; the transport (NCCL send/recv)
+ * is driven by the host between hk_step_begin and hk_step_end.  Halo buffers are DEVICE
+ * pointers owned by the engine (3 doubles per node, node-major). */
+int hk_set_halo(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr /* n_neighbors+1 */,
+                const int64_t* nodes);
+int hk_halo_buffers(hk_engine* e, int64_t neighbor, void** send_dev, void** recv_dev,
+                    int64_t* n_doubles);
+/* Split step for halo exchange: begin = contact + (first step: nothing) ... see DESIGN.md. */
+int hk_step_begin(hk_engine* e, int64_t t);   /* element forces of step t-1 are packed       */
+int hk_step_end(hk_engine* e, int64_t t, int64_t* n_deleted_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAKAI_B200_H */
