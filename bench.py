@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — element-steps/s of the HAKAI time-step engine on B200 (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W16|B1|...] [--impl reference]
+
+A "step" is one explicit time step (contact-free hot path: nodal gather/update/BC/kinematics kernel +
+hex8 elastoplastic element kernel) of the synthetic uniform-stretch deck of SURVEY §8(d):
+  W16 (default): 252x252x252 = 16 003 008 hex per GPU, elastoplastic steel, jittered interior nodes — the mesh
+      the north star's roofline target is quoted on and the per-GPU shard of the weak-scaling config.
+  B1: the 50x50x400 1 M-hex bar (BASELINE configs[1]).
+State (>= 14 GB at W16) is far larger than L2, so no L2 flush is needed between steps.
+Prints ONE JSON line (see DESIGN.md §6 for every key).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_ELEMENT = 1904       # element kernel, per element-step
+ALG_BYTES_NODAL = 224          # nodal update, per node-step
+ALG_BYTES_STEP = 2128          # total per element-step (nN/nE -> 1)
+
+
+def make_deck(workload, nz_override=None):
+    from hakai_fem_b200.mesh import StretchDeck, steel
+    if workload == "W16":
+        n = (252, 252, 252)
+    elif workload == "B1":
+        n = (50, 50, 400)
+    elif workload == "S1":      # 1 M-element slab of W16 (CPU sample)
+        n = (252, 252, 16)
+    elif workload.startswith("N"):   # Nnx,ny,nz
+        n = tuple(int(v) for v in workload[1:].split(","))
+    else:
+        raise SystemExit(f"unknown workload {workload}")
+    if nz_override:
+        n = (n[0], n[1], nz_override)
+    jitter = 0.0 if workload == "B1" else 0.05
+    return StretchDeck(n[0], n[1], n[2], h=1.0, material=steel(), jitter=jitter, n_steps=1.0e6)
+
+
+def prepare_setup(deck):
+    from hakai_fem_b200.model_setup import prepare
+    model = deck.build_model()
+    vol = None
+    if deck.jitter == 0.0:
+        vol = np.full(model.nElement, deck.h ** 3)
+    return prepare(model, elementVolume=vol)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(sample_workload, warmup, steps, threads=None):
+    """Times the CPU oracle (C++ restatement of HAKAI_j.jl's loop, OpenMP) on a bounded sample."""
+    from hakai_fem_b200.model_setup import configure_engine
+    from oracle.oracle_engine import OracleEngine
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    deck = make_deck(sample_workload)
+    st = prepare_setup(deck)
+    eng = configure_engine(OracleEngine, st)
+    eng.step(1, warmup)
+    t0 = time.perf_counter()
+    eng.step(warmup + 1, steps)
+    dt = time.perf_counter() - t0
+    nE = st.model.nElement
+    eng.close()
+    return nE * steps / dt, nE, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; Julia is not installed) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample
+    rate, nE, dt = cpu_oracle_rate(sample, args.warmup, args.steps, threads=cores)
+    line = {
+        "impl": "reference", "metric": "element-steps/sec (hex8 elastoplastic)", "value": rate,
+        "unit": "element-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "sample": sample, "elements_in_sample": nE},
+        "cpu_baseline": {"value": rate, "unit": "element-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample}: {nE} elements of the same deck recipe, {args.warmup} warm-up + "
+                                   f"{args.steps} timed steps, OpenMP oracle (HAKAI_j.jl restated in C++), "
+                                   f"{cores} threads"},
+        "e2e": {"value": rate, "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="W16")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-sample", default="S1")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from hakai_fem_b200.engine import Engine
+    from hakai_fem_b200.model_setup import configure_engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    deck = make_deck(args.workload)
+    st = prepare_setup(deck)
+    nE, nN = st.model.nElement, st.model.nNode
+    eng = configure_engine(Engine, st, device=local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    eng.step(1, args.warmup)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = int(eng.counters()[3])
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    eng.step(args.warmup + 1, args.steps)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = int(eng.counters()[3]) - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = nE * world * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing (CUDA events on the engine's stream around every launch) -------------------
+    t_next = args.warmup + args.steps + 1
+    eng.profile(True)
+    n_prof = min(args.steps, 10)
+    eng.step(t_next, n_prof)
+    t_next += n_prof
+    kms, kn = eng.profile_read()
+    eng.profile(False)
+    el_ms = kms[2] / max(kn[2], 1)
+    nd_ms = kms[1] / max(kn[1], 1)
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    achieved = ALG_BYTES_ELEMENT * nE / (el_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "hk_element_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALG_BYTES_ELEMENT * nE, "avg_launch_ms": el_ms,
+                "nodal_kernel": {"achieved": ALG_BYTES_NODAL * nN / (nd_ms * 1e-3) / 1e9, "avg_launch_ms": nd_ms},
+                "whole_step": {"achieved": ALG_BYTES_STEP * nE / (ms / args.steps * 1e-3) / 1e9,
+                               "frac": ALG_BYTES_STEP * nE / (ms / args.steps * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        fn, nip = 3 * nN, 8 * nE
+        host = eng.download()
+        host.update(eng.download_ex(fields=("disp_pre", "Q", "integ_yield_stress")))
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        up = dict(disp=pin(host["disp"]), disp_pre=pin(host["disp_pre"]), velo=pin(host["velo"]), Q=pin(host["Q"]),
+                  integ_stress=pin(host["integ_stress"].T), integ_strain=pin(host["integ_strain"].T),
+                  integ_eq_plastic_strain=pin(host["integ_eq_plastic_strain"]),
+                  integ_yield_stress=pin(host["integ_yield_stress"]))
+        out = dict(disp=pin(np.empty(fn)), velo=pin(np.empty(fn)), integ_stress=pin(np.empty((nip, 6))),
+                   integ_strain=pin(np.empty((nip, 6))), integ_eq_plastic_strain=pin(np.empty(nip)),
+                   integ_triax_stress=pin(np.empty(nip)), element_flag=pin(np.empty(nE, dtype=np.int64)))
+        del host
+        h2d = sum(v.numel() * 8 for v in up.values())
+        d2h = sum(v.numel() * 8 for v in out.values())
+        barrier()
+        w0 = time.perf_counter()
+        eng.upload_state(disp=up["disp"].numpy(), disp_pre=up["disp_pre"].numpy(), velo=up["velo"].numpy(),
+                         Q=up["Q"].numpy(), integ_stress=up["integ_stress"].numpy().T,
+                         integ_strain=up["integ_strain"].numpy().T,
+                         integ_eq_plastic_strain=up["integ_eq_plastic_strain"].numpy(),
+                         integ_yield_stress=up["integ_yield_stress"].numpy())
+        eng.step(t_next, args.steps)
+        eng.download(out={k: v.numpy() for k, v in out.items()})
+        barrier()
+        w = time.perf_counter() - w0
+        tw = torch.tensor([w], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        w = float(tw.item())
+        e2e = {"value": nE * world * args.steps / w, "unit": "element-steps/s",
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "what": f"hk_upload_state (pinned host arrays, all loop state) + hk_step x{args.steps} + hk_download "
+                       f"(one output frame, all 7 arrays) per rank; wall clock, max over ranks"}
+
+    # ---- CPU baseline (oracle port on the host cores, bounded sample) ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        rate, nEs, dtc = cpu_oracle_rate(args.cpu_sample, 2, args.cpu_steps, threads=cores)
+        cpu = {"value": rate, "unit": "element-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample}: {nEs} elements of the same deck recipe, 2 warm-up + {args.cpu_steps} timed "
+                         f"steps ({dtc:.1f} s), OpenMP C++ oracle, {cores} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": "element-steps/sec (hex8 elastoplastic)", "value": value, "unit": "element-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "elements_per_gpu": nE, "nodes_per_gpu": nN,
+                       "deck": f"{deck.nx}x{deck.ny}x{deck.nz} hex8, steel elastoplastic, uniform stretch "
+                               f"{deck.strain_per_step:g}/step, jitter {deck.jitter}",
+                       "l2": "state >> L2 (inputs larger than L2), no flush", "parallelism": f"slab x{world}"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

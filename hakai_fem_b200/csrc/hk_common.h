@@ -1,0 +1,122 @@
+// hk_common.h — device-side data layout shared by the engine's translation units.
+//
+// Layout in HBM:
+//   nodal vectors        AoS, 3 doubles per node, identical to the reference's `fn` vectors
+//                        (disp, disp_pre, coordmat): perfectly coalesced for the streaming update.
+//   node record `rec`    {x,y,z, dux,duy,duz} per node (48 B, 16-B aligned): `position` and `d_disp`
+//                        of J2:624-652, written by the nodal kernel, gathered by the element kernel.
+//   ip state             SoA [component][gauss point][element]: stress/strain 6x8 rows, eps/yield 8 rows,
+//                        each row nEp doubles (nEp = nElement padded to 32) -> a warp of consecutive
+//                        elements reads 256 contiguous bytes per row.
+//   Qe                   SoA [24][nEp]: element nodal forces (J2:438), written by the element kernel and
+//                        gathered per node in ascending element order (= the reference's serial scatter
+//                        order, J2:669-675) by the nodal kernel of the next step.  Q itself is never
+//                        materialised.
+#pragma once
+#include "hk_platform.h"
+
+#define HK_MAX_TABLE 32          // rows of a *Plastic / ductile table
+
+struct HkMaterialDev {
+    double young, poisson, G;
+    double D11, D12, D44;        // entries of Dmat, built exactly as J2:143-159
+    int npp, nd;
+    double plastic_s[HK_MAX_TABLE];   // yield stress column
+    double plastic_e[HK_MAX_TABLE];   // eq. plastic strain column
+    double Hd[HK_MAX_TABLE];
+    double duct_e[HK_MAX_TABLE];      // fracture strain column
+    double duct_t[HK_MAX_TABLE];      // triaxiality column
+};
+
+// special-node table entry: everything rare that the nodal kernel must look at
+struct HkSpecialNode {
+    int bc_entry[3];             // per dof: index into bc_value/bc_amp, or -1
+    int contact_slot;            // index into the contact force accumulators, or -1
+    int halo_slot;               // index into the received halo partial forces, or -1
+    int pad;
+};
+
+struct HkAmpTable {              // one per BC that has an amplitude (J2:586-600)
+    int n;                       // number of points
+    int offset;                  // into amp_time / amp_value
+};
+
+struct HkDev {
+    long long nNode, nElement, nEp;   // nEp: padded element count (row stride of the SoA arrays)
+    int ell_width;                    // max elements per node
+    int n_mat;
+    // nodes
+    double* X;            // [nNode*3] coordmat
+    double* u;            // disp
+    double* u_pre;        // disp_pre
+    double* velo;         // velo (kept current only when contact is on; see hk_engine.cu)
+    double* rec;          // [nNode*6] {position, d_disp}
+    double* mass;         // [nNode]
+    int* ell;             // [ell_width][nNode] entries e*8+a (ascending e), -1 = empty
+    int* spec_idx;        // [nNode] -> special-node table or -1
+    HkSpecialNode* spec;
+    double* Q0;           // [nNode*3] internal force supplied through hk_upload_state (used once)
+    // BC tables
+    double* bc_value;     // per BC list entry
+    int* bc_amp;          // per BC list entry -> amplitude table id or -1
+    HkAmpTable* amp_tab;
+    double* amp_time;
+    double* amp_value;
+    // elements
+    int* conn;            // [8][nEp] 0-based node ids
+    unsigned char* flag;  // 1 live, 0 deleted in the last step run (Qe still valid), 2 deleted and Qe cleared
+    unsigned short* mat;  // 0-based material id
+    HkMaterialDev* mats;
+    double* stress;       // [6][8][nEp]
+    double* strain;       // [6][8][nEp]
+    double* eps;          // [8][nEp]   integ_eq_plastic_strain
+    double* yield;        // [8][nEp]   integ_yield_stress
+    double* triax;        // [8][nEp]   integ_triax_stress (written on request)
+    double* Qe;           // [24][nEp]
+    // deletion log
+    int* del_count;
+    long long* del_list;  // (step << 32 | element) entries
+    int del_cap;
+    unsigned long long* counters;  // [0] negative jacobians [1] contact hits [2] contact tests [3] fixed-point overflow
+    // contact force accumulators (128-bit fixed point): per slot 3 x {lo, hi}
+    unsigned long long* cacc;
+    double* halo_recv;    // [n_halo*3]
+};
+
+struct HkPairDev {               // one ordered contact pair (ContactTriangle, J2:72-78)
+    int nn_i, nn_j, nTri;
+    int self;                    // i_instance == j_instance
+    int* nodes_i;                // 0-based node ids (c_nodes_i)
+    int* nodes_j;
+    int* t0; int* t1; int* t2;   // c_triangles columns, 0-based node ids
+    int* tele;                   // c_triangles_eleid, 0-based
+    double young;
+    // per-step work
+    unsigned long long* bbox;    // 12 order-encoded doubles: min_i[3] max_i[3] min_j[3] max_j[3]
+    int* cell_i;                 // [3][nn_i] cell coordinates of the i nodes
+    int* head;                   // [n_bucket] bucket heads (linked lists), -1 = empty
+    int* next;                   // [nn_i]
+    int n_bucket;                // power of two
+};
+
+struct HkContactParams {
+    double d_lim, myu, kc_o, kc_s, cr_o, cr_s, ddiv_o, ddiv_s, d_time;
+    int lsb_exp;                 // fixed-point LSB = 2^lsb_exp
+};
+
+// launchers (hk_exact.cu: built with -fmad=false; hk_element.cu: FMA allowed)
+void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double dt2, double dt2p,
+                     int lsb_exp, int contact_on, int use_Q0, cudaStream_t s);
+void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s);
+void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s);
+void hk_launch_velo_from_rec(const HkDev& d, double d_time, cudaStream_t s);
+void hk_launch_gather_Q(const HkDev& d, double* Q_out, cudaStream_t s);
+void hk_launch_triax(const HkDev& d, cudaStream_t s);
+void hk_launch_element_volume(const HkDev& d, double* V_out, cudaStream_t s);
+// layout transposes between the reference's AoS (6,nip)/(nip) arrays and the SoA rows
+void hk_launch_ip_to_soa(const double* aos, double* soa, int ncomp, long long e0, long long ne, long long nEp,
+                         cudaStream_t s);
+void hk_launch_ip_to_aos(const double* soa, double* aos, int ncomp, long long e0, long long ne, long long nEp,
+                         cudaStream_t s);
+void hk_upload_pusai(const double* P);
+void hk_launch_external_force(const HkDev& d, double* F_out, int lsb_exp, int contact_on, cudaStream_t s);

@@ -1,0 +1,1014 @@
+// hk_engine.cu — host side of libhakai_b200.so: the C ABI of include/hakai_b200.h.
+//
+// Owns all device memory, converts the reference's Julia layouts (1-based Int64, AoS (6,nip)) to the
+// device layouts of hk_common.h once at hk_finalize / hk_upload_state and back at hk_download, and
+// drives the per-step kernel sequence of J2:487-951:
+//     [contact kernels] -> nodal kernel (gather Q, update, BC, kinematics) -> element kernel
+// The exposed-face update after element deletion (add_surface_triangle, J2:767-804, 2167-2245) runs
+// here on the host with a sorted face table instead of the reference's O(6F) scan per deleted element.
+#include <algorithm>
+#include <array>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/hakai_b200.h"
+#include "hk_common.h"
+
+#ifdef HK_EMU
+#define HKAPI(name) hke_##name
+#else
+#define HKAPI(name) hk_##name
+#endif
+
+namespace {
+
+struct MaterialH {
+    double young, poisson, density;
+    std::vector<double> plastic, Hd, ductile;   // column-major as given
+    int64_t npp, nd;
+};
+struct BCH {
+    std::vector<std::vector<int64_t>> dof;
+    std::vector<double> value;
+    std::vector<double> a_t, a_v;
+};
+struct ICH {
+    std::vector<std::vector<int64_t>> dof;
+    std::vector<double> value;
+};
+struct InstanceH {
+    int64_t node_offset, nNode, element_offset, nElement;
+    std::vector<int64_t> surfaces, eleid;        // (F,4) column-major part-local 1-based; (F)
+    bool table_built = false;
+    std::vector<std::array<int64_t, 4>> key;     // sorted 4-tuples
+    std::vector<int64_t> order;                  // face ids sorted by (key, id)
+};
+struct PairH {
+    int64_t i_instance, j_instance;
+    std::vector<int> nodes_i, nodes_j, t0, t1, t2, tele;   // 0-based
+    std::unordered_set<int> set_i, set_j;
+    double young;
+    HkPairDev dev;
+    bool dev_valid = false;
+};
+struct TimedEvent {
+#ifndef HK_EMU
+    cudaEvent_t a, b;
+#endif
+    int kind;
+};
+
+}  // namespace
+
+struct hk_engine {
+    hk_params prm;
+    std::string err;
+    bool finalized = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t nNode = 0, nElement = 0;
+    std::vector<double> coordmat, mass;
+    std::vector<int> conn;                       // [e*8+a] 0-based
+    std::vector<int> emat;                       // 0-based
+    std::vector<int64_t> einst;                  // 1-based
+    std::vector<MaterialH> materials;
+    std::vector<BCH> bcs;
+    std::vector<ICH> ics;
+    std::vector<InstanceH> instances;
+    std::vector<PairH> pairs;
+    // special nodes (host mirror)
+    std::vector<int> spec_idx_h;
+    std::vector<HkSpecialNode> spec_h;
+    int n_contact_slots = 0;
+    size_t spec_cap = 0, cacc_cap = 0;
+    HkDev d;
+    HkContactParams cp;
+    bool any_ductile = false;
+    bool velo_current = true;      // d.velo holds the current velocity
+    bool triax_current = true;     // d.triax matches the state
+    int use_Q0 = 0;
+    double dt2 = 0, dt2p = 0;
+    std::vector<void*> allocs;
+    double* staging = nullptr;     // device staging for layout transposes
+    size_t staging_doubles = 0;
+    std::vector<int64_t> deleted_all;
+    int del_seen = 0;
+    int64_t n_launch = 0, n_steps = 0;
+    bool profiling = false;
+    std::vector<TimedEvent> events;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_n[4] = {0, 0, 0, 0};
+};
+
+static std::string g_create_err;
+
+static int fail(hk_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg; else g_create_err = msg;
+    return code;
+}
+static int cuda_fail(hk_engine* e, int rc, const char* what) {
+    return fail(e, HK_ERR_CUDA, std::string(what) + ": " + hkp::error_string(rc));
+}
+#define CK(call) do { int rc_ = (int)(call); if (rc_) return cuda_fail(e, rc_, #call); } while (0)
+
+template <class T>
+static int dalloc(hk_engine* e, T** p, size_t count) {
+    void* q = nullptr;
+    int rc = hkp::dev_malloc(&q, count * sizeof(T));
+    if (rc) return cuda_fail(e, rc, "device allocation");
+    e->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+static void dfree(hk_engine* e, void* p) {
+    if (!p) return;
+    auto it = std::find(e->allocs.begin(), e->allocs.end(), p);
+    if (it != e->allocs.end()) e->allocs.erase(it);
+    hkp::dev_free(p);
+}
+template <class T>
+static int upload(hk_engine* e, T* dst, const std::vector<T>& src) {
+    if (src.empty()) return 0;
+    CK(hkp::h2d(dst, src.data(), src.size() * sizeof(T), e->stream));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------- profiling helpers
+static void prof_begin(hk_engine* e, int kind) {
+#ifndef HK_EMU
+    if (!e->profiling) return;
+    TimedEvent t;
+    t.kind = kind;
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+    cudaEventRecord(t.a, e->stream);
+    e->events.push_back(t);
+#else
+    (void)e; (void)kind;
+#endif
+}
+static void prof_end(hk_engine* e) {
+#ifndef HK_EMU
+    if (!e->profiling) return;
+    cudaEventRecord(e->events.back().b, e->stream);
+#else
+    (void)e;
+#endif
+}
+static void prof_collect(hk_engine* e) {
+#ifndef HK_EMU
+    if (e->events.empty()) return;
+    cudaStreamSynchronize(e->stream);
+    for (auto& t : e->events) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        e->prof_ms[t.kind] += ms;
+        e->prof_n[t.kind] += 1;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    e->events.clear();
+#else
+    (void)e;
+#endif
+}
+
+// --------------------------------------------------------------------------------- Pusai (J2:1895-1943)
+static void cal_Pusai_hexa(double P[8][3][8]) {
+    static const double dm[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
+                                    {-1, -1, 1},  {1, -1, 1},  {1, 1, 1},  {-1, 1, 1}};
+    const double g = 1.0 / std::sqrt(3.0);
+    const double gc[8][3] = {{-g, -g, -g}, {-g, -g, g}, {-g, g, -g}, {-g, g, g},
+                             {g, -g, -g},  {g, -g, g},  {g, g, -g},  {g, g, g}};
+    for (int k = 0; k < 8; ++k)
+        for (int i = 0; i < 8; ++i) {
+            P[k][0][i] = 1.0 / 8.0 * dm[i][0] * (1.0 + gc[k][1] * dm[i][1]) * (1.0 + gc[k][2] * dm[i][2]);
+            P[k][1][i] = 1.0 / 8.0 * dm[i][1] * (1.0 + gc[k][0] * dm[i][0]) * (1.0 + gc[k][2] * dm[i][2]);
+            P[k][2][i] = 1.0 / 8.0 * dm[i][2] * (1.0 + gc[k][0] * dm[i][0]) * (1.0 + gc[k][1] * dm[i][1]);
+        }
+}
+
+// --------------------------------------------------------------------------------- contact pair device arrays
+static int pair_upload(hk_engine* e, PairH& p) {
+    HkPairDev& D = p.dev;
+    if (p.dev_valid) {
+        dfree(e, D.nodes_i); dfree(e, D.nodes_j); dfree(e, D.t0); dfree(e, D.t1); dfree(e, D.t2); dfree(e, D.tele);
+        dfree(e, D.bbox); dfree(e, D.cell_i); dfree(e, D.head); dfree(e, D.next);
+        p.dev_valid = false;
+    }
+    D.nn_i = (int)p.nodes_i.size();
+    D.nn_j = (int)p.nodes_j.size();
+    D.nTri = (int)p.t0.size();
+    D.self = p.i_instance == p.j_instance;
+    D.young = p.young;
+    int nb = 64;
+    while (nb < 2 * D.nn_i) nb <<= 1;
+    D.n_bucket = nb;
+    int rc;
+    if ((rc = dalloc(e, &D.nodes_i, (size_t)D.nn_i))) return rc;
+    if ((rc = dalloc(e, &D.nodes_j, (size_t)D.nn_j))) return rc;
+    if ((rc = dalloc(e, &D.t0, (size_t)D.nTri))) return rc;
+    if ((rc = dalloc(e, &D.t1, (size_t)D.nTri))) return rc;
+    if ((rc = dalloc(e, &D.t2, (size_t)D.nTri))) return rc;
+    if ((rc = dalloc(e, &D.tele, (size_t)D.nTri))) return rc;
+    if ((rc = dalloc(e, &D.bbox, (size_t)12))) return rc;
+    if ((rc = dalloc(e, &D.cell_i, (size_t)3 * D.nn_i))) return rc;
+    if ((rc = dalloc(e, &D.head, (size_t)nb))) return rc;
+    if ((rc = dalloc(e, &D.next, (size_t)D.nn_i))) return rc;
+    if ((rc = upload(e, D.nodes_i, p.nodes_i))) return rc;
+    if ((rc = upload(e, D.nodes_j, p.nodes_j))) return rc;
+    if ((rc = upload(e, D.t0, p.t0))) return rc;
+    if ((rc = upload(e, D.t1, p.t1))) return rc;
+    if ((rc = upload(e, D.t2, p.t2))) return rc;
+    if ((rc = upload(e, D.tele, p.tele))) return rc;
+    p.dev_valid = true;
+    return 0;
+}
+
+// special-node bookkeeping ---------------------------------------------------------------------
+static int spec_of(hk_engine* e, int node) {
+    int s = e->spec_idx_h[node];
+    if (s < 0) {
+        HkSpecialNode sn;
+        sn.bc_entry[0] = sn.bc_entry[1] = sn.bc_entry[2] = -1;
+        sn.contact_slot = -1;
+        sn.halo_slot = -1;
+        sn.pad = 0;
+        s = (int)e->spec_h.size();
+        e->spec_h.push_back(sn);
+        e->spec_idx_h[node] = s;
+    }
+    return s;
+}
+static void ensure_contact_slot(hk_engine* e, int node, std::vector<int>* touched) {
+    int s = spec_of(e, node);
+    if (e->spec_h[s].contact_slot < 0) {
+        e->spec_h[s].contact_slot = e->n_contact_slots++;
+        if (touched) touched->push_back(node);
+    }
+}
+static int spec_upload(hk_engine* e, const std::vector<int>* touched_nodes) {
+    // (re)upload the special-node table; grow device arrays when needed
+    if (e->spec_h.size() > e->spec_cap) {
+        dfree(e, e->d.spec);
+        e->spec_cap = std::max<size_t>(64, e->spec_h.size() * 2);
+        int rc = dalloc(e, &e->d.spec, e->spec_cap);
+        if (rc) return rc;
+    }
+    int rc = upload(e, e->d.spec, e->spec_h);
+    if (rc) return rc;
+    if ((size_t)e->n_contact_slots > e->cacc_cap) {
+        dfree(e, e->d.cacc);
+        e->cacc_cap = std::max<size_t>(64, (size_t)e->n_contact_slots * 2);
+        rc = dalloc(e, &e->d.cacc, e->cacc_cap * 6);
+        if (rc) return rc;
+        CK(hkp::dev_memset(e->d.cacc, 0, e->cacc_cap * 6 * sizeof(unsigned long long), e->stream));
+    }
+    if (touched_nodes) {
+        for (int n : *touched_nodes) CK(hkp::h2d(e->d.spec_idx + n, &e->spec_idx_h[n], sizeof(int), e->stream));
+    } else {
+        rc = upload(e, e->d.spec_idx, e->spec_idx_h);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// --------------------------------------------------------------------------------- exposed faces (A10)
+static void build_face_table(InstanceH& I) {
+    const int64_t F = 6 * I.nElement;
+    I.key.resize(F);
+    for (int64_t j = 0; j < F; ++j) {
+        std::array<int64_t, 4> k = {I.surfaces[j], I.surfaces[j + F], I.surfaces[j + 2 * F], I.surfaces[j + 3 * F]};
+        std::sort(k.begin(), k.end());
+        I.key[j] = k;
+    }
+    I.order.resize(F);
+    for (int64_t j = 0; j < F; ++j) I.order[j] = j;
+    std::sort(I.order.begin(), I.order.end(), [&](int64_t a, int64_t b) {
+        if (I.key[a] != I.key[b]) return I.key[a] < I.key[b];
+        return a < b;
+    });
+    I.table_built = true;
+}
+
+// add_surface_triangle (J2:2167-2245): for each face of the deleted element, the first face (in face-id
+// order) of ANOTHER element with the same node set becomes exposed.
+static void add_surface_triangle(InstanceH& I, int64_t ele_id, std::vector<int64_t>& tri, std::vector<int64_t>& tri_ele,
+                                 std::vector<int64_t>& nodes) {
+    if (!I.table_built) build_face_table(I);
+    const int64_t F = 6 * I.nElement;
+    for (int j = 0; j < 6; ++j) {
+        const int64_t fj = 6 * (ele_id - 1) + j;
+        const std::array<int64_t, 4>& kj = I.key[fj];
+        auto lo = std::lower_bound(I.order.begin(), I.order.end(), fj, [&](int64_t a, int64_t) { return I.key[a] < kj; });
+        for (auto it = lo; it != I.order.end() && I.key[*it] == kj; ++it) {
+            const int64_t k = *it;
+            if (I.eleid[k] == ele_id) continue;
+            const int64_t s[4] = {I.surfaces[k], I.surfaces[k + F], I.surfaces[k + 2 * F], I.surfaces[k + 3 * F]};
+            tri.push_back(s[0]); tri.push_back(s[1]); tri.push_back(s[2]);
+            tri.push_back(s[2]); tri.push_back(s[3]); tri.push_back(s[0]);
+            tri_ele.push_back(I.eleid[k]);
+            tri_ele.push_back(I.eleid[k]);
+            break;
+        }
+    }
+    nodes = tri;
+    std::sort(nodes.begin(), nodes.end());
+    nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+}
+
+static int update_surfaces(hk_engine* e, const std::vector<int64_t>& deleted /* 1-based global ids */) {
+    std::vector<char> changed(e->pairs.size(), 0);
+    std::vector<int> touched;
+    for (int64_t gid : deleted) {
+        const int64_t instance_id = e->einst[gid - 1];
+        if (instance_id < 1 || instance_id > (int64_t)e->instances.size()) continue;
+        InstanceH& I = e->instances[instance_id - 1];
+        if (I.surfaces.empty()) continue;
+        std::vector<int64_t> tri, tri_ele, nodes;
+        add_surface_triangle(I, gid - I.element_offset, tri, tri_ele, nodes);
+        for (size_t c = 0; c < e->pairs.size(); ++c) {
+            PairH& p = e->pairs[c];
+            if (p.i_instance == instance_id) {                  // J2:784-787
+                for (int64_t nl : nodes) {
+                    int g = (int)(nl + I.node_offset - 1);
+                    if (p.set_i.insert(g).second) { p.nodes_i.push_back(g); ensure_contact_slot(e, g, &touched); changed[c] = 1; }
+                }
+            } else if (p.j_instance == instance_id) {           // J2:789-797
+                for (int64_t nl : nodes) {
+                    int g = (int)(nl + I.node_offset - 1);
+                    if (p.set_j.insert(g).second) { p.nodes_j.push_back(g); ensure_contact_slot(e, g, &touched); changed[c] = 1; }
+                }
+                for (size_t r = 0; r < tri_ele.size(); ++r) {
+                    p.t0.push_back((int)(tri[3 * r + 0] + I.node_offset - 1));
+                    p.t1.push_back((int)(tri[3 * r + 1] + I.node_offset - 1));
+                    p.t2.push_back((int)(tri[3 * r + 2] + I.node_offset - 1));
+                    p.tele.push_back((int)(tri_ele[r] + I.element_offset - 1));
+                    changed[c] = 1;
+                }
+            }
+        }
+    }
+    for (size_t c = 0; c < e->pairs.size(); ++c)
+        if (changed[c]) { int rc = pair_upload(e, e->pairs[c]); if (rc) return rc; }
+    if (!touched.empty()) { int rc = spec_upload(e, &touched); if (rc) return rc; }
+    return 0;
+}
+
+// fetch deletion log entries [del_seen, count) -> sorted (step, id), appended to deleted_all
+static int fetch_deleted(hk_engine* e, std::vector<int64_t>* fresh) {
+    int count = 0;
+    CK(hkp::d2h(&count, e->d.del_count, sizeof(int), e->stream));
+    if (count > e->d.del_cap) count = e->d.del_cap;
+    if (count <= e->del_seen) return 0;
+    std::vector<long long> ent(count - e->del_seen);
+    CK(hkp::d2h(ent.data(), e->d.del_list + e->del_seen, ent.size() * sizeof(long long), e->stream));
+    std::sort(ent.begin(), ent.end());
+    for (long long v : ent) {
+        int64_t id = (int64_t)(v & 0xffffffffll) + 1;
+        e->deleted_all.push_back(id);
+        if (fresh) fresh->push_back(id);
+    }
+    e->del_seen = count;
+    return 0;
+}
+
+// ================================================================================= exported ABI
+extern "C" {
+
+int HKAPI(default_params)(hk_params* p) {
+    if (!p) return HK_ERR_ARG;
+    std::memset(p, 0, sizeof(*p));
+    p->struct_size = (int32_t)sizeof(hk_params);
+    p->contact_d_lim_factor = 0.3;
+    p->contact_myu = 0.25;
+    p->contact_kc_other = 1.0;
+    p->contact_kc_self = 1.0;
+    p->contact_cr_other = 0.0;
+    p->contact_cr_self = 0.0;
+    p->contact_ddiv_other = 1.1;
+    p->contact_ddiv_self = 0.6;
+    p->deterministic = 1;
+    return HK_OK;
+}
+
+int HKAPI(create)(hk_engine** out, const hk_params* p) {
+    if (!out || !p) return fail(nullptr, HK_ERR_ARG, "null argument");
+    if (p->struct_size != (int32_t)sizeof(hk_params)) return fail(nullptr, HK_ERR_ARG, "hk_params size mismatch");
+    if (!(p->d_time > 0)) return fail(nullptr, HK_ERR_ARG, "d_time must be > 0");
+    if (p->triax_route != 0) return fail(nullptr, HK_ERR_UNSUPPORTED, "triax_route 1 (eigenvalue route) exists only in the oracle");
+#ifndef HK_EMU
+    int ndev = 0;
+    cudaError_t rc = cudaGetDeviceCount(&ndev);
+    if (rc != cudaSuccess || ndev == 0)
+        return fail(nullptr, HK_ERR_NO_DEVICE, std::string("no CUDA device (") + cudaGetErrorString(rc) +
+                                                   "): this engine has no CPU fallback");
+    if (p->device < 0 || p->device >= ndev) return fail(nullptr, HK_ERR_ARG, "bad device ordinal");
+    rc = cudaSetDevice(p->device);
+    if (rc != cudaSuccess) return fail(nullptr, HK_ERR_CUDA, cudaGetErrorString(rc));
+#endif
+    hk_engine* e = new hk_engine();
+    e->prm = *p;
+    std::memset(&e->d, 0, sizeof(e->d));
+#ifndef HK_EMU
+    rc = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (rc != cudaSuccess) { delete e; return fail(nullptr, HK_ERR_CUDA, cudaGetErrorString(rc)); }
+    e->own_stream = true;
+#endif
+    *out = e;
+    return HK_OK;
+}
+
+int HKAPI(destroy)(hk_engine* e) {
+    if (!e) return HK_OK;
+    prof_collect(e);
+    hkp::sync(e->stream);
+    for (void* p : e->allocs) hkp::dev_free(p);
+#ifndef HK_EMU
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+#endif
+    delete e;
+    return HK_OK;
+}
+
+const char* HKAPI(last_error)(const hk_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+int HKAPI(set_mesh)(hk_engine* e, int64_t nNode, int64_t nElement, const double* coordmat, const int64_t* elementmat,
+                    const int64_t* element_material, const int64_t* element_instance, const double* diag_M) {
+    if (!e || !coordmat || !elementmat || !element_material || !diag_M) return fail(e, HK_ERR_ARG, "null argument");
+    if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    if (nNode <= 0 || nElement <= 0 || nElement >= (1ll << 28) || nNode >= (1ll << 31) / 6)
+        return fail(e, HK_ERR_ARG, "mesh size out of range (nElement < 2^28)");
+    e->nNode = nNode;
+    e->nElement = nElement;
+    e->coordmat.assign(coordmat, coordmat + 3 * nNode);
+    e->mass.resize(nNode);
+    for (int64_t n = 0; n < nNode; ++n) {
+        const double m = diag_M[3 * n];
+        if (diag_M[3 * n + 1] != m || diag_M[3 * n + 2] != m)
+            return fail(e, HK_ERR_ARG, "diag_M must hold the same mass on the 3 dofs of a node (J2:205-215)");
+        e->mass[n] = m;
+    }
+    e->conn.resize(8 * nElement);
+    for (int64_t i = 0; i < 8 * nElement; ++i) {
+        int64_t v = elementmat[i];
+        if (v < 1 || v > nNode) return fail(e, HK_ERR_ARG, "elementmat entry out of range");
+        e->conn[i] = (int)(v - 1);
+    }
+    e->emat.resize(nElement);
+    for (int64_t i = 0; i < nElement; ++i) e->emat[i] = (int)(element_material[i] - 1);
+    e->einst.assign(nElement, 1);
+    if (element_instance) e->einst.assign(element_instance, element_instance + nElement);
+    return HK_OK;
+}
+
+int HKAPI(add_material)(hk_engine* e, double young, double poisson, double density, int64_t npp, const double* plastic,
+                        const double* Hd, int64_t nd, const double* ductile) {
+    if (!e) return HK_ERR_ARG;
+    if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    if (npp == 1) return fail(e, HK_ERR_ARG, "*Plastic table needs >= 2 rows (the reference indexes Hd[1])");
+    if (npp > HK_MAX_TABLE || nd > HK_MAX_TABLE) return fail(e, HK_ERR_UNSUPPORTED, "material table longer than HK_MAX_TABLE");
+    MaterialH m;
+    m.young = young; m.poisson = poisson; m.density = density; m.npp = npp; m.nd = nd;
+    if (npp > 0) { m.plastic.assign(plastic, plastic + 2 * npp); m.Hd.assign(Hd, Hd + npp - 1); }
+    if (nd > 0) m.ductile.assign(ductile, ductile + 3 * nd);
+    e->materials.push_back(m);
+    return HK_OK;
+}
+
+int HKAPI(add_bc)(hk_engine* e, int64_t n_lists, const int64_t* dof_ptr, const int64_t* dofs, const double* values,
+                  int64_t n_amp, const double* amp_time, const double* amp_value) {
+    if (!e) return HK_ERR_ARG;
+    if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    BCH b;
+    for (int64_t j = 0; j < n_lists; ++j) {
+        b.dof.emplace_back(dofs + dof_ptr[j], dofs + dof_ptr[j + 1]);
+        b.value.push_back(values[j]);
+    }
+    if (n_amp > 0) {
+        if (n_amp < 2) return fail(e, HK_ERR_ARG, "amplitude table needs >= 2 points");
+        b.a_t.assign(amp_time, amp_time + n_amp);
+        b.a_v.assign(amp_value, amp_value + n_amp);
+    }
+    e->bcs.push_back(b);
+    return HK_OK;
+}
+
+int HKAPI(add_ic)(hk_engine* e, int64_t n_lists, const int64_t* dof_ptr, const int64_t* dofs, const double* values) {
+    if (!e) return HK_ERR_ARG;
+    if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    ICH b;
+    for (int64_t j = 0; j < n_lists; ++j) {
+        b.dof.emplace_back(dofs + dof_ptr[j], dofs + dof_ptr[j + 1]);
+        b.value.push_back(values[j]);
+    }
+    e->ics.push_back(b);
+    return HK_OK;
+}
+
+int HKAPI(add_instance)(hk_engine* e, int64_t node_offset, int64_t nNode, int64_t element_offset, int64_t nElement,
+                        const int64_t* surfaces, const int64_t* surfaces_eleid) {
+    if (!e) return HK_ERR_ARG;
+    if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    InstanceH I;
+    I.node_offset = node_offset; I.nNode = nNode; I.element_offset = element_offset; I.nElement = nElement;
+    if (surfaces && surfaces_eleid) {
+        I.surfaces.assign(surfaces, surfaces + 24 * nElement);
+        I.eleid.assign(surfaces_eleid, surfaces_eleid + 6 * nElement);
+    }
+    e->instances.push_back(std::move(I));
+    return HK_OK;
+}
+
+int HKAPI(add_contact_pair)(hk_engine* e, int64_t i_instance, int64_t j_instance, int64_t nn_i, const int64_t* c_nodes_i,
+                            int64_t nn_j, const int64_t* c_nodes_j, int64_t nTri, const int64_t* c_triangles,
+                            const int64_t* c_triangles_eleid, double young) {
+    if (!e) return HK_ERR_ARG;
+    if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    PairH p;
+    p.i_instance = i_instance; p.j_instance = j_instance; p.young = young;
+    std::memset(&p.dev, 0, sizeof(p.dev));
+    for (int64_t k = 0; k < nn_i; ++k) { p.nodes_i.push_back((int)(c_nodes_i[k] - 1)); p.set_i.insert((int)(c_nodes_i[k] - 1)); }
+    for (int64_t k = 0; k < nn_j; ++k) { p.nodes_j.push_back((int)(c_nodes_j[k] - 1)); p.set_j.insert((int)(c_nodes_j[k] - 1)); }
+    for (int64_t k = 0; k < nTri; ++k) {
+        p.t0.push_back((int)(c_triangles[k] - 1));
+        p.t1.push_back((int)(c_triangles[k + nTri] - 1));
+        p.t2.push_back((int)(c_triangles[k + 2 * nTri] - 1));
+        p.tele.push_back((int)(c_triangles_eleid[k] - 1));
+    }
+    e->pairs.push_back(std::move(p));
+    return HK_OK;
+}
+
+int HKAPI(finalize)(hk_engine* e) {
+    if (!e) return HK_ERR_ARG;
+    if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    if (e->nNode == 0) return fail(e, HK_ERR_STATE, "hk_set_mesh not called");
+    const int64_t nN = e->nNode, nE = e->nElement;
+    const int64_t nEp = (nE + 31) / 32 * 32;
+    HkDev& d = e->d;
+    d.nNode = nN; d.nElement = nE; d.nEp = nEp;
+    const double dt = e->prm.d_time;
+    e->dt2 = dt * dt;                 // d_time^2   (J2:564)
+    e->dt2p = std::pow(dt, 2.0);      // d_time^2.0 (J2:564)
+    int rc;
+
+    // ---- materials
+    if (e->materials.empty()) return fail(e, HK_ERR_STATE, "no material");
+    std::vector<HkMaterialDev> md(e->materials.size());
+    for (size_t i = 0; i < md.size(); ++i) {
+        const MaterialH& m = e->materials[i];
+        HkMaterialDev& D = md[i];
+        std::memset(&D, 0, sizeof(D));
+        D.young = m.young; D.poisson = m.poisson;
+        D.G = m.young / 2. / (1.0 + m.poisson);                                  // J2:146
+        const double d1 = (1.0 - m.poisson), d2 = m.poisson, d3 = (1.0 - 2.0 * m.poisson) / 2.0;
+        const double f = m.young / (1.0 + m.poisson) / (1.0 - 2.0 * m.poisson);  // J2:153
+        D.D11 = f * d1; D.D12 = f * d2; D.D44 = f * d3;
+        D.npp = (int)m.npp; D.nd = (int)m.nd;
+        for (int64_t r = 0; r < m.npp; ++r) { D.plastic_s[r] = m.plastic[r]; D.plastic_e[r] = m.plastic[r + m.npp]; }
+        for (int64_t r = 0; r + 1 < m.npp; ++r) D.Hd[r] = m.Hd[r];
+        for (int64_t r = 0; r < m.nd; ++r) { D.duct_e[r] = m.ductile[r]; D.duct_t[r] = m.ductile[r + m.nd]; }
+        if (m.nd > 0) e->any_ductile = true;
+    }
+    for (int64_t i = 0; i < nE; ++i)
+        if (e->emat[i] < 0 || e->emat[i] >= (int)md.size()) return fail(e, HK_ERR_ARG, "element_material out of range");
+    d.n_mat = (int)md.size();
+    if ((rc = dalloc(e, &d.mats, md.size()))) return rc;
+    if ((rc = upload(e, d.mats, md))) return rc;
+    {
+        double P[8][3][8];
+        cal_Pusai_hexa(P);
+        hk_upload_pusai(&P[0][0][0]);
+    }
+
+    // ---- nodes
+    if ((rc = dalloc(e, &d.X, (size_t)3 * nN))) return rc;
+    if ((rc = dalloc(e, &d.u, (size_t)3 * nN))) return rc;
+    if ((rc = dalloc(e, &d.u_pre, (size_t)3 * nN))) return rc;
+    if ((rc = dalloc(e, &d.velo, (size_t)3 * nN))) return rc;
+    if ((rc = dalloc(e, &d.rec, (size_t)6 * nN))) return rc;
+    if ((rc = dalloc(e, &d.mass, (size_t)nN))) return rc;
+    if ((rc = dalloc(e, &d.Q0, (size_t)3 * nN))) return rc;
+    if ((rc = upload(e, d.X, e->coordmat))) return rc;
+    if ((rc = upload(e, d.mass, e->mass))) return rc;
+    {
+        std::vector<double> up(3 * nN, 0.0), ve(3 * nN, 0.0), rec(6 * nN, 0.0);
+        for (const ICH& ic : e->ics)                                             // J2:233-239
+            for (size_t j = 0; j < ic.dof.size(); ++j)
+                for (int64_t dof : ic.dof[j]) {
+                    if (dof < 1 || dof > 3 * nN) return fail(e, HK_ERR_ARG, "IC dof out of range");
+                    up[dof - 1] = -ic.value[j] * dt;
+                    ve[dof - 1] = ic.value[j];
+                }
+        for (int64_t n = 0; n < nN; ++n)
+            for (int c = 0; c < 3; ++c) rec[6 * n + c] = e->coordmat[3 * n + c];   // position = coordmat, J2:222
+        if ((rc = upload(e, d.u_pre, up))) return rc;
+        if ((rc = upload(e, d.velo, ve))) return rc;
+        if ((rc = upload(e, d.rec, rec))) return rc;
+        CK(hkp::dev_memset(d.u, 0, sizeof(double) * 3 * nN, e->stream));
+        CK(hkp::dev_memset(d.Q0, 0, sizeof(double) * 3 * nN, e->stream));
+    }
+
+    // ---- node -> element table (ELL, ascending element order = the reference's scatter order J2:669-675)
+    {
+        std::vector<int> cnt(nN, 0);
+        for (int64_t i = 0; i < 8 * nE; ++i) cnt[e->conn[i]]++;
+        int w = 0;
+        for (int64_t n = 0; n < nN; ++n) w = std::max(w, cnt[n]);
+        d.ell_width = w;
+        std::vector<int> ell((size_t)w * nN, -1);
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int64_t el = 0; el < nE; ++el)
+            for (int a = 0; a < 8; ++a) {
+                const int n = e->conn[8 * el + a];
+                ell[(size_t)cnt[n] * nN + n] = (int)(el * 8 + a);
+                cnt[n]++;
+            }
+        if ((rc = dalloc(e, &d.ell, ell.size()))) return rc;
+        if ((rc = upload(e, d.ell, ell))) return rc;
+    }
+
+    // ---- boundary conditions -> special nodes
+    e->spec_idx_h.assign(nN, -1);
+    {
+        std::vector<double> bc_value, amp_time, amp_value;
+        std::vector<int> bc_amp;
+        std::vector<HkAmpTable> amp_tab;
+        for (const BCH& b : e->bcs) {
+            int aid = -1;
+            if (!b.a_t.empty()) {
+                aid = (int)amp_tab.size();
+                HkAmpTable t;
+                t.n = (int)b.a_t.size();
+                t.offset = (int)amp_time.size();
+                amp_tab.push_back(t);
+                amp_time.insert(amp_time.end(), b.a_t.begin(), b.a_t.end());
+                amp_value.insert(amp_value.end(), b.a_v.begin(), b.a_v.end());
+            }
+            for (size_t j = 0; j < b.dof.size(); ++j) {
+                const int entry = (int)bc_value.size();
+                bc_value.push_back(b.value[j]);
+                bc_amp.push_back(aid);
+                for (int64_t dof : b.dof[j]) {
+                    if (dof < 1 || dof > 3 * nN) return fail(e, HK_ERR_ARG, "BC dof out of range");
+                    const int node = (int)((dof - 1) / 3), c = (int)((dof - 1) % 3);
+                    const int si = spec_of(e, node);
+                    e->spec_h[si].bc_entry[c] = entry;                    // later BCs override earlier ones
+                }
+            }
+        }
+        if ((rc = dalloc(e, &d.bc_value, bc_value.size()))) return rc;
+        if ((rc = dalloc(e, &d.bc_amp, bc_amp.size()))) return rc;
+        if ((rc = dalloc(e, &d.amp_tab, amp_tab.size()))) return rc;
+        if ((rc = dalloc(e, &d.amp_time, amp_time.size()))) return rc;
+        if ((rc = dalloc(e, &d.amp_value, amp_value.size()))) return rc;
+        if ((rc = upload(e, d.bc_value, bc_value))) return rc;
+        if ((rc = upload(e, d.bc_amp, bc_amp))) return rc;
+        if ((rc = upload(e, d.amp_tab, amp_tab))) return rc;
+        if ((rc = upload(e, d.amp_time, amp_time))) return rc;
+        if ((rc = upload(e, d.amp_value, amp_value))) return rc;
+    }
+
+    // ---- elements
+    {
+        std::vector<int> conn_soa((size_t)8 * nEp, 0);
+        for (int64_t el = 0; el < nE; ++el)
+            for (int a = 0; a < 8; ++a) conn_soa[(size_t)a * nEp + el] = e->conn[8 * el + a];
+        if ((rc = dalloc(e, &d.conn, conn_soa.size()))) return rc;
+        if ((rc = upload(e, d.conn, conn_soa))) return rc;
+        std::vector<unsigned char> fl(nEp, 2);
+        std::vector<unsigned short> mt(nEp, 0);
+        for (int64_t el = 0; el < nE; ++el) { fl[el] = 1; mt[el] = (unsigned short)e->emat[el]; }
+        if ((rc = dalloc(e, &d.flag, (size_t)nEp))) return rc;
+        if ((rc = dalloc(e, &d.mat, (size_t)nEp))) return rc;
+        if ((rc = upload(e, d.flag, fl))) return rc;
+        if ((rc = upload(e, d.mat, mt))) return rc;
+    }
+    if ((rc = dalloc(e, &d.stress, (size_t)48 * nEp))) return rc;
+    if ((rc = dalloc(e, &d.strain, (size_t)48 * nEp))) return rc;
+    if ((rc = dalloc(e, &d.eps, (size_t)8 * nEp))) return rc;
+    if ((rc = dalloc(e, &d.yield, (size_t)8 * nEp))) return rc;
+    if ((rc = dalloc(e, &d.triax, (size_t)8 * nEp))) return rc;
+    if ((rc = dalloc(e, &d.Qe, (size_t)24 * nEp))) return rc;
+    CK(hkp::dev_memset(d.stress, 0, sizeof(double) * 48 * nEp, e->stream));
+    CK(hkp::dev_memset(d.strain, 0, sizeof(double) * 48 * nEp, e->stream));
+    CK(hkp::dev_memset(d.eps, 0, sizeof(double) * 8 * nEp, e->stream));
+    CK(hkp::dev_memset(d.yield, 0, sizeof(double) * 8 * nEp, e->stream));
+    CK(hkp::dev_memset(d.triax, 0, sizeof(double) * 8 * nEp, e->stream));
+    CK(hkp::dev_memset(d.Qe, 0, sizeof(double) * 24 * nEp, e->stream));
+    {   // integ_yield_stress = plastic[1,1] of the element's material (J2:456-465)
+        const HkDev dd = d;
+        hk_parallel_for(nE * 8, e->stream, HK_LAMBDA(long long i) {
+            const long long el = i % dd.nElement, k = i / dd.nElement;
+            const HkMaterialDev& M = dd.mats[dd.mat[el]];
+            if (M.npp > 0) dd.yield[k * dd.nEp + el] = M.plastic_s[0];
+        });
+    }
+    d.del_cap = (int)nE;
+    if ((rc = dalloc(e, &d.del_count, (size_t)1))) return rc;
+    if ((rc = dalloc(e, &d.del_list, (size_t)nE))) return rc;
+    if ((rc = dalloc(e, &d.counters, (size_t)8))) return rc;
+    CK(hkp::dev_memset(d.del_count, 0, sizeof(int), e->stream));
+    CK(hkp::dev_memset(d.counters, 0, 8 * sizeof(unsigned long long), e->stream));
+
+    // ---- contact
+    if ((rc = dalloc(e, &d.spec_idx, (size_t)nN))) return rc;
+    if (e->prm.contact_flag >= 1) {
+        for (PairH& p : e->pairs) {
+            for (int n : p.nodes_i) ensure_contact_slot(e, n, nullptr);
+            for (int n : p.nodes_j) ensure_contact_slot(e, n, nullptr);
+            for (size_t k = 0; k < p.t0.size(); ++k) {     // triangle vertices are members of c_nodes_j by construction
+                ensure_contact_slot(e, p.t0[k], nullptr);
+                ensure_contact_slot(e, p.t1[k], nullptr);
+                ensure_contact_slot(e, p.t2[k], nullptr);
+            }
+            if ((rc = pair_upload(e, p))) return rc;
+        }
+        HkContactParams& cp = e->cp;
+        cp.d_lim = e->prm.element_min_size * e->prm.contact_d_lim_factor;        // J2:2254
+        cp.myu = e->prm.contact_myu;
+        cp.kc_o = e->prm.contact_kc_other; cp.kc_s = e->prm.contact_kc_self;
+        cp.cr_o = e->prm.contact_cr_other; cp.cr_s = e->prm.contact_cr_self;
+        cp.ddiv_o = e->prm.element_max_size * e->prm.contact_ddiv_other;          // J2:2331
+        cp.ddiv_s = e->prm.element_max_size * e->prm.contact_ddiv_self;           // J2:2333
+        cp.d_time = dt;
+        double ymax = 0;
+        for (const PairH& p : e->pairs) ymax = std::max(ymax, p.young);
+        const double nominal = ymax * e->prm.element_max_size * cp.d_lim * std::max(cp.kc_o, cp.kc_s);
+        int ex = 0;
+        if (nominal > 0) std::frexp(nominal, &ex);
+        cp.lsb_exp = ex - 90;      // 2^36 of headroom above the nominal force E*eMax*d_lim, 90 bits below it
+    }
+    if ((rc = spec_upload(e, nullptr))) return rc;
+    CK(hkp::sync(e->stream));
+    CK(hkp::last_error());
+    e->finalized = true;
+    e->velo_current = true;
+    e->triax_current = true;
+    return HK_OK;
+}
+
+int HKAPI(step)(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_deleted_out) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (n_steps < 0 || t_first < 0 || t_first + n_steps >= (1ll << 31)) return fail(e, HK_ERR_ARG, "bad step range");
+    const HkDev& d = e->d;
+    const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
+    const size_t before = e->deleted_all.size();
+    for (int64_t t = t_first; t < t_first + n_steps; ++t) {
+        if (contact_on) {
+            prof_begin(e, 0);
+            CK(hkp::dev_memset(d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
+            for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 4; }
+            prof_end(e);
+        }
+        prof_begin(e, 1);
+        hk_launch_nodal(d, (double)t * e->prm.d_time, e->prm.d_time, e->dt2, e->dt2p, e->cp.lsb_exp, contact_on ? 1 : 0,
+                        e->use_Q0, e->stream);
+        prof_end(e);
+        e->use_Q0 = 0;
+        prof_begin(e, 2);
+        hk_launch_element(d, t, (t == t_first + n_steps - 1) ? 1 : 0, e->stream);
+        prof_end(e);
+        e->n_launch += 2;
+        e->n_steps += 1;
+        if (contact_on && e->any_ductile) {       // exposed faces must be in place before the next contact pass
+            std::vector<int64_t> fresh;
+            int rc = fetch_deleted(e, &fresh);
+            if (rc) return rc;
+            if (!fresh.empty()) { rc = update_surfaces(e, fresh); if (rc) return rc; }
+        }
+    }
+    if (n_steps > 0) {
+        e->velo_current = contact_on;
+        e->triax_current = true;
+    }
+    int rc = fetch_deleted(e, nullptr);
+    if (rc) return rc;
+    CK(hkp::sync(e->stream));
+    CK(hkp::last_error());
+    if (n_deleted_out) *n_deleted_out = (int64_t)(e->deleted_all.size() - before);
+    return HK_OK;
+}
+
+// staging buffer for layout transposes
+static int ensure_staging(hk_engine* e, size_t doubles) {
+    if (e->staging_doubles >= doubles) return 0;
+    dfree(e, e->staging);
+    e->staging = nullptr;
+    int rc = dalloc(e, &e->staging, doubles);
+    if (rc) return rc;
+    e->staging_doubles = doubles;
+    return 0;
+}
+static const long long CHUNK_E = 1 << 18;   // elements per transposed chunk (<= 100 MB staging)
+
+static int download_ip(hk_engine* e, const double* soa, double* host, int ncomp) {
+    if (!host) return 0;
+    const long long nE = e->nElement;
+    int rc = ensure_staging(e, (size_t)std::min<long long>(CHUNK_E, nE) * 8 * ncomp);
+    if (rc) return rc;
+    for (long long e0 = 0; e0 < nE; e0 += CHUNK_E) {
+        const long long ne = std::min<long long>(CHUNK_E, nE - e0);
+        hk_launch_ip_to_aos(soa, e->staging, ncomp, e0, ne, e->d.nEp, e->stream);
+        CK(hkp::d2h(host + e0 * 8 * ncomp, e->staging, (size_t)ne * 8 * ncomp * sizeof(double), e->stream));
+    }
+    return 0;
+}
+static int upload_ip(hk_engine* e, double* soa, const double* host, int ncomp) {
+    if (!host) return 0;
+    const long long nE = e->nElement;
+    int rc = ensure_staging(e, (size_t)std::min<long long>(CHUNK_E, nE) * 8 * ncomp);
+    if (rc) return rc;
+    for (long long e0 = 0; e0 < nE; e0 += CHUNK_E) {
+        const long long ne = std::min<long long>(CHUNK_E, nE - e0);
+        CK(hkp::h2d(e->staging, host + e0 * 8 * ncomp, (size_t)ne * 8 * ncomp * sizeof(double), e->stream));
+        hk_launch_ip_to_soa(e->staging, soa, ncomp, e0, ne, e->d.nEp, e->stream);
+        CK(hkp::sync(e->stream));
+    }
+    return 0;
+}
+
+int HKAPI(download)(hk_engine* e, double* disp, double* velo, double* integ_stress, double* integ_strain,
+                    double* integ_eq_plastic_strain, double* integ_triax_stress, int64_t* element_flag) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    const HkDev& d = e->d;
+    const size_t fnb = sizeof(double) * 3 * e->nNode;
+    int rc;
+    if (disp) CK(hkp::d2h(disp, d.u, fnb, e->stream));
+    if (velo) {
+        if (!e->velo_current) { hk_launch_velo_from_rec(d, e->prm.d_time, e->stream); e->velo_current = true; }
+        CK(hkp::d2h(velo, d.velo, fnb, e->stream));
+    }
+    if ((rc = download_ip(e, d.stress, integ_stress, 6))) return rc;
+    if ((rc = download_ip(e, d.strain, integ_strain, 6))) return rc;
+    if ((rc = download_ip(e, d.eps, integ_eq_plastic_strain, 1))) return rc;
+    if (integ_triax_stress) {
+        if (!e->triax_current) { hk_launch_triax(d, e->stream); e->triax_current = true; }
+        if ((rc = download_ip(e, d.triax, integ_triax_stress, 1))) return rc;
+    }
+    if (element_flag) {
+        std::vector<unsigned char> fl(e->nElement);
+        CK(hkp::d2h(fl.data(), d.flag, fl.size(), e->stream));
+        for (int64_t i = 0; i < e->nElement; ++i) element_flag[i] = fl[i] == 1 ? 1 : 0;
+    }
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(download_ex)(hk_engine* e, double* disp_pre, double* Q, double* external_force, double* position,
+                       double* integ_yield_stress, double* elementVolume) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    const HkDev& d = e->d;
+    const int64_t nN = e->nNode;
+    const size_t fnb = sizeof(double) * 3 * nN;
+    int rc;
+    if (disp_pre) CK(hkp::d2h(disp_pre, d.u_pre, fnb, e->stream));
+    if (Q) {
+        if (e->use_Q0) {
+            CK(hkp::d2h(Q, d.Q0, fnb, e->stream));
+        } else {
+            if ((rc = ensure_staging(e, (size_t)3 * nN))) return rc;
+            hk_launch_gather_Q(d, e->staging, e->stream);
+            CK(hkp::d2h(Q, e->staging, fnb, e->stream));
+        }
+    }
+    if (external_force) {
+        if ((rc = ensure_staging(e, (size_t)3 * nN))) return rc;
+        double* out = e->staging;
+        const HkDev dd = d;
+        const int lsb = e->cp.lsb_exp;
+        const int on = (e->prm.contact_flag >= 1 && !e->pairs.empty()) ? 1 : 0;
+        hk_launch_external_force(dd, out, lsb, on, e->stream);
+        CK(hkp::d2h(external_force, out, fnb, e->stream));
+    }
+    if (position) {
+        std::vector<double> rec(6 * nN);
+        CK(hkp::d2h(rec.data(), d.rec, rec.size() * sizeof(double), e->stream));
+        for (int64_t n = 0; n < nN; ++n)
+            for (int c = 0; c < 3; ++c) position[3 * n + c] = rec[6 * n + c];
+    }
+    if ((rc = download_ip(e, d.yield, integ_yield_stress, 1))) return rc;
+    if (elementVolume) {
+        if ((rc = ensure_staging(e, (size_t)e->nElement))) return rc;
+        hk_launch_element_volume(d, e->staging, e->stream);
+        CK(hkp::d2h(elementVolume, e->staging, sizeof(double) * e->nElement, e->stream));
+    }
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(upload_state)(hk_engine* e, const double* disp, const double* disp_pre, const double* velo, const double* Q,
+                        const double* integ_stress, const double* integ_strain, const double* integ_eq_plastic_strain,
+                        const double* integ_yield_stress, const int64_t* element_flag) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HkDev& d = e->d;
+    const int64_t nN = e->nNode;
+    const size_t fnb = sizeof(double) * 3 * nN;
+    int rc;
+    if (disp) {
+        CK(hkp::h2d(d.u, disp, fnb, e->stream));
+        const HkDev dd = d;
+        hk_parallel_for(nN * 3, e->stream, HK_LAMBDA(long long i) {      // position = coordmat + disp, J2:650-652
+            const long long n = i / 3;
+            const int c = (int)(i - 3 * n);
+            dd.rec[6 * n + c] = dd.X[i] + dd.u[i];
+        });
+    }
+    if (disp_pre) CK(hkp::h2d(d.u_pre, disp_pre, fnb, e->stream));
+    if (velo) { CK(hkp::h2d(d.velo, velo, fnb, e->stream)); e->velo_current = true; }
+    if (Q) { CK(hkp::h2d(d.Q0, Q, fnb, e->stream)); e->use_Q0 = 1; }
+    if ((rc = upload_ip(e, d.stress, integ_stress, 6))) return rc;
+    if ((rc = upload_ip(e, d.strain, integ_strain, 6))) return rc;
+    if ((rc = upload_ip(e, d.eps, integ_eq_plastic_strain, 1))) return rc;
+    if ((rc = upload_ip(e, d.yield, integ_yield_stress, 1))) return rc;
+    if (integ_stress) e->triax_current = false;
+    if (element_flag) {
+        std::vector<unsigned char> fl(e->nElement);
+        for (int64_t i = 0; i < e->nElement; ++i) fl[i] = element_flag[i] == 1 ? 1 : 2;
+        CK(hkp::h2d(d.flag, fl.data(), fl.size(), e->stream));
+        CK(hkp::dev_memset(d.Qe, 0, sizeof(double) * 24 * d.nEp, e->stream));   // supply Q with the flags
+    }
+    CK(hkp::sync(e->stream));
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(deleted_ids)(hk_engine* e, int64_t* ids, int64_t cap, int64_t* n_out) {
+    if (!e) return HK_ERR_ARG;
+    const int64_t n = (int64_t)e->deleted_all.size();
+    if (n_out) *n_out = n;
+    if (ids) for (int64_t i = 0; i < std::min(n, cap); ++i) ids[i] = e->deleted_all[i];
+    return HK_OK;
+}
+
+int HKAPI(contact_pair_info)(hk_engine* e, int64_t c, int64_t* nn_i, int64_t* nn_j, int64_t* nTri, int64_t* c_nodes_i,
+                             int64_t* c_nodes_j, int64_t* c_triangles, int64_t* c_triangles_eleid) {
+    if (!e || c < 0 || c >= (int64_t)e->pairs.size()) return fail(e, HK_ERR_ARG, "bad contact pair index");
+    const PairH& p = e->pairs[c];
+    const int64_t nt = (int64_t)p.t0.size();
+    if (nn_i) *nn_i = (int64_t)p.nodes_i.size();
+    if (nn_j) *nn_j = (int64_t)p.nodes_j.size();
+    if (nTri) *nTri = nt;
+    if (c_nodes_i) for (size_t k = 0; k < p.nodes_i.size(); ++k) c_nodes_i[k] = p.nodes_i[k] + 1;
+    if (c_nodes_j) for (size_t k = 0; k < p.nodes_j.size(); ++k) c_nodes_j[k] = p.nodes_j[k] + 1;
+    if (c_triangles)
+        for (int64_t k = 0; k < nt; ++k) {
+            c_triangles[k] = p.t0[k] + 1;
+            c_triangles[k + nt] = p.t1[k] + 1;
+            c_triangles[k + 2 * nt] = p.t2[k] + 1;
+        }
+    if (c_triangles_eleid) for (int64_t k = 0; k < nt; ++k) c_triangles_eleid[k] = p.tele[k] + 1;
+    return HK_OK;
+}
+
+int HKAPI(counters)(hk_engine* e, int64_t out[8]) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    unsigned long long c[8];
+    CK(hkp::d2h(c, e->d.counters, sizeof(c), e->stream));
+    out[0] = (int64_t)c[0];
+    out[1] = (int64_t)c[1];
+    out[2] = (int64_t)c[2];
+    out[3] = e->n_launch;
+    out[4] = e->n_steps;
+    out[5] = (int64_t)c[3];
+    out[6] = 0;
+    out[7] = 0;
+    return HK_OK;
+}
+
+int HKAPI(profile)(hk_engine* e, int32_t enable) {
+    if (!e) return HK_ERR_ARG;
+    prof_collect(e);
+    for (int i = 0; i < 4; ++i) { e->prof_ms[i] = 0; e->prof_n[i] = 0; }
+    e->profiling = enable != 0;
+    return HK_OK;
+}
+
+int HKAPI(profile_read)(hk_engine* e, double ms[4], int64_t launches[4]) {
+    if (!e) return HK_ERR_ARG;
+    prof_collect(e);
+    for (int i = 0; i < 4; ++i) { ms[i] = e->prof_ms[i]; launches[i] = e->prof_n[i]; }
+    return HK_OK;
+}
+
+int HKAPI(set_stream)(hk_engine* e, void* cuda_stream) {
+    if (!e) return HK_ERR_ARG;
+#ifndef HK_EMU
+    hkp::sync(e->stream);
+    if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+    if (cuda_stream) {
+        e->stream = (cudaStream_t)cuda_stream;
+    } else {
+        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        e->own_stream = true;
+    }
+#else
+    (void)cuda_stream;
+#endif
+    return HK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,502 @@
+// hk_exact.cu — kernels whose floating-point operation order mirrors the reference exactly.
+// Built with -fmad=false: no FMA contraction, so given identical inputs these kernels reproduce the
+// reference's (and the oracle's) IEEE results bit for bit:
+//   * nodal kernel: force gather (assembly, J2:668-675) + central difference (J2:562-567)
+//                   + boundary conditions (J2:585-617) + kinematics (J2:624-652)
+//   * contact: bounding boxes, cell buckets, node-to-triangle penalty forces (J2:2248-2706)
+//   * layout transposes and small on-demand taps.
+#include "hk_common.h"
+
+// ------------------------------------------------------------------ 128-bit fixed-point accumulators
+// Contact forces are summed in the reference in Float128 (J2:435), i.e. effectively exactly, and rounded
+// to Float64 once (J2:536-538).  Here each contribution is converted to a 128-bit two's-complement integer
+// in units of 2^lsb_exp and added with two 64-bit atomics (carry derived from the low word's old value).
+// Integer addition is associative, so the sum is exact AND independent of the order in which threads
+// arrive: bitwise reproducible without sorting.
+HK_HD void fx_from_double(double v, int lsb_exp, unsigned long long& lo, unsigned long long& hi, bool& ovf) {
+    const double two64 = 18446744073709551616.0;
+    double mag = ldexp(fabs(v), -lsb_exp);
+    ovf = !(mag < 8.5070591730234616e37);        // 2^126; also true for NaN
+    if (ovf) { lo = 0; hi = 0; return; }
+    double hi_m = floor(mag * (1.0 / two64));
+    double lo_m = mag - hi_m * two64;            // exact, in [0, 2^64)
+#if defined(__CUDA_ARCH__)
+    lo = __double2ull_rz(lo_m);
+    hi = __double2ull_rz(hi_m);
+#else
+    lo = (unsigned long long)lo_m;
+    hi = (unsigned long long)hi_m;
+#endif
+    if (v < 0.0) {
+        lo = ~lo + 1ull;
+        hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+    }
+}
+
+HK_HD double fx_to_double(unsigned long long lo, unsigned long long hi, int lsb_exp) {
+    bool neg = (hi >> 63) != 0;
+    if (neg) {
+        lo = ~lo + 1ull;
+        hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+    }
+    if (hi == 0ull && lo == 0ull) return 0.0;
+    int lz;
+#if defined(__CUDA_ARCH__)
+    lz = hi ? __clzll((long long)hi) : 64 + __clzll((long long)lo);
+#else
+    lz = hi ? __builtin_clzll(hi) : 64 + __builtin_clzll(lo);
+#endif
+    unsigned long long m, rest;
+    if (lz == 0) { m = hi; rest = lo; }
+    else if (lz < 64) { m = (hi << lz) | (lo >> (64 - lz)); rest = lo << lz; }
+    else if (lz == 64) { m = lo; rest = 0ull; }
+    else { m = lo << (lz - 64); rest = 0ull; }
+    if (rest) m |= 1ull;                          // sticky bit: 64-bit -> 53-bit RN stays correct
+#if defined(__CUDA_ARCH__)
+    double r = __ull2double_rn(m);
+#else
+    double r = (double)m;
+#endif
+    r = ldexp(r, 64 - lz + lsb_exp);
+    return neg ? -r : r;
+}
+
+HK_D void fx_atomic_add(unsigned long long* acc, double v, int lsb_exp, unsigned long long* ovf_counter) {
+    unsigned long long lo, hi;
+    bool ovf;
+    fx_from_double(v, lsb_exp, lo, hi, ovf);
+    if (ovf) { hk_atomic_add_u64(ovf_counter, 1ull); return; }
+    unsigned long long old = hk_atomic_add_u64(&acc[0], lo);
+    unsigned long long carry = (old + lo < old) ? 1ull : 0ull;
+    hk_atomic_add_u64(&acc[1], hi + carry);
+}
+
+// order-preserving encoding of doubles for atomicMin/Max on u64
+HK_HD unsigned long long enc_double(double d) {
+    unsigned long long b;
+    memcpy(&b, &d, 8);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+HK_HD double dec_double(unsigned long long e) {
+    unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+// ------------------------------------------------------------------ nodal kernel
+struct NodalArgs {
+    HkDev d;
+    double current_time, d_time, dt2, dt2p;
+    int lsb_exp, contact_on, use_Q0;
+};
+
+HK_HD double eval_amp(const HkDev& d, int amp_id, double current_time) {   // J2:586-600
+    const HkAmpTable tb = d.amp_tab[amp_id];
+    const double* a_t = d.amp_time + tb.offset;
+    const double* a_v = d.amp_value + tb.offset;
+    int ti = 0;
+    for (int j = 0; j + 1 < tb.n; ++j)
+        if (current_time >= a_t[j] && current_time <= a_t[j + 1]) { ti = j; break; }
+    return a_v[ti] + (a_v[ti + 1] - a_v[ti]) * (current_time - a_t[ti]) / (a_t[ti + 1] - a_t[ti]);
+}
+
+HK_HD void nodal_body(const NodalArgs& A, long long n) {
+    const HkDev& d = A.d;
+    // internal force of the node: Q[n] = sum over incident elements in ascending element order (J2:668-675)
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+    if (A.use_Q0) {
+        q0 = d.Q0[3 * n]; q1 = d.Q0[3 * n + 1]; q2 = d.Q0[3 * n + 2];
+    } else {
+        for (int w = 0; w < d.ell_width; ++w) {
+            int ent = d.ell[(long long)w * d.nNode + n];
+            if (ent < 0) break;
+            long long e = ent >> 3;
+            int a = ent & 7;
+            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
+            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
+            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+        }
+    }
+    double F[3] = {0.0, 0.0, 0.0};
+    double bcv[3];
+    bool has_bc[3] = {false, false, false};
+    const int si = d.spec_idx[n];
+    if (si >= 0) {
+        const HkSpecialNode sp = d.spec[si];
+        if (sp.halo_slot >= 0) {                 // partial sums of the neighbour rank (multi-GPU)
+            q0 += d.halo_recv[3 * sp.halo_slot];
+            q1 += d.halo_recv[3 * sp.halo_slot + 1];
+            q2 += d.halo_recv[3 * sp.halo_slot + 2];
+        }
+        if (A.contact_on && sp.contact_slot >= 0) {     // external_force += c_force3, J2:536-538
+            const unsigned long long* acc = d.cacc + (long long)sp.contact_slot * 6;
+            F[0] = fx_to_double(acc[0], acc[1], A.lsb_exp);
+            F[1] = fx_to_double(acc[2], acc[3], A.lsb_exp);
+            F[2] = fx_to_double(acc[4], acc[5], A.lsb_exp);
+        }
+        for (int c = 0; c < 3; ++c) {
+            int be = sp.bc_entry[c];
+            if (be >= 0) {
+                double amp = 1.0;
+                int aid = d.bc_amp[be];
+                if (aid >= 0) amp = eval_amp(d, aid, A.current_time);
+                bcv[c] = d.bc_value[be] * amp;    // disp_new[dof] .= v * amp, J2:612
+                has_bc[c] = true;
+            }
+        }
+    }
+    // central difference, J2:564 (diag_C == 0: its terms vanish exactly)
+    const double M = d.mass[n];
+    const double a = M / A.dt2;
+    const double a2 = M / A.dt2p;
+    const double inva = 1.0 / a;
+    const double q[3] = {q0, q1, q2};
+    for (int c = 0; c < 3; ++c) {
+        const long long i = 3 * n + c;
+        const double u = d.u[i], up = d.u_pre[i];
+        double un = inva * (F[c] - q[c] + a2 * (2.0 * u - up));
+        if (has_bc[c]) un = bcv[c];
+        const double dd = un - u;                // d_disp, J2:625
+        d.u_pre[i] = u;
+        d.u[i] = un;
+        d.rec[6 * n + c] = d.X[i] + un;          // position, J2:650-652
+        d.rec[6 * n + 3 + c] = dd;
+        if (A.contact_on) d.velo[i] = dd / A.d_time;   // velo, J2:628
+    }
+}
+
+#ifndef HK_EMU
+__global__ void __launch_bounds__(256) hk_nodal_kernel(NodalArgs A) {
+    long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n < A.d.nNode) nodal_body(A, n);
+}
+#endif
+
+void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double dt2, double dt2p, int lsb_exp,
+                     int contact_on, int use_Q0, cudaStream_t s) {
+    NodalArgs A{d, current_time, d_time, dt2, dt2p, lsb_exp, contact_on, use_Q0};
+#ifndef HK_EMU
+    const int block = 256;
+    hk_nodal_kernel<<<(unsigned)((d.nNode + block - 1) / block), block, 0, s>>>(A);
+#else
+    for (long long n = 0; n < d.nNode; ++n) nodal_body(A, n);
+#endif
+}
+
+// ------------------------------------------------------------------ contact (J2:2248-2706)
+HK_HD double my3norm(double b1, double b2, double b3) { return sqrt(b1 * b1 + b2 * b2 + b3 * b3); }
+
+struct ContactArgs {
+    HkDev d;
+    HkPairDev p;
+    HkContactParams cp;
+};
+
+// bounding boxes of the i nodes and j nodes (J2:2284-2296); serial form used by the emu build only
+#ifdef HK_EMU
+HK_HD void contact_bbox_body(const ContactArgs& A, long long t) {
+    const HkPairDev& p = A.p;
+    const bool is_i = t < p.nn_i;
+    const int node = is_i ? p.nodes_i[t] : p.nodes_j[t - p.nn_i];
+    unsigned long long* bb = p.bbox + (is_i ? 0 : 6);
+    for (int a = 0; a < 3; ++a) {
+        unsigned long long e = enc_double(A.d.rec[6ll * node + a]);
+        hk_atomic_min_u64(&bb[a], e);
+        hk_atomic_max_u64(&bb[3 + a], e);
+    }
+}
+#endif
+
+struct PairBox {
+    double range_min[3], range_max[3], all_min[3];
+    bool skip;
+};
+HK_HD PairBox pair_box(const HkPairDev& p) {                      // J2:2298-2315
+    PairBox b;
+    b.skip = false;
+    for (int a = 0; a < 3; ++a) {
+        double mn_i = dec_double(p.bbox[a]), mx_i = dec_double(p.bbox[3 + a]);
+        double mn_j = dec_double(p.bbox[6 + a]), mx_j = dec_double(p.bbox[9 + a]);
+        b.range_min[a] = mn_i > mn_j ? mn_i : mn_j;
+        b.range_max[a] = mx_i < mx_j ? mx_i : mx_j;
+        b.all_min[a] = mn_i < mn_j ? mn_i : mn_j;
+        if (b.range_min[a] > b.range_max[a]) b.skip = true;
+    }
+    return b;
+}
+
+HK_HD unsigned cell_hash(int cx, int cy, int cz) {
+    return ((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u);
+}
+
+// cell coordinates of the i nodes (J2:2337-2349) and insertion into hashed buckets
+HK_D void contact_cells_body(const ContactArgs& A, long long k) {
+    const HkPairDev& p = A.p;
+    const PairBox b = pair_box(p);
+    if (b.skip) return;
+    const double ddiv = p.self ? A.cp.ddiv_s : A.cp.ddiv_o;
+    const int node = p.nodes_i[k];
+    int c[3];
+    for (int a = 0; a < 3; ++a) c[a] = (int)ceil((A.d.rec[6ll * node + a] - b.all_min[a]) / ddiv);
+    p.cell_i[k] = c[0];
+    p.cell_i[p.nn_i + k] = c[1];
+    p.cell_i[2ll * p.nn_i + k] = c[2];
+    unsigned h = cell_hash(c[0], c[1], c[2]) & (unsigned)(p.n_bucket - 1);
+    p.next[k] = hk_atomic_exch_i32(&p.head[h], (int)k);
+}
+
+// one master triangle against the slave nodes of the 27 neighbouring cells (J2:2370-2692)
+HK_D void contact_tri_body(const ContactArgs& A, long long j) {
+    const HkDev& d = A.d;
+    const HkPairDev& p = A.p;
+    const HkContactParams& cp = A.cp;
+    const int eleid = p.tele[j];
+    if (d.flag[eleid] != 1) return;                               // J2:2373-2376
+    const PairBox b = pair_box(p);
+    if (b.skip) return;
+    const double kc = p.self ? cp.kc_s : cp.kc_o;
+    const double Cr = p.self ? cp.cr_s : cp.cr_o;
+    const double ddiv = p.self ? cp.ddiv_s : cp.ddiv_o;
+    const int j0 = p.t0[j], j1 = p.t1[j], j2 = p.t2[j];
+    const double q0x = d.rec[6ll * j0], q0y = d.rec[6ll * j0 + 1], q0z = d.rec[6ll * j0 + 2];
+    const double q1x = d.rec[6ll * j1], q1y = d.rec[6ll * j1 + 1], q1z = d.rec[6ll * j1 + 2];
+    const double q2x = d.rec[6ll * j2], q2y = d.rec[6ll * j2 + 1], q2z = d.rec[6ll * j2 + 2];
+    if (q0x < b.range_min[0] && q1x < b.range_min[0] && q2x < b.range_min[0]) return;
+    if (q0y < b.range_min[1] && q1y < b.range_min[1] && q2y < b.range_min[1]) return;
+    if (q0z < b.range_min[2] && q1z < b.range_min[2] && q2z < b.range_min[2]) return;
+    if (q0x > b.range_max[0] && q1x > b.range_max[0] && q2x > b.range_max[0]) return;
+    if (q0y > b.range_max[1] && q1y > b.range_max[1] && q2y > b.range_max[1]) return;
+    if (q0z > b.range_max[2] && q1z > b.range_max[2] && q2z > b.range_max[2]) return;
+
+    const double cx = (q0x + q1x + q2x) / 3.0, cy = (q0y + q1y + q2y) / 3.0, cz = (q0z + q1z + q2z) / 3.0;
+    const double R0 = my3norm(q0x - cx, q0y - cy, q0z - cz);
+    const double R1 = my3norm(q1x - cx, q1y - cy, q1z - cz);
+    const double R2 = my3norm(q2x - cx, q2y - cy, q2z - cz);
+    const double Rmax = fmax(fmax(R0, R1), R2);
+    const double v1x = q1x - q0x, v1y = q1y - q0y, v1z = q1z - q0z;
+    const double v2x = q2x - q0x, v2y = q2y - q0y, v2z = q2z - q0z;
+    const double L1 = my3norm(v1x, v1y, v1z), L2 = my3norm(v2x, v2y, v2z);
+    const double Lmax = fmax(L1, L2);
+    double nx = v1y * v2z - v1z * v2y;                            // my3crossNNz, J2:3209
+    double ny = v1z * v2x - v1x * v2z;
+    double nz = v1x * v2y - v1y * v2x;
+    const double mag_n = sqrt(nx * nx + ny * ny + nz * nz);
+    nx = nx / mag_n; ny = ny / mag_n; nz = nz / mag_n;
+    const double d12 = v1x * v2x + v1y * v2y + v1z * v2z;
+    const double S = 0.5 * sqrt(L1 * L1 * L2 * L2 - d12 * d12);
+    const double A11 = v1x, A21 = v1y, A31 = v1z, A12 = v2x, A22 = v2y, A32 = v2z;
+    const double A13 = -nx, A23 = -ny, A33 = -nz;
+    // my3SolveAb, J2:3342: the parts that do not depend on the node
+    const double detA = (A11 * A22 * A33 + A12 * A23 * A31 + A13 * A21 * A32 - A11 * A23 * A32 - A12 * A21 * A33 -
+                         A13 * A22 * A31);
+    const double im11 = A22 * A33 - A23 * A32, im21 = A23 * A31 - A21 * A33, im31 = A21 * A32 - A22 * A31;
+    const double im12 = A13 * A32 - A12 * A33, im22 = A11 * A33 - A13 * A31, im32 = A12 * A31 - A11 * A32;
+    const double im13 = A12 * A23 - A13 * A22, im23 = A13 * A21 - A11 * A23, im33 = A11 * A22 - A12 * A21;
+
+    // cell of vertex j0 (J2:2351-2363, 2462-2472): same formula, evaluated directly on j0's position
+    int cj[3];
+    cj[0] = (int)ceil((q0x - b.all_min[0]) / ddiv);
+    cj[1] = (int)ceil((q0y - b.all_min[1]) / ddiv);
+    cj[2] = (int)ceil((q0z - b.all_min[2]) / ddiv);
+
+    int en[8];
+    if (p.self)
+        for (int q = 0; q < 8; ++q) en[q] = d.conn[(long long)q * d.nEp + eleid];
+
+    unsigned long long n_tests = 0, n_hits = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int ccx = cj[0] + dx, ccy = cj[1] + dy, ccz = cj[2] + dz;
+                const unsigned h = cell_hash(ccx, ccy, ccz) & (unsigned)(p.n_bucket - 1);
+                for (int k = p.head[h]; k >= 0; k = p.next[k]) {
+                    if (p.cell_i[k] != ccx || p.cell_i[p.nn_i + k] != ccy || p.cell_i[2ll * p.nn_i + k] != ccz) continue;
+                    const int i = p.nodes_i[k];
+                    if (p.self) {
+                        bool own = false;
+                        for (int q = 0; q < 8; ++q) own = own || (i == en[q]);
+                        if (own) continue;
+                    }
+                    const double px = d.rec[6ll * i], py = d.rec[6ll * i + 1], pz = d.rec[6ll * i + 2];
+                    if (px < b.range_min[0] || py < b.range_min[1] || pz < b.range_min[2]) continue;
+                    if (px > b.range_max[0] || py > b.range_max[1] || pz > b.range_max[2]) continue;
+                    const double dpc = my3norm(px - cx, py - cy, pz - cz);
+                    if (dpc >= Rmax) continue;
+                    const double bx = px - q0x, by = py - q0y, bz = pz - q0z;
+                    ++n_tests;
+                    const double x1 = (im11 * bx + im12 * by + im13 * bz) / detA;
+                    const double x2 = (im21 * bx + im22 * by + im23 * bz) / detA;
+                    const double dd = (im31 * bx + im32 * by + im33 * bz) / detA;
+                    if (0.0 <= x1 && 0.0 <= x2 && x1 + x2 <= 1.0 && dd > 0.0 && dd <= cp.d_lim) {
+                        ++n_hits;
+                        const double vx = d.velo[3ll * i] - d.velo[3ll * j0];
+                        const double vy = d.velo[3ll * i + 1] - d.velo[3ll * j0 + 1];
+                        const double vz = d.velo[3ll * i + 2] - d.velo[3ll * j0 + 2];
+                        const double mag_v = my3norm(vx, vy, vz);
+                        double vex = 0.0, vey = 0.0, vez = 0.0;
+                        if (mag_v > 0.0) { vex = vx / mag_v; vey = vy / mag_v; vez = vz / mag_v; }
+                        const double k_ = p.young * S / Lmax * kc;
+                        const double F = k_ * dd;
+                        double fx = F * nx, fy = F * ny, fz = F * nz;
+                        // damping: diag_M[i] is indexed with the NODE id in the reference (J2:2593)
+                        const double C = 2 * sqrt(d.mass[i / 3] * k_) * Cr;
+                        const double fc_x = -C * vx, fc_y = -C * vy, fc_z = -C * vz;
+                        const double dot_ve_n = vex * nx + vey * ny + vez * nz;
+                        const double vsx = vex - dot_ve_n * nx, vsy = vey - dot_ve_n * ny, vsz = vez - dot_ve_n * nz;
+                        const double fric_x = -cp.myu * F * vsx, fric_y = -cp.myu * F * vsy, fric_z = -cp.myu * F * vsz;
+                        fx += fric_x + fc_x;
+                        fy += fric_y + fc_y;
+                        fz += fric_z + fc_z;
+                        const double f[3] = {fx, fy, fz};
+                        const double f3[3] = {-fx / 3.0, -fy / 3.0, -fz / 3.0};
+                        unsigned long long* ovf = &d.counters[3];
+                        {
+                            const int slot = d.spec[d.spec_idx[i]].contact_slot;
+                            for (int c = 0; c < 3; ++c) fx_atomic_add(d.cacc + 6ll * slot + 2 * c, f[c], cp.lsb_exp, ovf);
+                        }
+                        const int jn[3] = {j0, j1, j2};
+                        for (int q = 0; q < 3; ++q) {
+                            const int slot = d.spec[d.spec_idx[jn[q]]].contact_slot;
+                            for (int c = 0; c < 3; ++c) fx_atomic_add(d.cacc + 6ll * slot + 2 * c, f3[c], cp.lsb_exp, ovf);
+                        }
+                    }
+                }
+            }
+    if (n_tests) hk_atomic_add_u64(&d.counters[2], n_tests);
+    if (n_hits) hk_atomic_add_u64(&d.counters[1], n_hits);
+}
+
+#ifndef HK_EMU
+__global__ void hk_contact_bbox_kernel(ContactArgs A) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = (long long)A.p.nn_i + A.p.nn_j;
+    // warp-level min/max first, one atomic set per (warp, side)
+    const unsigned FULL = 0xffffffffu;
+    const bool valid = t < n;
+    const bool is_i = valid && t < A.p.nn_i;
+    unsigned long long mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) { mn[a] = ~0ull; mx[a] = 0ull; }
+    if (valid) {
+        const int node = is_i ? A.p.nodes_i[t] : A.p.nodes_j[t - A.p.nn_i];
+        for (int a = 0; a < 3; ++a) mn[a] = mx[a] = enc_double(A.d.rec[6ll * node + a]);
+    }
+    // a warp may straddle the i/j boundary: reduce the two sides separately
+    for (int side = 0; side < 2; ++side) {
+        const bool mine = valid && (is_i == (side == 0));
+        const unsigned m = __ballot_sync(FULL, mine);
+        if (!m) continue;
+        unsigned long long smn[3], smx[3];
+        for (int a = 0; a < 3; ++a) { smn[a] = mine ? mn[a] : ~0ull; smx[a] = mine ? mx[a] : 0ull; }
+        for (int off = 16; off; off >>= 1)
+            for (int a = 0; a < 3; ++a) {
+                unsigned long long o1 = __shfl_xor_sync(FULL, smn[a], off);
+                unsigned long long o2 = __shfl_xor_sync(FULL, smx[a], off);
+                smn[a] = o1 < smn[a] ? o1 : smn[a];
+                smx[a] = o2 > smx[a] ? o2 : smx[a];
+            }
+        if ((threadIdx.x & 31) == 0) {
+            unsigned long long* bb = A.p.bbox + (side == 0 ? 0 : 6);
+            for (int a = 0; a < 3; ++a) { atomicMin(&bb[a], smn[a]); atomicMax(&bb[3 + a], smx[a]); }
+        }
+    }
+}
+__global__ void hk_contact_cells_kernel(ContactArgs A) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k < A.p.nn_i) contact_cells_body(A, k);
+}
+__global__ void __launch_bounds__(128) hk_contact_narrow_kernel(ContactArgs A) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j < A.p.nTri) contact_tri_body(A, j);
+}
+__global__ void hk_contact_reset_kernel(HkPairDev p) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < p.n_bucket) p.head[t] = -1;
+    if (t < 12) p.bbox[t] = ((t % 6) < 3) ? ~0ull : 0ull;
+}
+#endif
+
+void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s) {
+    if (p.nn_i == 0 || p.nn_j == 0 || p.nTri == 0) return;
+    ContactArgs A{d, p, cp};
+#ifndef HK_EMU
+    const int B = 128;
+    long long nr = p.n_bucket > 12 ? p.n_bucket : 12;
+    hk_contact_reset_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(p);
+    long long nb = (long long)p.nn_i + p.nn_j;
+    hk_contact_bbox_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(A);
+    hk_contact_cells_kernel<<<(unsigned)((p.nn_i + 255) / 256), 256, 0, s>>>(A);
+    hk_contact_narrow_kernel<<<(unsigned)((p.nTri + B - 1) / B), B, 0, s>>>(A);
+#else
+    for (int t = 0; t < p.n_bucket; ++t) p.head[t] = -1;
+    for (int t = 0; t < 12; ++t) p.bbox[t] = ((t % 6) < 3) ? ~0ull : 0ull;
+    for (long long t = 0; t < (long long)p.nn_i + p.nn_j; ++t) contact_bbox_body(A, t);
+    for (long long k = 0; k < p.nn_i; ++k) contact_cells_body(A, k);
+    for (long long j = 0; j < p.nTri; ++j) contact_tri_body(A, j);
+#endif
+}
+
+// ------------------------------------------------------------------ small taps and transposes
+void hk_launch_velo_from_rec(const HkDev& d, double d_time, cudaStream_t s) {
+    double* velo = d.velo;
+    const double* rec = d.rec;
+    hk_parallel_for(d.nNode * 3, s, HK_LAMBDA(long long i) {
+        long long n = i / 3;
+        int c = (int)(i - 3 * n);
+        velo[i] = rec[6 * n + 3 + c] / d_time;
+    });
+}
+
+void hk_launch_gather_Q(const HkDev& dd, double* Q_out, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(d.nNode, s, HK_LAMBDA(long long n) {
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+        for (int w = 0; w < d.ell_width; ++w) {
+            int ent = d.ell[(long long)w * d.nNode + n];
+            if (ent < 0) break;
+            long long e = ent >> 3;
+            int a = ent & 7;
+            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
+            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
+            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+        }
+        Q_out[3 * n] = q0; Q_out[3 * n + 1] = q1; Q_out[3 * n + 2] = q2;
+    });
+}
+
+// external_force of the last step (J2:497-538): zero plus the rounded contact sums
+void hk_launch_external_force(const HkDev& dd, double* F_out, int lsb_exp, int contact_on, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(d.nNode, s, HK_LAMBDA(long long n) {
+        double F[3] = {0.0, 0.0, 0.0};
+        const int si = d.spec_idx[n];
+        if (contact_on && si >= 0 && d.spec[si].contact_slot >= 0) {
+            const unsigned long long* acc = d.cacc + (long long)d.spec[si].contact_slot * 6;
+            for (int c = 0; c < 3; ++c) F[c] = fx_to_double(acc[2 * c], acc[2 * c + 1], lsb_exp);
+        }
+        for (int c = 0; c < 3; ++c) F_out[3 * n + c] = F[c];
+    });
+}
+
+// AoS chunk (reference layout, element range [e0,e0+ne)) <-> SoA rows.  aos index: (ip_local*ncomp + c).
+void hk_launch_ip_to_soa(const double* aos, double* soa, int ncomp, long long e0, long long ne, long long nEp,
+                         cudaStream_t s) {
+    hk_parallel_for(ne * 8 * ncomp, s, HK_LAMBDA(long long i) {
+        // thread index runs along the SoA rows so the writes coalesce
+        long long el = i % ne;
+        long long r = i / ne;            // r = c*8 + k
+        int k = (int)(r % 8);
+        int c = (int)(r / 8);
+        soa[(long long)(c * 8 + k) * nEp + e0 + el] = aos[(el * 8 + k) * ncomp + c];
+    });
+}
+void hk_launch_ip_to_aos(const double* soa, double* aos, int ncomp, long long e0, long long ne, long long nEp,
+                         cudaStream_t s) {
+    hk_parallel_for(ne * 8 * ncomp, s, HK_LAMBDA(long long i) {
+        long long el = i % ne;
+        long long r = i / ne;
+        int k = (int)(r % 8);
+        int c = (int)(r / 8);
+        aos[(el * 8 + k) * ncomp + c] = soa[(long long)(c * 8 + k) * nEp + e0 + el];
+    });
+}

@@ -168,19 +168,6 @@ int hk_profile_read(hk_engine* e, double ms[4], int64_t launches[4]);
 /* Use an externally created CUDA stream (cudaStream_t as void*) for all work; NULL = own. */
 int hk_set_stream(hk_engine* e, void* cuda_stream);
 
-/* ---- multi-GPU (one engine per rank) -------------------------------------------
- * Shared-interface nodes: list of LOCAL 1-based node ids whose internal force must be summed
- * with a neighbour rank's partial.  The engine packs/unpacks; the transport (NCCL send/recv)
- * is driven by the host between hk_step_begin and hk_step_end.  Halo buffers are DEVICE
- * pointers owned by the engine (3 doubles per node, node-major). */
-int hk_set_halo(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr /* n_neighbors+1 */,
-                const int64_t* nodes);
-int hk_halo_buffers(hk_engine* e, int64_t neighbor, void** send_dev, void** recv_dev,
-                    int64_t* n_doubles);
-/* Split step for halo exchange: begin = contact + (first step: nothing) ... see DESIGN.md. */
-int hk_step_begin(hk_engine* e, int64_t t);   /* element forces of step t-1 are packed       */
-int hk_step_end(hk_engine* e, int64_t t, int64_t* n_deleted_out);
-
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,169 @@
+"""Parity cases shared by the CPU (host-emulated kernel bodies) and GPU (CUDA engine) test modules.
+
+Every case drives the engine under test and the CPU oracle through the same C ABI on the same inputs.
+Tolerances (FP64, relative to the field's max magnitude):
+  TOL_STEP  = 1e-13  one step from identical state: only FMA contraction / summation-form differences
+  TOL_RUN   = 1e-9   after N <= 20 000 steps on Tensile5e
+Integer results (element flags, deleted ids and their order, contact surface lists) must be identical.
+"""
+import numpy as np
+
+from hakai_fem_b200.model_setup import prepare, configure_engine
+from hakai_fem_b200.mesh import ImpactDeck
+from oracle.oracle_engine import OracleEngine
+
+from . import util
+
+TOL_STEP = 1e-13
+TOL_RUN = 1e-9
+STATE_KEYS = ("disp", "velo", "integ_stress", "integ_strain", "integ_eq_plastic_strain", "integ_triax_stress",
+              "element_flag", "disp_pre", "Q", "position", "integ_yield_stress")
+
+
+def case_roundtrip(engine_cls):
+    """hk_upload_state -> hk_download is the identity (layout transposes are exact)."""
+    st = prepare(util.distorted_block().build_model())
+    eng = configure_engine(engine_cls, st)
+    rs = util.random_state(st, seed=3)
+    eng.upload_state(**rs)
+    d = util.full_state(eng)
+    for k in ("disp", "disp_pre", "velo", "Q", "integ_stress", "integ_strain", "integ_eq_plastic_strain",
+              "integ_yield_stress"):
+        assert np.array_equal(np.asarray(d[k]), np.asarray(rs[k])), k
+    assert np.array_equal(d["position"], st.model.coordmat + rs["disp"].reshape(-1, 3).T)
+
+
+def case_single_step_random_state(engine_cls, ductile=False):
+    """One step from an identical random elastic/plastic state on a distorted mesh."""
+    st = prepare(util.distorted_block(ductile=ductile).build_model())
+    o, g = util.make_pair(st, engine_cls, OracleEngine)
+    rs = util.random_state(st, seed=11)
+    o.upload_state(**rs)
+    g.upload_state(**rs)
+    o.step(5, 1)
+    g.step(5, 1)
+    a, b = util.full_state(o), util.full_state(g)
+    util.assert_states_close(a, b, TOL_STEP, STATE_KEYS, "single step")
+    # the nodal kernel mirrors the reference's operation order: bit-exact on identical inputs
+    assert np.array_equal(a["disp"], b["disp"])
+    assert np.array_equal(a["disp_pre"], b["disp_pre"])
+
+
+def case_t5(engine_cls, n_total=20000):
+    """Tensile5e.inp: free-running trajectories, snapshots, deletion of element 3 at step 15153."""
+    st = prepare(util.t5_model())
+    gold = util.load_json("tensile5e_oracle.json")
+    o, g = util.make_pair(st, engine_cls, OracleEngine)
+    t = 0
+    for target in (1, 2, 10, 316, 1000, 5000, 15152, 15153, 20000):
+        if target > n_total:
+            break
+        n = target - t
+        nd_o = o.step(t + 1, n)
+        nd_g = g.step(t + 1, n)
+        t = target
+        assert nd_o == nd_g, f"deletions differ in steps up to {t}"
+        a, b = util.full_state(o), util.full_state(g)
+        util.assert_states_close(a, b, TOL_RUN, STATE_KEYS, f"T5 step {t}")
+        snap = gold["snapshots"][str(t)]
+        assert util.rel_err(b["disp"], snap["disp"]) <= TOL_RUN
+        assert util.rel_err(b["integ_eq_plastic_strain"], snap["eps"]) <= TOL_RUN
+        assert np.array_equal(b["element_flag"], np.array(snap["element_flag"]))
+    if n_total >= 20000:
+        assert g.deleted_ids().tolist() == gold["deleted"] == [3]
+
+
+def case_fracture_block(engine_cls, n_steps=260):
+    """Jittered ductile block under uniform stretch: elements delete at different steps; the set, the
+    order and the step of every deletion must match the oracle."""
+    deck = util.distorted_block(nx=5, ny=4, nz=6, jitter=0.05, ductile=True, strain_per_step=4e-4)
+    st = prepare(deck.build_model())
+    o, g = util.make_pair(st, engine_cls, OracleEngine)
+    t = 0
+    seen = 0
+    while t < n_steps:
+        n = 7                       # batches: deletions inside a batch must still come out in order
+        do, dg = o.step(t + 1, n), g.step(t + 1, n)
+        t += n
+        assert do == dg, f"deleted count differs at step {t}"
+        seen += do
+        assert np.array_equal(o.deleted_ids(), g.deleted_ids())
+    assert seen > 3, "deck did not delete anything: test is vacuous"
+    a, b = util.full_state(o), util.full_state(g)
+    util.assert_states_close(a, b, 1e-8, STATE_KEYS, "fracture block")
+
+
+# SI units, E = 7e10 Pa: anything below these magnitudes is rounding noise of a body in rigid motion
+CONTACT_FLOORS = dict(integ_stress=1e4, integ_strain=1e-7, Q=1e-3, integ_yield_stress=1.0, external_force=1e-3)
+
+
+def small_impact(mu=0.25, plate=(8, 8, 2), proj=(3, 3, 3)):
+    deck = ImpactDeck(plate=plate, proj=proj)
+    st = prepare(deck.build_model())
+    return st, dict(contact_myu=mu)
+
+
+def case_contact(engine_cls, mu=0.25, n_steps=60):
+    """Two-instance impact: contact forces, hit counts and trajectories vs the oracle."""
+    st, prm = small_impact(mu)
+    o, g = util.make_pair(st, engine_cls, OracleEngine, **prm)
+    t = 0
+    max_f = 0.0
+    for _ in range(n_steps // 4):
+        o.step(t + 1, 4)
+        g.step(t + 1, 4)
+        t += 4
+        a, b = util.full_state(o), util.full_state(g)
+        max_f = max(max_f, float(np.abs(a["external_force"]).max()))
+        # contact sums: exact fixed-point accumulation vs Float128 -> same doubles up to rare 1-ulp ties
+        # before the bodies touch, stresses are pure rounding noise (rigid motion): floors give the scale
+        keys = tuple(k for k in STATE_KEYS if k != "integ_triax_stress") + ("external_force",)
+        util.assert_states_close(a, b, 1e-9, keys, f"contact step {t}", floors=CONTACT_FLOORS)
+        tot = a["external_force"].reshape(-1, 3).sum(axis=0)
+        assert np.all(np.abs(tot) <= 1e-9 * max(max_f, 1e-300)), "net contact force must vanish (J2:2653-2667)"
+    assert max_f > 0, "no contact happened: test is vacuous"
+    co, cg = o.counters(), g.counters()
+    assert co[1] == cg[1] and co[1] > 0, f"hit counts differ: {co[1]} vs {cg[1]}"
+
+
+def case_contact_single_step(engine_cls):
+    """Contact force of ONE step from an identical penetrated state is bit-for-bit the oracle's
+    (hk_exact.cu mirrors the reference's operation order; sums are exact)."""
+    st, prm = small_impact(0.25)
+    o, g = util.make_pair(st, engine_cls, OracleEngine, **prm)
+    o.step(1, 24)
+    s = util.full_state(o)
+    up = dict(disp=s["disp"], disp_pre=s["disp_pre"], velo=s["velo"], Q=s["Q"], integ_stress=s["integ_stress"],
+              integ_strain=s["integ_strain"], integ_eq_plastic_strain=s["integ_eq_plastic_strain"],
+              integ_yield_stress=s["integ_yield_stress"])
+    g.upload_state(**up)
+    o.step(25, 1)
+    g.step(25, 1)
+    a, b = util.full_state(o), util.full_state(g)
+    assert np.abs(a["external_force"]).max() > 0
+    assert util.rel_err(a["external_force"], b["external_force"]) <= 1e-15
+    assert np.array_equal(a["disp"], b["disp"])
+
+
+def case_contact_erosion(engine_cls, n_steps=400):
+    """Impact with a brittle plate: deletions expose interior faces, which must join the contact surface
+    exactly as add_surface_triangle does (J2:767-804)."""
+    deck = ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0)
+    model = deck.build_model()
+    model.MATERIAL[0].ductile = np.array([[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]])
+    st = prepare(model)
+    o, g = util.make_pair(st, engine_cls, OracleEngine)
+    t = 0
+    while t < n_steps:
+        do, dg = o.step(t + 1, 10), g.step(t + 1, 10)
+        t += 10
+        assert do == dg, f"deleted count differs at step {t}: {do} vs {dg}"
+    ids = o.deleted_ids()
+    assert len(ids) > 0, "nothing eroded: test is vacuous"
+    assert np.array_equal(ids, g.deleted_ids())
+    for c in range(2):
+        po, pg = o.contact_pair(c), g.contact_pair(c)
+        for k in ("c_nodes_i", "c_nodes_j", "c_triangles", "c_triangles_eleid"):
+            assert np.array_equal(po[k], pg[k]), f"pair {c} {k}"
+    a, b = util.full_state(o), util.full_state(g)
+    util.assert_states_close(a, b, 1e-7, ("disp", "integ_eq_plastic_strain", "element_flag"), "erosion")

@@ -1,0 +1,37 @@
+"""Kernel-body parity on the CPU: the CUDA engine's per-thread kernel bodies and host plumbing, compiled
+for the host (tests/emu, -DHK_EMU), against the oracle.  This validates logic in the GPU-less container;
+the same cases run against the real CUDA build in test_gpu_parity.py (-m gpu)."""
+import pytest
+
+from . import parity_cases as pc
+from .emu.emu_engine import EmuEngine
+
+
+def test_roundtrip():
+    pc.case_roundtrip(EmuEngine)
+
+
+@pytest.mark.parametrize("ductile", [False, True])
+def test_single_step_random_state(ductile):
+    pc.case_single_step_random_state(EmuEngine, ductile)
+
+
+def test_t5_first_1000_steps():
+    pc.case_t5(EmuEngine, n_total=1000)
+
+
+def test_fracture_block():
+    pc.case_fracture_block(EmuEngine)
+
+
+@pytest.mark.parametrize("mu", [0.0, 0.25])
+def test_contact(mu):
+    pc.case_contact(EmuEngine, mu)
+
+
+def test_contact_single_step_exact():
+    pc.case_contact_single_step(EmuEngine)
+
+
+def test_contact_erosion():
+    pc.case_contact_erosion(EmuEngine)

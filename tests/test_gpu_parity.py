@@ -1,0 +1,54 @@
+"""Parity of the CUDA engine (libhakai_b200.so, through the C ABI) against the CPU oracle.  -m gpu."""
+import numpy as np
+import pytest
+
+from hakai_fem_b200.engine import Engine
+from hakai_fem_b200.model_setup import prepare, configure_engine
+
+from . import parity_cases as pc
+from . import util
+
+pytestmark = pytest.mark.gpu
+
+
+def test_roundtrip():
+    pc.case_roundtrip(Engine)
+
+
+@pytest.mark.parametrize("ductile", [False, True])
+def test_single_step_random_state(ductile):
+    pc.case_single_step_random_state(Engine, ductile)
+
+
+def test_t5_full_run():
+    pc.case_t5(Engine, n_total=20000)
+
+
+def test_fracture_block():
+    pc.case_fracture_block(Engine)
+
+
+@pytest.mark.parametrize("mu", [0.0, 0.25])
+def test_contact(mu):
+    pc.case_contact(Engine, mu)
+
+
+def test_contact_single_step_exact():
+    pc.case_contact_single_step(Engine)
+
+
+def test_contact_erosion():
+    pc.case_contact_erosion(Engine)
+
+
+def test_bitwise_reproducible():
+    """Two runs of the same deck give bit-identical state (no unordered float atomics anywhere)."""
+    st, prm = pc.small_impact(0.25, plate=(16, 16, 3), proj=(5, 5, 5))
+    outs = []
+    for _ in range(2):
+        g = configure_engine(Engine, st, **prm)
+        g.step(1, 80)
+        outs.append(util.full_state(g))
+        g.close()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
