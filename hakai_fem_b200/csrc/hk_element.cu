@@ -3,33 +3,18 @@
 // Replaces cal_stress_hexa + cal_BVbar_hexa + cal_Bfinal (J2:1033-1371, 1705-1784, 1415-1519),
 // cal_triax_stress (J2:982-1022) and the fracture loop (J2:682-764) with ONE pass over the element:
 // node gather, Jacobians at the 8 Gauss points, mean-dilatation (B-bar) strain increment, J2 radial
-// return, state update, nodal force, triaxiality, ductile-damage deletion.
+// return, state update, nodal force, triaxiality, ductile-damage deletion.  The math (trilinear mode
+// form) is in hk_element_math.h.
 //
-// The reference builds the dense 6x24 Bfinal = B - BV + BVbar and multiplies; this kernel evaluates
-// the algebraically identical 3x3 tensor form:
-//     g_a(k)  = adj(J_k) * Pusai_k[:,a]            (= detJ_k * grad N_a at Gauss point k)
-//     Gbar_a  = sum_k g_a(k),  V = sum_k |detJ_k|  (BVbar rows = Gbar_a / (3V))
-//     L_k     = (sum_a du_a (x) g_a(k)) / detJ_k,  trbar = (sum_a du_a . Gbar_a) / V
-//     d_eps   = sym(L_k) + (trbar - tr L_k)/3 * I  (engineering shear)
-//     f_a     = sum_k s_k * g_a(k) + (sum_k p_k detJ_k)/V * Gbar_a,   s = dev(sigma), p = tr(sigma)/3
-// which is ~4x fewer flops and needs no 6x24 temporaries.  Results agree with the dense form to
-// rounding (tests/test_element_parity.py states the tolerance).
-#include "hk_common.h"
-
-// Pusai_mat[k][dir][node] (J2:1895-1943), computed on the host with the reference's expression
-#ifndef HK_EMU
-__constant__ double c_P[8][3][8];
-#else
-static double c_P[8][3][8];
-#endif
-
-void hk_upload_pusai(const double* P) {
-#ifndef HK_EMU
-    cudaMemcpyToSymbol(c_P, P, sizeof(double) * 192);
-#else
-    memcpy(c_P, P, sizeof(double) * 192);
-#endif
-}
+// Two kernels share that math:
+//   hk_element_tma_kernel   (default) persistent CTAs of 128 threads = tiles of 128 elements.  The ip state
+//       of a tile (14 rows x 1 KB per Gauss point) is streamed through a shared-memory ring by the TMA
+//       (cp.async.bulk global->shared with mbarrier completion, shared->global bulk stores), so HBM sees
+//       only 1 KB bursts, no state load ever stalls a math warp's scoreboard, and registers hold only
+//       the element's geometry modes and force accumulators.
+//   hk_element_simple_kernel  thread per element with plain coalesced loads (HK_ELEMENT_KERNEL=simple),
+//       kept as the A/B baseline for the profiles.
+#include "hk_element_math.h"
 
 struct ElemArgs {
     HkDev d;
@@ -37,29 +22,10 @@ struct ElemArgs {
     int write_triax;
 };
 
-// Jacobian, its adjugate (cofactor transpose) and determinant at Gauss point k
-HK_HD void jac_adj(const double x[8][3], int k, double adj[3][3], double& det) {
-    double J[3][3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            double s = 0.0;
-#pragma unroll
-            for (int a = 0; a < 8; ++a) s += c_P[k][r][a] * x[a][c];
-            J[r][c] = s;
-        }
-    // adj[i][j] such that inv(J) = adj / det  (same cofactors as J2:1445-1455)
-    adj[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-    adj[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
-    adj[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-    adj[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
-    adj[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
-    adj[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
-    adj[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
-    adj[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
-    adj[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-    det = J[0][0] * adj[0][0] + J[0][1] * adj[1][0] + J[0][2] * adj[2][0];
+HK_HD MatLite mat_lite(const HkMaterialDev* m) {
+    MatLite l;
+    l.D11 = m->D11; l.D12 = m->D12; l.D44 = m->D44; l.G3 = 3.0 * m->G; l.npp = m->npp; l.full = m;
+    return l;
 }
 
 HK_HD double triax_of(const double s[6]) {
@@ -70,189 +36,320 @@ HK_HD double triax_of(const double s[6]) {
     return (s[0] + s[1] + s[2]) / 3.0 / oeq;
 }
 
-HK_D void element_body(const ElemArgs& A, long long e) {
-    const HkDev& d = A.d;
-    const long long nEp = d.nEp;
+// ---- pieces shared by both kernels ------------------------------------------------------------------
+HK_D bool element_dead(const HkDev& d, long long e) {
     const unsigned char fl = d.flag[e];
-    if (fl != 1) {
-        if (fl == 0) {      // deleted during the previous step: its last force has been consumed, clear it
+    if (fl == 1) return false;
+    if (fl == 0) {      // deleted during the previous step: its last force has been consumed, clear it
 #pragma unroll
-            for (int r = 0; r < 24; ++r) d.Qe[(long long)r * nEp + e] = 0.0;
+        for (int r = 0; r < 24; ++r) d.Qe[(long long)r * d.nEp + e] = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) d.triax[(long long)k * nEp + e] = 0.0;   // zero stress -> triax 0 (J2:1012)
-            d.flag[e] = 2;
-        }
-        return;
+        for (int k = 0; k < 8; ++k) d.triax[(long long)k * d.nEp + e] = 0.0;   // zero stress -> triax 0 (J2:1012)
+        d.flag[e] = 2;
     }
-    const HkMaterialDev& M = d.mats[d.mat[e]];
+    return true;
+}
 
+HK_D void element_gather(const HkDev& d, long long e, HexModes& X, HexModes& U) {
     double x[8][3], du[8][3];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-        const long long n = d.conn[(long long)a * nEp + e];
+        const long long n = d.conn[(long long)a * d.nEp + e];
+#if defined(__CUDA_ARCH__)
+        const double2* r = reinterpret_cast<const double2*>(d.rec + 6 * n);
+        const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+        x[a][0] = r0.x; x[a][1] = r0.y; x[a][2] = r1.x;
+        du[a][0] = r1.y; du[a][1] = r2.x; du[a][2] = r2.y;
+#else
         const double* r = d.rec + 6 * n;
-#pragma unroll
         for (int c = 0; c < 3; ++c) { x[a][c] = r[c]; du[a][c] = r[3 + c]; }
+#endif
     }
+    hex_modes(x, X);
+    hex_modes(du, U);
+}
 
-    // ---- pass A: volume and mean gradients (cal_BVbar_hexa, J2:1705-1784)
-    double Gbar[8][3];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) Gbar[a][0] = Gbar[a][1] = Gbar[a][2] = 0.0;
-    double V = 0.0;
-    int negj = 0;
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) {
-        double adj[3][3], det;
-        jac_adj(x, k, adj, det);
-        if (det < 0) negj++;
-        V += fabs(det);
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                Gbar[a][i] += adj[i][0] * c_P[k][0][a] + adj[i][1] * c_P[k][1][a] + adj[i][2] * c_P[k][2][a];
-    }
-    if (negj) hk_atomic_add_u64(&d.counters[0], (unsigned long long)negj);
-    const double invV = 1.0 / V;
-    double trbar = 0.0;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) trbar += du[a][0] * Gbar[a][0] + du[a][1] * Gbar[a][1] + du[a][2] * Gbar[a][2];
-    trbar *= invV;
+// V = sum_k det_k and trbar = (sum_k det_k tr L_k) / V from the closed-form adjugate sums
+HK_HD void element_volume_terms(const HexModes& X, const HexModes& U, const double G[3][3][3], double& V, double& trbar) {
+    V = dot3(X.c0, G[0][0]) + dot3(X.h01, G[0][1]) + dot3(X.h02, G[0][2]);
+    const double tv = dot3(U.c0, G[0][0]) + dot3(U.h01, G[0][1]) + dot3(U.h02, G[0][2]) +
+                      dot3(U.c1, G[1][0]) + dot3(U.h01, G[1][1]) + dot3(U.h12, G[1][2]) +
+                      dot3(U.c2, G[2][0]) + dot3(U.h02, G[2][1]) + dot3(U.h12, G[2][2]);
+    trbar = tv / V;
+}
 
-    // ---- pass B: Gauss points
+HK_HD void acc_init(ElemAcc& acc) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc.M[r][m][0] = acc.M[r][m][1] = acc.M[r][m][2] = 0.0;
+    acc.pdet = 0.0; acc.v_e = 0.0; acc.t_e = 0.0; acc.negj = 0;
+}
+
+// ductile damage (J2:701-762): returns true when the element must be deleted
+HK_HD bool ductile_check(const HkMaterialDev& M, double v_sum, double t_sum) {
+    if (M.nd <= 0) return false;
+    const double v_e = v_sum / 8, t_e = t_sum / 8;
+    if (t_e < 0) return false;
+    const int nd = M.nd;
+    double fr_e = M.duct_e[nd - 1];
+    for (int j = 0; j + 1 < nd; ++j)
+        if (t_e >= M.duct_t[j] && t_e < M.duct_t[j + 1]) {
+            fr_e = M.duct_e[j] + (M.duct_e[j + 1] - M.duct_e[j]) / (M.duct_t[j + 1] - M.duct_t[j]) * (t_e - M.duct_t[j]);
+            break;
+        }
+    return v_e >= fr_e;
+}
+
+HK_D void element_finish(const ElemArgs& A, long long e, const HexModes& X, const ElemAcc& acc, double V) {
+    const HkDev& d = A.d;
+    double G[3][3][3];
+    adj_mode_sums(X, G);
     double f[8][3];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) f[a][0] = f[a][1] = f[a][2] = 0.0;
-    double pdet = 0.0, v_e = 0.0, t_e = 0.0;
-    const double G = M.G;
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) {
-        double adj[3][3], det;
-        jac_adj(x, k, adj, det);
-        double g[8][3];
-        double L[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                g[a][i] = adj[i][0] * c_P[k][0][a] + adj[i][1] * c_P[k][1][a] + adj[i][2] * c_P[k][2][a];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) L[i][j] += du[a][i] * g[a][j];
-        }
-        const double idet = 1.0 / det;
-        const double trL = (L[0][0] + L[1][1] + L[2][2]) * idet;
-        const double vol = (trbar - trL) * (1.0 / 3.0);
-        double de[6];
-        de[0] = L[0][0] * idet + vol;
-        de[1] = L[1][1] * idet + vol;
-        de[2] = L[2][2] * idet + vol;
-        de[3] = (L[0][1] + L[1][0]) * idet;
-        de[4] = (L[1][2] + L[2][1]) * idet;
-        de[5] = (L[0][2] + L[2][0]) * idet;
-
-        const long long row = (long long)k * nEp + e;
-        double s[6];
-        // trial stress = old + D*de   (J2:1205-1220)
-        s[0] = d.stress[0 * 8 * nEp + row] + (M.D11 * de[0] + M.D12 * de[1] + M.D12 * de[2]);
-        s[1] = d.stress[1 * 8 * nEp + row] + (M.D12 * de[0] + M.D11 * de[1] + M.D12 * de[2]);
-        s[2] = d.stress[2 * 8 * nEp + row] + (M.D12 * de[0] + M.D12 * de[1] + M.D11 * de[2]);
-        s[3] = d.stress[3 * 8 * nEp + row] + M.D44 * de[3];
-        s[4] = d.stress[4 * 8 * nEp + row] + M.D44 * de[4];
-        s[5] = d.stress[5 * 8 * nEp + row] + M.D44 * de[5];
-        double ep = d.eps[row];
-        if (M.npp > 0) {                          // J2 radial return, J2:1227-1285
-            const double mean = (s[0] + s[1] + s[2]) / 3.0;
-            const double t0 = s[0] - mean, t1 = s[1] - mean, t2 = s[2] - mean;
-            const double mises = sqrt(1.5 * (t0 * t0 + t1 * t1 + t2 * t2 + 2 * (s[3] * s[3]) + 2 * (s[4] * s[4]) +
-                                             2 * (s[5] * s[5])));
-            const double y = d.yield[row];
-            if (mises > y) {
-                int p_index = M.npp - 2;          // last segment extrapolates (J2:1261-1263)
-                for (int j = 1; j < M.npp; ++j)
-                    if (ep <= M.plastic_e[j]) { p_index = j - 1; break; }
-                const double H = M.Hd[p_index];
-                const double d_ep = (mises - y) / (3 * G + H);
-                const double ynew = y + H * d_ep;
-                const double fac = ynew / mises;
-                s[0] = t0 * fac + mean;
-                s[1] = t1 * fac + mean;
-                s[2] = t2 * fac + mean;
-                s[3] *= fac; s[4] *= fac; s[5] *= fac;
-                ep += d_ep;
-                d.eps[row] = ep;
-                d.yield[row] = ynew;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const long long idx = (long long)c * 8 * nEp + row;
-            d.strain[idx] += de[c];
-            d.stress[idx] = s[c];
-        }
-        // nodal force: s_dev * g_a (p-part is applied once after the loop)
-        const double p = (s[0] + s[1] + s[2]) * (1.0 / 3.0);
-        const double sx = s[0] - p, sy = s[1] - p, sz = s[2] - p;
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            f[a][0] += sx * g[a][0] + s[3] * g[a][1] + s[5] * g[a][2];
-            f[a][1] += s[3] * g[a][0] + sy * g[a][1] + s[4] * g[a][2];
-            f[a][2] += s[5] * g[a][0] + s[4] * g[a][1] + sz * g[a][2];
-        }
-        pdet += p * det;
-        const double tx = triax_of(s);
-        if (A.write_triax) d.triax[row] = tx;
-        v_e += ep;
-        t_e += tx;
-    }
-    const double pbar = pdet * invV;
+    element_forces(acc, G, acc.pdet / V, f);
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) d.Qe[(long long)(a * 3 + c) * nEp + e] = f[a][c] + pbar * Gbar[a][c];
+        for (int c = 0; c < 3; ++c) d.Qe[(long long)(a * 3 + c) * d.nEp + e] = f[a][c];
+    if (acc.negj) hk_atomic_add_u64(&d.counters[0], (unsigned long long)acc.negj);
+}
 
-    // ---- ductile damage / element deletion (J2:701-762)
-    if (M.nd > 0) {
-        v_e /= 8;
-        t_e /= 8;
-        if (!(t_e < 0)) {
-            const int nd = M.nd;
-            double fr_e = M.duct_e[nd - 1];
-            for (int j = 0; j + 1 < nd; ++j)
-                if (t_e >= M.duct_t[j] && t_e < M.duct_t[j + 1]) {
-                    fr_e = M.duct_e[j] + (M.duct_e[j + 1] - M.duct_e[j]) / (M.duct_t[j + 1] - M.duct_t[j]) * (t_e - M.duct_t[j]);
-                    break;
-                }
-            if (v_e >= fr_e) {
-                d.flag[e] = 0;
+HK_D void element_delete(const ElemArgs& A, long long e) {
+    const HkDev& d = A.d;
+    d.flag[e] = 0;
 #pragma unroll 1
-                for (int r = 0; r < 48; ++r) {
-                    d.stress[(long long)r * nEp + e] = 0.0;
-                    d.strain[(long long)r * nEp + e] = 0.0;
-                }
-                const int slot = hk_atomic_add_i32(d.del_count, 1);
-                if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
-            }
-        }
+    for (int r = 0; r < 48; ++r) {
+        d.stress[(long long)r * d.nEp + e] = 0.0;
+        d.strain[(long long)r * d.nEp + e] = 0.0;
     }
+    const int slot = hk_atomic_add_i32(d.del_count, 1);
+    if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
+}
+
+// ---- simple kernel: thread per element, state straight from global memory ---------------------------------
+HK_D void element_body_simple(const ElemArgs& A, long long e) {
+    const HkDev& d = A.d;
+    const long long nEp = d.nEp;
+    if (element_dead(d, e)) return;
+    const HkMaterialDev& M = d.mats[d.mat[e]];
+    const MatLite ML = mat_lite(&M);
+    HexModes X, U;
+    element_gather(d, e, X, U);
+    double V, trbar;
+    {
+        double G[3][3][3];
+        adj_mode_sums(X, G);
+        element_volume_terms(X, U, G, V, trbar);
+    }
+    ElemAcc acc;
+    acc_init(acc);
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const long long row = (long long)k * nEp + e;
+        double st[14];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            st[c] = d.stress[(long long)c * 8 * nEp + row];
+            st[6 + c] = d.strain[(long long)c * 8 * nEp + row];
+        }
+        st[12] = d.eps[row];
+        st[13] = d.yield[row];
+        const double ep_old = st[12];
+        const double tx = gauss_point(X, U, ML, k, trbar, st, acc);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            d.stress[(long long)c * 8 * nEp + row] = st[c];
+            d.strain[(long long)c * 8 * nEp + row] = st[6 + c];
+        }
+        if (st[12] != ep_old) { d.eps[row] = st[12]; d.yield[row] = st[13]; }
+        if (A.write_triax) d.triax[row] = tx;
+    }
+    element_finish(A, e, X, acc, V);
+    if (ductile_check(M, acc.v_e, acc.t_e)) element_delete(A, e);
 }
 
 #ifndef HK_EMU
-__global__ void __launch_bounds__(128) hk_element_kernel(ElemArgs A) {
+__global__ void __launch_bounds__(128, 2) hk_element_simple_kernel(ElemArgs A) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e < A.d.nElement) element_body(A, e);
+    if (e < A.d.nElement) element_body_simple(A, e);
+}
+
+// ---- TMA-staged kernel --------------------------------------------------------------------------------------
+#define HK_TILE 128                       // elements per tile = threads per CTA
+#define HK_ROWS 14                        // state rows per Gauss point: stress 6, strain 6, eps, yield
+#define HK_STAGES 5                       // ring depth (stages of 14 KB)
+#define HK_STAGE_DOUBLES (HK_ROWS * HK_TILE)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// global address of state row r (0..13) of Gauss point k for the tile starting at element e0
+__device__ __forceinline__ double* state_row(const HkDev& d, int r, int k, long long e0) {
+    if (r < 6) return d.stress + ((long long)(r * 8 + k) * d.nEp + e0);
+    if (r < 12) return d.strain + ((long long)((r - 6) * 8 + k) * d.nEp + e0);
+    if (r == 12) return d.eps + ((long long)k * d.nEp + e0);
+    return d.yield + ((long long)k * d.nEp + e0);
+}
+
+__global__ void __launch_bounds__(HK_TILE, 2) hk_element_tma_kernel(ElemArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_buf = reinterpret_cast<double*>(smem_raw);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(stage_buf + HK_STAGES * HK_STAGE_DOUBLES);
+    const HkDev& d = A.d;
+    const int tid = threadIdx.x;
+    const long long n_tiles = d.nEp / HK_TILE;
+    const long long first = blockIdx.x;
+    if (first >= n_tiles) return;
+    const long long my_tiles = (n_tiles - first + gridDim.x - 1) / gridDim.x;
+    const long long total_q = my_tiles * 8;                 // (tile, gauss point) work items of this CTA
+
+    if (tid == 0) {
+        for (int s = 0; s < HK_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer (thread 0): issue the loads of work item q into stage q % S
+    auto issue_load = [&](long long q) {
+        const int st = (int)(q % HK_STAGES);
+        const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
+        const int k = (int)(q & 7);
+        double* dst = stage_buf + st * HK_STAGE_DOUBLES;
+        mbar_expect_tx(&full[st], HK_ROWS * HK_TILE * 8);
+#pragma unroll 1
+        for (int r = 0; r < HK_ROWS; ++r) tma_load_1d(dst + r * HK_TILE, state_row(d, r, k, e0), HK_TILE * 8, &full[st]);
+    };
+    if (tid == 0)
+        for (long long q = 0; q < HK_STAGES - 1 && q < total_q; ++q) issue_load(q);
+
+    long long q = 0;
+    for (long long it = 0; it < my_tiles; ++it) {
+        const long long e0 = (first + it * gridDim.x) * HK_TILE;
+        const long long e = e0 + tid;
+        const bool live = !element_dead(d, e);              // padded elements carry flag 2
+        HexModes X, U;
+        ElemAcc acc;
+        double V = 1.0, trbar = 0.0;
+        const HkMaterialDev* Mt = &d.mats[0];
+        MatLite ML = mat_lite(Mt);
+        acc_init(acc);
+        if (live) {
+            Mt = &d.mats[d.mat[e]];
+            ML = mat_lite(Mt);
+            element_gather(d, e, X, U);
+            double G[3][3][3];
+            adj_mode_sums(X, G);
+            element_volume_terms(X, U, G, V, trbar);
+        }
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k, ++q) {
+            const int st = (int)(q % HK_STAGES);
+            double* sb = stage_buf + st * HK_STAGE_DOUBLES + tid;
+            mbar_wait(&full[st], (unsigned)((q / HK_STAGES) & 1));
+            if (live) {
+                double sv[14];
+#pragma unroll
+                for (int r = 0; r < HK_ROWS; ++r) sv[r] = sb[r * HK_TILE];
+                const double tx = gauss_point(X, U, ML, k, trbar, sv, acc);
+#pragma unroll
+                for (int r = 0; r < HK_ROWS; ++r) sb[r * HK_TILE] = sv[r];
+                if (A.write_triax) d.triax[(long long)k * d.nEp + e] = tx;
+            }
+            fence_async_smem();                              // generic-proxy smem writes -> visible to the TMA
+            __syncthreads();
+            if (tid == 0) {
+                double* src = stage_buf + st * HK_STAGE_DOUBLES;
+#pragma unroll 1
+                for (int r = 0; r < HK_ROWS; ++r) tma_store_1d(state_row(d, r, k, e0), src + r * HK_TILE, HK_TILE * 8);
+                tma_commit();
+                const long long qn = q + HK_STAGES - 1;      // refill the stage whose store was committed last round
+                if (qn < total_q) {
+                    tma_wait_read<1>();                      // all but the newest store group have read their smem
+                    issue_load(qn);
+                }
+            }
+        }
+        bool del = false;
+        if (live) {
+            element_finish(A, e, X, acc, V);
+            del = ductile_check(*Mt, acc.v_e, acc.t_e);
+        }
+        if (__syncthreads_or(del ? 1 : 0)) {                 // rare: zero the state of deleted elements AFTER the
+            if (tid == 0) { tma_wait_all<0>(); fence_async_all(); }   // bulk stores of this tile have landed
+            __syncthreads();
+            if (del) element_delete(A, e);
+        }
+    }
+    if (tid == 0) tma_wait_all<0>();
 }
 #endif
+
+static int g_elem_kernel = -1;   // 0 tma, 1 simple
 
 void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s) {
     ElemArgs A{d, step, write_triax};
 #ifndef HK_EMU
-    const int block = 128;
-    hk_element_kernel<<<(unsigned)((d.nElement + block - 1) / block), block, 0, s>>>(A);
+    if (g_elem_kernel < 0) {
+        const char* env = getenv("HK_ELEMENT_KERNEL");
+        g_elem_kernel = (env && strcmp(env, "simple") == 0) ? 1 : 0;
+    }
+    if (g_elem_kernel == 1) {
+        const int block = 128;
+        hk_element_simple_kernel<<<(unsigned)((d.nElement + block - 1) / block), block, 0, s>>>(A);
+        return;
+    }
+    static int n_sm = 0, smem_bytes = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        smem_bytes = HK_STAGES * HK_STAGE_DOUBLES * 8 + HK_STAGES * 8 + 64;
+        cudaFuncSetAttribute(hk_element_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    }
+    const long long n_tiles = d.nEp / HK_TILE;
+    long long grid = (long long)n_sm * 2;
+    if (grid > n_tiles) grid = n_tiles;
+    hk_element_tma_kernel<<<(unsigned)grid, HK_TILE, smem_bytes, s>>>(A);
 #else
-    for (long long e = 0; e < d.nElement; ++e) element_body(A, e);
+    for (long long e = 0; e < d.nElement; ++e) element_body_simple(A, e);
 #endif
 }
 
@@ -269,7 +366,7 @@ void hk_launch_triax(const HkDev& dd, cudaStream_t s) {
     });
 }
 
-// elementVolume[e] = sum_k |detJ_k| at the current position (J2:1168-1169)
+// elementVolume[e] = sum_k det_k at the current position (J2:1168-1169)
 void hk_launch_element_volume(const HkDev& dd, double* V_out, cudaStream_t s) {
     const HkDev d = dd;
     hk_parallel_for(d.nElement, s, HK_LAMBDA(long long e) {
@@ -278,12 +375,12 @@ void hk_launch_element_volume(const HkDev& dd, double* V_out, cudaStream_t s) {
             const long long n = d.conn[(long long)a * d.nEp + e];
             for (int c = 0; c < 3; ++c) x[a][c] = d.rec[6 * n + c];
         }
-        double V = 0.0;
-        for (int k = 0; k < 8; ++k) {
-            double adj[3][3], det;
-            jac_adj(x, k, adj, det);
-            V += fabs(det);
-        }
-        V_out[e] = V;
+        HexModes X;
+        hex_modes(x, X);
+        double G[3][3][3];
+        adj_mode_sums(X, G);
+        V_out[e] = dot3(X.c0, G[0][0]) + dot3(X.h01, G[0][1]) + dot3(X.h02, G[0][2]);
     });
 }
+
+void hk_upload_pusai(const double*) {}

@@ -547,7 +547,7 @@ int HKAPI(finalize)(hk_engine* e) {
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
     if (e->nNode == 0) return fail(e, HK_ERR_STATE, "hk_set_mesh not called");
     const int64_t nN = e->nNode, nE = e->nElement;
-    const int64_t nEp = (nE + 31) / 32 * 32;
+    const int64_t nEp = (nE + 127) / 128 * 128;   // tiles of 128 elements (hk_element_tma_kernel)
     HkDev& d = e->d;
     d.nNode = nN; d.nElement = nE; d.nEp = nEp;
     const double dt = e->prm.d_time;

@@ -103,19 +103,28 @@ HK_HD double eval_amp(const HkDev& d, int amp_id, double current_time) {   // J2
 
 HK_HD void nodal_body(const NodalArgs& A, long long n) {
     const HkDev& d = A.d;
-    // internal force of the node: Q[n] = sum over incident elements in ascending element order (J2:668-675)
+    // internal force of the node: Q[n] = sum over incident elements in ascending element order (J2:668-675).
+    // All table entries, then all force loads, are issued before the first add so the loads overlap; a missing
+    // entry contributes +0.0, which leaves the running sum bit-identical to skipping it.
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
     if (A.use_Q0) {
         q0 = d.Q0[3 * n]; q1 = d.Q0[3 * n + 1]; q2 = d.Q0[3 * n + 2];
     } else {
-        for (int w = 0; w < d.ell_width; ++w) {
-            int ent = d.ell[(long long)w * d.nNode + n];
-            if (ent < 0) break;
-            long long e = ent >> 3;
-            int a = ent & 7;
-            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
-            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
-            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+        for (int w0 = 0; w0 < d.ell_width; w0 += 8) {
+            int ent[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) ent[w] = (w0 + w < d.ell_width) ? d.ell[(long long)(w0 + w) * d.nNode + n] : -1;
+            double v[8][3];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const bool ok = ent[w] >= 0;
+                const long long e = ok ? (ent[w] >> 3) : 0;
+                const int a = ok ? (ent[w] & 7) : 0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[w][c] = ok ? d.Qe[(long long)(a * 3 + c) * d.nEp + e] : 0.0;
+            }
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { q0 += v[w][0]; q1 += v[w][1]; q2 += v[w][2]; }
         }
     }
     double F[3] = {0.0, 0.0, 0.0};
