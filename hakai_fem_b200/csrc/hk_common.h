@@ -64,7 +64,8 @@ struct HkDev {
     double* amp_value;
     // elements
     int* conn;            // [8][nEp] 0-based node ids
-    unsigned char* flag;  // 1 live, 0 deleted in the last step run (Qe still valid), 2 deleted and Qe cleared
+    unsigned char* flag;  // 1 live, 3 deleted this step (state not yet zeroed), 0 deleted in the last step run (Qe still
+                          // valid), 2 deleted and Qe cleared
     unsigned short* mat;  // 0-based material id
     HkMaterialDev* mats;
     double* stress;       // [6][8][nEp]
@@ -111,6 +112,7 @@ void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStre
 void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s);
 void hk_launch_velo_from_rec(const HkDev& d, double d_time, cudaStream_t s);
 void hk_launch_gather_Q(const HkDev& d, double* Q_out, cudaStream_t s);
+void hk_launch_flush_deleted(const HkDev& d, cudaStream_t s);
 void hk_launch_triax(const HkDev& d, cudaStream_t s);
 void hk_launch_element_volume(const HkDev& d, double* V_out, cudaStream_t s);
 // layout transposes between the reference's AoS (6,nip)/(nip) arrays and the SoA rows
@@ -119,4 +121,5 @@ void hk_launch_ip_to_soa(const double* aos, double* soa, int ncomp, long long e0
 void hk_launch_ip_to_aos(const double* soa, double* aos, int ncomp, long long e0, long long ne, long long nEp,
                          cudaStream_t s);
 void hk_upload_pusai(const double* P);
+long long hk_element_tile();   // nEp must be a multiple of this
 void hk_launch_external_force(const HkDev& d, double* F_out, int lsb_exp, int contact_on, cudaStream_t s);

@@ -175,10 +175,20 @@ __global__ void __launch_bounds__(128, 2) hk_element_simple_kernel(ElemArgs A) {
 }
 
 // ---- TMA-staged kernel --------------------------------------------------------------------------------------
-#define HK_TILE 128                       // elements per tile = threads per CTA
+// One persistent CTA per SM: HK_TILE consumer threads (one element each) + one producer warp.  The producer's
+// lane 0 drives the TMA: bulk loads of the next Gauss points' state rows into a ring of shared-memory stages
+// (completion on `full` mbarriers) and bulk stores of finished stages back to HBM (after all consumers arrived
+// on the stage's `done` mbarrier).  Consumers never execute a global load or store for ip state and never meet
+// at a CTA-wide barrier.
+#ifndef HK_TILE
+#define HK_TILE 224                       // elements per tile = consumer threads per CTA (7 warps + 1 producer warp = 256 threads -> 255 regs)
+#endif
 #define HK_ROWS 14                        // state rows per Gauss point: stress 6, strain 6, eps, yield
-#define HK_STAGES 5                       // ring depth (stages of 14 KB)
+#ifndef HK_STAGES
+#define HK_STAGES 8                       // ring depth (stages of HK_ROWS*HK_TILE*8 bytes)
+#endif
 #define HK_STAGE_DOUBLES (HK_ROWS * HK_TILE)
+#define HK_CTA_THREADS (HK_TILE + 32)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -186,6 +196,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned addr = smem_u32(bar);
@@ -219,7 +232,6 @@ __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wa
 template <int N>
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // global address of state row r (0..13) of Gauss point k for the tile starting at element e0
 __device__ __forceinline__ double* state_row(const HkDev& d, int r, int k, long long e0) {
@@ -229,37 +241,59 @@ __device__ __forceinline__ double* state_row(const HkDev& d, int r, int k, long 
     return d.yield + ((long long)k * d.nEp + e0);
 }
 
-__global__ void __launch_bounds__(HK_TILE, 2) hk_element_tma_kernel(ElemArgs A) {
+__global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_buf = reinterpret_cast<double*>(smem_raw);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(stage_buf + HK_STAGES * HK_STAGE_DOUBLES);
+    unsigned long long* done = full + HK_STAGES;
     const HkDev& d = A.d;
     const int tid = threadIdx.x;
     const long long n_tiles = d.nEp / HK_TILE;
     const long long first = blockIdx.x;
-    if (first >= n_tiles) return;
-    const long long my_tiles = (n_tiles - first + gridDim.x - 1) / gridDim.x;
+    const long long my_tiles = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
     const long long total_q = my_tiles * 8;                 // (tile, gauss point) work items of this CTA
 
     if (tid == 0) {
-        for (int s = 0; s < HK_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < HK_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], HK_TILE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // producer (thread 0): issue the loads of work item q into stage q % S
-    auto issue_load = [&](long long q) {
-        const int st = (int)(q % HK_STAGES);
-        const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
-        const int k = (int)(q & 7);
-        double* dst = stage_buf + st * HK_STAGE_DOUBLES;
-        mbar_expect_tx(&full[st], HK_ROWS * HK_TILE * 8);
+    if (tid >= HK_TILE) {
+        // ===== producer warp =====
+        if (tid != HK_TILE) return;
+        auto issue_load = [&](long long q) {
+            const int st = (int)(q % HK_STAGES);
+            const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
+            const int k = (int)(q & 7);
+            double* dst = stage_buf + st * HK_STAGE_DOUBLES;
+            mbar_expect_tx(&full[st], HK_ROWS * HK_TILE * 8);
 #pragma unroll 1
-        for (int r = 0; r < HK_ROWS; ++r) tma_load_1d(dst + r * HK_TILE, state_row(d, r, k, e0), HK_TILE * 8, &full[st]);
-    };
-    if (tid == 0)
-        for (long long q = 0; q < HK_STAGES - 1 && q < total_q; ++q) issue_load(q);
+            for (int r = 0; r < HK_ROWS; ++r)
+                tma_load_1d(dst + r * HK_TILE, state_row(d, r, k, e0), HK_TILE * 8, &full[st]);
+        };
+        for (long long q = 0; q < HK_STAGES && q < total_q; ++q) issue_load(q);
+        for (long long q = 0; q < total_q; ++q) {
+            const int st = (int)(q % HK_STAGES);
+            mbar_wait(&done[st], (unsigned)((q / HK_STAGES) & 1));      // every consumer finished item q
+            const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
+            const int k = (int)(q & 7);
+            const double* src = stage_buf + st * HK_STAGE_DOUBLES;
+#pragma unroll 1
+            for (int r = 0; r < HK_ROWS; ++r) tma_store_1d(state_row(d, r, k, e0), src + r * HK_TILE, HK_TILE * 8);
+            tma_commit();
+            // refill the stage whose store group was committed one round ago (it has been read by now)
+            const long long qn = q - 1 + HK_STAGES;
+            if (q >= 1 && qn < total_q) {
+                tma_wait_read<1>();
+                issue_load(qn);
+            }
+        }
+        tma_wait_all<0>();
+        return;
+    }
 
+    // ===== consumers: one element per thread =====
     long long q = 0;
     for (long long it = 0; it < my_tiles; ++it) {
         const long long e0 = (first + it * gridDim.x) * HK_TILE;
@@ -294,31 +328,19 @@ __global__ void __launch_bounds__(HK_TILE, 2) hk_element_tma_kernel(ElemArgs A) 
                 if (A.write_triax) d.triax[(long long)k * d.nEp + e] = tx;
             }
             fence_async_smem();                              // generic-proxy smem writes -> visible to the TMA
-            __syncthreads();
-            if (tid == 0) {
-                double* src = stage_buf + st * HK_STAGE_DOUBLES;
-#pragma unroll 1
-                for (int r = 0; r < HK_ROWS; ++r) tma_store_1d(state_row(d, r, k, e0), src + r * HK_TILE, HK_TILE * 8);
-                tma_commit();
-                const long long qn = q + HK_STAGES - 1;      // refill the stage whose store was committed last round
-                if (qn < total_q) {
-                    tma_wait_read<1>();                      // all but the newest store group have read their smem
-                    issue_load(qn);
-                }
-            }
+            mbar_arrive(&done[st]);
         }
-        bool del = false;
         if (live) {
             element_finish(A, e, X, acc, V);
-            del = ductile_check(*Mt, acc.v_e, acc.t_e);
-        }
-        if (__syncthreads_or(del ? 1 : 0)) {                 // rare: zero the state of deleted elements AFTER the
-            if (tid == 0) { tma_wait_all<0>(); fence_async_all(); }   // bulk stores of this tile have landed
-            __syncthreads();
-            if (del) element_delete(A, e);
+            if (ductile_check(*Mt, acc.v_e, acc.t_e)) {
+                // the state rows of this element are still in flight in bulk stores: only mark it here,
+                // hk_launch_flush_deleted zeroes stress/strain after this kernel (stream order)
+                d.flag[e] = 3;
+                const int slot = hk_atomic_add_i32(d.del_count, 1);
+                if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
+            }
         }
     }
-    if (tid == 0) tma_wait_all<0>();
 }
 #endif
 
@@ -341,16 +363,29 @@ void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStre
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        smem_bytes = HK_STAGES * HK_STAGE_DOUBLES * 8 + HK_STAGES * 8 + 64;
+        smem_bytes = HK_STAGES * HK_STAGE_DOUBLES * 8 + 2 * HK_STAGES * 8 + 64;
         cudaFuncSetAttribute(hk_element_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     }
     const long long n_tiles = d.nEp / HK_TILE;
-    long long grid = (long long)n_sm * 2;
+    long long grid = (long long)n_sm;
     if (grid > n_tiles) grid = n_tiles;
-    hk_element_tma_kernel<<<(unsigned)grid, HK_TILE, smem_bytes, s>>>(A);
+    hk_element_tma_kernel<<<(unsigned)grid, HK_CTA_THREADS, smem_bytes, s>>>(A);
 #else
     for (long long e = 0; e < d.nElement; ++e) element_body_simple(A, e);
 #endif
+}
+
+// zero stress/strain of elements the TMA kernel marked for deletion (flag 3 -> 0), J2:742-756
+void hk_launch_flush_deleted(const HkDev& dd, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(d.nElement, s, HK_LAMBDA(long long e) {
+        if (d.flag[e] != 3) return;
+        for (int r = 0; r < 48; ++r) {
+            d.stress[(long long)r * d.nEp + e] = 0.0;
+            d.strain[(long long)r * d.nEp + e] = 0.0;
+        }
+        d.flag[e] = 0;
+    });
 }
 
 // integ_triax_stress recomputed from the current stress (used when no step has written it yet)
@@ -384,3 +419,11 @@ void hk_launch_element_volume(const HkDev& dd, double* V_out, cudaStream_t s) {
 }
 
 void hk_upload_pusai(const double*) {}
+
+long long hk_element_tile() {
+#ifndef HK_EMU
+    return HK_TILE;
+#else
+    return 32;
+#endif
+}

@@ -547,7 +547,8 @@ int HKAPI(finalize)(hk_engine* e) {
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
     if (e->nNode == 0) return fail(e, HK_ERR_STATE, "hk_set_mesh not called");
     const int64_t nN = e->nNode, nE = e->nElement;
-    const int64_t nEp = (nE + 127) / 128 * 128;   // tiles of 128 elements (hk_element_tma_kernel)
+    const int64_t tile = hk_element_tile();
+    const int64_t nEp = (nE + tile - 1) / tile * tile;   // whole tiles for hk_element_tma_kernel
     HkDev& d = e->d;
     d.nNode = nN; d.nElement = nE; d.nEp = nEp;
     const double dt = e->prm.d_time;
@@ -773,6 +774,7 @@ int HKAPI(step)(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_delet
         hk_launch_element(d, t, (t == t_first + n_steps - 1) ? 1 : 0, e->stream);
         prof_end(e);
         e->n_launch += 2;
+        if (e->any_ductile) { hk_launch_flush_deleted(d, e->stream); e->n_launch += 1; }
         e->n_steps += 1;
         if (contact_on && e->any_ductile) {       // exposed faces must be in place before the next contact pass
             std::vector<int64_t> fresh;

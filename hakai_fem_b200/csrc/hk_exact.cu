@@ -101,36 +101,54 @@ HK_HD double eval_amp(const HkDev& d, int amp_id, double current_time) {   // J2
     return a_v[ti] + (a_v[ti + 1] - a_v[ti]) * (current_time - a_t[ti]) / (a_t[ti + 1] - a_t[ti]);
 }
 
+#if defined(__CUDA_ARCH__)
+#define HK_LDG(p) __ldg(p)
+#else
+#define HK_LDG(p) (*(p))
+#endif
+
 HK_HD void nodal_body(const NodalArgs& A, long long n) {
     const HkDev& d = A.d;
+    // ---- issue every independent load first (the kernel is a pure latency/bandwidth problem) -------------
+    int ent[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) ent[w] = (w < d.ell_width) ? HK_LDG(&d.ell[(long long)w * d.nNode + n]) : -1;
+    const int si = HK_LDG(&d.spec_idx[n]);
+    const double M = HK_LDG(&d.mass[n]);
+    double u[3], up[3], X[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { u[c] = d.u[3 * n + c]; up[c] = d.u_pre[3 * n + c]; X[c] = HK_LDG(&d.X[3 * n + c]); }
+
     // internal force of the node: Q[n] = sum over incident elements in ascending element order (J2:668-675).
-    // All table entries, then all force loads, are issued before the first add so the loads overlap; a missing
-    // entry contributes +0.0, which leaves the running sum bit-identical to skipping it.
+    // A missing entry contributes +0.0, which leaves the running sum bit-identical to skipping it.
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
     if (A.use_Q0) {
         q0 = d.Q0[3 * n]; q1 = d.Q0[3 * n + 1]; q2 = d.Q0[3 * n + 2];
     } else {
-        for (int w0 = 0; w0 < d.ell_width; w0 += 8) {
-            int ent[8];
+        double v[8][3];
 #pragma unroll
-            for (int w = 0; w < 8; ++w) ent[w] = (w0 + w < d.ell_width) ? d.ell[(long long)(w0 + w) * d.nNode + n] : -1;
-            double v[8][3];
+        for (int w = 0; w < 8; ++w) {
+            const bool ok = ent[w] >= 0;
+            const long long e = ok ? (ent[w] >> 3) : 0;
+            const int a = ok ? (ent[w] & 7) : 0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const bool ok = ent[w] >= 0;
-                const long long e = ok ? (ent[w] >> 3) : 0;
-                const int a = ok ? (ent[w] & 7) : 0;
+            for (int c = 0; c < 3; ++c) v[w][c] = ok ? HK_LDG(&d.Qe[(long long)(a * 3 + c) * d.nEp + e]) : 0.0;
+        }
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[w][c] = ok ? d.Qe[(long long)(a * 3 + c) * d.nEp + e] : 0.0;
-            }
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { q0 += v[w][0]; q1 += v[w][1]; q2 += v[w][2]; }
+        for (int w = 0; w < 8; ++w) { q0 += v[w][0]; q1 += v[w][1]; q2 += v[w][2]; }
+        for (int w = 8; w < d.ell_width; ++w) {          // irregular meshes: more than 8 elements at a node
+            const int en = d.ell[(long long)w * d.nNode + n];
+            if (en < 0) break;
+            const long long e = en >> 3;
+            const int a = en & 7;
+            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
+            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
+            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
         }
     }
     double F[3] = {0.0, 0.0, 0.0};
-    double bcv[3];
+    double bcv[3] = {0.0, 0.0, 0.0};
     bool has_bc[3] = {false, false, false};
-    const int si = d.spec_idx[n];
     if (si >= 0) {
         const HkSpecialNode sp = d.spec[si];
         if (sp.halo_slot >= 0) {                 // partial sums of the neighbour rank (multi-GPU)
@@ -156,23 +174,33 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
         }
     }
     // central difference, J2:564 (diag_C == 0: its terms vanish exactly)
-    const double M = d.mass[n];
     const double a = M / A.dt2;
     const double a2 = M / A.dt2p;
     const double inva = 1.0 / a;
     const double q[3] = {q0, q1, q2};
+    double un[3], dd[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        un[c] = inva * (F[c] - q[c] + a2 * (2.0 * u[c] - up[c]));
+        if (has_bc[c]) un[c] = bcv[c];
+        dd[c] = un[c] - u[c];                    // d_disp, J2:625
+    }
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
         const long long i = 3 * n + c;
-        const double u = d.u[i], up = d.u_pre[i];
-        double un = inva * (F[c] - q[c] + a2 * (2.0 * u - up));
-        if (has_bc[c]) un = bcv[c];
-        const double dd = un - u;                // d_disp, J2:625
-        d.u_pre[i] = u;
-        d.u[i] = un;
-        d.rec[6 * n + c] = d.X[i] + un;          // position, J2:650-652
-        d.rec[6 * n + 3 + c] = dd;
-        if (A.contact_on) d.velo[i] = dd / A.d_time;   // velo, J2:628
+        d.u_pre[i] = u[c];
+        d.u[i] = un[c];
+        if (A.contact_on) d.velo[i] = dd[c] / A.d_time;   // velo, J2:628
     }
+    // node record {position (J2:650-652), d_disp}: 48 contiguous bytes
+#if defined(__CUDA_ARCH__)
+    double2* r = reinterpret_cast<double2*>(d.rec + 6 * n);
+    r[0] = make_double2(X[0] + un[0], X[1] + un[1]);
+    r[1] = make_double2(X[2] + un[2], dd[0]);
+    r[2] = make_double2(dd[1], dd[2]);
+#else
+    for (int c = 0; c < 3; ++c) { d.rec[6 * n + c] = X[c] + un[c]; d.rec[6 * n + 3 + c] = dd[c]; }
+#endif
 }
 
 #ifndef HK_EMU
