@@ -187,7 +187,9 @@ def main():
     eng.step(1, args.warmup)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 3.0:      # first nvidia-smi sample before timing starts
+        time.sleep(0.05)
     l0 = int(eng.counters()[3])
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -24,7 +24,8 @@ struct ElemArgs {
 
 HK_HD MatLite mat_lite(const HkMaterialDev* m) {
     MatLite l;
-    l.D11 = m->D11; l.D12 = m->D12; l.D44 = m->D44; l.G3 = 3.0 * m->G; l.npp = m->npp; l.full = m;
+    l.D11 = m->D11; l.D12 = m->D12; l.D44 = m->D44; l.G3 = 3.0 * m->G; l.npp = m->npp;
+    l.pe = m->plastic_e; l.hd = m->Hd;
     return l;
 }
 
@@ -184,11 +185,9 @@ __global__ void __launch_bounds__(128, 2) hk_element_simple_kernel(ElemArgs A) {
 #define HK_TILE 224                       // elements per tile = consumer threads per CTA (7 warps + 1 producer warp = 256 threads -> 255 regs)
 #endif
 #define HK_ROWS 14                        // state rows per Gauss point: stress 6, strain 6, eps, yield
-#ifndef HK_STAGES
-#define HK_STAGES 8                       // ring depth (stages of HK_ROWS*HK_TILE*8 bytes)
-#endif
 #define HK_STAGE_DOUBLES (HK_ROWS * HK_TILE)
 #define HK_CTA_THREADS (HK_TILE + 32)
+#define HK_SMEM_MATS 8                    // materials whose hardening tables are cached in shared memory
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -233,6 +232,23 @@ template <int N>
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void modes_store(const HexModes& m, double* p) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        p[(0 + c) * HK_TILE] = m.c0[c];  p[(3 + c) * HK_TILE] = m.c1[c];  p[(6 + c) * HK_TILE] = m.c2[c];
+        p[(9 + c) * HK_TILE] = m.h01[c]; p[(12 + c) * HK_TILE] = m.h02[c]; p[(15 + c) * HK_TILE] = m.h12[c];
+        p[(18 + c) * HK_TILE] = m.h012[c];
+    }
+}
+__device__ __forceinline__ void modes_load(HexModes& m, const double* p) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        m.c0[c] = p[(0 + c) * HK_TILE];  m.c1[c] = p[(3 + c) * HK_TILE];  m.c2[c] = p[(6 + c) * HK_TILE];
+        m.h01[c] = p[(9 + c) * HK_TILE]; m.h02[c] = p[(12 + c) * HK_TILE]; m.h12[c] = p[(15 + c) * HK_TILE];
+        m.h012[c] = p[(18 + c) * HK_TILE];
+    }
+}
+
 // global address of state row r (0..13) of Gauss point k for the tile starting at element e0
 __device__ __forceinline__ double* state_row(const HkDev& d, int r, int k, long long e0) {
     if (r < 6) return d.stress + ((long long)(r * 8 + k) * d.nEp + e0);
@@ -241,11 +257,16 @@ __device__ __forceinline__ double* state_row(const HkDev& d, int r, int k, long 
     return d.yield + ((long long)k * d.nEp + e0);
 }
 
+// MODES: 0 = geometry/displacement modes in registers, 1 = displacement modes U in shared memory,
+//        2 = X and U in shared memory (thread-private columns; frees registers so ptxas can overlap more math)
+template <int STAGES, int MODES>
 __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_buf = reinterpret_cast<double*>(smem_raw);
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(stage_buf + HK_STAGES * HK_STAGE_DOUBLES);
-    unsigned long long* done = full + HK_STAGES;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(stage_buf + STAGES * HK_STAGE_DOUBLES);
+    unsigned long long* done = full + STAGES;
+    double* mat_tab = reinterpret_cast<double*>(done + STAGES);   // [HK_SMEM_MATS][2][HK_MAX_TABLE]
+    double* modes_buf = mat_tab + HK_SMEM_MATS * 2 * HK_MAX_TABLE;   // [42][HK_TILE] (MODES > 0)
     const HkDev& d = A.d;
     const int tid = threadIdx.x;
     const long long n_tiles = d.nEp / HK_TILE;
@@ -254,16 +275,22 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
     const long long total_q = my_tiles * 8;                 // (tile, gauss point) work items of this CTA
 
     if (tid == 0) {
-        for (int s = 0; s < HK_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], HK_TILE); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], HK_TILE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const bool tabs_in_smem = d.n_mat <= HK_SMEM_MATS;
+    if (tabs_in_smem)
+        for (int i = tid; i < d.n_mat * 2 * HK_MAX_TABLE; i += HK_CTA_THREADS) {
+            const int m = i / (2 * HK_MAX_TABLE), r = i % (2 * HK_MAX_TABLE);
+            mat_tab[i] = r < HK_MAX_TABLE ? d.mats[m].plastic_e[r] : d.mats[m].Hd[r - HK_MAX_TABLE];
+        }
     __syncthreads();
 
     if (tid >= HK_TILE) {
         // ===== producer warp =====
         if (tid != HK_TILE) return;
         auto issue_load = [&](long long q) {
-            const int st = (int)(q % HK_STAGES);
+            const int st = (int)(q % STAGES);
             const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
             const int k = (int)(q & 7);
             double* dst = stage_buf + st * HK_STAGE_DOUBLES;
@@ -272,10 +299,10 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
             for (int r = 0; r < HK_ROWS; ++r)
                 tma_load_1d(dst + r * HK_TILE, state_row(d, r, k, e0), HK_TILE * 8, &full[st]);
         };
-        for (long long q = 0; q < HK_STAGES && q < total_q; ++q) issue_load(q);
+        for (long long q = 0; q < STAGES && q < total_q; ++q) issue_load(q);
         for (long long q = 0; q < total_q; ++q) {
-            const int st = (int)(q % HK_STAGES);
-            mbar_wait(&done[st], (unsigned)((q / HK_STAGES) & 1));      // every consumer finished item q
+            const int st = (int)(q % STAGES);
+            mbar_wait(&done[st], (unsigned)((q / STAGES) & 1));      // every consumer finished item q
             const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
             const int k = (int)(q & 7);
             const double* src = stage_buf + st * HK_STAGE_DOUBLES;
@@ -283,7 +310,7 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
             for (int r = 0; r < HK_ROWS; ++r) tma_store_1d(state_row(d, r, k, e0), src + r * HK_TILE, HK_TILE * 8);
             tma_commit();
             // refill the stage whose store group was committed one round ago (it has been read by now)
-            const long long qn = q - 1 + HK_STAGES;
+            const long long qn = q - 1 + STAGES;
             if (q >= 1 && qn < total_q) {
                 tma_wait_read<1>();
                 issue_load(qn);
@@ -306,23 +333,30 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
         MatLite ML = mat_lite(Mt);
         acc_init(acc);
         if (live) {
-            Mt = &d.mats[d.mat[e]];
+            const int mi = d.mat[e];
+            Mt = &d.mats[mi];
             ML = mat_lite(Mt);
+            if (tabs_in_smem) { ML.pe = mat_tab + mi * 2 * HK_MAX_TABLE; ML.hd = ML.pe + HK_MAX_TABLE; }
             element_gather(d, e, X, U);
             double G[3][3][3];
             adj_mode_sums(X, G);
             element_volume_terms(X, U, G, V, trbar);
+            if (MODES >= 1) modes_store(U, modes_buf + tid);
+            if (MODES >= 2) modes_store(X, modes_buf + 21 * HK_TILE + tid);
         }
+        const bool need_triax = A.write_triax || Mt->nd > 0;
 #pragma unroll 1
         for (int k = 0; k < 8; ++k, ++q) {
-            const int st = (int)(q % HK_STAGES);
+            const int st = (int)(q % STAGES);
             double* sb = stage_buf + st * HK_STAGE_DOUBLES + tid;
-            mbar_wait(&full[st], (unsigned)((q / HK_STAGES) & 1));
+            mbar_wait(&full[st], (unsigned)((q / STAGES) & 1));
             if (live) {
                 double sv[14];
 #pragma unroll
                 for (int r = 0; r < HK_ROWS; ++r) sv[r] = sb[r * HK_TILE];
-                const double tx = gauss_point(X, U, ML, k, trbar, sv, acc);
+                if (MODES >= 1) modes_load(U, modes_buf + tid);
+                if (MODES >= 2) modes_load(X, modes_buf + 21 * HK_TILE + tid);
+                const double tx = gauss_point(X, U, ML, k, trbar, sv, acc, need_triax);
 #pragma unroll
                 for (int r = 0; r < HK_ROWS; ++r) sb[r * HK_TILE] = sv[r];
                 if (A.write_triax) d.triax[(long long)k * d.nEp + e] = tx;
@@ -331,6 +365,7 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
             mbar_arrive(&done[st]);
         }
         if (live) {
+            if (MODES >= 2) modes_load(X, modes_buf + 21 * HK_TILE + tid);
             element_finish(A, e, X, acc, V);
             if (ductile_check(*Mt, acc.v_e, acc.t_e)) {
                 // the state rows of this element are still in flight in bulk stores: only mark it here,
@@ -341,6 +376,20 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
             }
         }
     }
+}
+#endif
+
+#ifndef HK_EMU
+template <int STAGES, int MODES>
+static void launch_tma(const ElemArgs& A, unsigned grid, cudaStream_t s) {
+    const int smem_bytes = STAGES * HK_STAGE_DOUBLES * 8 + 2 * STAGES * 8 + HK_SMEM_MATS * 2 * HK_MAX_TABLE * 8 +
+                           (MODES > 0 ? 42 * HK_TILE * 8 : 0) + 64;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(hk_element_tma_kernel<STAGES, MODES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        configured = true;
+    }
+    hk_element_tma_kernel<STAGES, MODES><<<grid, HK_CTA_THREADS, smem_bytes, s>>>(A);
 }
 #endif
 
@@ -358,18 +407,25 @@ void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStre
         hk_element_simple_kernel<<<(unsigned)((d.nElement + block - 1) / block), block, 0, s>>>(A);
         return;
     }
-    static int n_sm = 0, smem_bytes = 0;
+    static int n_sm = 0, variant = 0;
     if (!n_sm) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        smem_bytes = HK_STAGES * HK_STAGE_DOUBLES * 8 + 2 * HK_STAGES * 8 + 64;
-        cudaFuncSetAttribute(hk_element_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        const char* v = getenv("HK_ELEMENT_VARIANT");
+        variant = v ? atoi(v) : 1;
     }
     const long long n_tiles = d.nEp / HK_TILE;
     long long grid = (long long)n_sm;
     if (grid > n_tiles) grid = n_tiles;
-    hk_element_tma_kernel<<<(unsigned)grid, HK_CTA_THREADS, smem_bytes, s>>>(A);
+    switch (variant) {
+        case 0: launch_tma<8, 0>(A, (unsigned)grid, s); break;
+        case 2: launch_tma<5, 2>(A, (unsigned)grid, s); break;
+        case 3: launch_tma<8, 1>(A, (unsigned)grid, s); break;
+        case 4: launch_tma<7, 2>(A, (unsigned)grid, s); break;
+        case 5: launch_tma<4, 1>(A, (unsigned)grid, s); break;
+        default: launch_tma<6, 1>(A, (unsigned)grid, s); break;   // measured best (profiles/)
+    }
 #else
     for (long long e = 0; e < d.nElement; ++e) element_body_simple(A, e);
 #endif

@@ -102,7 +102,8 @@ HK_HD void mode_rows(const HexModes& m, double s0, double s1, double s2, double 
 struct MatLite {                  // the per-Gauss-point scalars of a material, held in registers
     double D11, D12, D44, G3;     // Dmat entries (J2:143-159) and 3G
     int npp;
-    const HkMaterialDev* full;    // tables, touched only while yielding
+    const double* pe;             // plastic_e[] and Hd[] tables (shared memory in the TMA kernel), touched only
+    const double* hd;             // while yielding
 };
 
 struct ElemAcc {                  // per-element accumulators over the Gauss points
@@ -120,7 +121,7 @@ HK_HD double triax_from(double mean, double oeq) {       // J2:1010-1017
 // One Gauss point: strain increment, radial return, state update, force-mode accumulation.
 //   st[0..5] stress, st[6..11] strain, st[12] eps, st[13] yield: in = old state, out = new state
 HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt, int k, double trbar,
-                         double st[14], ElemAcc& acc) {
+                         double st[14], ElemAcc& acc, bool need_triax = true) {
     const double s0 = (k & 4) ? 1.0 : -1.0, s1 = (k & 2) ? 1.0 : -1.0, s2 = (k & 1) ? 1.0 : -1.0;
     double R[3][3], A[3][3];
     mode_rows(X, s0, s1, s2, R);
@@ -168,10 +169,12 @@ HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt
     if (Mt.npp > 0) {              // J2 radial return, J2:1227-1285
         const double y = st[13];
         if (mises > y) {
-            int p_index = Mt.npp - 2;                 // last segment extrapolates (J2:1261-1263)
-            for (int j = 1; j < Mt.npp; ++j)
-                if (ep <= Mt.full->plastic_e[j]) { p_index = j - 1; break; }
-            const double H = Mt.full->Hd[p_index];
+            // segment of the hardening table: first j with ep <= plastic[j,2] -> j-1, last segment extrapolates
+            // (J2:1255-1264).  The table is increasing (checked in hk_add_material), so the index is a count,
+            // which needs no dependent chain of loads.
+            int p_index = 0;
+            for (int j = 1; j + 1 < Mt.npp; ++j) p_index += (ep > Mt.pe[j]) ? 1 : 0;
+            const double H = Mt.hd[p_index];
             const double d_ep = (mises - y) / (Mt.G3 + H);
             const double ynew = y + H * d_ep;
             const double fac = ynew / mises;
@@ -208,7 +211,8 @@ HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt
             acc.M[r][3][c] += sab * T[c];
         }
     }
-    const double tx = triax_from(mean, oeq);
+    // triaxiality feeds only the ductile-damage criterion and the output frames: skipped otherwise
+    const double tx = need_triax ? triax_from(mean, oeq) : 0.0;
     acc.v_e += ep;
     acc.t_e += tx;
     return tx;

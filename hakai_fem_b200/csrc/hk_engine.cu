@@ -470,6 +470,9 @@ int HKAPI(add_material)(hk_engine* e, double young, double poisson, double densi
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
     if (npp == 1) return fail(e, HK_ERR_ARG, "*Plastic table needs >= 2 rows (the reference indexes Hd[1])");
     if (npp > HK_MAX_TABLE || nd > HK_MAX_TABLE) return fail(e, HK_ERR_UNSUPPORTED, "material table longer than HK_MAX_TABLE");
+    for (int64_t r = 1; r < npp; ++r)
+        if (!(plastic[npp + r] > plastic[npp + r - 1]))
+            return fail(e, HK_ERR_UNSUPPORTED, "*Plastic table: equivalent plastic strain column must be increasing");
     MaterialH m;
     m.young = young; m.poisson = poisson; m.density = density; m.npp = npp; m.nd = nd;
     if (npp > 0) { m.plastic.assign(plastic, plastic + 2 * npp); m.Hd.assign(Hd, Hd + npp - 1); }
