@@ -171,12 +171,29 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from hakai_fem_b200.multi import slab_deck, SlabRunner
     deck = make_deck(args.workload)
+    stream = torch.cuda.current_stream()
+    if world > 1:
+        # weak scaling (config W): the global mesh is nx x ny x (nz*world), split in z; every rank builds only its slab
+        deck, nbrs, halos = slab_deck(deck, rank, world)
+    else:
+        nbrs, halos = [], []
     st = prepare_setup(deck)
     nE, nN = st.model.nElement, st.model.nNode
-    eng = configure_engine(Engine, st, device=local_rank)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
+
+    def make_engine(**p):
+        e_ = Engine(**p)
+        e_.set_stream(stream.cuda_stream)
+        return e_
+    runner = SlabRunner(make_engine, st, nbrs, halos, torch.device("cuda", local_rank), sum_mass=True, device=local_rank)
+    eng = runner.engine
+
+    def run_steps(t0, n):
+        if world > 1:
+            runner.run(t0, n)          # halo pack -> NCCL send/recv -> hk_step, every step
+        else:
+            eng.step(t0, n)
 
     def barrier():
         if world > 1:
@@ -184,7 +201,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ---------------------------------------------------------------
-    eng.step(1, args.warmup)
+    run_steps(1, args.warmup)
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_wait = time.time()
@@ -194,7 +211,7 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    eng.step(args.warmup + 1, args.steps)
+    run_steps(args.warmup + 1, args.steps)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -210,7 +227,7 @@ def main():
     t_next = args.warmup + args.steps + 1
     eng.profile(True)
     n_prof = min(args.steps, 10)
-    eng.step(t_next, n_prof)
+    run_steps(t_next, n_prof)
     t_next += n_prof
     kms, kn = eng.profile_read()
     eng.profile(False)
@@ -254,7 +271,7 @@ def main():
                          integ_strain=up["integ_strain"].numpy().T,
                          integ_eq_plastic_strain=up["integ_eq_plastic_strain"].numpy(),
                          integ_yield_stress=up["integ_yield_stress"].numpy())
-        eng.step(t_next, args.steps)
+        run_steps(t_next, args.steps)
         eng.download(out={k: v.numpy() for k, v in out.items()})
         barrier()
         w = time.perf_counter() - w0
@@ -284,7 +301,8 @@ def main():
             "config": {"workload": args.workload, "elements_per_gpu": nE, "nodes_per_gpu": nN,
                        "deck": f"{deck.nx}x{deck.ny}x{deck.nz} hex8, steel elastoplastic, uniform stretch "
                                f"{deck.strain_per_step:g}/step, jitter {deck.jitter}",
-                       "l2": "state >> L2 (inputs larger than L2), no flush", "parallelism": f"slab x{world}"},
+                       "l2": "state >> L2 (inputs larger than L2), no flush", "parallelism": f"z-slab x{world}",
+                       "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -53,6 +53,16 @@ struct PairH {
     HkPairDev dev;
     bool dev_valid = false;
 };
+struct HaloNbr {
+    std::vector<int> nodes;        // local 0-based node ids
+    std::vector<int> slots;        // index into the dense halo node list
+    int* d_nodes = nullptr;
+    int* d_slots = nullptr;
+    double* send = nullptr;        // caller-owned device buffers
+    double* recv = nullptr;
+    std::vector<char> first;       // per entry: this neighbour is the first contributor of the slot
+    int* d_dummy = nullptr;
+};
 struct TimedEvent {
 #ifndef HK_EMU
     cudaEvent_t a, b;
@@ -78,6 +88,8 @@ struct hk_engine {
     std::vector<ICH> ics;
     std::vector<InstanceH> instances;
     std::vector<PairH> pairs;
+    std::vector<HaloNbr> halo;
+    int n_halo_nodes = 0;
     // special nodes (host mirror)
     std::vector<int> spec_idx_h;
     std::vector<HkSpecialNode> spec_h;
@@ -746,6 +758,28 @@ int HKAPI(finalize)(hk_engine* e) {
         if (nominal > 0) std::frexp(nominal, &ex);
         cp.lsb_exp = ex - 90;      // 2^36 of headroom above the nominal force E*eMax*d_lim, 90 bits below it
     }
+    // ---- halo (multi-GPU): dense slot per interface node; neighbours contribute in list order
+    if (!e->halo.empty()) {
+        std::vector<int> slot_of(nN, -1);
+        for (HaloNbr& h : e->halo) {
+            h.slots.resize(h.nodes.size());
+            for (size_t i = 0; i < h.nodes.size(); ++i) {
+                const int nd = h.nodes[i];
+                if (nd < 0 || nd >= nN) return fail(e, HK_ERR_ARG, "halo node out of range");
+                if (slot_of[nd] < 0) {
+                    slot_of[nd] = e->n_halo_nodes++;
+                    e->spec_h[spec_of(e, nd)].halo_slot = slot_of[nd];
+                }
+                h.slots[i] = slot_of[nd];
+            }
+            if ((rc = dalloc(e, &h.d_nodes, h.nodes.size()))) return rc;
+            if ((rc = dalloc(e, &h.d_slots, h.slots.size()))) return rc;
+            if ((rc = upload(e, h.d_nodes, h.nodes))) return rc;
+            if ((rc = upload(e, h.d_slots, h.slots))) return rc;
+        }
+        if ((rc = dalloc(e, &d.halo_recv, (size_t)3 * e->n_halo_nodes))) return rc;
+        CK(hkp::dev_memset(d.halo_recv, 0, sizeof(double) * 3 * e->n_halo_nodes, e->stream));
+    }
     if ((rc = spec_upload(e, nullptr))) return rc;
     CK(hkp::sync(e->stream));
     CK(hkp::last_error());
@@ -766,6 +800,16 @@ int HKAPI(step)(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_delet
             prof_begin(e, 0);
             CK(hkp::dev_memset(d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
             for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 4; }
+            prof_end(e);
+        }
+        if (!e->halo.empty()) {          // received partial forces -> halo_recv (fixed neighbour order)
+            prof_begin(e, 3);
+            CK(hkp::dev_memset(d.halo_recv, 0, sizeof(double) * 3 * e->n_halo_nodes, e->stream));
+            for (HaloNbr& h : e->halo) {
+                if (!h.recv) return fail(e, HK_ERR_STATE, "hk_halo_bind not called for every neighbour");
+                hk_launch_halo_accumulate(d, h.d_slots, (long long)h.slots.size(), h.recv, 0, e->stream);
+                e->n_launch += 1;
+            }
             prof_end(e);
         }
         prof_begin(e, 1);
@@ -996,6 +1040,37 @@ int HKAPI(profile_read)(hk_engine* e, double ms[4], int64_t launches[4]) {
     if (!e) return HK_ERR_ARG;
     prof_collect(e);
     for (int i = 0; i < 4; ++i) { ms[i] = e->prof_ms[i]; launches[i] = e->prof_n[i]; }
+    return HK_OK;
+}
+
+int HKAPI(set_halo)(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr, const int64_t* nodes) {
+    if (!e) return HK_ERR_ARG;
+    if (e->finalized) return fail(e, HK_ERR_STATE, "hk_set_halo must precede hk_finalize");
+    e->halo.clear();
+    for (int64_t i = 0; i < n_neighbors; ++i) {
+        HaloNbr h;
+        for (int64_t k = nbr_ptr[i]; k < nbr_ptr[i + 1]; ++k) h.nodes.push_back((int)(nodes[k] - 1));
+        e->halo.push_back(std::move(h));
+    }
+    return HK_OK;
+}
+
+int HKAPI(halo_bind)(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_dev) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (neighbor < 0 || neighbor >= (int64_t)e->halo.size()) return fail(e, HK_ERR_ARG, "bad neighbour index");
+    e->halo[neighbor].send = (double*)send_dev;
+    e->halo[neighbor].recv = (double*)recv_dev;
+    return HK_OK;
+}
+
+int HKAPI(halo_pack)(hk_engine* e) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    for (HaloNbr& h : e->halo) {
+        if (!h.send) return fail(e, HK_ERR_STATE, "hk_halo_bind not called for every neighbour");
+        hk_launch_halo_pack(e->d, h.d_nodes, (long long)h.nodes.size(), h.send, e->stream);
+        e->n_launch += 1;
+    }
+    CK(hkp::last_error());
     return HK_OK;
 }
 

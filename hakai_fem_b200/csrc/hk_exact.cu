@@ -501,6 +501,36 @@ void hk_launch_gather_Q(const HkDev& dd, double* Q_out, cudaStream_t s) {
     });
 }
 
+// partial internal force of the listed (interface) nodes, same gather order as the nodal kernel
+void hk_launch_halo_pack(const HkDev& dd, const int* nodes, long long n, double* out, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n, s, HK_LAMBDA(long long i) {
+        const long long nd = nodes[i];
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+        for (int w = 0; w < d.ell_width; ++w) {
+            const int ent = d.ell[(long long)w * d.nNode + nd];
+            if (ent < 0) break;
+            const long long e = ent >> 3;
+            const int a = ent & 7;
+            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
+            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
+            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+        }
+        out[3 * i] = q0; out[3 * i + 1] = q1; out[3 * i + 2] = q2;
+    });
+}
+
+// halo_recv[slot] (=|+=) recv[i]: neighbours are accumulated in a fixed order -> reproducible
+void hk_launch_halo_accumulate(const HkDev& dd, const int* slots, long long n, const double* recv, int first, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 3, s, HK_LAMBDA(long long j) {
+        const long long i = j / 3;
+        const int c = (int)(j - 3 * i);
+        const long long k = 3ll * slots[i] + c;
+        d.halo_recv[k] = first ? recv[j] : d.halo_recv[k] + recv[j];
+    });
+}
+
 // external_force of the last step (J2:497-538): zero plus the rounded contact sums
 void hk_launch_external_force(const HkDev& dd, double* F_out, int lsb_exp, int contact_on, cudaStream_t s) {
     const HkDev d = dd;

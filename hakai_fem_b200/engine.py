@@ -40,6 +40,7 @@ EXPORTS = [
     "default_params", "create", "destroy", "last_error", "set_mesh", "add_material", "add_bc", "add_ic",
     "add_instance", "add_contact_pair", "finalize", "step", "download", "download_ex", "upload_state",
     "deleted_ids", "contact_pair_info", "counters", "profile", "profile_read", "set_stream",
+    "set_halo", "halo_bind", "halo_pack",
 ]
 
 
@@ -258,6 +259,18 @@ class EngineBase:
         n = np.zeros(4, np.int64)
         self._chk(self._fn("profile_read")(self._h, _pf(ms), _pi(n)))
         return ms, n
+
+    # -- multi-GPU halo ---------------------------------------------------------------
+    def set_halo(self, node_lists):
+        """node_lists[i]: local 1-based ids of the nodes shared with neighbour i (call before finalize)."""
+        ptr, flat = _csr(node_lists)
+        self._chk(self._fn("set_halo")(self._h, c_i64(len(node_lists)), _pi(ptr), _pi(flat)))
+
+    def halo_bind(self, neighbor: int, send_ptr: int, recv_ptr: int):
+        self._chk(self._fn("halo_bind")(self._h, c_i64(neighbor), C.c_void_p(send_ptr), C.c_void_p(recv_ptr)))
+
+    def halo_pack(self):
+        self._chk(self._fn("halo_pack")(self._h))
 
     def set_stream(self, stream_ptr: int):
         self._chk(self._fn("set_stream")(self._h, C.c_void_p(stream_ptr)))

@@ -66,13 +66,15 @@ class StretchDeck:
     jitter: float = 0.0                   # interior node jitter, fraction of h (F16: 0.05)
     seed: int = 20240601
     name: str = "stretch"
+    layer_offset: int = 0                 # multi-GPU slabs: this block starts at global element layer `layer_offset`
+    global_nz: Optional[int] = None       # ... of a global mesh with `global_nz` element layers (None: nz)
 
     def _layers(self):
         per = (self.nx + 1) * (self.ny + 1)
         return per, self.nz + 1
 
     def coord_elem(self):
-        coord, em = block_arrays(self.nx, self.ny, self.nz, self.h)
+        coord, em = block_arrays(self.nx, self.ny, self.nz, self.h, origin=(0.0, 0.0, self.layer_offset * self.h))
         if self.jitter > 0:
             rng = np.random.default_rng(self.seed)
             nnx, nny, nnz = self.nx + 1, self.ny + 1, self.nz + 1
@@ -95,15 +97,23 @@ class StretchDeck:
         inst = Instance(name="Part-1-1", part_name="Part-1", part_id=1, material_id=1, node_offset=0, nNode=nN,
                         element_offset=0, nElement=nE, elements=np.arange(1, nE + 1))
         amp = Amplitude(name="Amp-1", time=np.array([0.0, end_time]), value=np.array([0.0, 1.0]))
-        lz = self.nz * self.h
+        gnz = self.global_nz if self.global_nz is not None else self.nz
+        lz = gnz * self.h
         layer = lambda k: np.arange(k * per + 1, (k + 1) * per + 1, dtype=np.int64)
         bc = BC(Nset_name="L%d" % (nl - 1), amp_name="Amp-1", amplitude=amp)
-        bc.dof = [layer(0) * 3, layer(nl - 1) * 3]
-        bc.value = [0.0, rate * lz * end_time]
+        if self.layer_offset == 0:                       # global bottom layer: u_z = 0
+            bc.dof.append(layer(0) * 3)
+            bc.value.append(0.0)
+        if self.layer_offset + self.nz == gnz:           # global top layer: driven
+            bc.dof.append(layer(nl - 1) * 3)
+            bc.value.append(rate * lz * end_time)
         ic = IC(Nset_name="L%d" % (nl - 1), type="VELOCITY")
-        for k in range(1, nl):
+        for k in range(nl):
+            kg = k + self.layer_offset
+            if kg == 0:
+                continue
             ic.dof.append(layer(k) * 3)
-            ic.value.append(rate * (k * self.h))
+            ic.value.append(rate * (kg * self.h))
         return Model(PART=[part], INSTANCE=[inst], NSET=[], ELSET=[], SURFACE=[], AMPLITUDE=[amp],
                      MATERIAL=[self.material], BC=[bc], IC=[ic], CP=[], nNode=nN, coordmat=coord, nElement=nE,
                      elementmat=em, element_material=np.ones(nE, np.int64), element_instance=np.ones(nE, np.int64),

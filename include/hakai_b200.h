@@ -168,6 +168,23 @@ int hk_profile_read(hk_engine* e, double ms[4], int64_t launches[4]);
 /* Use an externally created CUDA stream (cudaStream_t as void*) for all work; NULL = own. */
 int hk_set_stream(hk_engine* e, void* cuda_stream);
 
+/* ---- multi-GPU: one engine per rank over an element-block partition ------------------------
+ * Nodes on a partition interface exist on both ranks; each rank computes the internal force of its own
+ * elements only, so before the nodal update the partial sums must be exchanged and added.  The engine
+ * packs / unpacks; the transport (ncclSend/ncclRecv, here through torch.distributed) is the host's job:
+ *     hk_halo_pack(e)  ->  exchange send/recv buffers with every neighbour  ->  hk_step(e, t, 1, ..)
+ * Both ranks then update the shared nodes redundantly from identical inputs (a+b == b+a bitwise), so no
+ * position exchange is needed.
+ *   hk_set_halo       before hk_finalize.  nodes: LOCAL 1-based node ids shared with neighbour i, in an order
+ *                     both sides agree on (ascending global id); nbr_ptr: CSR offsets (n_neighbors+1).
+ *   hk_halo_bind      after hk_finalize.  send/recv: DEVICE buffers of 3*n_nodes(i) doubles owned by the caller
+ *                     (e.g. torch tensors registered with NCCL).
+ *   hk_halo_pack      fills every send buffer with this rank's partial Q of the shared nodes (stream-ordered).
+ * hk_step() adds the received partials, summed in neighbour order, to the gathered internal force. */
+int hk_set_halo(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr, const int64_t* nodes);
+int hk_halo_bind(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_dev);
+int hk_halo_pack(hk_engine* e);
+
 #ifdef __cplusplus
 }
 #endif

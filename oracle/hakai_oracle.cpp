@@ -1000,5 +1000,9 @@ int hko_profile_read(hk_engine*, double ms[4], int64_t launches[4]) {
     return HK_OK;
 }
 int hko_set_stream(hk_engine*, void*) { return HK_OK; }
+// the oracle is single-domain (the reference has no distributed code): halo calls are rejected
+int hko_set_halo(hk_engine* e, int64_t, const int64_t*, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_halo_bind(hk_engine* e, int64_t, void*, void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_halo_pack(hk_engine* e) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 
 }  // extern "C"

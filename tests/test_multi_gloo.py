@@ -1,0 +1,116 @@
+"""world_size-2 (and 3) CPU tests of the multi-GPU path: slab partition + force halos over gloo.
+
+Each rank drives the host-compiled kernel build (tests/emu) on its element block and exchanges interface
+partial forces with torch.distributed; rank 0 gathers the fields and compares them with ONE oracle run on
+the unpartitioned mesh.  Covers partition_model (general decks) and slab_deck (the bench's direct slab build)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, mode, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.model_setup import prepare
+        from hakai_fem_b200.multi import partition_model, slab_deck, SlabRunner
+        from hakai_fem_b200.mesh import StretchDeck, steel
+        from tests.emu.emu_engine import EmuEngine
+        n_steps = 90
+        if mode == "partition":
+            deck = StretchDeck(4, 3, 9, jitter=0.1, strain_per_step=8e-4,
+                               material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]))
+            gsetup = prepare(deck.build_model())
+            dom = partition_model(gsetup, world)[rank]
+            run = SlabRunner(EmuEngine, dom.setup, dom.neighbors, dom.halo_nodes, "cpu")
+            node_l2g, elem_l2g = dom.node_l2g, dom.elem_l2g
+        else:
+            deck = StretchDeck(3, 4, 3, jitter=0.08, strain_per_step=3e-4)
+            local, nbrs, halos = slab_deck(deck, rank, world)
+            lsetup = prepare(local.build_model())
+            run = SlabRunner(EmuEngine, lsetup, nbrs, halos, "cpu", sum_mass=True)
+            per = (deck.nx + 1) * (deck.ny + 1)
+            nloc = lsetup.model.nNode
+            node_l2g = np.arange(1, nloc + 1) + rank * deck.nz * per
+            elem_l2g = np.arange(1, lsetup.model.nElement + 1) + rank * lsetup.model.nElement
+            q.put(("coords", rank, lsetup.model.coordmat, node_l2g))
+        nd = run.run(1, n_steps)
+        d = run.engine.download()
+        q.put(("result", rank, dict(disp=d["disp"], eps=d["integ_eq_plastic_strain"], stress=np.asarray(d["integ_stress"]),
+                                    flag=d["element_flag"], node_l2g=node_l2g, elem_l2g=elem_l2g, nd=nd)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, mode):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (7 if mode == "slab" else 0) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    msgs = []
+    need = world * (2 if mode == "slab" else 1)
+    while len(msgs) < need:
+        msgs.append(q.get(timeout=300))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return msgs
+
+
+def _compare(msgs, gsetup, n_steps=90):
+    from hakai_fem_b200.model_setup import configure_engine
+    from oracle.oracle_engine import OracleEngine
+    o = configure_engine(OracleEngine, gsetup)
+    nd_ref = o.step(1, n_steps)
+    ref = o.download()
+    nd_tot = 0
+    for kind, rank, r in [m for m in msgs if m[0] == "result"]:
+        n = r["node_l2g"] - 1
+        e = r["elem_l2g"] - 1
+        gd = ref["disp"].reshape(-1, 3)[n].reshape(-1)
+        scale = np.abs(ref["disp"]).max()
+        assert np.abs(gd - r["disp"]).max() <= 1e-11 * scale, f"rank {rank} disp"
+        ip = (e[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        assert np.abs(ref["integ_eq_plastic_strain"][ip] - r["eps"]).max() <= 1e-11 * max(ref["integ_eq_plastic_strain"].max(), 1e-30)
+        assert np.abs(np.asarray(ref["integ_stress"])[:, ip] - r["stress"]).max() <= 1e-10 * np.abs(ref["integ_stress"]).max()
+        assert np.array_equal(ref["element_flag"][e], r["flag"]), f"rank {rank} flags"
+        nd_tot += r["nd"]
+    assert nd_tot == nd_ref
+    return nd_ref
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_run_matches_single_domain(world):
+    from hakai_fem_b200.model_setup import prepare
+    from hakai_fem_b200.mesh import StretchDeck, steel
+    msgs = _run(world, "partition")
+    deck = StretchDeck(4, 3, 9, jitter=0.1, strain_per_step=8e-4,
+                       material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]))
+    nd = _compare(msgs, prepare(deck.build_model()))
+    assert nd > 0, "deck should delete elements inside the window (fracture across ranks)"
+
+
+def test_slab_deck_matches_global_deck():
+    """The bench's per-rank slab build (no global mesh in memory) is the same problem as one global deck."""
+    from hakai_fem_b200.model_setup import prepare
+    from hakai_fem_b200.mesh import StretchDeck
+    world = 2
+    msgs = _run(world, "slab")
+    deck = StretchDeck(3, 4, 3 * world, jitter=0.0, strain_per_step=3e-4)
+    gm = deck.build_model()
+    for kind, rank, coord, l2g in [m for m in msgs if m[0] == "coords"]:      # the slabs carry their own jitter
+        gm.coordmat[:, l2g - 1] = coord
+    gm.PART[0].coordmat = gm.coordmat
+    _compare(msgs, prepare(gm))
