@@ -106,6 +106,7 @@ struct hk_engine {
     double* staging = nullptr;     // device staging for layout transposes
     size_t staging_doubles = 0;
     std::vector<int64_t> deleted_all;
+    size_t deleted_reported = 0;
     int del_seen = 0;
     int64_t n_launch = 0, n_steps = 0;
     bool profiling = false;
@@ -789,12 +790,11 @@ int HKAPI(finalize)(hk_engine* e) {
     return HK_OK;
 }
 
-int HKAPI(step)(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_deleted_out) {
-    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
-    if (n_steps < 0 || t_first < 0 || t_first + n_steps >= (1ll << 31)) return fail(e, HK_ERR_ARG, "bad step range");
+// enqueue the kernels of steps t_first .. t_first+n_steps-1 on the engine's stream (no host synchronisation
+// unless contact surfaces may change: exposed faces must be in place before the next contact pass)
+static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps) {
     const HkDev& d = e->d;
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
-    const size_t before = e->deleted_all.size();
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
         if (contact_on) {
             prof_begin(e, 0);
@@ -823,7 +823,7 @@ int HKAPI(step)(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_delet
         e->n_launch += 2;
         if (e->any_ductile) { hk_launch_flush_deleted(d, e->stream); e->n_launch += 1; }
         e->n_steps += 1;
-        if (contact_on && e->any_ductile) {       // exposed faces must be in place before the next contact pass
+        if (contact_on && e->any_ductile) {
             std::vector<int64_t> fresh;
             int rc = fetch_deleted(e, &fresh);
             if (rc) return rc;
@@ -834,12 +834,35 @@ int HKAPI(step)(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_delet
         e->velo_current = contact_on;
         e->triax_current = true;
     }
+    return HK_OK;
+}
+
+int HKAPI(step_enqueue)(hk_engine* e, int64_t t_first, int64_t n_steps) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (n_steps < 0 || t_first < 0 || t_first + n_steps >= (1ll << 31)) return fail(e, HK_ERR_ARG, "bad step range");
+    if (!e->halo.empty() && n_steps > 1) return fail(e, HK_ERR_ARG, "with halos, exchange and step one step at a time");
+    int rc = enqueue_steps(e, t_first, n_steps);
+    if (rc) return rc;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(sync)(hk_engine* e, int64_t* n_deleted_out) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    const size_t before = e->deleted_reported;
     int rc = fetch_deleted(e, nullptr);
     if (rc) return rc;
     CK(hkp::sync(e->stream));
     CK(hkp::last_error());
+    e->deleted_reported = e->deleted_all.size();
     if (n_deleted_out) *n_deleted_out = (int64_t)(e->deleted_all.size() - before);
     return HK_OK;
+}
+
+int HKAPI(step)(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_deleted_out) {
+    int rc = HKAPI(step_enqueue)(e, t_first, n_steps);
+    if (rc) return rc;
+    return HKAPI(sync)(e, n_deleted_out);
 }
 
 // staging buffer for layout transposes

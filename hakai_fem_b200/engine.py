@@ -40,7 +40,7 @@ EXPORTS = [
     "default_params", "create", "destroy", "last_error", "set_mesh", "add_material", "add_bc", "add_ic",
     "add_instance", "add_contact_pair", "finalize", "step", "download", "download_ex", "upload_state",
     "deleted_ids", "contact_pair_info", "counters", "profile", "profile_read", "set_stream",
-    "set_halo", "halo_bind", "halo_pack",
+    "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync",
 ]
 
 
@@ -171,6 +171,14 @@ class EngineBase:
     def step(self, t_first: int, n_steps: int = 1) -> int:
         nd = c_i64(0)
         self._chk(self._fn("step")(self._h, c_i64(t_first), c_i64(n_steps), C.byref(nd)))
+        return nd.value
+
+    def step_enqueue(self, t_first: int, n_steps: int = 1):
+        self._chk(self._fn("step_enqueue")(self._h, c_i64(t_first), c_i64(n_steps)))
+
+    def sync(self) -> int:
+        nd = c_i64(0)
+        self._chk(self._fn("sync")(self._h, C.byref(nd)))
         return nd.value
 
     # -- taps ---------------------------------------------------------------------------

@@ -1,0 +1,148 @@
+"""Host driver: the Python twin of `hakai(fname)` (HAKAI-v0.0.2/Julia/HAKAI_j.jl:81-978) with the loop
+body replaced by the engine's C ABI.
+
+    python -m hakai_fem_b200.host path/to/deck.inp [outdir]
+
+Same entry semantics as `julia HAKAI_j.jl deck.inp`: reads the Abaqus deck, runs floor(end_time/d_time) steps
+of fixed size, writes `file000.vtk` before the loop and one ASCII legacy VTK frame every
+d_out = floor(time_num/output_num) steps (output_num = 100, J2:471-472), in the reference's field order and
+`%1.6e` format.  Between frames the engine advances `d_out` steps on the GPU with no host round trip; state is
+downloaded only when a frame is written.  (The reference's frame-buffer overflow for step counts that are not
+a multiple of output_num, SURVEY §3.1, is not reproduced: frames beyond 100 are simply written.)
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+from .inp import read_inp_file
+from .model_setup import prepare, configure_engine
+
+
+def cal_node_stress_strain(nNode, elementmat, integ_num, integ):
+    """J2:3408-3486: Gauss points -> element mean -> nodal mean over incident elements -> von Mises."""
+    nE = elementmat.shape[1]
+    st = np.asarray(integ["integ_stress"]).T.reshape(nE, integ_num, 6).sum(axis=1) / integ_num
+    sn = np.asarray(integ["integ_strain"]).T.reshape(nE, integ_num, 6).sum(axis=1) / integ_num
+    ep = integ["integ_eq_plastic_strain"].reshape(nE, integ_num).sum(axis=1) / integ_num
+    tx = integ["integ_triax_stress"].reshape(nE, integ_num).sum(axis=1) / integ_num
+    node_stress = np.zeros((nNode, 6))
+    node_strain = np.zeros((nNode, 6))
+    node_ep = np.zeros(nNode)
+    node_tx = np.zeros(nNode)
+    inc = np.zeros(nNode)
+    for k in range(8):
+        idx = elementmat[k] - 1
+        np.add.at(node_stress, idx, st)
+        np.add.at(node_strain, idx, sn)
+        np.add.at(node_ep, idx, ep)
+        np.add.at(node_tx, idx, tx)
+        np.add.at(inc, idx, 1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        node_stress /= inc[:, None]
+        node_strain /= inc[:, None]
+        node_ep /= inc
+        node_tx /= inc
+    ox, oy, oz, txy, tyz, txz = (node_stress[:, i] for i in range(6))
+    mises = np.sqrt(0.5 * ((ox - oy) ** 2 + (oy - oz) ** 2 + (ox - oz) ** 2 + 6 * (txy ** 2 + tyz ** 2 + txz ** 2)))
+    return dict(node_stress=node_stress, node_strain=node_strain, node_eq_plastic_strain=node_ep,
+                node_mises_stress=mises, node_triax_stress=node_tx)
+
+
+def _flush(a):
+    a = np.array(a, dtype=np.float64, copy=True)
+    a[np.abs(a) < 1e-16] = 0.0                                   # J2:3531-3559
+    return a
+
+
+def write_vtk(outdir, index, coordmat, elementmat, element_flag, disp, velo, nd):
+    """J2:3517-3717 — ASCII legacy VTK, same sections, order and `%1.6e` format."""
+    nNode = coordmat.shape[1]
+    disp3 = _flush(disp.reshape(nNode, 3))
+    velo3 = _flush(velo.reshape(nNode, 3))
+    ns, ne = _flush(nd["node_stress"]), _flush(nd["node_strain"])
+    mises, eps, triax = (_flush(nd[k]) for k in ("node_mises_stress", "node_eq_plastic_strain", "node_triax_stress"))
+    os.makedirs(outdir, exist_ok=True)
+    fname = os.path.join(outdir, "file%03d.vtk" % index)
+    live = np.flatnonzero(np.asarray(element_flag) == 1)
+    with open(fname, "w") as f:
+        f.write("# vtk DataFile Version 2.0\nTest\nASCII\nDATASET UNSTRUCTURED_GRID\n")
+        f.write("POINTS %d float\n" % nNode)
+        np.savetxt(f, coordmat.T, fmt="%1.6e")
+        f.write("CELLS %d %d\n" % (len(live), len(live) * 9))
+        cells = np.concatenate([np.full((len(live), 1), 8, np.int64), (elementmat[:, live] - 1).T], axis=1)
+        np.savetxt(f, cells, fmt="%d")
+        f.write("CELL_TYPES %d\n" % len(live))
+        f.write("12\n" * len(live))
+        f.write("POINT_DATA %d\n" % nNode)
+        f.write("VECTORS DISPLACEMENT float\n")
+        np.savetxt(f, disp3, fmt="%1.6e")
+
+        def scalar(name, v):
+            f.write("SCALARS %s float 1\nLOOKUP_TABLE default\n" % name)
+            np.savetxt(f, v, fmt="%1.6e")
+        for name, v in (("Vx", velo3[:, 0]), ("Vy", velo3[:, 1]), ("Vz", velo3[:, 2]),
+                        ("E11", ne[:, 0]), ("E22", ne[:, 1]), ("E33", ne[:, 2]), ("E12", ne[:, 3]), ("E23", ne[:, 4]),
+                        ("E13", ne[:, 5]), ("EQ_PSTRAIN", eps),
+                        ("S11", ns[:, 0]), ("S22", ns[:, 1]), ("S33", ns[:, 2]), ("S12", ns[:, 3]), ("S23", ns[:, 4]),
+                        ("S13", ns[:, 5]), ("MISES_STRESS", mises), ("TRIAX_STRESS", triax)):
+            scalar(name, v)
+    return fname
+
+
+def hakai(fname, outdir="temp", engine_cls=None, output_num=100, write_frames=True, verbose=True, **params):
+    """hakai(fname), J2:81.  Returns the engine (state on the GPU) and the list of frame files."""
+    if engine_cls is None:
+        from .engine import Engine as engine_cls               # the CUDA engine; raises without a GPU
+    log = print if verbose else (lambda *a, **k: None)
+    model = read_inp_file(fname)
+    log("nNode:", model.nNode)
+    log("nElement:", model.nElement)
+    log("contact_flag:", model.contact_flag)
+    setup = prepare(model)
+    log("mass_scaling:", model.mass_scaling)
+    log("time_num:", setup.time_num)
+    log("elementMinSize:", setup.elementMinSize)
+    log("elementMaxSize:", setup.elementMaxSize)
+    eng = configure_engine(engine_cls, setup, **params)
+    n_total = int(math.floor(setup.time_num))                  # `for t = 1 : time_num` with Float64 time_num
+    d_out = int(math.floor(setup.time_num / output_num))       # J2:472
+    frames = []
+
+    def frame(index):
+        d = eng.download()
+        nd = cal_node_stress_strain(model.nNode, model.elementmat, 8, d)
+        frames.append(write_vtk(outdir, index, model.coordmat, model.elementmat, d["element_flag"], d["disp"],
+                                d["velo"], nd))
+    if write_frames:
+        frame(0)                                                # J2:478-480
+    t0 = time.perf_counter()
+    t, i_out = 0, 1
+    while t < n_total:
+        n = min(d_out, n_total - t) if d_out > 0 else n_total - t
+        ndel = eng.step(t + 1, n)
+        t += n
+        if ndel:
+            flags = eng.download(fields=("element_flag",))["element_flag"]
+            log("Element deleted:", int(flags.sum()), "/", model.nElement)       # J2:736
+        if write_frames and d_out > 0 and t % d_out == 0:       # rem(t, d_out) == 0, J2:932
+            frame(i_out)
+            i_out += 1
+        log("\r%.4e / %.4e     " % (t * setup.d_time, model.end_time), end="")
+    log("\n%.3f seconds for %d steps" % (time.perf_counter() - t0, n_total))
+    return eng, frames
+
+
+def main(argv=None):
+    argv = sys.argv[1:] if argv is None else argv
+    if not argv:
+        raise SystemExit("usage: python -m hakai_fem_b200.host deck.inp [outdir]")
+    hakai(argv[0], argv[1] if len(argv) > 1 else "temp")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+# HakaiB200.jl — thin ccall binding of libhakai_b200.so (include/hakai_b200.h) for HAKAI_j.jl.
+#
+# NOT EXECUTED IN THE BUILD IMAGE (no Julia there); it is the binding a maintainer adds next to HAKAI_j.jl.
+# Every wrapper passes the reference's own arrays (column-major, 1-based Int64 / Float64) untouched: the
+# library converts layouts itself.  INTEGRATION.md shows the patch to hakai().
+module HakaiB200
+
+const LIB = get(ENV, "HAKAI_B200_LIB", joinpath(@__DIR__, "..", "libhakai_b200.so"))
+
+# struct hk_params (include/hakai_b200.h); field order and types must match
+mutable struct Params
+    struct_size::Int32
+    device::Int32
+    d_time::Float64
+    element_min_size::Float64
+    element_max_size::Float64
+    contact_flag::Int32
+    triax_route::Int32
+    contact_d_lim_factor::Float64
+    contact_myu::Float64
+    contact_kc_other::Float64
+    contact_kc_self::Float64
+    contact_cr_other::Float64
+    contact_cr_self::Float64
+    contact_ddiv_other::Float64
+    contact_ddiv_self::Float64
+    deterministic::Int32
+    reserved::Int32
+    Params() = new()
+end
+
+struct Engine
+    ptr::Ptr{Cvoid}
+end
+
+function check(e, rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:hk_last_error, LIB), Cstring, (Ptr{Cvoid},), e))
+    error("libhakai_b200: code $rc: $msg")
+end
+
+function default_params()
+    p = Params()
+    rc = ccall((:hk_default_params, LIB), Cint, (Ref{Params},), p)
+    rc == 0 || error("hk_default_params failed")
+    return p
+end
+
+function create(p::Params)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:hk_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{Params}), out, p)
+    check(C_NULL, rc)          # fails loudly when there is no CUDA device: no CPU fallback
+    return Engine(out[])
+end
+
+destroy(e::Engine) = ccall((:hk_destroy, LIB), Cint, (Ptr{Cvoid},), e.ptr)
+
+function csr(lists)
+    ptr = Int64[0]
+    flat = Int64[]
+    for l in lists
+        append!(flat, l)
+        push!(ptr, length(flat))
+    end
+    return ptr, flat
+end
+
+set_mesh(e, coordmat::Matrix{Float64}, elementmat::Matrix{Int}, element_material::Vector{Int},
+         element_instance::Vector{Int}, diag_M::Vector{Float64}) =
+    check(e.ptr, ccall((:hk_set_mesh, LIB), Cint,
+          (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+          e.ptr, size(coordmat, 2), size(elementmat, 2), coordmat, elementmat, element_material, element_instance, diag_M))
+
+function add_material(e, m)    # m::MaterialType (readInpFile_j.jl:84-96)
+    npp = size(m.plastic, 1); nd = size(m.ductile, 1)
+    check(e.ptr, ccall((:hk_add_material, LIB), Cint,
+          (Ptr{Cvoid}, Float64, Float64, Float64, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+          e.ptr, m.young, m.poisson, m.density, npp, npp > 0 ? m.plastic : C_NULL, npp > 1 ? m.Hd : C_NULL,
+          nd, nd > 0 ? m.ductile : C_NULL))
+end
+
+function add_bc(e, bc)         # bc::BCType (readInpFile_j.jl:98-104)
+    ptr, flat = csr(bc.dof)
+    has_amp = length(bc.amp_name) > 0
+    at = has_amp ? Float64.(bc.amplitude.time) : Float64[]
+    av = has_amp ? Float64.(bc.amplitude.value) : Float64[]
+    check(e.ptr, ccall((:hk_add_bc, LIB), Cint,
+          (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+          e.ptr, length(bc.dof), ptr, flat, Float64.(bc.value), length(at), at, av))
+end
+
+function add_ic(e, ic)         # ic::ICType (readInpFile_j.jl:106-111)
+    ptr, flat = csr(ic.dof)
+    check(e.ptr, ccall((:hk_add_ic, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+          e.ptr, length(ic.dof), ptr, flat, Float64.(ic.value)))
+end
+
+add_instance(e, inst) =        # inst::InstanceType after get_element_face (HAKAI_j.jl:255-261)
+    check(e.ptr, ccall((:hk_add_instance, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}),
+          e.ptr, inst.node_offset, inst.nNode, inst.element_offset, inst.nElement, inst.surfaces, inst.surfaces_eleid))
+
+add_contact_pair(e, i_instance, j_instance, ct) =   # ct::ContactTriangle (HAKAI_j.jl:72-78, 361-398)
+    check(e.ptr, ccall((:hk_add_contact_pair, LIB), Cint,
+          (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Float64),
+          e.ptr, i_instance, j_instance, length(ct.c_nodes_i), ct.c_nodes_i, length(ct.c_nodes_j), ct.c_nodes_j,
+          size(ct.c_triangles, 1), ct.c_triangles, ct.c_triangles_eleid, ct.young))
+
+finalize!(e) = check(e.ptr, ccall((:hk_finalize, LIB), Cint, (Ptr{Cvoid},), e.ptr))
+
+function step!(e, t_first::Integer, n_steps::Integer)
+    nd = Ref{Int64}(0)
+    check(e.ptr, ccall((:hk_step, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ref{Int64}), e.ptr, t_first, n_steps, nd))
+    return nd[]
+end
+
+download!(e, disp, velo, integ_stress, integ_strain, integ_eq_plastic_strain, integ_triax_stress, element_flag) =
+    check(e.ptr, ccall((:hk_download, LIB), Cint,
+          (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+          e.ptr, disp, velo, integ_stress, integ_strain, integ_eq_plastic_strain, integ_triax_stress, element_flag))
+
+end # module

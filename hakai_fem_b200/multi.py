@@ -189,7 +189,8 @@ class SlabRunner:
         return self.engine.step(t, 1)
 
     def run(self, t_first: int, n_steps: int) -> int:
-        nd = 0
+        """Enqueues pack -> exchange -> step for every step without blocking the host, then synchronises once."""
         for t in range(t_first, t_first + n_steps):
-            nd += self.step(t)
-        return nd
+            self.halo.exchange()
+            self.engine.step_enqueue(t, 1)
+        return self.engine.sync()

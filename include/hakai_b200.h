@@ -123,6 +123,13 @@ int hk_finalize(hk_engine* e);
  * receives the number of elements deleted during these steps (J2:733-736). */
 int hk_step(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_deleted_out);
 
+/* hk_step = hk_step_enqueue + hk_sync.  hk_step_enqueue only enqueues the kernels on the engine's stream (it
+ * still synchronises internally when contact surfaces may change after a deletion); hk_sync waits for them and
+ * reports the elements deleted since the previous hk_sync/hk_step.  The multi-GPU driver enqueues
+ * pack -> send/recv -> step for many steps without blocking the host. */
+int hk_step_enqueue(hk_engine* e, int64_t t_first, int64_t n_steps);
+int hk_sync(hk_engine* e, int64_t* n_deleted_out);
+
 /* Output taps (A13): fills caller-owned arrays in the reference's layouts; NULL = skip.
  *   disp, velo                       f64 (fn)
  *   integ_stress, integ_strain       f64 (6,nip) column-major

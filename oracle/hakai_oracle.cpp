@@ -933,6 +933,21 @@ int hko_step(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_deleted_
     return HK_OK;
 }
 
+static int64_t g_pending_deleted = 0;
+int hko_step_enqueue(hk_engine* e, int64_t t_first, int64_t n_steps) {
+    int64_t nd = 0;
+    int rc = hko_step(e, t_first, n_steps, &nd);
+    if (e) e->counters[7] += nd;     // reported by the next hko_sync
+    (void)g_pending_deleted;
+    return rc;
+}
+int hko_sync(hk_engine* e, int64_t* n_deleted_out) {
+    if (!e) return HK_ERR_ARG;
+    if (n_deleted_out) *n_deleted_out = e->counters[7];
+    e->counters[7] = 0;
+    return HK_OK;
+}
+
 int hko_download(hk_engine* e, double* disp, double* velo, double* integ_stress, double* integ_strain,
                  double* integ_eq_plastic_strain, double* integ_triax_stress, int64_t* element_flag) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
