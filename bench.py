@@ -240,8 +240,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     achieved = ALG_BYTES_ELEMENT * nE / (el_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "hk_element_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tr_path):      # dram__bytes_read+write per element from the committed ncu --set full capture
+        traffic = json.load(open(tr_path))["element_kernel_dram_bytes_per_element"] * nE
+    kname = "hk_element_simple_kernel" if os.environ.get("HK_ELEMENT_KERNEL") == "simple" else "hk_element_tma_kernel"
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_ELEMENT * nE, "avg_launch_ms": el_ms,
                 "nodal_kernel": {"achieved": ALG_BYTES_NODAL * nN / (nd_ms * 1e-3) / 1e9, "avg_launch_ms": nd_ms},
                 "whole_step": {"achieved": ALG_BYTES_STEP * nE / (ms / args.steps * 1e-3) / 1e9,

@@ -201,7 +201,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned addr = smem_u32(bar);
-    unsigned ok;
+    unsigned ok, spins = 0;
     do {
         asm volatile(
             "{\n"
@@ -212,6 +212,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
             : "=r"(ok)
             : "r"(addr), "r"(parity)
             : "memory");
+        if (!ok && ++spins > 100000000u) __trap();      // a protocol bug must fail loudly, never hang the GPU
     } while (!ok);
 }
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
@@ -224,6 +225,9 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
                  "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -259,7 +263,9 @@ __device__ __forceinline__ double* state_row(const HkDev& d, int r, int k, long 
 
 // MODES: 0 = geometry/displacement modes in registers, 1 = displacement modes U in shared memory,
 //        2 = X and U in shared memory (thread-private columns; frees registers so ptxas can overlap more math)
-template <int STAGES, int MODES>
+//   PF: > 0 = the producer also issues cp.async.bulk.prefetch.L2 for the work item PF stages beyond the ring, so
+//        the depth of DRAM prefetch is no longer bounded by shared-memory capacity
+template <int STAGES, int MODES, int PF>
 __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_buf = reinterpret_cast<double*>(smem_raw);
@@ -298,6 +304,13 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
 #pragma unroll 1
             for (int r = 0; r < HK_ROWS; ++r)
                 tma_load_1d(dst + r * HK_TILE, state_row(d, r, k, e0), HK_TILE * 8, &full[st]);
+            if (PF > 0 && q + PF < total_q) {
+                const long long qp = q + PF;
+                const long long ep0 = (first + (qp >> 3) * gridDim.x) * HK_TILE;
+                const int kp = (int)(qp & 7);
+#pragma unroll 1
+                for (int r = 0; r < HK_ROWS; ++r) tma_prefetch_l2(state_row(d, r, kp, ep0), HK_TILE * 8);
+            }
         };
         for (long long q = 0; q < STAGES && q < total_q; ++q) issue_load(q);
         for (long long q = 0; q < total_q; ++q) {
@@ -380,16 +393,16 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
 #endif
 
 #ifndef HK_EMU
-template <int STAGES, int MODES>
+template <int STAGES, int MODES, int PF>
 static void launch_tma(const ElemArgs& A, unsigned grid, cudaStream_t s) {
     const int smem_bytes = STAGES * HK_STAGE_DOUBLES * 8 + 2 * STAGES * 8 + HK_SMEM_MATS * 2 * HK_MAX_TABLE * 8 +
-                           (MODES > 0 ? 42 * HK_TILE * 8 : 0) + 64;
+                           21 * MODES * HK_TILE * 8 + 64;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(hk_element_tma_kernel<STAGES, MODES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaFuncSetAttribute(hk_element_tma_kernel<STAGES, MODES, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         configured = true;
     }
-    hk_element_tma_kernel<STAGES, MODES><<<grid, HK_CTA_THREADS, smem_bytes, s>>>(A);
+    hk_element_tma_kernel<STAGES, MODES, PF><<<grid, HK_CTA_THREADS, smem_bytes, s>>>(A);
 }
 #endif
 
@@ -418,13 +431,13 @@ void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStre
     const long long n_tiles = d.nEp / HK_TILE;
     long long grid = (long long)n_sm;
     if (grid > n_tiles) grid = n_tiles;
-    switch (variant) {
-        case 0: launch_tma<8, 0>(A, (unsigned)grid, s); break;
-        case 2: launch_tma<5, 2>(A, (unsigned)grid, s); break;
-        case 3: launch_tma<8, 1>(A, (unsigned)grid, s); break;
-        case 4: launch_tma<7, 2>(A, (unsigned)grid, s); break;
-        case 5: launch_tma<4, 1>(A, (unsigned)grid, s); break;
-        default: launch_tma<6, 1>(A, (unsigned)grid, s); break;   // measured best (profiles/)
+    switch (variant) {                                   // A/B history: profiles/r1_element_kernel_variants.md
+        case 0: launch_tma<8, 0, 0>(A, (unsigned)grid, s); break;
+        case 2: launch_tma<6, 2, 0>(A, (unsigned)grid, s); break;
+        case 3: launch_tma<7, 1, 0>(A, (unsigned)grid, s); break;
+        case 4: launch_tma<6, 1, 8>(A, (unsigned)grid, s); break;
+        case 5: launch_tma<4, 1, 0>(A, (unsigned)grid, s); break;
+        default: launch_tma<6, 1, 0>(A, (unsigned)grid, s); break;   // measured best
     }
 #else
     for (long long e = 0; e < d.nElement; ++e) element_body_simple(A, e);
