@@ -1,0 +1,75 @@
+"""Error behaviour of the C ABI (argument / call-order checks), exercised on the host-compiled build of the
+engine sources (tests/emu) — the CUDA library shares this code but needs a device to create an engine."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hakai_fem_b200.engine import HakaiError, HkParams
+from hakai_fem_b200.mesh import StretchDeck
+from hakai_fem_b200.model_setup import prepare, configure_engine
+
+from .emu.emu_engine import EmuEngine, load
+
+
+def test_params_size_and_dt_checked():
+    lib = load()
+    p = HkParams()
+    lib.hke_default_params(C.byref(p))
+    h = C.c_void_p()
+    p.d_time = 1e-7
+    p.struct_size = 12
+    assert lib.hke_create(C.byref(h), C.byref(p)) == -1          # HK_ERR_ARG
+    with pytest.raises(HakaiError):
+        EmuEngine(d_time=0.0)
+    with pytest.raises(HakaiError) as ei:
+        EmuEngine(d_time=1e-7, triax_route=1)
+    assert "oracle" in str(ei.value)
+
+
+def test_call_order_and_ranges():
+    st = prepare(StretchDeck(2, 2, 2).build_model())
+    e = EmuEngine(d_time=st.d_time)
+    with pytest.raises(HakaiError):
+        e.finalize()                                             # no mesh yet
+    with pytest.raises(HakaiError):
+        e.step(1, 1)                                             # not finalised
+    m = st.model
+    bad = m.elementmat.copy()
+    bad[0, 0] = m.nNode + 1
+    with pytest.raises(HakaiError):
+        e.set_mesh(m.coordmat, bad, m.element_material, m.element_instance, st.diag_M)
+    dm = st.diag_M.copy()
+    dm[1] *= 2
+    with pytest.raises(HakaiError) as ei:
+        e.set_mesh(m.coordmat, m.elementmat, m.element_material, m.element_instance, dm)
+    assert "same mass" in str(ei.value)
+    e.set_mesh(m.coordmat, m.elementmat, m.element_material, m.element_instance, st.diag_M)
+    with pytest.raises(HakaiError):
+        e.add_material(1.0, 0.3, 1.0, plastic=np.array([[1.0, 0.0]]), Hd=None)           # one-row *Plastic table
+    with pytest.raises(HakaiError):
+        e.add_material(1.0, 0.3, 1.0, plastic=np.array([[1.0, 0.0], [2.0, 0.0]]), Hd=np.array([1.0]))   # not increasing
+    e.add_material(210000.0, 0.3, 7.8e-9)
+    e.add_bc([np.array([3 * m.nNode + 1])], [0.0])               # dof out of range: reported at finalize
+    with pytest.raises(HakaiError):
+        e.finalize()
+
+
+def test_finalize_twice_and_halo_multi_step_rejected():
+    st = prepare(StretchDeck(2, 2, 2).build_model())
+
+    def with_halo(**p):
+        e = EmuEngine(**p)
+        e.set_halo([np.array([1, 2, 3])])
+        return e
+    e = configure_engine(with_halo, st)
+    with pytest.raises(HakaiError):
+        e.finalize()
+    with pytest.raises(HakaiError):
+        e.step(1, 1)                                             # halo buffers not bound
+    send, recv = np.zeros(9), np.zeros(9)
+    e.halo_bind(0, send.ctypes.data, recv.ctypes.data)
+    e.halo_pack()
+    e.step(1, 1)
+    with pytest.raises(HakaiError):
+        e.step(2, 2)                                             # with halos: one step per exchange
