@@ -5,9 +5,9 @@
 //                        (disp, disp_pre, coordmat): perfectly coalesced for the streaming update.
 //   node record `rec`    {x,y,z, dux,duy,duz} per node (48 B, 16-B aligned): `position` and `d_disp`
 //                        of J2:624-652, written by the nodal kernel, gathered by the element kernel.
-//   ip state             SoA [component][gauss point][element]: stress/strain 6x8 rows, eps/yield 8 rows,
-//                        each row nEp doubles (nEp = nElement padded to 32) -> a warp of consecutive
-//                        elements reads 256 contiguous bytes per row.
+//   ip state             tile-blocked SoA [tile][gauss point][row 14][TL]: the state of one Gauss point of one tile
+//                        of TL consecutive elements is a single contiguous burst (39 KB at TL = 352) that the
+//                        TMA moves with one bulk copy; within it consecutive elements are consecutive doubles.
 //   Qe                   SoA [24][nEp]: element nodal forces (J2:438), written by the element kernel and
 //                        gathered per node in ascending element order (= the reference's serial scatter
 //                        order, J2:669-675) by the nodal kernel of the next step.  Q itself is never
@@ -68,10 +68,10 @@ struct HkDev {
                           // valid), 2 deleted and Qe cleared
     unsigned short* mat;  // 0-based material id
     HkMaterialDev* mats;
-    double* stress;       // [6][8][nEp]
-    double* strain;       // [6][8][nEp]
-    double* eps;          // [8][nEp]   integ_eq_plastic_strain
-    double* yield;        // [8][nEp]   integ_yield_stress
+    double* ips;          // ip state, tile-blocked: [tile][gauss point 8][row 14][TL] with rows 0-5 stress, 6-11 strain,
+                          // 12 eps (integ_eq_plastic_strain), 13 yield (integ_yield_stress): the 14 rows x TL
+                          // elements of one Gauss point of one tile are ONE contiguous burst (14*TL*8 bytes)
+    int TL;               // layout tile = elements per tile of the element kernel in use; nEp % TL == 0
     double* triax;        // [8][nEp]   integ_triax_stress (written on request)
     double* Qe;           // [24][nEp]
     // deletion log
@@ -83,6 +83,13 @@ struct HkDev {
     unsigned long long* cacc;
     double* halo_recv;    // [n_halo*3]
 };
+
+// index of (row, gauss point k, element e) in HkDev::ips
+HK_HD long long hk_ip(const HkDev& d, int row, int k, long long e) {
+    const long long t = e / d.TL;
+    const long long j = e - t * d.TL;
+    return ((t * 8 + k) * 14 + row) * d.TL + j;
+}
 
 struct HkPairDev {               // one ordered contact pair (ContactTriangle, J2:72-78)
     int nn_i, nn_j, nTri;
@@ -119,10 +126,11 @@ void hk_launch_halo_accumulate(const HkDev& d, const int* slots, long long n, co
 void hk_launch_triax(const HkDev& d, cudaStream_t s);
 void hk_launch_element_volume(const HkDev& d, double* V_out, cudaStream_t s);
 // layout transposes between the reference's AoS (6,nip)/(nip) arrays and the SoA rows
-void hk_launch_ip_to_soa(const double* aos, double* soa, int ncomp, long long e0, long long ne, long long nEp,
-                         cudaStream_t s);
-void hk_launch_ip_to_aos(const double* soa, double* aos, int ncomp, long long e0, long long ne, long long nEp,
-                         cudaStream_t s);
+// rows [row0, row0+ncomp) of the ip state <-> the reference's (ncomp, nip) array, element range [e0, e0+ne)
+void hk_launch_ip_to_dev(const double* aos, const HkDev& d, int row0, int ncomp, long long e0, long long ne, cudaStream_t s);
+void hk_launch_ip_to_aos(const HkDev& d, double* aos, int row0, int ncomp, long long e0, long long ne, cudaStream_t s);
+// triax [8][nEp] -> (nip) of the reference
+void hk_launch_triax_to_aos(const HkDev& d, double* aos, long long e0, long long ne, cudaStream_t s);
 void hk_upload_pusai(const double* P);
 long long hk_element_tile();   // nEp must be a multiple of this
 void hk_launch_external_force(const HkDev& d, double* F_out, int lsb_exp, int contact_on, cudaStream_t s);

@@ -16,16 +16,25 @@
 //       kept as the A/B baseline for the profiles.
 #include "hk_element_math.h"
 
+// HK_ELEMENT_VARIANT: >= 10 TMEM kernel (tile 352), < 10 TMA kernel variants (tile 224); default 11
+static int element_variant() {
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("HK_ELEMENT_VARIANT"); variant = v ? atoi(v) : 11; }
+    return variant;
+}
+
 struct ElemArgs {
     HkDev d;
     long long step;
     int write_triax;
+    int fast;          // MatLite::fast
 };
 
 HK_HD MatLite mat_lite(const HkMaterialDev* m) {
     MatLite l;
     l.D11 = m->D11; l.D12 = m->D12; l.D44 = m->D44; l.G3 = 3.0 * m->G; l.npp = m->npp;
     l.pe = m->plastic_e; l.hd = m->Hd;
+    l.fast = 1;
     return l;
 }
 
@@ -119,10 +128,8 @@ HK_D void element_delete(const ElemArgs& A, long long e) {
     const HkDev& d = A.d;
     d.flag[e] = 0;
 #pragma unroll 1
-    for (int r = 0; r < 48; ++r) {
-        d.stress[(long long)r * d.nEp + e] = 0.0;
-        d.strain[(long long)r * d.nEp + e] = 0.0;
-    }
+    for (int k = 0; k < 8; ++k)
+        for (int r = 0; r < 12; ++r) d.ips[hk_ip(d, r, k, e)] = 0.0;
     const int slot = hk_atomic_add_i32(d.del_count, 1);
     if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
 }
@@ -133,7 +140,8 @@ HK_D void element_body_simple(const ElemArgs& A, long long e) {
     const long long nEp = d.nEp;
     if (element_dead(d, e)) return;
     const HkMaterialDev& M = d.mats[d.mat[e]];
-    const MatLite ML = mat_lite(&M);
+    MatLite ML = mat_lite(&M);
+    ML.fast = A.fast;
     HexModes X, U;
     element_gather(d, e, X, U);
     double V, trbar;
@@ -147,22 +155,16 @@ HK_D void element_body_simple(const ElemArgs& A, long long e) {
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
         const long long row = (long long)k * nEp + e;
+        double* sp = d.ips + hk_ip(d, 0, k, e);
+        const long long TL = d.TL;
         double st[14];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            st[c] = d.stress[(long long)c * 8 * nEp + row];
-            st[6 + c] = d.strain[(long long)c * 8 * nEp + row];
-        }
-        st[12] = d.eps[row];
-        st[13] = d.yield[row];
+        for (int r = 0; r < 14; ++r) st[r] = sp[r * TL];
         const double ep_old = st[12];
         const double tx = gauss_point(X, U, ML, k, trbar, st, acc);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            d.stress[(long long)c * 8 * nEp + row] = st[c];
-            d.strain[(long long)c * 8 * nEp + row] = st[6 + c];
-        }
-        if (st[12] != ep_old) { d.eps[row] = st[12]; d.yield[row] = st[13]; }
+        for (int r = 0; r < 12; ++r) sp[r * TL] = st[r];
+        if (st[12] != ep_old) { sp[12 * TL] = st[12]; sp[13 * TL] = st[13]; }
         if (A.write_triax) d.triax[row] = tx;
     }
     element_finish(A, e, X, acc, V);
@@ -253,12 +255,9 @@ __device__ __forceinline__ void modes_load(HexModes& m, const double* p) {
     }
 }
 
-// global address of state row r (0..13) of Gauss point k for the tile starting at element e0
-__device__ __forceinline__ double* state_row(const HkDev& d, int r, int k, long long e0) {
-    if (r < 6) return d.stress + ((long long)(r * 8 + k) * d.nEp + e0);
-    if (r < 12) return d.strain + ((long long)((r - 6) * 8 + k) * d.nEp + e0);
-    if (r == 12) return d.eps + ((long long)k * d.nEp + e0);
-    return d.yield + ((long long)k * d.nEp + e0);
+// global address of the state of Gauss point k of the tile starting at element e0: 14 rows x TL doubles, contiguous
+__device__ __forceinline__ double* stage_base(const HkDev& d, int k, long long e0) {
+    return d.ips + ((e0 / d.TL) * 8 + k) * 14 * d.TL;
 }
 
 // MODES: 0 = geometry/displacement modes in registers, 1 = displacement modes U in shared memory,
@@ -301,15 +300,11 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
             const int k = (int)(q & 7);
             double* dst = stage_buf + st * HK_STAGE_DOUBLES;
             mbar_expect_tx(&full[st], HK_ROWS * HK_TILE * 8);
-#pragma unroll 1
-            for (int r = 0; r < HK_ROWS; ++r)
-                tma_load_1d(dst + r * HK_TILE, state_row(d, r, k, e0), HK_TILE * 8, &full[st]);
+            tma_load_1d(dst, stage_base(d, k, e0), HK_ROWS * HK_TILE * 8, &full[st]);
             if (PF > 0 && q + PF < total_q) {
                 const long long qp = q + PF;
                 const long long ep0 = (first + (qp >> 3) * gridDim.x) * HK_TILE;
-                const int kp = (int)(qp & 7);
-#pragma unroll 1
-                for (int r = 0; r < HK_ROWS; ++r) tma_prefetch_l2(state_row(d, r, kp, ep0), HK_TILE * 8);
+                tma_prefetch_l2(stage_base(d, (int)(qp & 7), ep0), HK_ROWS * HK_TILE * 8);
             }
         };
         for (long long q = 0; q < STAGES && q < total_q; ++q) issue_load(q);
@@ -319,8 +314,7 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
             const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
             const int k = (int)(q & 7);
             const double* src = stage_buf + st * HK_STAGE_DOUBLES;
-#pragma unroll 1
-            for (int r = 0; r < HK_ROWS; ++r) tma_store_1d(state_row(d, r, k, e0), src + r * HK_TILE, HK_TILE * 8);
+            tma_store_1d(stage_base(d, k, e0), src, HK_ROWS * HK_TILE * 8);
             tma_commit();
             // refill the stage whose store group was committed one round ago (it has been read by now)
             const long long qn = q - 1 + STAGES;
@@ -349,6 +343,7 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
             const int mi = d.mat[e];
             Mt = &d.mats[mi];
             ML = mat_lite(Mt);
+            ML.fast = A.fast;
             if (tabs_in_smem) { ML.pe = mat_tab + mi * 2 * HK_MAX_TABLE; ML.hd = ML.pe + HK_MAX_TABLE; }
             element_gather(d, e, X, U);
             double G[3][3][3];
@@ -393,6 +388,277 @@ __global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemA
 #endif
 
 #ifndef HK_EMU
+#include "hk_tmem.h"
+// ---- TMEM kernel ----------------------------------------------------------------------------------------------
+// Same ring and producer as hk_element_tma_kernel, but ALL per-element state that must survive the Gauss-point
+// loop (geometry modes X, displacement modes U, the 36 force-mode accumulators M: 78 doubles) lives in tensor
+// memory, one TMEM lane per thread (hk_tmem.h).  Registers then hold only the temporaries of one Gauss point, so
+// the CTA grows from 7 to 11 consumer warps per SM (352 elements per tile) — the kernel is issue/latency bound,
+// not bandwidth bound (profiles/), so warps are what it needs.  Every lane runs the full math (dead or padded
+// elements get a unit cube with zero displacement, which leaves their state rows bit-unchanged), so the
+// warp-collective tcgen05.ld/st never execute under divergence.
+#define HK_TILE_T 352
+#define HK_CTA_T (HK_TILE_T + 32)
+#define HK_STAGE_T (HK_ROWS * HK_TILE_T)
+#define HK_TCOLS 168                      // columns per thread: X [0,42) U [48,90) M [96,168)
+
+__device__ __forceinline__ void tmem_store_modes(uint32_t t, const HexModes& m) {
+    double v[24];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        v[0 + c] = m.c0[c]; v[3 + c] = m.c1[c]; v[6 + c] = m.c2[c]; v[9 + c] = m.h01[c];
+        v[12 + c] = m.h02[c]; v[15 + c] = m.h12[c]; v[18 + c] = m.h012[c];
+    }
+    v[21] = v[22] = v[23] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) tmem_st_doubles<4>(t + 8 * i, v + 4 * i);
+    tmem_st_doubles<1>(t + 40, v + 20);
+}
+__device__ __forceinline__ void tmem_load_modes(uint32_t t, HexModes& m) {
+    uint32_t w[42];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) tmem_ld_x8(t + 8 * i, w + 8 * i);
+    tmem_ld_x2(t + 40, w + 40);
+    tmem_wait_ld();
+    double v[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) v[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        m.c0[c] = v[0 + c]; m.c1[c] = v[3 + c]; m.c2[c] = v[6 + c]; m.h01[c] = v[9 + c];
+        m.h02[c] = v[12 + c]; m.h12[c] = v[15 + c]; m.h012[c] = v[18 + c];
+    }
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_buf = reinterpret_cast<double*>(smem_raw);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(stage_buf + STAGES * HK_STAGE_T);
+    unsigned long long* done = full + STAGES;
+    double* mat_tab = reinterpret_cast<double*>(done + STAGES);
+    uint32_t* tbase_s = reinterpret_cast<uint32_t*>(mat_tab + HK_SMEM_MATS * 2 * HK_MAX_TABLE);
+    const HkDev& d = A.d;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long n_tiles = d.nEp / HK_TILE_T;
+    const long long first = blockIdx.x;
+    const long long my_tiles = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_q = my_tiles * 8;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], HK_TILE_T); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tbase_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    const bool tabs_in_smem = d.n_mat <= HK_SMEM_MATS;
+    if (tabs_in_smem)
+        for (int i = tid; i < d.n_mat * 2 * HK_MAX_TABLE; i += HK_CTA_T) {
+            const int m = i / (2 * HK_MAX_TABLE), r = i % (2 * HK_MAX_TABLE);
+            mat_tab[i] = r < HK_MAX_TABLE ? d.mats[m].plastic_e[r] : d.mats[m].Hd[r - HK_MAX_TABLE];
+        }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tbase = *tbase_s;
+
+    if (tid >= HK_TILE_T) {
+        // ===== producer warp (same protocol as hk_element_tma_kernel) =====
+        if (tid == HK_TILE_T) {
+            auto issue_load = [&](long long q) {
+                const int st = (int)(q % STAGES);
+                const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE_T;
+                const int k = (int)(q & 7);
+                double* dst = stage_buf + st * HK_STAGE_T;
+                mbar_expect_tx(&full[st], HK_ROWS * HK_TILE_T * 8);
+                tma_load_1d(dst, stage_base(d, k, e0), HK_ROWS * HK_TILE_T * 8, &full[st]);
+            };
+            for (long long q = 0; q < STAGES && q < total_q; ++q) issue_load(q);
+            for (long long q = 0; q < total_q; ++q) {
+                const int st = (int)(q % STAGES);
+                mbar_wait(&done[st], (unsigned)((q / STAGES) & 1));
+                const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE_T;
+                const int k = (int)(q & 7);
+                const double* src = stage_buf + st * HK_STAGE_T;
+                tma_store_1d(stage_base(d, k, e0), src, HK_ROWS * HK_TILE_T * 8);
+                tma_commit();
+                const long long qn = q - 1 + STAGES;
+                if (q >= 1 && qn < total_q) {
+                    tma_wait_read<1>();
+                    issue_load(qn);
+                }
+            }
+            tma_wait_all<0>();
+        }
+    } else {
+        // ===== consumers =====
+        const uint32_t tcol = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * HK_TCOLS);
+        const uint32_t tX = tcol, tU = tcol + 48, tM = tcol + 96;
+        long long q = 0;
+        for (long long it = 0; it < my_tiles; ++it) {
+            const long long e0 = (first + it * gridDim.x) * HK_TILE_T;
+            const long long e = e0 + tid;
+            const bool live = !element_dead(d, e);
+            const HkMaterialDev* Mt = &d.mats[0];
+            double V = 0.125, trbar = 0.0;
+            int mi = 0;
+            {
+                HexModes X, U;
+                if (live) {
+                    mi = d.mat[e];
+                    element_gather(d, e, X, U);
+                } else {                                     // unit cube at rest: finite math, state rows unchanged
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        X.c0[c] = X.c1[c] = X.c2[c] = X.h01[c] = X.h02[c] = X.h12[c] = X.h012[c] = 0.0;
+                        U.c0[c] = U.c1[c] = U.c2[c] = U.h01[c] = U.h02[c] = U.h12[c] = U.h012[c] = 0.0;
+                    }
+                    X.c0[0] = X.c1[1] = X.c2[2] = 0.5;
+                }
+                double G[3][3][3];
+                adj_mode_sums(X, G);
+                element_volume_terms(X, U, G, V, trbar);
+                __syncwarp();
+                tmem_store_modes(tX, X);
+                tmem_store_modes(tU, U);
+            }
+            {
+                double z[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int i = 0; i < 9; ++i) tmem_st_doubles<4>(tM + 8 * i, z);
+            }
+            tmem_wait_st();
+            Mt = &d.mats[mi];
+            MatLite ML = mat_lite(Mt);
+            ML.fast = A.fast;
+            if (tabs_in_smem) { ML.pe = mat_tab + mi * 2 * HK_MAX_TABLE; ML.hd = ML.pe + HK_MAX_TABLE; }
+            const bool need_triax = A.write_triax || Mt->nd > 0;
+            double pdet = 0.0, v_e = 0.0, t_e = 0.0;
+            int negj = 0;
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k, ++q) {
+                const int st = (int)(q % STAGES);
+                double* sb = stage_buf + st * HK_STAGE_T + tid;
+                mbar_wait(&full[st], (unsigned)((q / STAGES) & 1));
+                __syncwarp();
+                if (A.fast == 2) {                           // experiment: memory pipeline only (no math)
+#pragma unroll
+                    for (int r = 0; r < HK_ROWS; ++r) sb[r * HK_TILE_T] = sb[r * HK_TILE_T] + 0.0;
+                    fence_async_smem();
+                    mbar_arrive(&done[st]);
+                    continue;
+                }
+                const double s0 = (k & 4) ? 1.0 : -1.0, s1 = (k & 2) ? 1.0 : -1.0, s2 = (k & 1) ? 1.0 : -1.0;
+                double Aj[3][3], det;
+                {
+                    HexModes X;
+                    tmem_load_modes(tX, X);
+                    gp_geometry(X, s0, s1, s2, Aj, det);
+                }
+                if (det < 0) negj++;
+                const double idet = hk_rcp(det);
+                double de[6];
+                {
+                    HexModes U;
+                    tmem_load_modes(tU, U);
+                    gp_strain(U, Aj, idet, trbar, s0, s1, s2, de);
+                }
+                GpStress g;
+                {
+                    double sv[14];
+#pragma unroll
+                    for (int r = 0; r < HK_ROWS; ++r) sv[r] = sb[r * HK_TILE_T];
+                    gp_stress(ML, sv, de, need_triax, g);
+#pragma unroll
+                    for (int r = 0; r < HK_ROWS; ++r) sb[r * HK_TILE_T] = sv[r];
+                }
+                pdet += g.mean * det;
+                v_e += g.ep;
+                t_e += g.tx;
+                if (A.write_triax && live) d.triax[(long long)k * d.nEp + e] = g.tx;
+                const double sa[3] = {s1, s0, s0};
+                const double sb_[3] = {s2, s2, s1};
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    double T[3];
+                    gp_T(g, Aj[r], T);
+                    uint32_t w[24];
+                    tmem_ld_x8(tM + 24 * r, w);
+                    tmem_ld_x8(tM + 24 * r + 8, w + 8);
+                    tmem_ld_x8(tM + 24 * r + 16, w + 16);
+                    tmem_wait_ld();
+                    const double coef[4] = {1.0, sa[r], sb_[r], sa[r] * sb_[r]};
+                    double mo[12];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int i = m * 3 + c;
+                            mo[i] = fma(coef[m], T[c], __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]));
+                        }
+                    tmem_st_doubles<4>(tM + 24 * r, mo);
+                    tmem_st_doubles<4>(tM + 24 * r + 8, mo + 4);
+                    tmem_st_doubles<4>(tM + 24 * r + 16, mo + 8);
+                }
+                tmem_wait_st();
+                fence_async_smem();
+                mbar_arrive(&done[st]);
+            }
+            // ---- element epilogue: forces from the modes parked in TMEM
+            __syncwarp();
+            ElemAcc acc;
+            {
+                uint32_t w[72];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) tmem_ld_x8(tM + 8 * i, w + 8 * i);
+                tmem_wait_ld();
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int i = r * 12 + m * 3 + c;
+                            acc.M[r][m][c] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+                        }
+            }
+            acc.pdet = pdet; acc.v_e = v_e; acc.t_e = t_e; acc.negj = negj;
+            HexModes X;
+            tmem_load_modes(tX, X);
+            if (live) {
+                element_finish(A, e, X, acc, V);
+                if (ductile_check(*Mt, acc.v_e, acc.t_e)) {
+                    d.flag[e] = 3;                           // zeroed by hk_launch_flush_deleted (stream order)
+                    const int slot = hk_atomic_add_i32(d.del_count, 1);
+                    if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
+}
+
+template <int STAGES>
+static void launch_tmem(const ElemArgs& A, int n_sm, cudaStream_t s) {
+    const int smem_bytes = STAGES * HK_STAGE_T * 8 + 2 * STAGES * 8 + HK_SMEM_MATS * 2 * HK_MAX_TABLE * 8 + 64;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(hk_element_tmem_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        configured = true;
+    }
+    const long long n_tiles = A.d.nEp / HK_TILE_T;
+    long long grid = n_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    hk_element_tmem_kernel<STAGES><<<(unsigned)grid, HK_CTA_T, smem_bytes, s>>>(A);
+}
+#endif
+
+#ifndef HK_EMU
 template <int STAGES, int MODES, int PF>
 static void launch_tma(const ElemArgs& A, unsigned grid, cudaStream_t s) {
     const int smem_bytes = STAGES * HK_STAGE_DOUBLES * 8 + 2 * STAGES * 8 + HK_SMEM_MATS * 2 * HK_MAX_TABLE * 8 +
@@ -409,7 +675,9 @@ static void launch_tma(const ElemArgs& A, unsigned grid, cudaStream_t s) {
 static int g_elem_kernel = -1;   // 0 tma, 1 simple
 
 void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s) {
-    ElemArgs A{d, step, write_triax};
+    static int fast = -1;
+    if (fast < 0) { const char* f = getenv("HK_ELEMENT_FASTMATH"); fast = f ? atoi(f) : 1; }
+    ElemArgs A{d, step, write_triax, fast};
 #ifndef HK_EMU
     if (g_elem_kernel < 0) {
         const char* env = getenv("HK_ELEMENT_KERNEL");
@@ -425,12 +693,19 @@ void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStre
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        const char* v = getenv("HK_ELEMENT_VARIANT");
-        variant = v ? atoi(v) : 1;
+        variant = element_variant();
     }
     const long long n_tiles = d.nEp / HK_TILE;
     long long grid = (long long)n_sm;
     if (grid > n_tiles) grid = n_tiles;
+    if (variant >= 10) {                                 // TMEM kernels (tile 352)
+        switch (variant) {
+            case 10: launch_tmem<5>(A, n_sm, s); break;
+            case 12: launch_tmem<3>(A, n_sm, s); break;
+            default: launch_tmem<4>(A, n_sm, s); break;        // 11: measured best
+        }
+        return;
+    }
     switch (variant) {                                   // A/B history: profiles/r1_element_kernel_variants.md
         case 0: launch_tma<8, 0, 0>(A, (unsigned)grid, s); break;
         case 2: launch_tma<6, 2, 0>(A, (unsigned)grid, s); break;
@@ -449,10 +724,8 @@ void hk_launch_flush_deleted(const HkDev& dd, cudaStream_t s) {
     const HkDev d = dd;
     hk_parallel_for(d.nElement, s, HK_LAMBDA(long long e) {
         if (d.flag[e] != 3) return;
-        for (int r = 0; r < 48; ++r) {
-            d.stress[(long long)r * d.nEp + e] = 0.0;
-            d.strain[(long long)r * d.nEp + e] = 0.0;
-        }
+        for (int k = 0; k < 8; ++k)
+            for (int r = 0; r < 12; ++r) d.ips[hk_ip(d, r, k, e)] = 0.0;
         d.flag[e] = 0;
     });
 }
@@ -465,7 +738,7 @@ void hk_launch_triax(const HkDev& dd, cudaStream_t s) {
         const long long k = i / d.nElement;
         const long long row = k * d.nEp + e;
         double sg[6];
-        for (int c = 0; c < 6; ++c) sg[c] = d.stress[(long long)c * 8 * d.nEp + row];
+        for (int c = 0; c < 6; ++c) sg[c] = d.ips[hk_ip(d, c, (int)k, e)];
         d.triax[row] = triax_of(sg);
     });
 }
@@ -489,9 +762,9 @@ void hk_launch_element_volume(const HkDev& dd, double* V_out, cudaStream_t s) {
 
 void hk_upload_pusai(const double*) {}
 
-long long hk_element_tile() {
+long long hk_element_tile() {      // layout tile TL of the ip state = tile of the element kernel that will run
 #ifndef HK_EMU
-    return HK_TILE;
+    return element_variant() >= 10 ? HK_TILE_T : HK_TILE;
 #else
     return 32;
 #endif

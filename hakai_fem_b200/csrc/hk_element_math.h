@@ -29,6 +29,33 @@
 
 #define HK_G 0.57735026918962576451      /* 1/sqrt(3) */
 
+// Reciprocal and reciprocal square root without the IEEE slow paths: hardware seed (MUFU.RCP64H / RSQ64H,
+// ~20 good bits) + two Newton steps = full double precision to ~1 ulp, ~6 instructions and no branch, versus
+// ~25 instructions plus a divergent special-case branch for `1.0/x` and `sqrt(x)`.  Arguments here are
+// Jacobians, von Mises stresses and yield stresses: finite, normal, non-zero (zero is guarded by the caller).
+HK_HD double hk_rcp(double a) {
+#if defined(__CUDA_ARCH__)
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    x = fma(x, fma(-a, x, 1.0), x);
+    x = fma(x, fma(-a, x, 1.0), x);
+    return x;
+#else
+    return 1.0 / a;
+#endif
+}
+HK_HD double hk_rsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+    double x;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    x = fma(x * fma(-a * x, x, 1.0), 0.5, x);        // x += x*(1 - a x^2)/2
+    x = fma(x * fma(-a * x, x, 1.0), 0.5, x);
+    return x;
+#else
+    return 1.0 / sqrt(a);
+#endif
+}
+
 struct HexModes {                 // coefficients of a nodal 3-vector field, pre-scaled
     double c0[3], c1[3], c2[3];   // c_d / 1   (already * 1/8)
     double h01[3], h02[3], h12[3];// g * c_dd'
@@ -102,6 +129,7 @@ HK_HD void mode_rows(const HexModes& m, double s0, double s1, double s2, double 
 struct MatLite {                  // the per-Gauss-point scalars of a material, held in registers
     double D11, D12, D44, G3;     // Dmat entries (J2:143-159) and 3G
     int npp;
+    int fast;                     // 1: MUFU-seeded rcp/rsqrt (default); 0: IEEE division / sqrt (A/B switch)
     const double* pe;             // plastic_e[] and Hd[] tables (shared memory in the TMA kernel), touched only
     const double* hd;             // while yielding
 };
@@ -113,46 +141,52 @@ struct ElemAcc {                  // per-element accumulators over the Gauss poi
     int negj;
 };
 
-HK_HD double triax_from(double mean, double oeq) {       // J2:1010-1017
+HK_HD double triax_from(double mean, double oeq, double inv_oeq) {       // J2:1010-1017
     if (oeq < 1E-10) return 0.0;
-    return mean / oeq;
+    return mean * inv_oeq;
 }
 
-// One Gauss point: strain increment, radial return, state update, force-mode accumulation.
-//   st[0..5] stress, st[6..11] strain, st[12] eps, st[13] yield: in = old state, out = new state
-HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt, int k, double trbar,
-                         double st[14], ElemAcc& acc, bool need_triax = true) {
-    const double s0 = (k & 4) ? 1.0 : -1.0, s1 = (k & 2) ? 1.0 : -1.0, s2 = (k & 1) ? 1.0 : -1.0;
-    double R[3][3], A[3][3];
+// ---- one Gauss point, in pieces (the TMEM kernel interleaves them with tensor-memory loads) -----------------
+// geometry: adjugate columns A_r and det J at the Gauss point with signs (s0,s1,s2)
+HK_HD void gp_geometry(const HexModes& X, double s0, double s1, double s2, double A[3][3], double& det) {
+    double R[3][3];
     mode_rows(X, s0, s1, s2, R);
     cross3(R[1], R[2], A[0]);
     cross3(R[2], R[0], A[1]);
     cross3(R[0], R[1], A[2]);
-    const double det = dot3(R[0], A[0]);
-    if (det < 0) acc.negj++;
-    const double idet = 1.0 / det;
+    det = dot3(R[0], A[0]);
+}
+
+// strain increment (engineering shear) with the mean-dilatation correction
+HK_HD void gp_strain(const HexModes& U, const double A[3][3], double idet, double trbar, double s0, double s1, double s2,
+                     double de[6]) {
     double D[3][3];
     mode_rows(U, s0, s1, s2, D);
     // L[i][j] * det = sum_r D_r[i] A_r[j]
-    double de[6];
-    {
-        const double l00 = D[0][0] * A[0][0] + D[1][0] * A[1][0] + D[2][0] * A[2][0];
-        const double l11 = D[0][1] * A[0][1] + D[1][1] * A[1][1] + D[2][1] * A[2][1];
-        const double l22 = D[0][2] * A[0][2] + D[1][2] * A[1][2] + D[2][2] * A[2][2];
-        const double l01 = D[0][0] * A[0][1] + D[1][0] * A[1][1] + D[2][0] * A[2][1];
-        const double l10 = D[0][1] * A[0][0] + D[1][1] * A[1][0] + D[2][1] * A[2][0];
-        const double l12 = D[0][1] * A[0][2] + D[1][1] * A[1][2] + D[2][1] * A[2][2];
-        const double l21 = D[0][2] * A[0][1] + D[1][2] * A[1][1] + D[2][2] * A[2][1];
-        const double l02 = D[0][0] * A[0][2] + D[1][0] * A[1][2] + D[2][0] * A[2][2];
-        const double l20 = D[0][2] * A[0][0] + D[1][2] * A[1][0] + D[2][2] * A[2][0];
-        const double vol = (trbar - (l00 + l11 + l22) * idet) * (1.0 / 3.0);     // mean-dilatation correction
-        de[0] = l00 * idet + vol;
-        de[1] = l11 * idet + vol;
-        de[2] = l22 * idet + vol;
-        de[3] = (l01 + l10) * idet;
-        de[4] = (l12 + l21) * idet;
-        de[5] = (l02 + l20) * idet;
-    }
+    const double l00 = D[0][0] * A[0][0] + D[1][0] * A[1][0] + D[2][0] * A[2][0];
+    const double l11 = D[0][1] * A[0][1] + D[1][1] * A[1][1] + D[2][1] * A[2][1];
+    const double l22 = D[0][2] * A[0][2] + D[1][2] * A[1][2] + D[2][2] * A[2][2];
+    const double l01 = D[0][0] * A[0][1] + D[1][0] * A[1][1] + D[2][0] * A[2][1];
+    const double l10 = D[0][1] * A[0][0] + D[1][1] * A[1][0] + D[2][1] * A[2][0];
+    const double l12 = D[0][1] * A[0][2] + D[1][1] * A[1][2] + D[2][1] * A[2][2];
+    const double l21 = D[0][2] * A[0][1] + D[1][2] * A[1][1] + D[2][2] * A[2][1];
+    const double l02 = D[0][0] * A[0][2] + D[1][0] * A[1][2] + D[2][0] * A[2][2];
+    const double l20 = D[0][2] * A[0][0] + D[1][2] * A[1][0] + D[2][2] * A[2][0];
+    const double vol = (trbar - (l00 + l11 + l22) * idet) * (1.0 / 3.0);     // mean-dilatation correction
+    de[0] = l00 * idet + vol;
+    de[1] = l11 * idet + vol;
+    de[2] = l22 * idet + vol;
+    de[3] = (l01 + l10) * idet;
+    de[4] = (l12 + l21) * idet;
+    de[5] = (l02 + l20) * idet;
+}
+
+struct GpStress {                 // deviatoric stress t0,t1,t2 (normal) + shear, mean stress, eps, triaxiality
+    double t0, t1, t2, s3, s4, s5, mean, ep, tx;
+};
+
+// elastic predictor, J2 radial return, state update.  st[0..5] stress, st[6..11] strain, st[12] eps, st[13] yield
+HK_HD void gp_stress(const MatLite& Mt, double st[14], const double de[6], bool need_triax, GpStress& o) {
     // trial stress = old + D*de  (J2:1205-1220)
     double s[6];
     s[0] = st[0] + (Mt.D11 * de[0] + Mt.D12 * de[1] + Mt.D12 * de[2]);
@@ -163,7 +197,16 @@ HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt
     s[5] = st[5] + Mt.D44 * de[5];
     const double mean = (s[0] + s[1] + s[2]) * (1.0 / 3.0);
     double t0 = s[0] - mean, t1 = s[1] - mean, t2 = s[2] - mean;
-    const double mises = sqrt(1.5 * (t0 * t0 + t1 * t1 + t2 * t2 + 2.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5])));
+    const double j2x = 1.5 * (t0 * t0 + t1 * t1 + t2 * t2 + 2.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]));
+    double inv_oeq, mises;
+    if (Mt.fast) {
+        inv_oeq = hk_rsqrt(fmax(j2x, 1e-300));              // 1/sqrt(3 J2); j2x == 0 (unstressed) -> mises = 0
+        mises = j2x * inv_oeq;
+        mises = fma(0.5 * inv_oeq, fma(-mises, mises, j2x), mises);     // one Newton step on the square root itself
+    } else {
+        mises = sqrt(j2x);
+        inv_oeq = 1.0 / fmax(mises, 1e-300);
+    }
     double oeq = mises;            // sqrt(3 J2) of the FINAL stress: the trial value, or the new yield stress
     double ep = st[12];
     if (Mt.npp > 0) {              // J2 radial return, J2:1227-1285
@@ -175,9 +218,9 @@ HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt
             int p_index = 0;
             for (int j = 1; j + 1 < Mt.npp; ++j) p_index += (ep > Mt.pe[j]) ? 1 : 0;
             const double H = Mt.hd[p_index];
-            const double d_ep = (mises - y) / (Mt.G3 + H);
+            const double d_ep = Mt.fast ? (mises - y) * hk_rcp(Mt.G3 + H) : (mises - y) / (Mt.G3 + H);
             const double ynew = y + H * d_ep;
-            const double fac = ynew / mises;
+            const double fac = ynew * inv_oeq;
             t0 *= fac; t1 *= fac; t2 *= fac;
             s[3] *= fac; s[4] *= fac; s[5] *= fac;
             s[0] = t0 + mean; s[1] = t1 + mean; s[2] = t2 + mean;
@@ -185,6 +228,7 @@ HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt
             st[12] = ep;
             st[13] = ynew;
             oeq = ynew;
+            if (need_triax) inv_oeq = Mt.fast ? hk_rcp(ynew) : 1.0 / ynew;
         }
     }
 #pragma unroll
@@ -192,16 +236,38 @@ HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt
         st[6 + c] += de[c];
         st[c] = s[c];
     }
-    // force modes with the deviatoric stress; the mean part is added once per element (pbar * G)
-    acc.pdet += mean * det;
+    o.t0 = t0; o.t1 = t1; o.t2 = t2; o.s3 = s[3]; o.s4 = s[4]; o.s5 = s[5];
+    o.mean = mean; o.ep = ep;
+    // triaxiality feeds only the ductile-damage criterion and the output frames: skipped otherwise
+    o.tx = need_triax ? triax_from(mean, oeq, inv_oeq) : 0.0;
+}
+
+// T_r = s_dev * A_r  (the mean part is added once per element as pbar * G)
+HK_HD void gp_T(const GpStress& g, const double Ar[3], double T[3]) {
+    T[0] = g.t0 * Ar[0] + g.s3 * Ar[1] + g.s5 * Ar[2];
+    T[1] = g.s3 * Ar[0] + g.t1 * Ar[1] + g.s4 * Ar[2];
+    T[2] = g.s5 * Ar[0] + g.s4 * Ar[1] + g.t2 * Ar[2];
+}
+
+// One Gauss point: strain increment, radial return, state update, force-mode accumulation.
+HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt, int k, double trbar,
+                         double st[14], ElemAcc& acc, bool need_triax = true) {
+    const double s0 = (k & 4) ? 1.0 : -1.0, s1 = (k & 2) ? 1.0 : -1.0, s2 = (k & 1) ? 1.0 : -1.0;
+    double A[3][3], det;
+    gp_geometry(X, s0, s1, s2, A, det);
+    if (det < 0) acc.negj++;
+    const double idet = Mt.fast ? hk_rcp(det) : 1.0 / det;
+    double de[6];
+    gp_strain(U, A, idet, trbar, s0, s1, s2, de);
+    GpStress g;
+    gp_stress(Mt, st, de, need_triax, g);
+    acc.pdet += g.mean * det;
     const double sa[3] = {s1, s0, s0};        // sign of the lower / higher "other" direction for r = 0,1,2
     const double sb[3] = {s2, s2, s1};
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const double T0 = t0 * A[r][0] + s[3] * A[r][1] + s[5] * A[r][2];
-        const double T1 = s[3] * A[r][0] + t1 * A[r][1] + s[4] * A[r][2];
-        const double T2 = s[5] * A[r][0] + s[4] * A[r][1] + t2 * A[r][2];
-        const double T[3] = {T0, T1, T2};
+        double T[3];
+        gp_T(g, A[r], T);
         const double sab = sa[r] * sb[r];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -211,11 +277,9 @@ HK_HD double gauss_point(const HexModes& X, const HexModes& U, const MatLite& Mt
             acc.M[r][3][c] += sab * T[c];
         }
     }
-    // triaxiality feeds only the ductile-damage criterion and the output frames: skipped otherwise
-    const double tx = need_triax ? triax_from(mean, oeq) : 0.0;
-    acc.v_e += ep;
-    acc.t_e += tx;
-    return tx;
+    acc.v_e += g.ep;
+    acc.t_e += g.tx;
+    return g.tx;
 }
 
 // nodal forces from the accumulated modes:  f = adjoint( M + pbar * G )

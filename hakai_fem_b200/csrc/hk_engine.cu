@@ -704,16 +704,11 @@ int HKAPI(finalize)(hk_engine* e) {
         if ((rc = upload(e, d.flag, fl))) return rc;
         if ((rc = upload(e, d.mat, mt))) return rc;
     }
-    if ((rc = dalloc(e, &d.stress, (size_t)48 * nEp))) return rc;
-    if ((rc = dalloc(e, &d.strain, (size_t)48 * nEp))) return rc;
-    if ((rc = dalloc(e, &d.eps, (size_t)8 * nEp))) return rc;
-    if ((rc = dalloc(e, &d.yield, (size_t)8 * nEp))) return rc;
+    d.TL = (int)tile;
+    if ((rc = dalloc(e, &d.ips, (size_t)112 * nEp))) return rc;
     if ((rc = dalloc(e, &d.triax, (size_t)8 * nEp))) return rc;
     if ((rc = dalloc(e, &d.Qe, (size_t)24 * nEp))) return rc;
-    CK(hkp::dev_memset(d.stress, 0, sizeof(double) * 48 * nEp, e->stream));
-    CK(hkp::dev_memset(d.strain, 0, sizeof(double) * 48 * nEp, e->stream));
-    CK(hkp::dev_memset(d.eps, 0, sizeof(double) * 8 * nEp, e->stream));
-    CK(hkp::dev_memset(d.yield, 0, sizeof(double) * 8 * nEp, e->stream));
+    CK(hkp::dev_memset(d.ips, 0, sizeof(double) * 112 * nEp, e->stream));
     CK(hkp::dev_memset(d.triax, 0, sizeof(double) * 8 * nEp, e->stream));
     CK(hkp::dev_memset(d.Qe, 0, sizeof(double) * 24 * nEp, e->stream));
     {   // integ_yield_stress = plastic[1,1] of the element's material (J2:456-465)
@@ -721,7 +716,7 @@ int HKAPI(finalize)(hk_engine* e) {
         hk_parallel_for(nE * 8, e->stream, HK_LAMBDA(long long i) {
             const long long el = i % dd.nElement, k = i / dd.nElement;
             const HkMaterialDev& M = dd.mats[dd.mat[el]];
-            if (M.npp > 0) dd.yield[k * dd.nEp + el] = M.plastic_s[0];
+            if (M.npp > 0) dd.ips[hk_ip(dd, 13, (int)k, el)] = M.plastic_s[0];
         });
     }
     d.del_cap = (int)nE;
@@ -877,19 +872,20 @@ static int ensure_staging(hk_engine* e, size_t doubles) {
 }
 static const long long CHUNK_E = 1 << 18;   // elements per transposed chunk (<= 100 MB staging)
 
-static int download_ip(hk_engine* e, const double* soa, double* host, int ncomp) {
+static int download_ip(hk_engine* e, int row0, double* host, int ncomp) {   // row0 < 0: triax
     if (!host) return 0;
     const long long nE = e->nElement;
     int rc = ensure_staging(e, (size_t)std::min<long long>(CHUNK_E, nE) * 8 * ncomp);
     if (rc) return rc;
     for (long long e0 = 0; e0 < nE; e0 += CHUNK_E) {
         const long long ne = std::min<long long>(CHUNK_E, nE - e0);
-        hk_launch_ip_to_aos(soa, e->staging, ncomp, e0, ne, e->d.nEp, e->stream);
+        if (row0 < 0) hk_launch_triax_to_aos(e->d, e->staging, e0, ne, e->stream);
+        else hk_launch_ip_to_aos(e->d, e->staging, row0, ncomp, e0, ne, e->stream);
         CK(hkp::d2h(host + e0 * 8 * ncomp, e->staging, (size_t)ne * 8 * ncomp * sizeof(double), e->stream));
     }
     return 0;
 }
-static int upload_ip(hk_engine* e, double* soa, const double* host, int ncomp) {
+static int upload_ip(hk_engine* e, int row0, const double* host, int ncomp) {
     if (!host) return 0;
     const long long nE = e->nElement;
     int rc = ensure_staging(e, (size_t)std::min<long long>(CHUNK_E, nE) * 8 * ncomp);
@@ -897,7 +893,7 @@ static int upload_ip(hk_engine* e, double* soa, const double* host, int ncomp) {
     for (long long e0 = 0; e0 < nE; e0 += CHUNK_E) {
         const long long ne = std::min<long long>(CHUNK_E, nE - e0);
         CK(hkp::h2d(e->staging, host + e0 * 8 * ncomp, (size_t)ne * 8 * ncomp * sizeof(double), e->stream));
-        hk_launch_ip_to_soa(e->staging, soa, ncomp, e0, ne, e->d.nEp, e->stream);
+        hk_launch_ip_to_dev(e->staging, e->d, row0, ncomp, e0, ne, e->stream);
         CK(hkp::sync(e->stream));
     }
     return 0;
@@ -914,12 +910,12 @@ int HKAPI(download)(hk_engine* e, double* disp, double* velo, double* integ_stre
         if (!e->velo_current) { hk_launch_velo_from_rec(d, e->prm.d_time, e->stream); e->velo_current = true; }
         CK(hkp::d2h(velo, d.velo, fnb, e->stream));
     }
-    if ((rc = download_ip(e, d.stress, integ_stress, 6))) return rc;
-    if ((rc = download_ip(e, d.strain, integ_strain, 6))) return rc;
-    if ((rc = download_ip(e, d.eps, integ_eq_plastic_strain, 1))) return rc;
+    if ((rc = download_ip(e, 0, integ_stress, 6))) return rc;
+    if ((rc = download_ip(e, 6, integ_strain, 6))) return rc;
+    if ((rc = download_ip(e, 12, integ_eq_plastic_strain, 1))) return rc;
     if (integ_triax_stress) {
         if (!e->triax_current) { hk_launch_triax(d, e->stream); e->triax_current = true; }
-        if ((rc = download_ip(e, d.triax, integ_triax_stress, 1))) return rc;
+        if ((rc = download_ip(e, -1, integ_triax_stress, 1))) return rc;
     }
     if (element_flag) {
         std::vector<unsigned char> fl(e->nElement);
@@ -962,7 +958,7 @@ int HKAPI(download_ex)(hk_engine* e, double* disp_pre, double* Q, double* extern
         for (int64_t n = 0; n < nN; ++n)
             for (int c = 0; c < 3; ++c) position[3 * n + c] = rec[6 * n + c];
     }
-    if ((rc = download_ip(e, d.yield, integ_yield_stress, 1))) return rc;
+    if ((rc = download_ip(e, 13, integ_yield_stress, 1))) return rc;
     if (elementVolume) {
         if ((rc = ensure_staging(e, (size_t)e->nElement))) return rc;
         hk_launch_element_volume(d, e->staging, e->stream);
@@ -992,10 +988,10 @@ int HKAPI(upload_state)(hk_engine* e, const double* disp, const double* disp_pre
     if (disp_pre) CK(hkp::h2d(d.u_pre, disp_pre, fnb, e->stream));
     if (velo) { CK(hkp::h2d(d.velo, velo, fnb, e->stream)); e->velo_current = true; }
     if (Q) { CK(hkp::h2d(d.Q0, Q, fnb, e->stream)); e->use_Q0 = 1; }
-    if ((rc = upload_ip(e, d.stress, integ_stress, 6))) return rc;
-    if ((rc = upload_ip(e, d.strain, integ_strain, 6))) return rc;
-    if ((rc = upload_ip(e, d.eps, integ_eq_plastic_strain, 1))) return rc;
-    if ((rc = upload_ip(e, d.yield, integ_yield_stress, 1))) return rc;
+    if ((rc = upload_ip(e, 0, integ_stress, 6))) return rc;
+    if ((rc = upload_ip(e, 6, integ_strain, 6))) return rc;
+    if ((rc = upload_ip(e, 12, integ_eq_plastic_strain, 1))) return rc;
+    if ((rc = upload_ip(e, 13, integ_yield_stress, 1))) return rc;
     if (integ_stress) e->triax_current = false;
     if (element_flag) {
         std::vector<unsigned char> fl(e->nElement);

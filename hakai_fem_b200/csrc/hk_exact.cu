@@ -545,25 +545,32 @@ void hk_launch_external_force(const HkDev& dd, double* F_out, int lsb_exp, int c
     });
 }
 
-// AoS chunk (reference layout, element range [e0,e0+ne)) <-> SoA rows.  aos index: (ip_local*ncomp + c).
-void hk_launch_ip_to_soa(const double* aos, double* soa, int ncomp, long long e0, long long ne, long long nEp,
-                         cudaStream_t s) {
+// reference layout (ncomp, nip) chunk for elements [e0,e0+ne)  <->  rows [row0,row0+ncomp) of the blocked ip state
+void hk_launch_ip_to_dev(const double* aos, const HkDev& dd, int row0, int ncomp, long long e0, long long ne, cudaStream_t s) {
+    const HkDev d = dd;
     hk_parallel_for(ne * 8 * ncomp, s, HK_LAMBDA(long long i) {
-        // thread index runs along the SoA rows so the writes coalesce
-        long long el = i % ne;
+        long long el = i % ne;           // thread index runs along elements so the device-side accesses coalesce
         long long r = i / ne;            // r = c*8 + k
         int k = (int)(r % 8);
         int c = (int)(r / 8);
-        soa[(long long)(c * 8 + k) * nEp + e0 + el] = aos[(el * 8 + k) * ncomp + c];
+        d.ips[hk_ip(d, row0 + c, k, e0 + el)] = aos[(el * 8 + k) * ncomp + c];
     });
 }
-void hk_launch_ip_to_aos(const double* soa, double* aos, int ncomp, long long e0, long long ne, long long nEp,
-                         cudaStream_t s) {
+void hk_launch_ip_to_aos(const HkDev& dd, double* aos, int row0, int ncomp, long long e0, long long ne, cudaStream_t s) {
+    const HkDev d = dd;
     hk_parallel_for(ne * 8 * ncomp, s, HK_LAMBDA(long long i) {
         long long el = i % ne;
         long long r = i / ne;
         int k = (int)(r % 8);
         int c = (int)(r / 8);
-        aos[(el * 8 + k) * ncomp + c] = soa[(long long)(c * 8 + k) * nEp + e0 + el];
+        aos[(el * 8 + k) * ncomp + c] = d.ips[hk_ip(d, row0 + c, k, e0 + el)];
+    });
+}
+void hk_launch_triax_to_aos(const HkDev& dd, double* aos, long long e0, long long ne, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(ne * 8, s, HK_LAMBDA(long long i) {
+        long long el = i % ne;
+        int k = (int)(i / ne);
+        aos[el * 8 + k] = d.triax[(long long)k * d.nEp + e0 + el];
     });
 }
