@@ -244,7 +244,9 @@ def main():
     tr_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tr_path):      # dram__bytes_read+write per element from the committed ncu --set full capture
         traffic = json.load(open(tr_path))["element_kernel_dram_bytes_per_element"] * nE
-    kname = "hk_element_simple_kernel" if os.environ.get("HK_ELEMENT_KERNEL") == "simple" else "hk_element_tma_kernel"
+    variant = int(os.environ.get("HK_ELEMENT_VARIANT", "11"))
+    kname = ("hk_element_simple_kernel" if os.environ.get("HK_ELEMENT_KERNEL") == "simple"
+             else "hk_element_tmem_kernel" if variant >= 10 else "hk_element_tma_kernel")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_ELEMENT * nE, "avg_launch_ms": el_ms,
