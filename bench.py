@@ -116,7 +116,7 @@ def cpu_oracle_rate(sample_workload, warmup, steps, threads=None):
     return nE * steps / dt, nE, dt
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's CPU algorithm (oracle port; Julia is not installed) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,10 +136,18 @@ def run_reference(args):
                                    f"{cores} threads"},
         "e2e": {"value": rate, "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # libraries (NCCL, torchrun) print to stdout; the contract is ONE JSON line there, so everything else goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -154,7 +162,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import torch
@@ -312,7 +320,7 @@ def main():
                        "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -787,7 +787,7 @@ int HKAPI(finalize)(hk_engine* e) {
 
 // enqueue the kernels of steps t_first .. t_first+n_steps-1 on the engine's stream (no host synchronisation
 // unless contact surfaces may change: exposed faces must be in place before the next contact pass)
-static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps) {
+static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end) {
     const HkDev& d = e->d;
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
@@ -813,7 +813,7 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps) {
         prof_end(e);
         e->use_Q0 = 0;
         prof_begin(e, 2);
-        hk_launch_element(d, t, (t == t_first + n_steps - 1) ? 1 : 0, e->stream);
+        hk_launch_element(d, t, (frame_at_end && t == t_first + n_steps - 1) ? 1 : 0, e->stream);
         prof_end(e);
         e->n_launch += 2;
         if (e->any_ductile) { hk_launch_flush_deleted(d, e->stream); e->n_launch += 1; }
@@ -827,19 +827,25 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps) {
     }
     if (n_steps > 0) {
         e->velo_current = contact_on;
-        e->triax_current = true;
+        e->triax_current = frame_at_end;      // otherwise hk_download recomputes it from the current stress
     }
     return HK_OK;
 }
 
-int HKAPI(step_enqueue)(hk_engine* e, int64_t t_first, int64_t n_steps) {
+static int step_enqueue_impl(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     if (n_steps < 0 || t_first < 0 || t_first + n_steps >= (1ll << 31)) return fail(e, HK_ERR_ARG, "bad step range");
     if (!e->halo.empty() && n_steps > 1) return fail(e, HK_ERR_ARG, "with halos, exchange and step one step at a time");
-    int rc = enqueue_steps(e, t_first, n_steps);
+    int rc = enqueue_steps(e, t_first, n_steps, frame_at_end);
     if (rc) return rc;
     CK(hkp::last_error());
     return HK_OK;
+}
+
+// asynchronous form: no output frame is implied, so integ_triax_stress is not stored (hk_download derives it from
+// the stress when asked)
+int HKAPI(step_enqueue)(hk_engine* e, int64_t t_first, int64_t n_steps) {
+    return step_enqueue_impl(e, t_first, n_steps, false);
 }
 
 int HKAPI(sync)(hk_engine* e, int64_t* n_deleted_out) {
@@ -854,8 +860,9 @@ int HKAPI(sync)(hk_engine* e, int64_t* n_deleted_out) {
     return HK_OK;
 }
 
+// synchronous form: the caller typically writes a frame after it, so the last step stores integ_triax_stress
 int HKAPI(step)(hk_engine* e, int64_t t_first, int64_t n_steps, int64_t* n_deleted_out) {
-    int rc = HKAPI(step_enqueue)(e, t_first, n_steps);
+    int rc = step_enqueue_impl(e, t_first, n_steps, true);
     if (rc) return rc;
     return HKAPI(sync)(e, n_deleted_out);
 }
