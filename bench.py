@@ -223,6 +223,8 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
+    print(f"[rank {rank}] host enqueue time of the timed steps: {getattr(runner, 'last_enqueue_s', 0.0) * 1e3:.1f} ms "
+          f"of {ms:.1f} ms", file=sys.stderr)
     clocks = sampler.stop()
     launches = int(eng.counters()[3]) - l0
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -241,6 +243,12 @@ def main():
     eng.profile(False)
     el_ms = kms[2] / max(kn[2], 1)
     nd_ms = kms[1] / max(kn[1], 1)
+    per_rank = None
+    if world > 1:          # kernel times of every rank: the exchange makes the slowest GPU set the pace
+        tk = torch.tensor([el_ms, nd_ms * max(kn[1], 1) / max(kn[2], 1)], dtype=torch.float64, device="cuda")
+        allk = [torch.zeros_like(tk) for _ in range(world)]
+        dist.all_gather(allk, tk)
+        per_rank = [{"rank": i, "element_ms": float(a[0]), "nodal_ms_per_step": float(a[1])} for i, a in enumerate(allk)]
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
@@ -317,7 +325,7 @@ def main():
                        "deck": f"{deck.nx}x{deck.ny}x{deck.nz} hex8, steel elastoplastic, uniform stretch "
                                f"{deck.strain_per_step:g}/step, jitter {deck.jitter}",
                        "l2": "state >> L2 (inputs larger than L2), no flush", "parallelism": f"z-slab x{world}",
-                       "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step},
+                       "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step, "per_rank_kernel_ms": per_rank},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         emit(line)

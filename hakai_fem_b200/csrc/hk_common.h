@@ -114,7 +114,8 @@ struct HkContactParams {
 
 // launchers (hk_exact.cu: built with -fmad=false; hk_element.cu: FMA allowed)
 void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double dt2, double dt2p,
-                     int lsb_exp, int contact_on, int use_Q0, cudaStream_t s);
+                     int lsb_exp, int contact_on, int use_Q0, int mode, const int* list, long long n_list,
+                     cudaStream_t s);
 void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s);
 void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s);
 void hk_launch_velo_from_rec(const HkDev& d, double d_time, cudaStream_t s);

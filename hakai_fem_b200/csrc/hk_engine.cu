@@ -90,6 +90,8 @@ struct hk_engine {
     std::vector<PairH> pairs;
     std::vector<HaloNbr> halo;
     int n_halo_nodes = 0;
+    int* d_halo_list = nullptr;    // node id of every halo slot (nodal kernel mode 2)
+    int64_t begun_t = -1;          // step opened by hk_step_begin
     // special nodes (host mirror)
     std::vector<int> spec_idx_h;
     std::vector<HkSpecialNode> spec_h;
@@ -773,6 +775,12 @@ int HKAPI(finalize)(hk_engine* e) {
             if ((rc = upload(e, h.d_nodes, h.nodes))) return rc;
             if ((rc = upload(e, h.d_slots, h.slots))) return rc;
         }
+        {
+            std::vector<int> list(e->n_halo_nodes, 0);
+            for (int64_t nd = 0; nd < nN; ++nd) if (slot_of[nd] >= 0) list[slot_of[nd]] = (int)nd;
+            if ((rc = dalloc(e, &e->d_halo_list, list.size()))) return rc;
+            if ((rc = upload(e, e->d_halo_list, list))) return rc;
+        }
         if ((rc = dalloc(e, &d.halo_recv, (size_t)3 * e->n_halo_nodes))) return rc;
         CK(hkp::dev_memset(d.halo_recv, 0, sizeof(double) * 3 * e->n_halo_nodes, e->stream));
     }
@@ -786,16 +794,26 @@ int HKAPI(finalize)(hk_engine* e) {
 }
 
 // enqueue the kernels of steps t_first .. t_first+n_steps-1 on the engine's stream (no host synchronisation
-// unless contact surfaces may change: exposed faces must be in place before the next contact pass)
-static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end) {
+// unless contact surfaces may change: exposed faces must be in place before the next contact pass).
+// phase 0: whole step; phase 1: everything that does not need the halo (contact + nodal update of non-interface
+// nodes); phase 2: the rest (received partials, interface nodes, element kernel).
+static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end, int phase) {
     const HkDev& d = e->d;
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
-        if (contact_on) {
+        if (phase != 2 && contact_on) {
             prof_begin(e, 0);
             CK(hkp::dev_memset(d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
             for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 4; }
             prof_end(e);
+        }
+        if (phase == 1) {
+            prof_begin(e, 1);
+            hk_launch_nodal(d, (double)t * e->prm.d_time, e->prm.d_time, e->dt2, e->dt2p, e->cp.lsb_exp,
+                            contact_on ? 1 : 0, e->use_Q0, 1, nullptr, 0, e->stream);
+            prof_end(e);
+            e->n_launch += 1;
+            continue;
         }
         if (!e->halo.empty()) {          // received partial forces -> halo_recv (fixed neighbour order)
             prof_begin(e, 3);
@@ -808,8 +826,12 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
             prof_end(e);
         }
         prof_begin(e, 1);
-        hk_launch_nodal(d, (double)t * e->prm.d_time, e->prm.d_time, e->dt2, e->dt2p, e->cp.lsb_exp, contact_on ? 1 : 0,
-                        e->use_Q0, e->stream);
+        if (phase == 2)
+            hk_launch_nodal(d, (double)t * e->prm.d_time, e->prm.d_time, e->dt2, e->dt2p, e->cp.lsb_exp,
+                            contact_on ? 1 : 0, e->use_Q0, 2, e->d_halo_list, e->n_halo_nodes, e->stream);
+        else
+            hk_launch_nodal(d, (double)t * e->prm.d_time, e->prm.d_time, e->dt2, e->dt2p, e->cp.lsb_exp,
+                            contact_on ? 1 : 0, e->use_Q0, 0, nullptr, 0, e->stream);
         prof_end(e);
         e->use_Q0 = 0;
         prof_begin(e, 2);
@@ -825,7 +847,7 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
             if (!fresh.empty()) { rc = update_surfaces(e, fresh); if (rc) return rc; }
         }
     }
-    if (n_steps > 0) {
+    if (n_steps > 0 && phase != 1) {
         e->velo_current = contact_on;
         e->triax_current = frame_at_end;      // otherwise hk_download recomputes it from the current stress
     }
@@ -836,7 +858,7 @@ static int step_enqueue_impl(hk_engine* e, int64_t t_first, int64_t n_steps, boo
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     if (n_steps < 0 || t_first < 0 || t_first + n_steps >= (1ll << 31)) return fail(e, HK_ERR_ARG, "bad step range");
     if (!e->halo.empty() && n_steps > 1) return fail(e, HK_ERR_ARG, "with halos, exchange and step one step at a time");
-    int rc = enqueue_steps(e, t_first, n_steps, frame_at_end);
+    int rc = enqueue_steps(e, t_first, n_steps, frame_at_end, 0);
     if (rc) return rc;
     CK(hkp::last_error());
     return HK_OK;
@@ -846,6 +868,29 @@ static int step_enqueue_impl(hk_engine* e, int64_t t_first, int64_t n_steps, boo
 // the stress when asked)
 int HKAPI(step_enqueue)(hk_engine* e, int64_t t_first, int64_t n_steps) {
     return step_enqueue_impl(e, t_first, n_steps, false);
+}
+
+// split step for the multi-GPU driver: hk_step_begin(t) runs what does not depend on the halo (so it overlaps the
+// NCCL exchange), hk_step_finish(t) the rest.  hk_step_begin + hk_step_finish == hk_step_enqueue(t, 1).
+int HKAPI(step_begin)(hk_engine* e, int64_t t) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (e->begun_t >= 0) return fail(e, HK_ERR_STATE, "hk_step_begin called twice without hk_step_finish");
+    if (e->use_Q0) return fail(e, HK_ERR_STATE, "uploaded Q cannot be combined with the split step");
+    int rc = enqueue_steps(e, t, 1, false, 1);
+    if (rc) return rc;
+    e->begun_t = t;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(step_finish)(hk_engine* e, int64_t t) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (e->begun_t != t) return fail(e, HK_ERR_STATE, "hk_step_finish without matching hk_step_begin");
+    e->begun_t = -1;
+    int rc = enqueue_steps(e, t, 1, false, 2);
+    if (rc) return rc;
+    CK(hkp::last_error());
+    return HK_OK;
 }
 
 int HKAPI(sync)(hk_engine* e, int64_t* n_deleted_out) {

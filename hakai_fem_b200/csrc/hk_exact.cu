@@ -89,6 +89,9 @@ struct NodalArgs {
     HkDev d;
     double current_time, d_time, dt2, dt2p;
     int lsb_exp, contact_on, use_Q0;
+    int mode;                 // 0: every node; 1: all but the halo (interface) nodes; 2: only the nodes in `list`
+    const int* list;
+    long long n_list;
 };
 
 HK_HD double eval_amp(const HkDev& d, int amp_id, double current_time) {   // J2:586-600
@@ -114,6 +117,7 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) ent[w] = (w < d.ell_width) ? HK_LDG(&d.ell[(long long)w * d.nNode + n]) : -1;
     const int si = HK_LDG(&d.spec_idx[n]);
+    if (A.mode == 1 && si >= 0 && d.spec[si].halo_slot >= 0) return;    // updated after the halo exchange (mode 2)
     const double M = HK_LDG(&d.mass[n]);
     double u[3], up[3], X[3];
 #pragma unroll
@@ -206,18 +210,24 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
 #ifndef HK_EMU
 __global__ void __launch_bounds__(256) hk_nodal_kernel(NodalArgs A) {
     long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (n < A.d.nNode) nodal_body(A, n);
+    if (A.mode == 2) {
+        if (n < A.n_list) nodal_body(A, A.list[n]);
+    } else if (n < A.d.nNode) {
+        nodal_body(A, n);
+    }
 }
 #endif
 
 void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double dt2, double dt2p, int lsb_exp,
-                     int contact_on, int use_Q0, cudaStream_t s) {
-    NodalArgs A{d, current_time, d_time, dt2, dt2p, lsb_exp, contact_on, use_Q0};
+                     int contact_on, int use_Q0, int mode, const int* list, long long n_list, cudaStream_t s) {
+    NodalArgs A{d, current_time, d_time, dt2, dt2p, lsb_exp, contact_on, use_Q0, mode, list, n_list};
+    const long long n = mode == 2 ? n_list : d.nNode;
+    if (n <= 0) return;
 #ifndef HK_EMU
     const int block = 256;
-    hk_nodal_kernel<<<(unsigned)((d.nNode + block - 1) / block), block, 0, s>>>(A);
+    hk_nodal_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(A);
 #else
-    for (long long n = 0; n < d.nNode; ++n) nodal_body(A, n);
+    for (long long i = 0; i < n; ++i) nodal_body(A, mode == 2 ? (long long)list[i] : i);
 #endif
 }
 

@@ -40,7 +40,7 @@ EXPORTS = [
     "default_params", "create", "destroy", "last_error", "set_mesh", "add_material", "add_bc", "add_ic",
     "add_instance", "add_contact_pair", "finalize", "step", "download", "download_ex", "upload_state",
     "deleted_ids", "contact_pair_info", "counters", "profile", "profile_read", "set_stream",
-    "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync",
+    "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
 ]
 
 
@@ -175,6 +175,12 @@ class EngineBase:
 
     def step_enqueue(self, t_first: int, n_steps: int = 1):
         self._chk(self._fn("step_enqueue")(self._h, c_i64(t_first), c_i64(n_steps)))
+
+    def step_begin(self, t: int):
+        self._chk(self._fn("step_begin")(self._h, c_i64(t)))
+
+    def step_finish(self, t: int):
+        self._chk(self._fn("step_finish")(self._h, c_i64(t)))
 
     def sync(self) -> int:
         nd = c_i64(0)

@@ -191,6 +191,11 @@ int hk_set_stream(hk_engine* e, void* cuda_stream);
 int hk_set_halo(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr, const int64_t* nodes);
 int hk_halo_bind(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_dev);
 int hk_halo_pack(hk_engine* e);
+/* Split form of hk_step_enqueue(e, t, 1) that overlaps the exchange with compute:
+ *     hk_halo_pack -> start send/recv -> hk_step_begin(t) [contact, nodal update of all non-interface nodes]
+ *                  -> wait send/recv  -> hk_step_finish(t) [add partials, interface nodes, element kernel] */
+int hk_step_begin(hk_engine* e, int64_t t);
+int hk_step_finish(hk_engine* e, int64_t t);
 
 #ifdef __cplusplus
 }

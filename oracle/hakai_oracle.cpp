@@ -1019,5 +1019,7 @@ int hko_set_stream(hk_engine*, void*) { return HK_OK; }
 int hko_set_halo(hk_engine* e, int64_t, const int64_t*, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_halo_bind(hk_engine* e, int64_t, void*, void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_halo_pack(hk_engine* e) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_step_begin(hk_engine* e, int64_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_step_finish(hk_engine* e, int64_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 
 }  // extern "C"
