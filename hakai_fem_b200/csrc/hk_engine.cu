@@ -875,7 +875,6 @@ int HKAPI(step_enqueue)(hk_engine* e, int64_t t_first, int64_t n_steps) {
 int HKAPI(step_begin)(hk_engine* e, int64_t t) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     if (e->begun_t >= 0) return fail(e, HK_ERR_STATE, "hk_step_begin called twice without hk_step_finish");
-    if (e->use_Q0) return fail(e, HK_ERR_STATE, "uploaded Q cannot be combined with the split step");
     int rc = enqueue_steps(e, t, 1, false, 1);
     if (rc) return rc;
     e->begun_t = t;

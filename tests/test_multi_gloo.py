@@ -114,3 +114,50 @@ def test_slab_deck_matches_global_deck():
         gm.coordmat[:, l2g - 1] = coord
     gm.PART[0].coordmat = gm.coordmat
     _compare(msgs, prepare(gm))
+
+
+def _worker_upload(rank, world, port, q):
+    """Split step after hk_upload_state(Q=...): the uploaded local partial force + the neighbour's halo partial."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.model_setup import prepare
+        from hakai_fem_b200.multi import slab_deck, SlabRunner
+        from hakai_fem_b200.mesh import StretchDeck
+        from tests.emu.emu_engine import EmuEngine
+        deck = StretchDeck(3, 3, 3, jitter=0.05, strain_per_step=5e-4)
+        outs = []
+        for mode in ("plain", "reupload"):
+            local, nbrs, halos = slab_deck(deck, rank, world)
+            run = SlabRunner(EmuEngine, prepare(local.build_model()), nbrs, halos, "cpu", sum_mass=True)
+            run.run(1, 10)
+            if mode == "reupload":                       # download everything, upload it again, continue
+                d = run.engine.download()
+                ex = run.engine.download_ex(fields=("disp_pre", "Q", "integ_yield_stress"))
+                run.engine.upload_state(disp=d["disp"], disp_pre=ex["disp_pre"], velo=d["velo"], Q=ex["Q"],
+                                        integ_stress=d["integ_stress"], integ_strain=d["integ_strain"],
+                                        integ_eq_plastic_strain=d["integ_eq_plastic_strain"],
+                                        integ_yield_stress=ex["integ_yield_stress"])
+            run.run(11, 10)
+            outs.append(run.engine.download())
+        same = all(np.array_equal(np.asarray(outs[0][k]), np.asarray(outs[1][k])) for k in ("disp", "integ_stress", "integ_eq_plastic_strain"))
+        q.put((rank, same))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_upload_state_then_split_step_is_transparent():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_upload, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
