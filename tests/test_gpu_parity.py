@@ -52,3 +52,11 @@ def test_bitwise_reproducible():
         g.close()
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize("name,n_steps,expect_deleted", [("bullet_impact", 3000, 13), ("metal_cutting", 3000, 30),
+                                                          ("charpy", 1500, 0), ("car_crash_n2k", 1500, 0)])
+def test_reference_deck(name, n_steps, expect_deleted):
+    """The reference's own example decks through the CUDA engine vs the oracle (see tests/test_reference_decks.py)."""
+    from .test_reference_decks import run_deck
+    run_deck(Engine, name, n_steps, expect_deleted)

@@ -105,3 +105,61 @@ def assert_states_close(a, b, tol, keys=None, what="", floors=None):
 
 def make_pair(setup, engine_cls, oracle_cls, **params):
     return configure_engine(oracle_cls, setup, **params), configure_engine(engine_cls, setup, **params)
+
+
+# ---- reference example decks as fixtures (scripts/make_deck_fixtures.py) ------------------------------------
+DECK_FILES = {
+    "bullet_impact": "HAKAI-v0.0.0/input/bullet-impact.inp",
+    "metal_cutting": "HAKAI-v0.0.0/input/metal-cutting.inp",
+    "charpy": "HAKAI-v0.0.1/input/Charpy-test-v0.0.1.inp",
+    "projectile": "HAKAI-v0.0.1/input/projectile-impact-d1mm.inp",
+    "car_crash_n2k": "HAKAI-v0.0.2/input/car-crash-N2k.inp",
+    "crash_tube": "HAKAI-v0.0.1/input/crash-tube-80-350-solid.inp",
+    "tensile_test": "HAKAI-v0.0.0/input/Tensile-test.inp",
+}
+
+
+def deck_setup(name):
+    """Setup of one of the reference's example decks rebuilt from tests/golden/deck_<name>.npz."""
+    from hakai_fem_b200.model_setup import Setup, ContactTriangle
+    z = np.load(os.path.join(GOLDEN, f"deck_{name}.npz"))
+    sc = z["scalars"]
+    d_time, time_num, emin, emax = (float(v) for v in sc[:4])
+    cflag, n_mat, n_bc, n_ic, n_inst, n_ct = (int(v) for v in sc[4:10])
+    mats = []
+    for i in range(n_mat):
+        y, p, rho = z[f"mat{i}_s"]
+        m = I.Material(name=f"m{i}", density=float(rho), young=float(y), poisson=float(p))
+        m.plastic = z[f"mat{i}_plastic"].reshape(-1, 2)
+        if m.plastic.shape[0] > 1:
+            m.Hd = (m.plastic[1:, 0] - m.plastic[:-1, 0]) / (m.plastic[1:, 1] - m.plastic[:-1, 1])
+        m.ductile = z[f"mat{i}_ductile"].reshape(-1, 3)
+        mats.append(m)
+    bcs = []
+    for i in range(n_bc):
+        nl, has_amp = (int(v) for v in z[f"bc{i}_n"])
+        amp = z[f"bc{i}_amp"]
+        bc = I.BC(amp_name="Amp" if has_amp else "", amplitude=I.Amplitude(name="Amp", time=amp[0], value=amp[1]))
+        bc.dof = [z[f"bc{i}_dof{j}"] for j in range(nl)]
+        bc.value = list(z[f"bc{i}_value"])
+        bcs.append(bc)
+    ics = []
+    for i in range(n_ic):
+        vals = list(z[f"ic{i}_value"])
+        ics.append(I.IC(type="VELOCITY", dof=[z[f"ic{i}_dof{j}"] for j in range(len(vals))], value=vals))
+    coord, em = z["coordmat"], z["elementmat"]
+    insts = []
+    if cflag >= 1:
+        for i in range(n_inst):
+            no, nn, eo, ne, mid = (int(v) for v in z[f"inst{i}_s"])
+            insts.append(I.Instance(name=f"i{i}", node_offset=no, nNode=nn, element_offset=eo, nElement=ne, material_id=mid,
+                                    surfaces=z[f"inst{i}_surfaces"], surfaces_eleid=z[f"inst{i}_eleid"]))
+    model = I.Model(PART=[], INSTANCE=insts, NSET=[], ELSET=[], SURFACE=[], AMPLITUDE=[], MATERIAL=mats, BC=bcs, IC=ics,
+                    CP=[], nNode=coord.shape[1], coordmat=coord, nElement=em.shape[1], elementmat=em,
+                    element_material=z["element_material"], element_instance=z["element_instance"], d_time=d_time,
+                    end_time=d_time * time_num, mass_scaling=1.0, contact_flag=cflag)
+    st = Setup(model, d_time, time_num, None, z["diag_M"], emin, emax)
+    for c in range(n_ct):
+        a, b, young = z[f"ct{c}_s"]
+        st.CT.append(ContactTriangle(int(a), int(b), z[f"ct{c}_ni"], z[f"ct{c}_nj"], z[f"ct{c}_tri"], z[f"ct{c}_te"], float(young)))
+    return st
