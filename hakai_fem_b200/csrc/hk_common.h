@@ -71,6 +71,7 @@ struct HkDev {
     double* ips;          // ip state, tile-blocked: [tile][gauss point 8][row 14][TL] with rows 0-5 stress, 6-11 strain,
                           // 12 eps (integ_eq_plastic_strain), 13 yield (integ_yield_stress): the 14 rows x TL
                           // elements of one Gauss point of one tile are ONE contiguous burst (14*TL*8 bytes)
+    int element_mode;     // hk_params.element_mode (1: reference-order kernel)
     int TL;               // layout tile = elements per tile of the element kernel in use; nEp % TL == 0
     double* triax;        // [8][nEp]   integ_triax_stress (written on request)
     double* Qe;           // [24][nEp]
@@ -133,5 +134,6 @@ void hk_launch_ip_to_aos(const HkDev& d, double* aos, int row0, int ncomp, long 
 // triax [8][nEp] -> (nip) of the reference
 void hk_launch_triax_to_aos(const HkDev& d, double* aos, long long e0, long long ne, cudaStream_t s);
 void hk_upload_pusai(const double* P);
+void hk_launch_element_exact(const HkDev& d, long long step, int write_triax, cudaStream_t s);
 long long hk_element_tile();   // nEp must be a multiple of this
 void hk_launch_external_force(const HkDev& d, double* F_out, int lsb_exp, int contact_on, cudaStream_t s);

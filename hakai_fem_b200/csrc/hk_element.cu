@@ -675,6 +675,7 @@ static void launch_tma(const ElemArgs& A, unsigned grid, cudaStream_t s) {
 static int g_elem_kernel = -1;   // 0 tma, 1 simple
 
 void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s) {
+    if (d.element_mode == 1) { hk_launch_element_exact(d, step, write_triax, s); return; }
     static int fast = -1;
     if (fast < 0) { const char* f = getenv("HK_ELEMENT_FASTMATH"); fast = f ? atoi(f) : 1; }
     ElemArgs A{d, step, write_triax, fast};
@@ -760,7 +761,6 @@ void hk_launch_element_volume(const HkDev& dd, double* V_out, cudaStream_t s) {
     });
 }
 
-void hk_upload_pusai(const double*) {}
 
 long long hk_element_tile() {      // layout tile TL of the ip state = tile of the element kernel that will run
 #ifndef HK_EMU

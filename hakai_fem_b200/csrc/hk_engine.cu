@@ -569,6 +569,7 @@ int HKAPI(finalize)(hk_engine* e) {
     const int64_t nEp = (nE + tile - 1) / tile * tile;   // whole tiles for hk_element_tma_kernel
     HkDev& d = e->d;
     d.nNode = nN; d.nElement = nE; d.nEp = nEp;
+    d.element_mode = e->prm.element_mode;
     const double dt = e->prm.d_time;
     e->dt2 = dt * dt;                 // d_time^2   (J2:564)
     e->dt2p = std::pow(dt, 2.0);      // d_time^2.0 (J2:564)

@@ -584,3 +584,230 @@ void hk_launch_triax_to_aos(const HkDev& dd, double* aos, long long e0, long lon
         aos[el * 8 + k] = d.triax[(long long)k * d.nEp + e0 + el];
     });
 }
+
+
+// ------------------------------------------------------------------ reference-order element kernel (element_mode 1)
+// cal_stress_hexa + cal_BVbar_hexa + cal_Bfinal + cal_triax_stress + the fracture loop exactly as the reference
+// evaluates them (J2:1033-1371, 1705-1784, 1415-1519, 982-1022, 701-762): dense 6x24 Bfinal, left-to-right sums,
+// no FMA (this translation unit is built with -fmad=false).  One thread per element; ~10x slower than the fast
+// kernel.  Its purpose is parity: with it the whole engine is bit-identical to the CPU oracle, including the
+// contact ties that depend on the last bit of a nodal position.
+#ifndef HK_EMU
+__device__ double x_P[8][3][8];
+#else
+static double x_P[8][3][8];
+#endif
+
+void hk_upload_pusai(const double* P) {
+#ifndef HK_EMU
+    cudaMemcpyToSymbol(x_P, P, sizeof(double) * 192);
+#else
+    memcpy(x_P, P, sizeof(double) * 192);
+#endif
+}
+
+struct ExactArgs {
+    HkDev d;
+    long long step;
+    int write_triax;
+};
+
+HK_D void exact_jac(const double P1[3][8], const double ep[3][8], double J[3][3]) {
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) J[r][c] = 0.0;
+    for (int i = 0; i < 8; ++i) {
+        J[0][0] += P1[0][i] * ep[0][i]; J[0][1] += P1[0][i] * ep[1][i]; J[0][2] += P1[0][i] * ep[2][i];
+        J[1][0] += P1[1][i] * ep[0][i]; J[1][1] += P1[1][i] * ep[1][i]; J[1][2] += P1[1][i] * ep[2][i];
+        J[2][0] += P1[2][i] * ep[0][i]; J[2][1] += P1[2][i] * ep[1][i]; J[2][2] += P1[2][i] * ep[2][i];
+    }
+}
+HK_D double exact_det3(const double J[3][3]) {
+    return (J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
+            J[0][0] * J[1][2] * J[2][1] - J[0][1] * J[1][0] * J[2][2] - J[0][2] * J[1][1] * J[2][0]);
+}
+HK_D void exact_inv3(const double J[3][3], double div_v, double iJ[3][3]) {
+    iJ[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * div_v;
+    iJ[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * div_v;
+    iJ[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * div_v;
+    iJ[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * div_v;
+    iJ[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * div_v;
+    iJ[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * div_v;
+    iJ[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * div_v;
+    iJ[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * div_v;
+    iJ[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * div_v;
+}
+
+HK_D void element_body_exact(const ExactArgs& A, long long e) {
+    const HkDev& d = A.d;
+    const unsigned char fl = d.flag[e];
+    if (fl != 1) {
+        if (fl == 0) {
+            for (int r = 0; r < 24; ++r) d.Qe[(long long)r * d.nEp + e] = 0.0;
+            for (int k = 0; k < 8; ++k) d.triax[(long long)k * d.nEp + e] = 0.0;
+            d.flag[e] = 2;
+        }
+        return;
+    }
+    const HkMaterialDev& M = d.mats[d.mat[e]];
+    double Dm[6][6];
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) Dm[r][c] = 0.0;
+    Dm[0][0] = Dm[1][1] = Dm[2][2] = M.D11;
+    Dm[0][1] = Dm[0][2] = Dm[1][0] = Dm[1][2] = Dm[2][0] = Dm[2][1] = M.D12;
+    Dm[3][3] = Dm[4][4] = Dm[5][5] = M.D44;
+    double d_u[24], ep[3][8];
+    for (int i = 0; i < 8; ++i) {
+        const long long n = d.conn[(long long)i * d.nEp + e];
+        for (int c = 0; c < 3; ++c) { ep[c][i] = d.rec[6 * n + c]; d_u[i * 3 + c] = d.rec[6 * n + 3 + c]; }
+    }
+    // cal_BVbar_hexa
+    double BVbar[144];
+    for (int i = 0; i < 144; ++i) BVbar[i] = 0.0;
+    double V = 0.0;
+    int negj = 0;
+    for (int k = 0; k < 8; ++k) {
+        double J[3][3], iJ[3][3];
+        exact_jac(x_P[k], ep, J);
+        double detJi = exact_det3(J);
+        if (detJi < 0) { detJi = fabs(detJi); negj++; }
+        V += detJi;
+        const double div_v = 1.0 / detJi;
+        exact_inv3(J, div_v, iJ);
+        for (int i = 0; i < 8; ++i) {
+            const double Pix = iJ[0][0] * x_P[k][0][i] + iJ[0][1] * x_P[k][1][i] + iJ[0][2] * x_P[k][2][i];
+            const double Piy = iJ[1][0] * x_P[k][0][i] + iJ[1][1] * x_P[k][1][i] + iJ[1][2] * x_P[k][2][i];
+            const double Piz = iJ[2][0] * x_P[k][0][i] + iJ[2][1] * x_P[k][1][i] + iJ[2][2] * x_P[k][2][i];
+            for (int r = 0; r < 3; ++r) {
+                BVbar[r + 6 * (i * 3 + 0)] += Pix / 3.0 * detJi;
+                BVbar[r + 6 * (i * 3 + 1)] += Piy / 3.0 * detJi;
+                BVbar[r + 6 * (i * 3 + 2)] += Piz / 3.0 * detJi;
+            }
+        }
+    }
+    for (int i = 0; i < 144; ++i) BVbar[i] = BVbar[i] / V;
+    if (negj) hk_atomic_add_u64(&d.counters[0], (unsigned long long)negj);
+
+    double Qe[24];
+    for (int j = 0; j < 24; ++j) Qe[j] = 0.0;
+    double v_e = 0.0, t_e = 0.0;
+    for (int k = 0; k < 8; ++k) {
+        double Bf[144];
+        for (int q = 0; q < 144; ++q) Bf[q] = 0.0;
+        double J[3][3], iJ[3][3];
+        exact_jac(x_P[k], ep, J);
+        const double detJ = exact_det3(J);
+        const double div_v = 1.0 / detJ;
+        exact_inv3(J, div_v, iJ);
+        for (int i = 0; i < 8; ++i) {
+            const double Pix = iJ[0][0] * x_P[k][0][i] + iJ[0][1] * x_P[k][1][i] + iJ[0][2] * x_P[k][2][i];
+            const double Piy = iJ[1][0] * x_P[k][0][i] + iJ[1][1] * x_P[k][1][i] + iJ[1][2] * x_P[k][2][i];
+            const double Piz = iJ[2][0] * x_P[k][0][i] + iJ[2][1] * x_P[k][1][i] + iJ[2][2] * x_P[k][2][i];
+            const int c0 = i * 3, c1 = i * 3 + 1, c2 = i * 3 + 2;
+            Bf[0 + 6 * c0] += Pix; Bf[1 + 6 * c1] += Piy; Bf[2 + 6 * c2] += Piz;
+            Bf[3 + 6 * c0] += Piy; Bf[3 + 6 * c1] += Pix;
+            Bf[4 + 6 * c1] += Piz; Bf[4 + 6 * c2] += Piy;
+            Bf[5 + 6 * c0] += Piz; Bf[5 + 6 * c2] += Pix;
+            for (int r = 0; r < 3; ++r) {
+                Bf[r + 6 * c0] += -Pix / 3.0 + BVbar[r + 6 * c0];
+                Bf[r + 6 * c1] += -Piy / 3.0 + BVbar[r + 6 * c1];
+                Bf[r + 6 * c2] += -Piz / 3.0 + BVbar[r + 6 * c2];
+            }
+        }
+        double de[6], dov[6];
+        for (int r = 0; r < 6; ++r) {
+            double s = Bf[r] * d_u[0];
+            for (int c = 1; c < 24; ++c) s += Bf[r + 6 * c] * d_u[c];
+            de[r] = s;
+        }
+        for (int r = 0; r < 6; ++r) {
+            double s = Dm[r][0] * de[0];
+            for (int c = 1; c < 6; ++c) s += Dm[r][c] * de[c];
+            dov[r] = s;
+        }
+        double pre[6], fin[6];
+        for (int r = 0; r < 6; ++r) { pre[r] = d.ips[hk_ip(d, r, k, e)]; fin[r] = pre[r] + dov[r]; }
+        double ep_ = d.ips[hk_ip(d, 12, k, e)];
+        if (M.npp > 0) {
+            double tri[6];
+            for (int r = 0; r < 6; ++r) tri[r] = pre[r] + dov[r];
+            const double mean_stress = (tri[0] + tri[1] + tri[2]) / 3.0;
+            const double tds[6] = {tri[0] - mean_stress, tri[1] - mean_stress, tri[2] - mean_stress, tri[3], tri[4], tri[5]};
+            const double mises = sqrt(1.5 * (tds[0] * tds[0] + tds[1] * tds[1] + tds[2] * tds[2] + 2 * (tds[3] * tds[3]) +
+                                             2 * (tds[4] * tds[4]) + 2 * (tds[5] * tds[5])));
+            const double y = d.ips[hk_ip(d, 13, k, e)];
+            if (mises > y) {
+                int p_index = 1;
+                for (int j = 2; j <= M.npp; ++j) {
+                    if (ep_ <= M.plastic_e[j - 1]) { p_index = j - 1; break; }
+                    if (j == M.npp) p_index = j - 1;
+                }
+                const double H = M.Hd[p_index - 1];
+                const double d_ep = (mises - y) / (3 * M.G + H);
+                const double fac_num = (y + H * d_ep);
+                for (int r = 0; r < 6; ++r) {
+                    const double fds = tds[r] * fac_num / mises;
+                    fin[r] = fds + (r < 3 ? mean_stress : 0.0);
+                }
+                ep_ = ep_ + d_ep;
+                d.ips[hk_ip(d, 12, k, e)] = ep_;
+                d.ips[hk_ip(d, 13, k, e)] = y + H * d_ep;
+            }
+        }
+        for (int r = 0; r < 6; ++r) {
+            d.ips[hk_ip(d, 6 + r, k, e)] += de[r];
+            d.ips[hk_ip(d, r, k, e)] = fin[r];
+        }
+        for (int j = 0; j < 24; ++j) {
+            double s = Bf[6 * j] * fin[0];
+            for (int r = 1; r < 6; ++r) s += Bf[r + 6 * j] * fin[r];
+            Qe[j] += 1.0 * 1.0 * 1.0 * detJ * s;
+        }
+        // cal_triax_stress, invariant form (the oracle's triax_route 0)
+        const double ox = fin[0], oy = fin[1], oz = fin[2], txy = fin[3], tyz = fin[4], txz = fin[5];
+        const double oeq = sqrt(0.5 * ((ox - oy) * (ox - oy) + (oy - oz) * (oy - oz) + (ox - oz) * (ox - oz) +
+                                       6 * (txy * txy + tyz * tyz + txz * txz)));
+        double tx = 0.0;
+        if (!(oeq < 1E-10)) tx = (ox + oy + oz) / 3.0 / oeq;
+        if (A.write_triax) d.triax[(long long)k * d.nEp + e] = tx;
+        v_e += ep_;
+        t_e += tx;
+    }
+    for (int j = 0; j < 24; ++j) d.Qe[(long long)j * d.nEp + e] = Qe[j];
+    // fracture, J2:701-762
+    if (M.nd > 0) {
+        v_e /= 8;
+        t_e /= 8;
+        if (!(t_e < 0)) {
+            const int nd = M.nd;
+            double fr_e = M.duct_e[nd - 1];
+            for (int j = 0; j + 1 < nd; ++j)
+                if (t_e >= M.duct_t[j] && t_e < M.duct_t[j + 1]) {
+                    fr_e = M.duct_e[j] + (M.duct_e[j + 1] - M.duct_e[j]) / (M.duct_t[j + 1] - M.duct_t[j]) * (t_e - M.duct_t[j]);
+                    break;
+                }
+            if (v_e >= fr_e) {
+                d.flag[e] = 0;
+                for (int k = 0; k < 8; ++k)
+                    for (int r = 0; r < 12; ++r) d.ips[hk_ip(d, r, k, e)] = 0.0;
+                const int slot = hk_atomic_add_i32(d.del_count, 1);
+                if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
+            }
+        }
+    }
+}
+
+#ifndef HK_EMU
+__global__ void __launch_bounds__(64) hk_element_exact_kernel(ExactArgs A) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e < A.d.nElement) element_body_exact(A, e);
+}
+#endif
+
+void hk_launch_element_exact(const HkDev& d, long long step, int write_triax, cudaStream_t s) {
+    ExactArgs A{d, step, write_triax};
+#ifndef HK_EMU
+    hk_element_exact_kernel<<<(unsigned)((d.nElement + 63) / 64), 64, 0, s>>>(A);
+#else
+    for (long long e = 0; e < d.nElement; ++e) element_body_exact(A, e);
+#endif
+}

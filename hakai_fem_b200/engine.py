@@ -32,7 +32,7 @@ class HkParams(C.Structure):
         ("contact_kc_other", c_f64), ("contact_kc_self", c_f64),
         ("contact_cr_other", c_f64), ("contact_cr_self", c_f64),
         ("contact_ddiv_other", c_f64), ("contact_ddiv_self", c_f64),
-        ("deterministic", C.c_int32), ("reserved", C.c_int32),
+        ("deterministic", C.c_int32), ("element_mode", C.c_int32),
     ]
 
 

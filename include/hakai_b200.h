@@ -56,7 +56,10 @@ typedef struct hk_params {
     double  contact_ddiv_other;   /* cell size factor 1.1*elementMaxSize          J2:2331       */
     double  contact_ddiv_self;    /* 0.6*elementMaxSize for self contact          J2:2333       */
     int32_t deterministic;        /* 1 (default): reproducible assembly and contact sums        */
-    int32_t reserved;
+    int32_t element_mode;         /* 0 (default): fast element kernel (mode form, FMA) — within 1e-13/step of the
+                                     reference arithmetic.  1: reference-order kernel: the dense 6x24 Bfinal algebra of
+                                     J2:1033-1371 in the reference's operation order without FMA — bit-identical to the
+                                     CPU oracle (and ~10x slower); resolves contact ties like the reference          */
 } hk_params;
 
 int hk_default_params(hk_params* p);

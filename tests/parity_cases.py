@@ -167,3 +167,19 @@ def case_contact_erosion(engine_cls, n_steps=400):
             assert np.array_equal(po[k], pg[k]), f"pair {c} {k}"
     a, b = util.full_state(o), util.full_state(g)
     util.assert_states_close(a, b, 1e-7, ("disp", "integ_eq_plastic_strain", "element_flag"), "erosion")
+
+
+def case_exact_mode_bitwise(engine_cls, cases=(("t5", 3000), ("crash_tube", 800), ("bullet_impact", 1500))):
+    """hk_params.element_mode = 1 (reference-order element kernel, no FMA): the whole engine — nodal update, contact,
+    element forces, triaxiality, deletion — is BIT-IDENTICAL to the oracle, including the self-contact deck whose hit
+    set depends on the last bit of nodal positions."""
+    for name, n in cases:
+        st = prepare(util.t5_model()) if name == "t5" else util.deck_setup(name)
+        o = configure_engine(OracleEngine, st)
+        g = configure_engine(engine_cls, st, element_mode=1)
+        assert o.step(1, n) == g.step(1, n)
+        a, b = util.full_state(o), util.full_state(g)
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (name, k)
+        assert np.array_equal(o.deleted_ids(), g.deleted_ids())
+        assert o.counters()[1] == g.counters()[1]

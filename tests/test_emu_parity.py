@@ -35,3 +35,7 @@ def test_contact_single_step_exact():
 
 def test_contact_erosion():
     pc.case_contact_erosion(EmuEngine)
+
+
+def test_exact_mode_bitwise():
+    pc.case_exact_mode_bitwise(EmuEngine)

@@ -60,3 +60,8 @@ def test_reference_deck(name, n_steps, expect_deleted):
     """The reference's own example decks through the CUDA engine vs the oracle (see tests/test_reference_decks.py)."""
     from .test_reference_decks import run_deck
     run_deck(Engine, name, n_steps, expect_deleted)
+
+
+def test_exact_mode_bitwise():
+    """On the B200: element_mode=1 reproduces the CPU oracle bit for bit (IEEE FP64, -fmad=false)."""
+    pc.case_exact_mode_bitwise(Engine)
