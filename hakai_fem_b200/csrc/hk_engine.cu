@@ -91,6 +91,10 @@ struct hk_engine {
     std::vector<HaloNbr> halo;
     int n_halo_nodes = 0;
     int* d_halo_list = nullptr;    // node id of every halo slot (nodal kernel mode 2)
+    std::vector<int> node_list[3]; // multi-GPU contact: 0 own-export, 1 ghost-import, 2 surface nodes (force exchange)
+    int* d_node_list[3] = {nullptr, nullptr, nullptr};
+    long long* d_import_src = nullptr;
+    bool contact_done = false;     // hk_contact_enqueue already ran the contact pass of the next step
     int64_t begun_t = -1;          // step opened by hk_step_begin
     // special nodes (host mirror)
     std::vector<int> spec_idx_h;
@@ -802,7 +806,9 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
     const HkDev& d = e->d;
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
-        if (phase != 2 && contact_on) {
+        if (phase != 2 && contact_on && e->contact_done) {
+            e->contact_done = false;             // done by hk_contact_enqueue (+ force exchange) for this step
+        } else if (phase != 2 && contact_on) {
             prof_begin(e, 0);
             CK(hkp::dev_memset(d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
             for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 4; }
@@ -1141,6 +1147,81 @@ int HKAPI(halo_pack)(hk_engine* e) {
         hk_launch_halo_pack(e->d, h.d_nodes, (long long)h.nodes.size(), h.send, e->stream);
         e->n_launch += 1;
     }
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(set_node_list)(hk_engine* e, int32_t which, int64_t n, const int64_t* nodes) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (which < 0 || which > 2) return fail(e, HK_ERR_ARG, "bad list id");
+    std::vector<int>& L = e->node_list[which];
+    L.resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (nodes[i] < 1 || nodes[i] > e->nNode) return fail(e, HK_ERR_ARG, "node id out of range");
+        L[i] = (int)(nodes[i] - 1);
+        if (which == 2 && (e->spec_idx_h[L[i]] < 0 || e->spec_h[e->spec_idx_h[L[i]]].contact_slot < 0))
+            return fail(e, HK_ERR_ARG, "surface list holds a node that is in no contact pair");
+    }
+    dfree(e, e->d_node_list[which]);
+    e->d_node_list[which] = nullptr;
+    int rc = dalloc(e, &e->d_node_list[which], L.size());
+    if (rc) return rc;
+    return upload(e, e->d_node_list[which], L);
+}
+
+int HKAPI(nodes_export)(hk_engine* e, void* out_dev) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (!e->velo_current) { hk_launch_velo_from_rec(e->d, e->prm.d_time, e->stream); e->velo_current = true; }
+    hk_launch_nodes_export(e->d, e->d_node_list[0], (long long)e->node_list[0].size(), (double*)out_dev, e->stream);
+    e->n_launch += 1;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(nodes_import)(hk_engine* e, const void* in_dev, const int64_t* src_index) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    const size_t n = e->node_list[1].size();
+    if (src_index) {               // (re)register where each ghost's record sits in the gathered buffer
+        std::vector<long long> src(src_index, src_index + n);
+        dfree(e, e->d_import_src);
+        e->d_import_src = nullptr;
+        int rc = dalloc(e, &e->d_import_src, n);
+        if (rc) return rc;
+        if ((rc = upload(e, e->d_import_src, src))) return rc;
+    }
+    if (n && !e->d_import_src) return fail(e, HK_ERR_STATE, "hk_nodes_import: source index never given");
+    hk_launch_nodes_import(e->d, e->d_node_list[1], e->d_import_src, (long long)n, (const double*)in_dev, e->stream);
+    e->n_launch += 1;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(contact_enqueue)(hk_engine* e) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
+    if (!contact_on) return HK_OK;
+    prof_begin(e, 0);
+    CK(hkp::dev_memset(e->d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
+    for (PairH& p : e->pairs) { hk_launch_contact(e->d, p.dev, e->cp, e->stream); e->n_launch += 4; }
+    prof_end(e);
+    e->contact_done = true;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(contact_export)(hk_engine* e, void* out_dev) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    hk_launch_cacc_export(e->d, e->d_node_list[2], (long long)e->node_list[2].size(), (unsigned long long*)out_dev, e->stream);
+    e->n_launch += 1;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(contact_import)(hk_engine* e, const void* in_dev, int64_t n_ranks) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    hk_launch_cacc_import(e->d, e->d_node_list[2], (long long)e->node_list[2].size(), (const unsigned long long*)in_dev,
+                          (long long)n_ranks, e->stream);
+    e->n_launch += 1;
     CK(hkp::last_error());
     return HK_OK;
 }

@@ -541,6 +541,56 @@ void hk_launch_halo_accumulate(const HkDev& dd, const int* slots, long long n, c
     });
 }
 
+// {position, velocity} of listed nodes -> out (6 doubles per node); and the inverse for ghost copies
+void hk_launch_nodes_export(const HkDev& dd, const int* nodes, long long n, double* out, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 6, s, HK_LAMBDA(long long j) {
+        const long long i = j / 6;
+        const int c = (int)(j - 6 * i);
+        const long long nd = nodes[i];
+        out[j] = c < 3 ? d.rec[6 * nd + c] : d.velo[3 * nd + c - 3];
+    });
+}
+void hk_launch_nodes_import(const HkDev& dd, const int* nodes, const long long* src, long long n, const double* in,
+                            cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 6, s, HK_LAMBDA(long long j) {
+        const long long i = j / 6;
+        const int c = (int)(j - 6 * i);
+        const long long nd = nodes[i];
+        const double v = in[6 * src[i] + c];
+        if (c < 3) d.rec[6 * nd + c] = v; else d.velo[3 * nd + c - 3] = v;
+    });
+}
+// contact accumulators of the listed nodes -> out (6 x u64 per node); import = exact 128-bit sum over n_ranks records
+void hk_launch_cacc_export(const HkDev& dd, const int* nodes, long long n, unsigned long long* out, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 6, s, HK_LAMBDA(long long j) {
+        const long long i = j / 6;
+        const int w = (int)(j - 6 * i);
+        const int slot = d.spec[d.spec_idx[nodes[i]]].contact_slot;
+        out[j] = d.cacc[6ll * slot + w];
+    });
+}
+void hk_launch_cacc_import(const HkDev& dd, const int* nodes, long long n, const unsigned long long* in, long long n_ranks,
+                           cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 3, s, HK_LAMBDA(long long j) {
+        const long long i = j / 3;
+        const int c = (int)(j - 3 * i);
+        unsigned long long lo = 0ull, hi = 0ull;
+        for (long long r = 0; r < n_ranks; ++r) {
+            const unsigned long long* p = in + (r * n + i) * 6 + 2 * c;
+            const unsigned long long nlo = lo + p[0];
+            hi += p[1] + (nlo < lo ? 1ull : 0ull);
+            lo = nlo;
+        }
+        const int slot = d.spec[d.spec_idx[nodes[i]]].contact_slot;
+        d.cacc[6ll * slot + 2 * c] = lo;
+        d.cacc[6ll * slot + 2 * c + 1] = hi;
+    });
+}
+
 // external_force of the last step (J2:497-538): zero plus the rounded contact sums
 void hk_launch_external_force(const HkDev& dd, double* F_out, int lsb_exp, int contact_on, cudaStream_t s) {
     const HkDev d = dd;

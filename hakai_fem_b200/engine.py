@@ -41,6 +41,7 @@ EXPORTS = [
     "add_instance", "add_contact_pair", "finalize", "step", "download", "download_ex", "upload_state",
     "deleted_ids", "contact_pair_info", "counters", "profile", "profile_read", "set_stream",
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
+    "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
 ]
 
 
@@ -285,6 +286,27 @@ class EngineBase:
 
     def halo_pack(self):
         self._chk(self._fn("halo_pack")(self._h))
+
+    # -- multi-GPU contact ---------------------------------------------------------------
+    def set_node_list(self, which: int, nodes):
+        a = _i64(nodes)
+        self._chk(self._fn("set_node_list")(self._h, C.c_int32(which), c_i64(len(a)), _pi(a)))
+
+    def nodes_export(self, out_ptr: int):
+        self._chk(self._fn("nodes_export")(self._h, C.c_void_p(out_ptr)))
+
+    def nodes_import(self, in_ptr: int, src_index=None):
+        a = None if src_index is None else _i64(src_index)
+        self._chk(self._fn("nodes_import")(self._h, C.c_void_p(in_ptr), _pi(a)))
+
+    def contact_enqueue(self):
+        self._chk(self._fn("contact_enqueue")(self._h))
+
+    def contact_export(self, out_ptr: int):
+        self._chk(self._fn("contact_export")(self._h, C.c_void_p(out_ptr)))
+
+    def contact_import(self, in_ptr: int, n_ranks: int):
+        self._chk(self._fn("contact_import")(self._h, C.c_void_p(in_ptr), c_i64(n_ranks)))
 
     def set_stream(self, stream_ptr: int):
         self._chk(self._fn("set_stream")(self._h, C.c_void_p(stream_ptr)))

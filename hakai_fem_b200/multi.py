@@ -29,6 +29,7 @@ class LocalDomain:
     elem_l2g: np.ndarray
     neighbors: List[int] = field(default_factory=list)
     halo_nodes: List[np.ndarray] = field(default_factory=list)     # local 1-based ids per neighbour
+    contact: object = None             # ContactLists when the model has contact
 
 
 def _restrict_dofs(dof_lists, values, g2l):
@@ -43,12 +44,24 @@ def _restrict_dofs(dof_lists, values, g2l):
     return out_d, out_v
 
 
+@dataclass
+class ContactLists:
+    """Per-rank lists of the contact-surface all-gather (local 1-based node ids)."""
+    export_nodes: np.ndarray           # surface nodes this rank owns (ascending global id)
+    import_nodes: np.ndarray           # ghost copies of surface nodes owned elsewhere
+    import_src: np.ndarray             # index of each ghost's record in the gathered buffer (rank*maxlen + position)
+    surface_nodes: np.ndarray          # ALL surface nodes in global order (same order on every rank)
+    maxlen: int                        # padded length of one rank's export block
+
+
 def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
     """Splits a (small) global model into contiguous element blocks.  Used by the tests and for general
-    decks; the 16 M/GPU bench builds each slab directly (slab_deck) without materialising the global mesh."""
+    decks; the 16 M/GPU bench builds each slab directly (slab_deck) without materialising the global mesh.
+
+    With contact, every rank receives the GLOBAL contact node lists (nodes it does not hold are appended as ghost
+    nodes that no element references) and the master triangles of its own elements; exposed-face updates after
+    element deletion are not propagated across ranks yet."""
     m = setup.model
-    if m.contact_flag:
-        raise NotImplementedError("multi-GPU contact is not implemented")
     nE = m.nElement
     bounds = [(nE * r) // n_ranks for r in range(n_ranks + 1)]
     owners_of_node = [set() for _ in range(m.nNode + 1)]
@@ -60,8 +73,17 @@ def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
         for n in nodes:
             owners_of_node[n].add(r)
         locals_.append((el, nodes))
+    surf = np.zeros(0, np.int64)
+    if m.contact_flag:
+        surf = np.unique(np.concatenate([np.concatenate([ct.c_nodes_i, ct.c_nodes_j, ct.c_triangles.reshape(-1)])
+                                         for ct in setup.CT]))
+        owner = np.array([min(owners_of_node[n]) for n in surf])
+        export_lists = [surf[owner == r] for r in range(n_ranks)]
+        maxlen = max(len(x) for x in export_lists)
     for r in range(n_ranks):
-        el, nodes = locals_[r]
+        el, nodes_own = locals_[r]
+        ghosts = np.setdiff1d(surf, nodes_own) if m.contact_flag else np.zeros(0, np.int64)
+        nodes = np.concatenate([nodes_own, ghosts])              # local numbering: own nodes, then ghosts
         g2l = np.zeros(m.nNode + 1, np.int64)
         g2l[nodes] = np.arange(1, len(nodes) + 1)
         em = g2l[m.elementmat[:, el]]
@@ -84,10 +106,24 @@ def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
                     np.repeat(setup.diag_M.reshape(-1, 3)[nodes - 1, 0], 3),     # global (summed) mass
                     setup.elementMinSize, setup.elementMaxSize)
         dom = LocalDomain(r, lst, nodes, el + 1)
+        if m.contact_flag:
+            from .model_setup import ContactTriangle
+            e_g2l = np.zeros(nE + 1, np.int64)
+            e_g2l[el + 1] = np.arange(1, len(el) + 1)
+            lm.INSTANCE = []                                      # no cross-rank exposed-face update yet
+            for ct in setup.CT:
+                mine = e_g2l[ct.c_triangles_eleid] > 0
+                lst.CT.append(ContactTriangle(ct.i_instance, ct.j_instance, g2l[ct.c_nodes_i], g2l[ct.c_nodes_j],
+                                              g2l[ct.c_triangles[mine]], e_g2l[ct.c_triangles_eleid[mine]], ct.young))
+            src = np.zeros(len(ghosts), np.int64)
+            for i, gnode in enumerate(ghosts):
+                o = int(owner[np.searchsorted(surf, gnode)])
+                src[i] = o * maxlen + int(np.searchsorted(export_lists[o], gnode))
+            dom.contact = ContactLists(g2l[export_lists[r]], g2l[ghosts], src, g2l[surf], maxlen)
         for q in range(n_ranks):
             if q == r:
                 continue
-            shared = np.array([n for n in nodes if q in owners_of_node[n]], np.int64)
+            shared = np.array([n for n in nodes_own if q in owners_of_node[n]], np.int64)
             if len(shared):
                 dom.neighbors.append(q)
                 dom.halo_nodes.append(g2l[shared])
@@ -168,11 +204,42 @@ def exchange_sum(values_per_nbr, neighbors, device):
     return [r.cpu().numpy() for r in recv]
 
 
+class ContactExchanger:
+    """All-gather of contact-surface node {position, velocity} and of the fixed-point force accumulators."""
+
+    def __init__(self, engine, lists: ContactLists, world: int, device):
+        import torch
+        self.engine, self.lists, self.world = engine, lists, world
+        self.send_nodes = torch.zeros(lists.maxlen * 6, dtype=torch.float64, device=device)
+        self.all_nodes = torch.zeros(world * lists.maxlen * 6, dtype=torch.float64, device=device)
+        n_surf = len(lists.surface_nodes)
+        self.send_acc = torch.zeros(n_surf * 6, dtype=torch.int64, device=device)
+        self.all_acc = torch.zeros(world * n_surf * 6, dtype=torch.int64, device=device)
+        engine.set_node_list(0, lists.export_nodes)
+        engine.set_node_list(1, lists.import_nodes)
+        engine.set_node_list(2, lists.surface_nodes)
+        self._first = True
+
+    def run(self):
+        """positions -> ghosts, contact pass on the local triangles, exact sum of the forces over ranks."""
+        import torch.distributed as dist
+        eng = self.engine
+        eng.nodes_export(self.send_nodes.data_ptr())
+        dist.all_gather(list(self.all_nodes.chunk(self.world)), self.send_nodes)
+        eng.nodes_import(self.all_nodes.data_ptr(), self.lists.import_src if self._first else None)
+        self._first = False
+        eng.contact_enqueue()
+        eng.contact_export(self.send_acc.data_ptr())
+        dist.all_gather(list(self.all_acc.chunk(self.world)), self.send_acc)
+        eng.contact_import(self.all_acc.data_ptr(), self.world)
+
+
 class SlabRunner:
     """Engine + halo exchange of one rank.  `engine_cls` is Engine (CUDA) — the CPU tests pass the
     host-compiled kernel build, whose "device" pointers are host pointers."""
 
-    def __init__(self, engine_cls, setup: Setup, neighbors, halo_nodes, torch_device, sum_mass=False, **params):
+    def __init__(self, engine_cls, setup: Setup, neighbors, halo_nodes, torch_device, sum_mass=False, contact=None,
+                 world=1, **params):
         self.setup = setup
         if sum_mass and neighbors:
             # interface nodes: add the neighbour's partial lumped mass (J2:201-215 summed over ALL elements)
@@ -190,9 +257,12 @@ class SlabRunner:
             return eng
         self.engine = configure_engine(with_halo, setup, **params)
         self.halo = HaloExchanger(self.engine, neighbors, halo_nodes, torch_device)
+        self.contact = ContactExchanger(self.engine, contact, world, torch_device) if contact is not None else None
         self.nElement = model.nElement
 
     def step(self, t: int) -> int:
+        if self.contact is not None:
+            self.contact.run()
         self.halo.exchange()
         return self.engine.step(t, 1)
 
@@ -201,6 +271,8 @@ class SlabRunner:
         import time as _time
         _t0 = _time.perf_counter()
         for t in range(t_first, t_first + n_steps):
+            if self.contact is not None:
+                self.contact.run()
             if self.halo.neighbors:
                 reqs = self.halo.start()             # partial forces on their way ...
                 self.engine.step_begin(t)            # ... while all non-interface nodes are updated

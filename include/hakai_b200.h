@@ -200,6 +200,26 @@ int hk_halo_pack(hk_engine* e);
 int hk_step_begin(hk_engine* e, int64_t t);
 int hk_step_finish(hk_engine* e, int64_t t);
 
+/* ---- multi-GPU contact: contact-surface nodes all-gathered ---------------------------------------
+ * Every rank holds the GLOBAL contact node lists (nodes it does not own are appended to its mesh as "ghost" nodes
+ * that no element references) and the master triangles of the elements it owns.  Per step, before hk_step_*:
+ *     hk_nodes_export(own)   -> all-gather {position, velocity} of the surface nodes each rank owns
+ *     hk_nodes_import(ghost) -> ghost copies refreshed
+ *     hk_contact_enqueue     -> bounding boxes / cells / narrow phase on the local triangles (same cell grid and
+ *                               hit tests as single-GPU because the node lists are global)
+ *     hk_contact_export      -> all-gather the 128-bit fixed-point force accumulators of the surface nodes
+ *     hk_contact_import      -> exact integer sum over ranks (order independent => identical on every rank)
+ * then the usual (halo) step, which skips its own contact pass once.
+ *   list ids: LOCAL 1-based node ids; buffers: DEVICE memory owned by the caller.
+ *   export/import node record: 6 doubles {x,y,z,vx,vy,vz}; accumulator record: 6 x uint64 per node. */
+int hk_set_node_list(hk_engine* e, int32_t which /* 0 own-export, 1 ghost-import, 2 surface (force exchange) */,
+                     int64_t n, const int64_t* nodes);
+int hk_nodes_export(hk_engine* e, void* out_dev);                 /* list 0 -> 6 doubles per node            */
+int hk_nodes_import(hk_engine* e, const void* in_dev, const int64_t* src_index /* host, n(list 1) */);
+int hk_contact_enqueue(hk_engine* e);                             /* contact pass of the NEXT step, now     */
+int hk_contact_export(hk_engine* e, void* out_dev);               /* list 2 -> 6 uint64 per node             */
+int hk_contact_import(hk_engine* e, const void* in_dev, int64_t n_ranks);   /* sum of n_ranks records per node */
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,3 +161,58 @@ def test_upload_state_then_split_step_is_transparent():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
+
+
+def _worker_contact(rank, world, port, q):
+    """Two-body impact split over ranks: contact-surface all-gather + exact force exchange."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.model_setup import prepare
+        from hakai_fem_b200.multi import partition_model, SlabRunner
+        from hakai_fem_b200.mesh import ImpactDeck
+        from tests.emu.emu_engine import EmuEngine
+        gsetup = prepare(ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3)).build_model())
+        dom = partition_model(gsetup, world)[rank]
+        run = SlabRunner(EmuEngine, dom.setup, dom.neighbors, dom.halo_nodes, "cpu", contact=dom.contact, world=world,
+                         contact_myu=0.25)
+        run.run(1, 40)
+        d = run.engine.download()
+        n_own = len(dom.node_l2g) - len(dom.contact.import_nodes)
+        q.put((rank, dict(disp=d["disp"][:3 * n_own], eps=d["integ_eq_plastic_strain"], node_l2g=dom.node_l2g[:n_own],
+                          elem_l2g=dom.elem_l2g, hits=int(run.engine.counters()[1]), n_ghost=len(dom.contact.import_nodes))))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_contact_across_ranks_matches_single_domain(world):
+    from hakai_fem_b200.model_setup import prepare, configure_engine
+    from hakai_fem_b200.mesh import ImpactDeck
+    from oracle.oracle_engine import OracleEngine
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_contact, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gsetup = prepare(ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3)).build_model())
+    o = configure_engine(OracleEngine, gsetup, contact_myu=0.25)
+    o.step(1, 40)
+    ref = o.download()
+    assert o.counters()[1] > 0
+    assert sum(r["hits"] for _, r in res) == o.counters()[1], "every hit is found by exactly one rank"
+    assert any(r["n_ghost"] > 0 for _, r in res)
+    scale = np.abs(ref["disp"]).max()
+    for rank, r in res:
+        n = r["node_l2g"] - 1
+        assert np.abs(ref["disp"].reshape(-1, 3)[n].reshape(-1) - r["disp"]).max() <= 1e-10 * scale, f"rank {rank}"
+        ip = ((r["elem_l2g"] - 1)[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        assert np.abs(ref["integ_eq_plastic_strain"][ip] - r["eps"]).max() <= 1e-10 * max(ref["integ_eq_plastic_strain"].max(), 1e-30)
