@@ -1231,12 +1231,7 @@ int HKAPI(set_stream)(hk_engine* e, void* cuda_stream) {
 #ifndef HK_EMU
     hkp::sync(e->stream);
     if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
-    if (cuda_stream) {
-        e->stream = (cudaStream_t)cuda_stream;
-    } else {
-        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
-        e->own_stream = true;
-    }
+    e->stream = (cudaStream_t)cuda_stream;      // NULL is a valid handle: the CUDA legacy default stream
 #else
     (void)cuda_stream;
 #endif

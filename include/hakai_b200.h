@@ -175,7 +175,9 @@ int hk_counters(hk_engine* e, int64_t out[8]);
 int hk_profile(hk_engine* e, int32_t enable);
 int hk_profile_read(hk_engine* e, double ms[4], int64_t launches[4]);
 
-/* Use an externally created CUDA stream (cudaStream_t as void*) for all work; NULL = own. */
+/* Run all work on the caller's CUDA stream (cudaStream_t as void*).  NULL is the CUDA legacy default stream (what
+ * torch.cuda.current_stream().cuda_stream returns by default), so that NCCL ops enqueued by the host framework are
+ * ordered with the engine's kernels.  Without this call the engine uses a private non-blocking stream. */
 int hk_set_stream(hk_engine* e, void* cuda_stream);
 
 /* ---- multi-GPU: one engine per rank over an element-block partition ------------------------
