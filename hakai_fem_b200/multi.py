@@ -64,20 +64,21 @@ def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
     m = setup.model
     nE = m.nElement
     bounds = [(nE * r) // n_ranks for r in range(n_ranks + 1)]
-    owners_of_node = [set() for _ in range(m.nNode + 1)]
+    # holds[r, n] = rank r holds node n (bit matrix: n_ranks x nNode+1); owner = lowest rank holding it
+    holds = np.zeros((n_ranks, m.nNode + 1), bool)
     doms = []
     locals_ = []
     for r in range(n_ranks):
         el = np.arange(bounds[r], bounds[r + 1])
         nodes = np.unique(m.elementmat[:, el])                    # ascending global ids
-        for n in nodes:
-            owners_of_node[n].add(r)
+        holds[r, nodes] = True
         locals_.append((el, nodes))
+    first_holder = np.argmax(holds, axis=0)
     surf = np.zeros(0, np.int64)
     if m.contact_flag:
         surf = np.unique(np.concatenate([np.concatenate([ct.c_nodes_i, ct.c_nodes_j, ct.c_triangles.reshape(-1)])
                                          for ct in setup.CT]))
-        owner = np.array([min(owners_of_node[n]) for n in surf])
+        owner = first_holder[surf]
         export_lists = [surf[owner == r] for r in range(n_ranks)]
         maxlen = max(len(x) for x in export_lists)
     for r in range(n_ranks):
@@ -115,15 +116,16 @@ def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
                 mine = e_g2l[ct.c_triangles_eleid] > 0
                 lst.CT.append(ContactTriangle(ct.i_instance, ct.j_instance, g2l[ct.c_nodes_i], g2l[ct.c_nodes_j],
                                               g2l[ct.c_triangles[mine]], e_g2l[ct.c_triangles_eleid[mine]], ct.young))
+            g_owner = first_holder[ghosts]
             src = np.zeros(len(ghosts), np.int64)
-            for i, gnode in enumerate(ghosts):
-                o = int(owner[np.searchsorted(surf, gnode)])
-                src[i] = o * maxlen + int(np.searchsorted(export_lists[o], gnode))
+            for o in range(n_ranks):
+                sel = g_owner == o
+                src[sel] = o * maxlen + np.searchsorted(export_lists[o], ghosts[sel])
             dom.contact = ContactLists(g2l[export_lists[r]], g2l[ghosts], src, g2l[surf], maxlen)
         for q in range(n_ranks):
             if q == r:
                 continue
-            shared = np.array([n for n in nodes_own if q in owners_of_node[n]], np.int64)
+            shared = nodes_own[holds[q, nodes_own]]
             if len(shared):
                 dom.neighbors.append(q)
                 dom.halo_nodes.append(g2l[shared])
