@@ -95,6 +95,9 @@ struct hk_engine {
     int* d_node_list[3] = {nullptr, nullptr, nullptr};
     long long* d_import_src = nullptr;
     bool contact_done = false;     // hk_contact_enqueue already ran the contact pass of the next step
+    // multi-GPU erosion: instance tables are GLOBAL; these map global (1-based) ids to engine-local 0-based ids or -1
+    std::vector<int> g_node_map, g_elem_map;
+    std::vector<int64_t> g_einst;  // instance of every GLOBAL element
     int64_t begun_t = -1;          // step opened by hk_step_begin
     // special nodes (host mirror)
     std::vector<int> spec_idx_h;
@@ -338,33 +341,46 @@ static void add_surface_triangle(InstanceH& I, int64_t ele_id, std::vector<int64
     nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
 }
 
-static int update_surfaces(hk_engine* e, const std::vector<int64_t>& deleted /* 1-based global ids */) {
+// `deleted`: 1-based element ids — engine-local ids normally; GLOBAL ids when the multi-GPU maps are set
+// (hk_set_global_maps): then the instance tables are global, nodes are translated through g_node_map and only
+// triangles of locally owned elements are kept (another rank owns the others).
+static int update_surfaces(hk_engine* e, const std::vector<int64_t>& deleted) {
+    const bool global = !e->g_node_map.empty();
     std::vector<char> changed(e->pairs.size(), 0);
     std::vector<int> touched;
     for (int64_t gid : deleted) {
-        const int64_t instance_id = e->einst[gid - 1];
+        const int64_t instance_id = global ? e->g_einst[gid - 1] : e->einst[gid - 1];
         if (instance_id < 1 || instance_id > (int64_t)e->instances.size()) continue;
         InstanceH& I = e->instances[instance_id - 1];
         if (I.surfaces.empty()) continue;
         std::vector<int64_t> tri, tri_ele, nodes;
         add_surface_triangle(I, gid - I.element_offset, tri, tri_ele, nodes);
+        auto node_of = [&](int64_t part_local) -> int {
+            const int64_t g = part_local + I.node_offset;           // 1-based (global) node id
+            return global ? e->g_node_map[g - 1] : (int)(g - 1);
+        };
         for (size_t c = 0; c < e->pairs.size(); ++c) {
             PairH& p = e->pairs[c];
             if (p.i_instance == instance_id) {                  // J2:784-787
                 for (int64_t nl : nodes) {
-                    int g = (int)(nl + I.node_offset - 1);
+                    const int g = node_of(nl);
+                    if (g < 0) return fail(e, HK_ERR_STATE, "exposed node is not present on this rank (ghost set too small)");
                     if (p.set_i.insert(g).second) { p.nodes_i.push_back(g); ensure_contact_slot(e, g, &touched); changed[c] = 1; }
                 }
             } else if (p.j_instance == instance_id) {           // J2:789-797
                 for (int64_t nl : nodes) {
-                    int g = (int)(nl + I.node_offset - 1);
+                    const int g = node_of(nl);
+                    if (g < 0) return fail(e, HK_ERR_STATE, "exposed node is not present on this rank (ghost set too small)");
                     if (p.set_j.insert(g).second) { p.nodes_j.push_back(g); ensure_contact_slot(e, g, &touched); changed[c] = 1; }
                 }
                 for (size_t r = 0; r < tri_ele.size(); ++r) {
-                    p.t0.push_back((int)(tri[3 * r + 0] + I.node_offset - 1));
-                    p.t1.push_back((int)(tri[3 * r + 1] + I.node_offset - 1));
-                    p.t2.push_back((int)(tri[3 * r + 2] + I.node_offset - 1));
-                    p.tele.push_back((int)(tri_ele[r] + I.element_offset - 1));
+                    const int64_t ge = tri_ele[r] + I.element_offset;   // 1-based (global) element id
+                    const int le = global ? e->g_elem_map[ge - 1] : (int)(ge - 1);
+                    if (le < 0) continue;                               // owned by another rank
+                    p.t0.push_back(node_of(tri[3 * r + 0]));
+                    p.t1.push_back(node_of(tri[3 * r + 1]));
+                    p.t2.push_back(node_of(tri[3 * r + 2]));
+                    p.tele.push_back(le);
                     changed[c] = 1;
                 }
             }
@@ -847,7 +863,7 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
         e->n_launch += 2;
         if (e->any_ductile) { hk_launch_flush_deleted(d, e->stream); e->n_launch += 1; }
         e->n_steps += 1;
-        if (contact_on && e->any_ductile) {
+        if (contact_on && e->any_ductile && e->g_node_map.empty()) {      // multi-GPU: the host drives hk_apply_deleted
             std::vector<int64_t> fresh;
             int rc = fetch_deleted(e, &fresh);
             if (rc) return rc;
@@ -1193,6 +1209,36 @@ int HKAPI(nodes_import)(hk_engine* e, const void* in_dev, const int64_t* src_ind
     hk_launch_nodes_import(e->d, e->d_node_list[1], e->d_import_src, (long long)n, (const double*)in_dev, e->stream);
     e->n_launch += 1;
     CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(set_global_maps)(hk_engine* e, int64_t n_global_nodes, const int64_t* node_map, int64_t n_global_elements,
+                           const int64_t* elem_map, const int64_t* element_instance) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (!node_map || !elem_map || !element_instance) return fail(e, HK_ERR_ARG, "null argument");
+    e->g_node_map.resize(n_global_nodes);
+    for (int64_t i = 0; i < n_global_nodes; ++i) {
+        if (node_map[i] > e->nNode) return fail(e, HK_ERR_ARG, "node_map entry out of range");
+        e->g_node_map[i] = (int)(node_map[i] - 1);              // 0 (absent) -> -1
+    }
+    e->g_elem_map.resize(n_global_elements);
+    e->g_einst.assign(element_instance, element_instance + n_global_elements);
+    for (int64_t i = 0; i < n_global_elements; ++i) {
+        if (elem_map[i] > e->nElement) return fail(e, HK_ERR_ARG, "elem_map entry out of range");
+        e->g_elem_map[i] = (int)(elem_map[i] - 1);
+    }
+    return HK_OK;
+}
+
+int HKAPI(apply_deleted)(hk_engine* e, int64_t n, const int64_t* global_ids) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (e->g_node_map.empty()) return fail(e, HK_ERR_STATE, "hk_set_global_maps not called");
+    std::vector<int64_t> ids(global_ids, global_ids + n);
+    for (int64_t g : ids)
+        if (g < 1 || g > (int64_t)e->g_elem_map.size()) return fail(e, HK_ERR_ARG, "global element id out of range");
+    int rc = update_surfaces(e, ids);
+    if (rc) return rc;
+    CK(hkp::sync(e->stream));
     return HK_OK;
 }
 

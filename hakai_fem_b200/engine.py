@@ -42,6 +42,7 @@ EXPORTS = [
     "deleted_ids", "contact_pair_info", "counters", "profile", "profile_read", "set_stream",
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
+    "set_global_maps", "apply_deleted",
 ]
 
 
@@ -307,6 +308,14 @@ class EngineBase:
 
     def contact_import(self, in_ptr: int, n_ranks: int):
         self._chk(self._fn("contact_import")(self._h, C.c_void_p(in_ptr), c_i64(n_ranks)))
+
+    def set_global_maps(self, node_map, elem_map, element_instance):
+        nm, em, ei = _i64(node_map), _i64(elem_map), _i64(element_instance)
+        self._chk(self._fn("set_global_maps")(self._h, c_i64(len(nm)), _pi(nm), c_i64(len(em)), _pi(em), _pi(ei)))
+
+    def apply_deleted(self, global_ids):
+        a = _i64(global_ids)
+        self._chk(self._fn("apply_deleted")(self._h, c_i64(len(a)), _pi(a)))
 
     def set_stream(self, stream_ptr: int):
         self._chk(self._fn("set_stream")(self._h, C.c_void_p(stream_ptr)))

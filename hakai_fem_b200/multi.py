@@ -6,8 +6,13 @@ elements touch; nodes on a partition interface are duplicated.  Per time step
     batch_isend_irecv with the neighbours   NCCL send/recv over NVLink (gloo in the CPU tests)
     engine.step(t, 1)                       adds the received partials, then the usual nodal + element kernels
 Both sides of an interface then update the shared nodes redundantly from bit-identical inputs
-(a + b == b + a), so positions never need to be exchanged.  Contact across ranks is not implemented yet
-(DESIGN.md §7); fracture is rank-local and works unchanged.
+(a + b == b + a), so positions never need to be exchanged.  Fracture is rank-local.
+
+Contact across ranks (ContactExchanger): every rank tests the GLOBAL slave-node lists against the master
+triangles of its own elements; surface-node states travel by all-gather, the fixed-point force accumulators by
+an exact integer all-gather + sum.  When elements can be deleted (ductile material + contact), the faces they
+expose join the contact surface on every rank (ErosionMaps, hk_apply_deleted): one host synchronisation and one
+small all-gather of the fresh deleted ids per step.
 """
 from __future__ import annotations
 
@@ -45,6 +50,16 @@ def _restrict_dofs(dof_lists, values, g2l):
 
 
 @dataclass
+class ErosionMaps:
+    """What a rank needs to replay add_surface_triangle (J2:2167-2245) for elements deleted on ANY rank."""
+    node_map: np.ndarray               # global node (0-based index) -> local 1-based id, 0 = not on this rank
+    elem_map: np.ndarray               # global element -> local 1-based id, 0 = owned by another rank
+    element_instance: np.ndarray       # instance of every global element
+    owner: np.ndarray                  # global node id (1-based index, [0] unused) -> owning rank
+    n_held: int                        # local ids 1..n_held are nodes of own elements, the rest are ghosts
+
+
+@dataclass
 class ContactLists:
     """Per-rank lists of the contact-surface all-gather (local 1-based node ids)."""
     export_nodes: np.ndarray           # surface nodes this rank owns (ascending global id)
@@ -52,6 +67,25 @@ class ContactLists:
     import_src: np.ndarray             # index of each ghost's record in the gathered buffer (rank*maxlen + position)
     surface_nodes: np.ndarray          # ALL surface nodes in global order (same order on every rank)
     maxlen: int                        # padded length of one rank's export block
+    erosion: ErosionMaps = None        # set when deletions can expose new faces
+
+
+def build_contact_lists(surf, owner, g2l, n_held, rank, n_ranks, erosion=None) -> ContactLists:
+    """`surf`: ascending global ids of all current contact-surface nodes; `owner[g]`: rank whose copy is
+    authoritative; `g2l`: global -> local 1-based (0 = absent).  Identical `surf` on every rank."""
+    own = owner[surf]
+    export_lists = [surf[own == r] for r in range(n_ranks)]
+    maxlen = max(1, max(len(x) for x in export_lists))
+    loc = g2l[surf]
+    if np.any(loc == 0):
+        raise ValueError("contact-surface node missing on rank %d (ghost set too small)" % rank)
+    ghost = surf[loc > n_held]                                     # copies no local element updates
+    g_owner = owner[ghost]
+    src = np.zeros(len(ghost), np.int64)
+    for o in range(n_ranks):
+        sel = g_owner == o
+        src[sel] = o * maxlen + np.searchsorted(export_lists[o], ghost[sel])
+    return ContactLists(g2l[export_lists[rank]], g2l[ghost], src, loc, maxlen, erosion)
 
 
 def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
@@ -59,8 +93,9 @@ def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
     decks; the 16 M/GPU bench builds each slab directly (slab_deck) without materialising the global mesh.
 
     With contact, every rank receives the GLOBAL contact node lists (nodes it does not hold are appended as ghost
-    nodes that no element references) and the master triangles of its own elements; exposed-face updates after
-    element deletion are not propagated across ranks yet."""
+    nodes that no element references) and the master triangles of its own elements.  If a material can fail, the
+    ghost set is every node of the instances in contact (any of them may become exposed) and the rank gets the
+    global instance face tables + ErosionMaps."""
     m = setup.model
     nE = m.nElement
     bounds = [(nE * r) // n_ranks for r in range(n_ranks + 1)]
@@ -75,15 +110,22 @@ def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
         locals_.append((el, nodes))
     first_holder = np.argmax(holds, axis=0)
     surf = np.zeros(0, np.int64)
+    candidates = surf
+    erosion = False
     if m.contact_flag:
         surf = np.unique(np.concatenate([np.concatenate([ct.c_nodes_i, ct.c_nodes_j, ct.c_triangles.reshape(-1)])
                                          for ct in setup.CT]))
-        owner = first_holder[surf]
-        export_lists = [surf[owner == r] for r in range(n_ranks)]
-        maxlen = max(len(x) for x in export_lists)
+        candidates = surf
+        erosion = (any(mat.ductile.shape[0] > 0 for mat in m.MATERIAL)
+                   and any(len(ins.surfaces) > 0 for ins in m.INSTANCE))
+        if erosion:
+            inst = sorted({i for ct in setup.CT for i in (ct.i_instance, ct.j_instance)})
+            candidates = np.unique(np.concatenate(
+                [surf] + [np.arange(m.INSTANCE[i - 1].node_offset + 1,
+                                    m.INSTANCE[i - 1].node_offset + m.INSTANCE[i - 1].nNode + 1) for i in inst]))
     for r in range(n_ranks):
         el, nodes_own = locals_[r]
-        ghosts = np.setdiff1d(surf, nodes_own) if m.contact_flag else np.zeros(0, np.int64)
+        ghosts = np.setdiff1d(candidates, nodes_own) if m.contact_flag else np.zeros(0, np.int64)
         nodes = np.concatenate([nodes_own, ghosts])              # local numbering: own nodes, then ghosts
         g2l = np.zeros(m.nNode + 1, np.int64)
         g2l[nodes] = np.arange(1, len(nodes) + 1)
@@ -111,17 +153,18 @@ def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
             from .model_setup import ContactTriangle
             e_g2l = np.zeros(nE + 1, np.int64)
             e_g2l[el + 1] = np.arange(1, len(el) + 1)
-            lm.INSTANCE = []                                      # no cross-rank exposed-face update yet
+            maps = None
+            if erosion:                                           # GLOBAL face tables (copied: the engine mutates its own)
+                lm.INSTANCE = [copy.copy(ins) for ins in m.INSTANCE]
+                maps = ErosionMaps(g2l[1:].copy(), e_g2l[1:].copy(), np.asarray(m.element_instance, np.int64),
+                                   first_holder.astype(np.int64), len(nodes_own))
+            else:
+                lm.INSTANCE = []
             for ct in setup.CT:
                 mine = e_g2l[ct.c_triangles_eleid] > 0
                 lst.CT.append(ContactTriangle(ct.i_instance, ct.j_instance, g2l[ct.c_nodes_i], g2l[ct.c_nodes_j],
                                               g2l[ct.c_triangles[mine]], e_g2l[ct.c_triangles_eleid[mine]], ct.young))
-            g_owner = first_holder[ghosts]
-            src = np.zeros(len(ghosts), np.int64)
-            for o in range(n_ranks):
-                sel = g_owner == o
-                src[sel] = o * maxlen + np.searchsorted(export_lists[o], ghosts[sel])
-            dom.contact = ContactLists(g2l[export_lists[r]], g2l[ghosts], src, g2l[surf], maxlen)
+            dom.contact = build_contact_lists(surf, first_holder, g2l, len(nodes_own), r, n_ranks, maps)
         for q in range(n_ranks):
             if q == r:
                 continue
@@ -209,9 +252,23 @@ def exchange_sum(values_per_nbr, neighbors, device):
 class ContactExchanger:
     """All-gather of contact-surface node {position, velocity} and of the fixed-point force accumulators."""
 
-    def __init__(self, engine, lists: ContactLists, world: int, device):
+    def __init__(self, engine, lists: ContactLists, world: int, device, rank=None, node_l2g=None, n_pairs=0):
+        self.engine, self.world, self.device = engine, world, device
+        self.rank, self.node_l2g, self.n_pairs = rank, node_l2g, n_pairs
+        self.erosion = lists.erosion
+        if self.erosion is not None:
+            if rank is None or node_l2g is None:
+                raise ValueError("erosion across ranks needs rank and node_l2g")
+            er = self.erosion
+            engine.set_global_maps(er.node_map, er.elem_map, er.element_instance)
+            self._g2l = np.concatenate([[0], er.node_map])
+            self._surf0 = np.asarray(node_l2g)[lists.surface_nodes - 1]
+        self.set_lists(lists)
+
+    def set_lists(self, lists: ContactLists):
         import torch
-        self.engine, self.lists, self.world = engine, lists, world
+        engine, world, device = self.engine, self.world, self.device
+        self.lists = lists
         self.send_nodes = torch.zeros(lists.maxlen * 6, dtype=torch.float64, device=device)
         self.all_nodes = torch.zeros(world * lists.maxlen * 6, dtype=torch.float64, device=device)
         n_surf = len(lists.surface_nodes)
@@ -221,6 +278,35 @@ class ContactExchanger:
         engine.set_node_list(1, lists.import_nodes)
         engine.set_node_list(2, lists.surface_nodes)
         self._first = True
+
+    def exchange_deleted(self, fresh_global):
+        """All ranks apply the same ascending list of GLOBAL element ids deleted in the step that just ended
+        (the reference visits them in element order, J2:767-804), then rebuild the surface lists if they grew."""
+        import torch
+        import torch.distributed as dist
+        n = torch.tensor([len(fresh_global)], dtype=torch.int64, device=self.device)
+        counts = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(counts, n)
+        counts = [int(c.item()) for c in counts]
+        if sum(counts) == 0:
+            return 0
+        cap = max(counts)
+        mine = torch.zeros(cap, dtype=torch.int64, device=self.device)
+        mine[:len(fresh_global)] = torch.as_tensor(np.asarray(fresh_global, np.int64), device=self.device)
+        got = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(got, mine)
+        ids = np.sort(np.concatenate([g[:c].cpu().numpy() for g, c in zip(got, counts)]))
+        self.engine.apply_deleted(ids)
+        l2g = np.asarray(self.node_l2g)
+        parts = [self._surf0]
+        for c in range(self.n_pairs):
+            info = self.engine.contact_pair(c)
+            parts += [l2g[info["c_nodes_i"] - 1], l2g[info["c_nodes_j"] - 1]]
+        surf = np.unique(np.concatenate(parts))
+        if len(surf) != len(self.lists.surface_nodes):
+            er = self.erosion
+            self.set_lists(build_contact_lists(surf, er.owner, self._g2l, er.n_held, self.rank, self.world, er))
+        return len(ids)
 
     def run(self):
         """positions -> ghosts, contact pass on the local triangles, exact sum of the forces over ranks."""
@@ -241,7 +327,7 @@ class SlabRunner:
     host-compiled kernel build, whose "device" pointers are host pointers."""
 
     def __init__(self, engine_cls, setup: Setup, neighbors, halo_nodes, torch_device, sum_mass=False, contact=None,
-                 world=1, **params):
+                 world=1, rank=None, node_l2g=None, elem_l2g=None, **params):
         self.setup = setup
         if sum_mass and neighbors:
             # interface nodes: add the neighbour's partial lumped mass (J2:201-215 summed over ALL elements)
@@ -259,19 +345,41 @@ class SlabRunner:
             return eng
         self.engine = configure_engine(with_halo, setup, **params)
         self.halo = HaloExchanger(self.engine, neighbors, halo_nodes, torch_device)
-        self.contact = ContactExchanger(self.engine, contact, world, torch_device) if contact is not None else None
+        self.contact = (ContactExchanger(self.engine, contact, world, torch_device, rank, node_l2g, len(setup.CT))
+                        if contact is not None else None)
+        self.erosion = self.contact is not None and self.contact.erosion is not None
+        if self.erosion and elem_l2g is None:
+            raise ValueError("erosion across ranks needs elem_l2g")
+        self.elem_l2g = None if elem_l2g is None else np.asarray(elem_l2g, np.int64)
         self.nElement = model.nElement
+
+    @classmethod
+    def from_domain(cls, engine_cls, dom: LocalDomain, torch_device, world, **params):
+        return cls(engine_cls, dom.setup, dom.neighbors, dom.halo_nodes, torch_device, contact=dom.contact,
+                   world=world, rank=dom.rank, node_l2g=dom.node_l2g, elem_l2g=dom.elem_l2g, **params)
+
+    def _after_step(self) -> int:
+        """Erosion across ranks: one host sync per step (the deleted set decides the next step's contact surface)."""
+        n = self.engine.sync()
+        fresh = self.engine.deleted_ids()[-n:] if n else np.zeros(0, np.int64)
+        self.contact.exchange_deleted(self.elem_l2g[np.asarray(fresh, np.int64) - 1])
+        return n
 
     def step(self, t: int) -> int:
         if self.contact is not None:
             self.contact.run()
         self.halo.exchange()
-        return self.engine.step(t, 1)
+        n = self.engine.step(t, 1)
+        if self.erosion:
+            self.contact.exchange_deleted(self.elem_l2g[self.engine.deleted_ids()[-n:] - 1] if n
+                                          else np.zeros(0, np.int64))
+        return n
 
     def run(self, t_first: int, n_steps: int) -> int:
         """Enqueues pack -> exchange -> step for every step without blocking the host, then synchronises once."""
         import time as _time
         _t0 = _time.perf_counter()
+        n_del = 0
         for t in range(t_first, t_first + n_steps):
             if self.contact is not None:
                 self.contact.run()
@@ -282,5 +390,7 @@ class SlabRunner:
                 self.engine.step_finish(t)           # interface nodes, element kernel
             else:
                 self.engine.step_enqueue(t, 1)
+            if self.erosion:
+                n_del += self._after_step()
         self.last_enqueue_s = _time.perf_counter() - _t0      # host time to enqueue (diagnostic)
-        return self.engine.sync()
+        return n_del + self.engine.sync()

@@ -221,6 +221,14 @@ int hk_nodes_import(hk_engine* e, const void* in_dev, const int64_t* src_index /
 int hk_contact_enqueue(hk_engine* e);                             /* contact pass of the NEXT step, now     */
 int hk_contact_export(hk_engine* e, void* out_dev);               /* list 2 -> 6 uint64 per node             */
 int hk_contact_import(hk_engine* e, const void* in_dev, int64_t n_ranks);   /* sum of n_ranks records per node */
+/* Erosion of contact surfaces across ranks (add_surface_triangle, J2:767-804, 2167-2245).  The instance face tables
+ * given to hk_add_instance are then the GLOBAL ones; the maps translate global 1-based ids to this rank's local
+ * 1-based ids (0 = not present / not owned).  After every step the host all-gathers the freshly deleted GLOBAL
+ * element ids (ascending) and every rank applies the same list: node lists grow identically everywhere, each new
+ * triangle is kept by the rank that owns its element. */
+int hk_set_global_maps(hk_engine* e, int64_t n_global_nodes, const int64_t* node_map,
+                       int64_t n_global_elements, const int64_t* elem_map, const int64_t* element_instance);
+int hk_apply_deleted(hk_engine* e, int64_t n, const int64_t* global_ids);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 """-m gpu, needs >= 2 devices (skipped on single-GPU boxes): the multi-GPU paths over NCCL — force halos with
-fracture, and contact across ranks (surface all-gather + exact force exchange) — against one oracle run."""
+fracture, contact across ranks (surface all-gather + exact force exchange), and erosion of the contact surface
+across ranks — against one oracle run."""
 import os
 import sys
 
@@ -13,6 +14,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
+def _global_setup(mode):
+    from hakai_fem_b200.model_setup import prepare
+    from hakai_fem_b200.mesh import ImpactDeck, StretchDeck, steel
+    if mode == "contact":
+        return prepare(ImpactDeck(plate=(40, 40, 6), proj=(9, 9, 9)).build_model()), dict(contact_myu=0.25), 40
+    if mode == "erosion":                                  # brittle plate: deletions expose new contact faces
+        model = ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0).build_model()
+        model.MATERIAL[0].ductile = np.array([[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]])
+        return prepare(model), {}, 400
+    deck = StretchDeck(12, 10, 24, jitter=0.1, strain_per_step=8e-4,
+                       material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]))
+    return prepare(deck.build_model()), {}, 90
+
+
 def _worker(rank, world, port, mode, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -21,19 +36,8 @@ def _worker(rank, world, port, mode, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from hakai_fem_b200.engine import Engine
-        from hakai_fem_b200.model_setup import prepare
         from hakai_fem_b200.multi import partition_model, SlabRunner
-        from hakai_fem_b200.mesh import ImpactDeck, StretchDeck, steel
-        if mode == "contact":
-            gsetup = prepare(ImpactDeck(plate=(40, 40, 6), proj=(9, 9, 9)).build_model())
-            prm = dict(contact_myu=0.25)
-            n_steps = 40
-        else:
-            deck = StretchDeck(12, 10, 24, jitter=0.1, strain_per_step=8e-4,
-                               material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]))
-            gsetup = prepare(deck.build_model())
-            prm = {}
-            n_steps = 90
+        gsetup, prm, n_steps = _global_setup(mode)
         dom = partition_model(gsetup, world)[rank]
         stream = torch.cuda.current_stream()
 
@@ -41,28 +45,29 @@ def _worker(rank, world, port, mode, q):
             e = Engine(**p)
             e.set_stream(stream.cuda_stream)
             return e
-        run = SlabRunner(make, dom.setup, dom.neighbors, dom.halo_nodes, torch.device("cuda", rank), contact=dom.contact,
-                         world=world, device=rank, **prm)
+        run = SlabRunner.from_domain(make, dom, torch.device("cuda", rank), world, device=rank, **prm)
         nd = run.run(1, n_steps)
         d = run.engine.download()
-        n_own = len(dom.node_l2g) - (len(dom.contact.import_nodes) if dom.contact else 0)
+        n_own = len(np.unique(dom.setup.model.elementmat))          # held nodes come first, ghosts after
         q.put((rank, dict(disp=d["disp"][:3 * n_own], eps=d["integ_eq_plastic_strain"], flag=d["element_flag"],
-                          node_l2g=dom.node_l2g[:n_own], elem_l2g=dom.elem_l2g, hits=int(run.engine.counters()[1]), nd=nd)))
+                          node_l2g=dom.node_l2g[:n_own], elem_l2g=dom.elem_l2g, hits=int(run.engine.counters()[1]), nd=nd,
+                          deleted=dom.elem_l2g[run.engine.deleted_ids() - 1],
+                          n_surf=len(run.contact.lists.surface_nodes) if run.contact else 0,
+                          n_surf0=len(dom.contact.surface_nodes) if dom.contact else 0)))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["fracture", "contact"])
+@pytest.mark.parametrize("mode", ["fracture", "contact", "erosion"])
 def test_two_gpus_match_single_domain_oracle(mode):
-    from hakai_fem_b200.model_setup import prepare, configure_engine
-    from hakai_fem_b200.mesh import ImpactDeck, StretchDeck, steel
+    from hakai_fem_b200.model_setup import configure_engine
     from oracle.oracle_engine import OracleEngine
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29200 + (os.getpid() % 2000) + (1 if mode == "contact" else 0)
+    port = 29200 + (os.getpid() % 2000) + ("fracture", "contact", "erosion").index(mode)
     procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -70,27 +75,24 @@ def test_two_gpus_match_single_domain_oracle(mode):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    if mode == "contact":
-        gsetup = prepare(ImpactDeck(plate=(40, 40, 6), proj=(9, 9, 9)).build_model())
-        o = configure_engine(OracleEngine, gsetup, contact_myu=0.25)
-        n_steps = 40
-    else:
-        deck = StretchDeck(12, 10, 24, jitter=0.1, strain_per_step=8e-4,
-                           material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]))
-        gsetup = prepare(deck.build_model())
-        o = configure_engine(OracleEngine, gsetup)
-        n_steps = 90
+    gsetup, prm, n_steps = _global_setup(mode)
+    o = configure_engine(OracleEngine, gsetup, **prm)
     nd_ref = o.step(1, n_steps)
     ref = o.download()
     scale = np.abs(ref["disp"]).max()
+    tol = 1e-7 if mode == "erosion" else 1e-9               # same bound as the single-GPU erosion case
     for rank, r in res:
         n = r["node_l2g"] - 1
-        assert np.abs(ref["disp"].reshape(-1, 3)[n].reshape(-1) - r["disp"]).max() <= 1e-9 * scale, f"rank {rank} disp"
+        assert np.abs(ref["disp"].reshape(-1, 3)[n].reshape(-1) - r["disp"]).max() <= tol * scale, f"rank {rank} disp"
         e = r["elem_l2g"] - 1
         ip = (e[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
-        assert np.abs(ref["integ_eq_plastic_strain"][ip] - r["eps"]).max() <= 1e-9 * max(ref["integ_eq_plastic_strain"].max(), 1e-30)
+        assert np.abs(ref["integ_eq_plastic_strain"][ip] - r["eps"]).max() <= tol * max(ref["integ_eq_plastic_strain"].max(), 1e-30)
         assert np.array_equal(ref["element_flag"][e], r["flag"])
     if mode == "contact":
         assert sum(r["hits"] for _, r in res) == o.counters()[1] > 0
+    elif mode == "erosion":
+        got = np.sort(np.concatenate([r["deleted"] for _, r in res]))
+        assert len(got) > 0 and np.array_equal(got, np.sort(o.deleted_ids())), "deleted-element set differs"
+        assert any(r["n_surf"] > r["n_surf0"] for _, r in res), "contact surface never grew"
     else:
         assert sum(r["nd"] for _, r in res) == nd_ref > 0

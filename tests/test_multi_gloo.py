@@ -216,3 +216,84 @@ def test_contact_across_ranks_matches_single_domain(world):
         assert np.abs(ref["disp"].reshape(-1, 3)[n].reshape(-1) - r["disp"]).max() <= 1e-10 * scale, f"rank {rank}"
         ip = ((r["elem_l2g"] - 1)[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
         assert np.abs(ref["integ_eq_plastic_strain"][ip] - r["eps"]).max() <= 1e-10 * max(ref["integ_eq_plastic_strain"].max(), 1e-30)
+
+
+def _erosion_setup():
+    from hakai_fem_b200.model_setup import prepare
+    from hakai_fem_b200.mesh import ImpactDeck
+    model = ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0).build_model()
+    model.MATERIAL[0].ductile = np.array([[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]])
+    return prepare(model)
+
+
+def _worker_erosion(rank, world, port, q):
+    """Brittle plate split over ranks: faces exposed by deletions on one rank join the contact surface on all."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.multi import partition_model, SlabRunner
+        from tests.emu.emu_engine import EmuEngine
+        dom = partition_model(_erosion_setup(), world)[rank]
+        assert dom.contact.erosion is not None
+        run = SlabRunner.from_domain(EmuEngine, dom, "cpu", world)
+        n_del = run.run(1, 400)
+        d = run.engine.download()
+        n_own = dom.contact.erosion.n_held
+        pairs = []
+        for c in range(len(dom.setup.CT)):
+            info = run.engine.contact_pair(c)
+            pairs.append(dict(nodes_i=dom.node_l2g[info["c_nodes_i"] - 1], nodes_j=dom.node_l2g[info["c_nodes_j"] - 1],
+                              tri=dom.node_l2g[info["c_triangles"] - 1], tele=dom.elem_l2g[info["c_triangles_eleid"] - 1]))
+        q.put((rank, dict(disp=d["disp"][:3 * n_own], eps=d["integ_eq_plastic_strain"], flag=d["element_flag"],
+                          node_l2g=dom.node_l2g[:n_own], elem_l2g=dom.elem_l2g, n_del=n_del,
+                          deleted=dom.elem_l2g[run.engine.deleted_ids() - 1], pairs=pairs,
+                          n_surf=len(run.contact.lists.surface_nodes), n_surf0=len(dom.contact.surface_nodes))))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_erosion_across_ranks_matches_single_domain(world):
+    from hakai_fem_b200.model_setup import configure_engine
+    from oracle.oracle_engine import OracleEngine
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_erosion, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = configure_engine(OracleEngine, _erosion_setup())
+    o.step(1, 400)
+    ref = o.download()
+    ids = o.deleted_ids()
+    assert len(ids) > 0, "nothing eroded: test is vacuous"
+    got = np.concatenate([res[r]["deleted"] for r in range(world)])
+    assert np.array_equal(np.sort(got), np.sort(ids)), "deleted-element set differs"
+    assert sum(res[r]["n_del"] for r in range(world)) == len(ids)
+    assert any(res[r]["n_surf"] > res[r]["n_surf0"] for r in range(world)), "surface never grew"
+    for c in range(2):
+        po = o.contact_pair(c)
+        for r in range(world):                                   # node lists: identical, same order, on every rank
+            assert np.array_equal(res[r]["pairs"][c]["nodes_i"], po["c_nodes_i"]), (c, r)
+            assert np.array_equal(res[r]["pairs"][c]["nodes_j"], po["c_nodes_j"]), (c, r)
+        tri = np.concatenate([np.column_stack([res[r]["pairs"][c]["tri"], res[r]["pairs"][c]["tele"]])
+                              for r in range(world)])
+        want = np.column_stack([po["c_triangles"], po["c_triangles_eleid"]])
+        assert len(tri) == len(want)                             # every triangle lives on exactly one rank
+        assert np.array_equal(tri[np.lexsort(tri.T[::-1])], want[np.lexsort(want.T[::-1])])
+    scale = np.abs(ref["disp"]).max()
+    for r in range(world):
+        n = res[r]["node_l2g"] - 1
+        e = res[r]["elem_l2g"] - 1
+        want = ref["disp"].reshape(-1, 3)[n].reshape(-1)
+        assert np.abs(res[r]["disp"] - want).max() <= 1e-7 * scale
+        assert np.array_equal(res[r]["flag"], ref["element_flag"][e])
+        ep = ref["integ_eq_plastic_strain"].reshape(-1, 8)[e].reshape(-1)
+        assert np.abs(res[r]["eps"] - ep).max() <= 1e-7 * max(np.abs(ep).max(), 1e-30)
