@@ -176,11 +176,10 @@ def _worker_contact(rank, world, port, q):
         from tests.emu.emu_engine import EmuEngine
         gsetup = prepare(ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3)).build_model())
         dom = partition_model(gsetup, world)[rank]
-        run = SlabRunner(EmuEngine, dom.setup, dom.neighbors, dom.halo_nodes, "cpu", contact=dom.contact, world=world,
-                         contact_myu=0.25)
+        run = SlabRunner.from_domain(EmuEngine, dom, "cpu", world, contact_myu=0.25)
         run.run(1, 40)
         d = run.engine.download()
-        n_own = len(dom.node_l2g) - len(dom.contact.import_nodes)
+        n_own = len(np.unique(dom.setup.model.elementmat))          # held nodes first, ghosts after
         q.put((rank, dict(disp=d["disp"][:3 * n_own], eps=d["integ_eq_plastic_strain"], node_l2g=dom.node_l2g[:n_own],
                           elem_l2g=dom.elem_l2g, hits=int(run.engine.counters()[1]), n_ghost=len(dom.contact.import_nodes))))
         dist.barrier()
