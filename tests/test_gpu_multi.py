@@ -59,15 +59,17 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["fracture", "contact", "erosion"])
-def test_two_gpus_match_single_domain_oracle(mode):
+@pytest.mark.parametrize("mode,world", [("fracture", 2), ("contact", 2), ("erosion", 2), ("erosion", 1)])
+def test_ranks_match_single_domain_oracle(mode, world):
+    """world == 1 runs the whole domain-runner path (global maps, hk_apply_deleted, list rebuild, NCCL calls) on a
+    single-GPU box, where the 2-rank cases are skipped."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     from hakai_fem_b200.model_setup import configure_engine
     from oracle.oracle_engine import OracleEngine
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29200 + (os.getpid() % 2000) + ("fracture", "contact", "erosion").index(mode)
+    port = 29200 + (os.getpid() % 2000) + ("fracture", "contact", "erosion").index(mode) + 10 * world
     procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
