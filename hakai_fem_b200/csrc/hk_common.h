@@ -137,6 +137,8 @@ void hk_launch_ip_to_dev(const double* aos, const HkDev& d, int row0, int ncomp,
 void hk_launch_ip_to_aos(const HkDev& d, double* aos, int row0, int ncomp, long long e0, long long ne, cudaStream_t s);
 // triax [8][nEp] -> (nip) of the reference
 void hk_launch_triax_to_aos(const HkDev& d, double* aos, long long e0, long long ne, cudaStream_t s);
+void hk_launch_element_means(const HkDev& d, double* emean, cudaStream_t s);                 // [14][nEp]
+void hk_launch_node_means(const HkDev& d, const double* emean, double* out, int raw, cudaStream_t s);   // [16][nNode]
 void hk_upload_pusai(const double* P);
 void hk_launch_element_exact(const HkDev& d, long long step, int write_triax, cudaStream_t s);
 long long hk_element_tile();   // nEp must be a multiple of this

@@ -1000,6 +1000,35 @@ int HKAPI(download)(hk_engine* e, double* disp, double* velo, double* integ_stre
     return HK_OK;
 }
 
+int HKAPI(node_output)(hk_engine* e, double* node_stress, double* node_strain, double* node_eq_plastic_strain,
+                       double* node_mises_stress, double* node_triax_stress, double* inc_num, int32_t raw) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    const HkDev& d = e->d;
+    if (!e->triax_current) { hk_launch_triax(d, e->stream); e->triax_current = true; }
+    double* emean = nullptr;
+    double* out = nullptr;
+    int rc = dalloc(e, &emean, (size_t)14 * d.nEp);
+    if (!rc) rc = dalloc(e, &out, (size_t)16 * d.nNode);
+    if (rc) { dfree(e, emean); dfree(e, out); return rc; }
+    hk_launch_element_means(d, emean, e->stream);
+    hk_launch_node_means(d, emean, out, raw ? 1 : 0, e->stream);
+    e->n_launch += 2;
+    const size_t nb = sizeof(double) * (size_t)d.nNode;
+    int err = 0;
+    if (node_stress) err |= hkp::d2h(node_stress, out, 6 * nb, e->stream);
+    if (node_strain) err |= hkp::d2h(node_strain, out + 6 * d.nNode, 6 * nb, e->stream);
+    if (node_eq_plastic_strain) err |= hkp::d2h(node_eq_plastic_strain, out + 12 * d.nNode, nb, e->stream);
+    if (node_mises_stress && !raw) err |= hkp::d2h(node_mises_stress, out + 13 * d.nNode, nb, e->stream);
+    if (node_triax_stress) err |= hkp::d2h(node_triax_stress, out + 14 * d.nNode, nb, e->stream);
+    if (inc_num) err |= hkp::d2h(inc_num, out + 15 * d.nNode, nb, e->stream);
+    err |= hkp::sync(e->stream);
+    dfree(e, emean);
+    dfree(e, out);
+    if (err) return fail(e, HK_ERR_CUDA, "hk_node_output: copy failed");
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
 int HKAPI(download_ex)(hk_engine* e, double* disp_pre, double* Q, double* external_force, double* position,
                        double* integ_yield_stress, double* elementVolume) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");

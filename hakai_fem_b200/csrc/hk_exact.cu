@@ -635,6 +635,46 @@ void hk_launch_triax_to_aos(const HkDev& dd, double* aos, long long e0, long lon
     });
 }
 
+// ------------------------------------------------------------------ cal_node_stress_strain on the device (J2:3408-3486)
+// element means (J2:3428-3440): rows 0-5 stress, 6-11 strain, 12 eps, 13 triax; the 8 Gauss points are summed in order
+void hk_launch_element_means(const HkDev& dd, double* emean, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(d.nElement * 14, s, HK_LAMBDA(long long i) {
+        const long long e = i % d.nElement;
+        const int row = (int)(i / d.nElement);
+        double a = 0.0;
+        if (row < 13) for (int k = 0; k < 8; ++k) a += d.ips[hk_ip(d, row, k, e)];
+        else for (int k = 0; k < 8; ++k) a += d.triax[(long long)k * d.nEp + e];
+        emean[(long long)row * d.nEp + e] = a / 8.0;
+    });
+}
+// nodal means (J2:3442-3482): the node-centric table lists a node's elements in ascending order, which is the order
+// the reference's element loop adds them in.  out: [16][nNode] = stress 6, strain 6, eps, mises, triax, inc_num
+void hk_launch_node_means(const HkDev& dd, const double* emean, double* out, int raw, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(d.nNode, s, HK_LAMBDA(long long n) {
+        double acc[14];
+        for (int r = 0; r < 14; ++r) acc[r] = 0.0;
+        double inc = 0.0;
+        for (int w = 0; w < d.ell_width; ++w) {
+            const int ent = d.ell[(long long)w * d.nNode + n];
+            if (ent < 0) break;
+            const long long e = ent >> 3;
+            for (int r = 0; r < 14; ++r) acc[r] += emean[(long long)r * d.nEp + e];
+            inc += 1.0;
+        }
+        if (!raw) for (int r = 0; r < 14; ++r) acc[r] /= inc;          // 0/0 = NaN for unreferenced nodes, as J2:3464-3469
+        for (int r = 0; r < 13; ++r) out[(long long)r * d.nNode + n] = acc[r];
+        out[14ll * d.nNode + n] = acc[13];
+        out[15ll * d.nNode + n] = inc;
+        if (!raw) {
+            const double ox = acc[0], oy = acc[1], oz = acc[2], txy = acc[3], tyz = acc[4], txz = acc[5];
+            out[13ll * d.nNode + n] = sqrt(0.5 * ((ox - oy) * (ox - oy) + (oy - oz) * (oy - oz) + (ox - oz) * (ox - oz) +
+                                                  6 * (txy * txy + tyz * tyz + txz * txz)));      // J2:3471-3480
+        }
+    });
+}
+
 
 // ------------------------------------------------------------------ reference-order element kernel (element_mode 1)
 // cal_stress_hexa + cal_BVbar_hexa + cal_Bfinal + cal_triax_stress + the fracture loop exactly as the reference

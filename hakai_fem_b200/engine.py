@@ -42,7 +42,7 @@ EXPORTS = [
     "deleted_ids", "contact_pair_info", "counters", "profile", "profile_read", "set_stream",
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
-    "set_global_maps", "apply_deleted",
+    "set_global_maps", "apply_deleted", "node_output",
 ]
 
 
@@ -243,6 +243,20 @@ class EngineBase:
              f(integ_eq_plastic_strain), f(integ_yield_stress)]
         fl = None if element_flag is None else _i64(element_flag)
         self._chk(self._fn("upload_state")(self._h, *[_pf(x) for x in a], _pi(fl)))
+
+    def node_output(self, raw: bool = False):
+        """cal_node_stress_strain (J2:3408-3486) on the device; same dict as host.cal_node_stress_strain
+        (+ inc_num).  raw=True: undivided sums, no von Mises (partitioned meshes)."""
+        nN = self.nNode
+        ns, ne = np.zeros((6, nN)), np.zeros((6, nN))
+        ep, mi, tx, inc = np.zeros(nN), np.zeros(nN), np.zeros(nN), np.zeros(nN)
+        self._chk(self._fn("node_output")(self._h, _pf(ns), _pf(ne), _pf(ep), None if raw else _pf(mi), _pf(tx),
+                                          _pf(inc), C.c_int32(1 if raw else 0)))
+        out = dict(node_stress=np.ascontiguousarray(ns.T), node_strain=np.ascontiguousarray(ne.T),
+                   node_eq_plastic_strain=ep, node_triax_stress=tx, inc_num=inc)
+        if not raw:
+            out["node_mises_stress"] = mi
+        return out
 
     def deleted_ids(self) -> np.ndarray:
         n = c_i64(0)

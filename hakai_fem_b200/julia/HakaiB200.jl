@@ -118,4 +118,12 @@ download!(e, disp, velo, integ_stress, integ_strain, integ_eq_plastic_strain, in
           (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
           e.ptr, disp, velo, integ_stress, integ_strain, integ_eq_plastic_strain, integ_triax_stress, element_flag))
 
+# cal_node_stress_strain (HAKAI_j.jl:3408-3486) on the device: fills the NodeDataType arrays (node_stress and node_strain
+# are (nNode,6) Julia matrices).  Replaces `node_data = cal_node_stress_strain(...)` at HAKAI_j.jl:478, 936.
+node_output!(e, nd) =          # nd::NodeDataType (HAKAI_j.jl:43-50)
+    check(e.ptr, ccall((:hk_node_output, LIB), Cint,
+          (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32),
+          e.ptr, nd.node_stress, nd.node_strain, nd.node_eq_plastic_strain, nd.node_mises_stress, nd.node_triax_stress,
+          C_NULL, 0))
+
 end # module

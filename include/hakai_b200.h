@@ -149,6 +149,17 @@ int hk_download(hk_engine* e, double* disp, double* velo,
 int hk_download_ex(hk_engine* e, double* disp_pre, double* Q, double* external_force,
                    double* position, double* integ_yield_stress, double* elementVolume);
 
+/* Output tap computed on the device: cal_node_stress_strain (J2:3408-3486).  Gauss points -> element mean ->
+ * mean over the elements incident to a node (deleted ones included, in ascending element order like the reference's
+ * loop) -> von Mises of the nodal stress.  Fills NodeDataType (J2:43-50) arrays in Julia's layout; NULL = skip.
+ *   node_stress, node_strain f64 (nNode,6) column-major; node_eq_plastic_strain, node_mises_stress,
+ *   node_triax_stress f64 (nNode); inc_num f64 (nNode) = number of incident elements (J2:3456-3460).
+ * raw != 0: sums are NOT divided by inc_num and node_mises_stress is not written — for partitioned meshes, where
+ * the host adds the neighbours' sums of the interface nodes first.  Moves 15 doubles per node to the host instead
+ * of 112 per element. */
+int hk_node_output(hk_engine* e, double* node_stress, double* node_strain, double* node_eq_plastic_strain,
+                   double* node_mises_stress, double* node_triax_stress, double* inc_num, int32_t raw);
+
 /* Overwrite loop-carried state (tests, restart).  NULL = keep.  Layouts as hk_download*. */
 int hk_upload_state(hk_engine* e, const double* disp, const double* disp_pre, const double* velo,
                     const double* Q, const double* integ_stress, const double* integ_strain,

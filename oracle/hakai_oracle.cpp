@@ -957,6 +957,47 @@ int hko_download(hk_engine* e, double* disp, double* velo, double* integ_stress,
     return HK_OK;
 }
 
+// cal_node_stress_strain, J2:3408-3486, loop for loop (Julia (nNode,6) column-major outputs)
+int hko_node_output(hk_engine* e, double* node_stress, double* node_strain, double* node_eq_plastic_strain,
+                    double* node_mises_stress, double* node_triax_stress, double* inc_num, int32_t raw) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    const int64_t nN = e->nNode, nE = e->nElement;
+    std::vector<double> es(nE * 6), en(nE * 6), ep(nE), et(nE);
+    for (int64_t i = 0; i < nE; ++i) {                                     // J2:3428-3440
+        for (int c = 0; c < 6; ++c) {
+            double a = 0.0, b = 0.0;
+            for (int k = 0; k < 8; ++k) { a += e->integ_stress[(i * 8 + k) * 6 + c]; b += e->integ_strain[(i * 8 + k) * 6 + c]; }
+            es[i * 6 + c] = a / 8; en[i * 6 + c] = b / 8;
+        }
+        double a = e->integ_eq_plastic_strain[i * 8], b = e->integ_triax_stress[i * 8];
+        for (int k = 1; k < 8; ++k) { a += e->integ_eq_plastic_strain[i * 8 + k]; b += e->integ_triax_stress[i * 8 + k]; }
+        ep[i] = a / 8; et[i] = b / 8;
+    }
+    std::vector<double> ns(nN * 6, 0.0), nn(nN * 6, 0.0), np_(nN, 0.0), nt(nN, 0.0), inc(nN, 0.0), mises(nN, 0.0);
+    for (int64_t i = 0; i < nE; ++i)                                       // J2:3442-3454
+        for (int k = 0; k < 8; ++k) {
+            const int64_t nd = e->elementmat[i * 8 + k] - 1;
+            for (int c = 0; c < 6; ++c) { ns[c * nN + nd] += es[i * 6 + c]; nn[c * nN + nd] += en[i * 6 + c]; }
+            np_[nd] += ep[i];
+            nt[nd] += et[i];
+        }
+    for (int64_t i = 0; i < nE; ++i)                                       // J2:3456-3460
+        for (int k = 0; k < 8; ++k) inc[e->elementmat[i * 8 + k] - 1] += 1.0;
+    if (!raw)
+        for (int64_t i = 0; i < nN; ++i) {                                 // J2:3463-3481
+            for (int c = 0; c < 6; ++c) { ns[c * nN + i] /= inc[i]; nn[c * nN + i] /= inc[i]; }
+            np_[i] /= inc[i];
+            nt[i] /= inc[i];
+            const double ox = ns[i], oy = ns[nN + i], oz = ns[2 * nN + i], txy = ns[3 * nN + i], tyz = ns[4 * nN + i],
+                         txz = ns[5 * nN + i];
+            mises[i] = std::sqrt(0.5 * ((ox - oy) * (ox - oy) + (oy - oz) * (oy - oz) + (ox - oz) * (ox - oz) +
+                                        6 * (txy * txy + tyz * tyz + txz * txz)));
+        }
+    cp(node_stress, ns); cp(node_strain, nn); cp(node_eq_plastic_strain, np_); cp(node_triax_stress, nt); cp(inc_num, inc);
+    if (!raw) cp(node_mises_stress, mises);
+    return HK_OK;
+}
+
 int hko_download_ex(hk_engine* e, double* disp_pre, double* Q, double* external_force, double* position,
                     double* integ_yield_stress, double* elementVolume) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");

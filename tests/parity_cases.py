@@ -93,6 +93,34 @@ def case_fracture_block(engine_cls, n_steps=260):
     util.assert_states_close(a, b, 1e-8, STATE_KEYS, "fracture block")
 
 
+def case_node_output(engine_cls):
+    """hk_node_output = cal_node_stress_strain (J2:3408-3486) on the device: bit-identical to the oracle's loop on an
+    identical ip state (same summation orders), equal to the NumPy host twin up to summation order, and consistent
+    with it after a real run with deletions."""
+    from hakai_fem_b200.host import cal_node_stress_strain
+    deck = util.distorted_block(nx=5, ny=4, nz=6, jitter=0.05, ductile=True, strain_per_step=4e-4)
+    st = prepare(deck.build_model())
+    o, g = util.make_pair(st, engine_cls, OracleEngine)
+    rs = util.random_state(st, seed=5)
+    o.upload_state(**rs)
+    g.upload_state(**rs)
+    a, b = o.node_output(), g.node_output()
+    for k in ("node_stress", "node_strain", "node_eq_plastic_strain", "node_mises_stress", "inc_num"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(b["inc_num"], np.bincount(st.model.elementmat.reshape(-1) - 1, minlength=st.model.nNode))
+    raw = g.node_output(raw=True)
+    assert np.array_equal(raw["node_stress"] / raw["inc_num"][:, None], b["node_stress"])
+    assert "node_mises_stress" not in raw
+    o.step(1, 200)                                    # with deletions (zeroed stress of dead elements is averaged in)
+    nd = g.step(1, 200)
+    assert nd > 0
+    a, b = o.node_output(), g.node_output()
+    h = cal_node_stress_strain(st.model.nNode, st.model.elementmat, 8, g.download())
+    for k in ("node_stress", "node_strain", "node_eq_plastic_strain", "node_mises_stress", "node_triax_stress"):
+        assert util.rel_err(h[k], b[k]) <= 1e-13, f"host twin {k}: {util.rel_err(h[k], b[k])}"
+        assert util.rel_err(a[k], b[k]) <= 1e-8, f"oracle {k}: {util.rel_err(a[k], b[k])}"
+
+
 # SI units, E = 7e10 Pa: anything below these magnitudes is rounding noise of a body in rigid motion
 CONTACT_FLOORS = dict(integ_stress=1e4, integ_strain=1e-7, Q=1e-3, integ_yield_stress=1.0, external_force=1e-3)
 
