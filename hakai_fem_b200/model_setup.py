@@ -37,17 +37,22 @@ def cal_Pusai_hexa() -> np.ndarray:
     return P
 
 
-def element_volumes(coordmat: np.ndarray, elementmat: np.ndarray, chunk: int = 1 << 20) -> np.ndarray:
-    """elementVolume[e] = sum_k det(Pusai_k * e_position')  (J2:183-198)."""
-    P = cal_Pusai_hexa()
+def element_volumes(coordmat: np.ndarray, elementmat: np.ndarray, chunk: int = 1 << 19) -> np.ndarray:
+    """elementVolume[e] = sum_k my3det(Pusai_k * e_position')  (J2:183-198, my3det J2:3235-3243: Sarrus, same term
+    order; Gauss points added in order)."""
+    P24 = cal_Pusai_hexa().reshape(24, 8)                      # rows k*3+dir
     nE = elementmat.shape[1]
     V = np.zeros(nE)
     X = np.ascontiguousarray(coordmat.T)                       # (nN,3)
     for s in range(0, nE, chunk):
         em = elementmat[:, s:s + chunk].T - 1                  # (n,8)
-        ep = X[em]                                             # (n,8,3)
-        J = np.einsum("kdi,nic->nkdc", P, ep)                  # (n,8,3,3)
-        V[s:s + chunk] = np.linalg.det(J).sum(axis=1)
+        J = np.matmul(P24, X[em])                              # (n,24,3): J[n, k*3+d, c]
+        acc = np.zeros(J.shape[0])
+        for k in range(8):
+            a, b, c = J[:, 3 * k], J[:, 3 * k + 1], J[:, 3 * k + 2]            # rows of the 3x3 Jacobian
+            acc += (a[:, 0] * b[:, 1] * c[:, 2] + a[:, 1] * b[:, 2] * c[:, 0] + a[:, 2] * b[:, 0] * c[:, 1]
+                    - a[:, 0] * b[:, 2] * c[:, 1] - a[:, 1] * b[:, 0] * c[:, 2] - a[:, 2] * b[:, 1] * c[:, 0])
+        V[s:s + chunk] = acc
     return V
 
 
