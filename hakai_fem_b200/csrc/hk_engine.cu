@@ -1261,12 +1261,17 @@ int HKAPI(set_global_maps)(hk_engine* e, int64_t n_global_nodes, const int64_t* 
 
 int HKAPI(apply_deleted)(hk_engine* e, int64_t n, const int64_t* global_ids) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
-    if (e->g_node_map.empty()) return fail(e, HK_ERR_STATE, "hk_set_global_maps not called");
+    const bool global = !e->g_node_map.empty();
+    const int64_t limit = global ? (int64_t)e->g_elem_map.size() : e->nElement;
     std::vector<int64_t> ids(global_ids, global_ids + n);
     for (int64_t g : ids)
-        if (g < 1 || g > (int64_t)e->g_elem_map.size()) return fail(e, HK_ERR_ARG, "global element id out of range");
+        if (g < 1 || g > limit) return fail(e, HK_ERR_ARG, "element id out of range");
     int rc = update_surfaces(e, ids);
     if (rc) return rc;
+    if (!global) {                       // restart of a single-domain run: the replayed ids are part of the history
+        e->deleted_all.insert(e->deleted_all.end(), ids.begin(), ids.end());
+        e->deleted_reported = e->deleted_all.size();
+    }
     CK(hkp::sync(e->stream));
     return HK_OK;
 }

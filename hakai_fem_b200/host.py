@@ -134,8 +134,10 @@ def _write_vtk_binary(outdir, index, coordmat, elementmat, element_flag, disp, v
 
 
 def hakai(fname, outdir="temp", engine_cls=None, output_num=100, write_frames=True, verbose=True,
-          node_output="device", vtk_format="ascii", **params):
-    """hakai(fname), J2:81.  Returns the engine (state on the GPU) and the list of frame files."""
+          node_output="device", vtk_format="ascii", checkpoint=None, checkpoint_frames=10, resume=None, **params):
+    """hakai(fname), J2:81.  Returns the engine (state on the GPU) and the list of frame files.
+    checkpoint: file rewritten every `checkpoint_frames` frames (checkpoint.py); resume: checkpoint to continue
+    from (frames already written are kept; numbering continues)."""
     if node_output not in ("device", "host") or vtk_format not in ("ascii", "binary"):
         raise ValueError("node_output: device|host, vtk_format: ascii|binary")
     if engine_cls is None:
@@ -164,12 +166,17 @@ def hakai(fname, outdir="temp", engine_cls=None, output_num=100, write_frames=Tr
             nd = cal_node_stress_strain(model.nNode, model.elementmat, 8, d)
         frames.append(write_vtk(outdir, index, model.coordmat, model.elementmat, d["element_flag"], d["disp"],
                                 d["velo"], nd, binary=(vtk_format == "binary")))
-    if write_frames:
+    t, i_out = 0, 1
+    if resume is not None:
+        from .checkpoint import load_checkpoint
+        t = load_checkpoint(eng, resume)
+        i_out = t // d_out + 1 if d_out > 0 else 1
+        log("resumed at step", t)
+    elif write_frames:
         frame(0)                                                # J2:478-480
     t0 = time.perf_counter()
-    t, i_out = 0, 1
     while t < n_total:
-        n = min(d_out, n_total - t) if d_out > 0 else n_total - t
+        n = min(d_out - t % d_out, n_total - t) if d_out > 0 else n_total - t
         ndel = eng.step(t + 1, n)
         t += n
         if ndel:
@@ -177,6 +184,9 @@ def hakai(fname, outdir="temp", engine_cls=None, output_num=100, write_frames=Tr
             log("Element deleted:", int(flags.sum()), "/", model.nElement)       # J2:736
         if write_frames and d_out > 0 and t % d_out == 0:       # rem(t, d_out) == 0, J2:932
             frame(i_out)
+            if checkpoint is not None and i_out % checkpoint_frames == 0:
+                from .checkpoint import save_checkpoint
+                save_checkpoint(eng, checkpoint, t)
             i_out += 1
         log("\r%.4e / %.4e     " % (t * setup.d_time, model.end_time), end="")
     log("\n%.3f seconds for %d steps" % (time.perf_counter() - t0, n_total))

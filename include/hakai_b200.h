@@ -240,6 +240,10 @@ int hk_contact_import(hk_engine* e, const void* in_dev, int64_t n_ranks);   /* s
 int hk_set_global_maps(hk_engine* e, int64_t n_global_nodes, const int64_t* node_map,
                        int64_t n_global_elements, const int64_t* elem_map, const int64_t* element_instance);
 int hk_apply_deleted(hk_engine* e, int64_t n, const int64_t* global_ids);
+/* Without hk_set_global_maps (single-domain engine) hk_apply_deleted is the RESTART hook: ids are the engine's own
+ * 1-based element ids in their original deletion order (hk_deleted_ids of the checkpointed run); the exposed-face
+ * updates are replayed and the ids are recorded as already deleted.  State itself comes back through
+ * hk_upload_state (hakai_fem_b200/checkpoint.py). */
 
 #ifdef __cplusplus
 }

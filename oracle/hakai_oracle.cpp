@@ -439,6 +439,33 @@ static void append_unique(std::vector<int64_t>& v, const std::vector<int64_t>& a
     }
 }
 
+// update contact surface, J2:767-804
+static void update_contact_surface(hk_engine* E, const std::vector<int64_t>& deleted_element) {
+    if (E->prm.contact_flag > 0) {
+        for (int64_t i : deleted_element) {
+            int64_t instance_id = E->element_instance[i - 1];
+            const InstanceO& I = E->INSTANCE[instance_id - 1];
+            int64_t ele_id = i - I.element_offset;
+            std::vector<int64_t> add_tri, add_eleid, add_nodes;
+            add_surface_triangle(I, ele_id, add_tri, add_eleid, add_nodes);
+            for (ContactTriangleO& ct : E->CT) {
+                if (ct.i_instance == instance_id) {
+                    append_unique(ct.c_nodes_i, add_nodes, I.node_offset);
+                } else if (ct.j_instance == instance_id) {
+                    append_unique(ct.c_nodes_j, add_nodes, I.node_offset);
+                    for (int64_t x : add_eleid) ct.c_triangles_eleid.push_back(x + I.element_offset);
+                    for (size_t r = 0; r < add_tri.size() / 3; ++r) {
+                        ct.t0.push_back(add_tri[3 * r + 0] + I.node_offset);
+                        ct.t1.push_back(add_tri[3 * r + 1] + I.node_offset);
+                        ct.t2.push_back(add_tri[3 * r + 2] + I.node_offset);
+                    }
+                }
+            }
+        }
+    }
+}
+
+
 // ---------------------------------------------------------------- cal_contact_force (J2:2248-2706)
 static void cal_contact_force(hk_engine* E) {
     const double* position = E->position.data();
@@ -718,29 +745,7 @@ static void one_step(hk_engine* E, int64_t t, int64_t* n_deleted) {
         }
     }
 
-    // update contact surface, J2:767-804
-    if (E->prm.contact_flag > 0) {
-        for (int64_t i : deleted_element) {
-            int64_t instance_id = E->element_instance[i - 1];
-            const InstanceO& I = E->INSTANCE[instance_id - 1];
-            int64_t ele_id = i - I.element_offset;
-            std::vector<int64_t> add_tri, add_eleid, add_nodes;
-            add_surface_triangle(I, ele_id, add_tri, add_eleid, add_nodes);
-            for (ContactTriangleO& ct : E->CT) {
-                if (ct.i_instance == instance_id) {
-                    append_unique(ct.c_nodes_i, add_nodes, I.node_offset);
-                } else if (ct.j_instance == instance_id) {
-                    append_unique(ct.c_nodes_j, add_nodes, I.node_offset);
-                    for (int64_t x : add_eleid) ct.c_triangles_eleid.push_back(x + I.element_offset);
-                    for (size_t r = 0; r < add_tri.size() / 3; ++r) {
-                        ct.t0.push_back(add_tri[3 * r + 0] + I.node_offset);
-                        ct.t1.push_back(add_tri[3 * r + 1] + I.node_offset);
-                        ct.t2.push_back(add_tri[3 * r + 2] + I.node_offset);
-                    }
-                }
-            }
-        }
-    }
+    update_contact_surface(E, deleted_element);                              // J2:767-804
     for (int64_t i : deleted_element) E->deleted_all.push_back(i);
     if (n_deleted) *n_deleted += (int64_t)deleted_element.size();
     E->counters[4] += 1;
@@ -1067,7 +1072,14 @@ int hko_contact_enqueue(hk_engine* e) { return fail(e, HK_ERR_UNSUPPORTED, "orac
 int hko_contact_export(hk_engine* e, void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_contact_import(hk_engine* e, const void*, int64_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_set_global_maps(hk_engine* e, int64_t, const int64_t*, int64_t, const int64_t*, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
-int hko_apply_deleted(hk_engine* e, int64_t, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_apply_deleted(hk_engine* e, int64_t n, const int64_t* ids) {           // restart: replay + record (local ids)
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    std::vector<int64_t> v(ids, ids + n);
+    for (int64_t g : v) if (g < 1 || g > e->nElement) return fail(e, HK_ERR_ARG, "element id out of range");
+    update_contact_surface(e, v);
+    for (int64_t g : v) e->deleted_all.push_back(g);
+    return HK_OK;
+}
 int hko_step_begin(hk_engine* e, int64_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_step_finish(hk_engine* e, int64_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 

@@ -197,6 +197,54 @@ def case_contact_erosion(engine_cls, n_steps=400):
     util.assert_states_close(a, b, 1e-7, ("disp", "integ_eq_plastic_strain", "element_flag"), "erosion")
 
 
+# ---------------------------------------------------------------- checkpoint / resume (hakai_fem_b200/checkpoint.py)
+def erosion_setup():
+    model = ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0).build_model()
+    model.MATERIAL[0].ductile = np.array([[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]])
+    return prepare(model)
+
+
+def fracture_setup():
+    return prepare(util.distorted_block(nx=5, ny=4, nz=6, jitter=0.05, ductile=True, strain_per_step=4e-4).build_model())
+
+
+def check_resume(engine_cls, setup_fn, t_save, t_end, tmp_path, **prm):
+    a = configure_engine(engine_cls, setup_fn(), **prm)
+    a.step(1, t_save)
+    n_before = len(a.deleted_ids())
+    path = str(tmp_path / "ck.npz")
+    _ck().save_checkpoint(a, path, t_save)
+    a.step(t_save + 1, t_end - t_save)
+    b = configure_engine(engine_cls, setup_fn(), **prm)
+    t = _ck().load_checkpoint(b, path)
+    assert t == t_save
+    assert len(b.deleted_ids()) == n_before
+    nb = b.step(t + 1, t_end - t)
+    assert nb == len(a.deleted_ids()) - n_before, "only deletions after the checkpoint are reported as new"
+    sa, sb = util.full_state(a), util.full_state(b)
+    for k in STATE_KEYS:
+        assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])), k
+    assert np.array_equal(a.deleted_ids(), b.deleted_ids())
+    return a, b, n_before
+
+
+
+def _ck():
+    from hakai_fem_b200 import checkpoint
+    return checkpoint
+
+
+def case_checkpoint_resume(engine_cls, tmp_path):
+    a, b, n_before = check_resume(engine_cls, erosion_setup, 57, 120, tmp_path)
+    assert 0 < n_before < len(a.deleted_ids()), "checkpoint must fall between deletions"
+    for c in range(2):
+        pa, pb = a.contact_pair(c), b.contact_pair(c)
+        for k in ("c_nodes_i", "c_nodes_j", "c_triangles", "c_triangles_eleid"):
+            assert np.array_equal(pa[k], pb[k]), f"pair {c} {k}"
+    a, _, n_before = check_resume(engine_cls, fracture_setup, 61, 100, tmp_path)
+    assert 0 < n_before < len(a.deleted_ids())
+
+
 def case_exact_mode_bitwise(engine_cls, cases=(("t5", 3000), ("crash_tube", 800), ("bullet_impact", 1500))):
     """hk_params.element_mode = 1 (reference-order element kernel, no FMA): the whole engine — nodal update, contact,
     element forces, triaxiality, deletion — is BIT-IDENTICAL to the oracle, including the self-contact deck whose hit

@@ -41,6 +41,10 @@ def test_node_output():
     pc.case_node_output(Engine)
 
 
+def test_checkpoint_resume_bitwise(tmp_path):
+    pc.case_checkpoint_resume(Engine, tmp_path)
+
+
 def test_contact_erosion():
     pc.case_contact_erosion(Engine)
 

@@ -99,3 +99,16 @@ def test_binary_frames_and_device_node_output_match_the_reference_route(tmp_path
     want = np.array([l.split() for l in last_txt[i:i + nN]], float)
     assert np.allclose(got["DISPLACEMENT"], want, rtol=2e-6, atol=1e-12)
     assert os.path.getsize(runs["bin"][-1]) < 0.5 * os.path.getsize(runs["dev"][-1])
+
+
+def test_resume_from_checkpoint_writes_identical_frames(tmp_path):
+    deck = StretchDeck(2, 2, 3, n_steps=100, strain_per_step=4e-4, jitter=0.05)
+    path = tmp_path / "d.inp"
+    deck.write_inp(str(path))
+    ck = str(tmp_path / "ck.npz")
+    _, full = hakai(str(path), str(tmp_path / "a"), engine_cls=OracleEngine, verbose=False, checkpoint=ck,
+                    checkpoint_frames=40)                      # written at frame 40 and 80; the last one survives
+    _, tail = hakai(str(path), str(tmp_path / "b"), engine_cls=OracleEngine, verbose=False, resume=ck)
+    assert [os.path.basename(f) for f in tail] == ["file%03d.vtk" % i for i in range(81, 101)]
+    for f in tail:
+        assert open(f).read() == open(os.path.join(str(tmp_path / "a"), os.path.basename(f))).read()
