@@ -244,19 +244,32 @@ class EngineBase:
         fl = None if element_flag is None else _i64(element_flag)
         self._chk(self._fn("upload_state")(self._h, *[_pf(x) for x in a], _pi(fl)))
 
-    def node_output(self, raw: bool = False):
+    def node_output(self, raw: bool = False, out=None):
         """cal_node_stress_strain (J2:3408-3486) on the device; same dict as host.cal_node_stress_strain
-        (+ inc_num).  raw=True: undivided sums, no von Mises (partitioned meshes)."""
+        (+ inc_num).  raw=True: undivided sums, no von Mises (partitioned meshes).  `out`: optional dict of
+        caller-owned C-contiguous float64 buffers (e.g. pinned) keyed like the result; node_stress / node_strain
+        buffers have shape (6, nNode) — Julia's (nNode,6) column-major — and come back as (nNode,6) views."""
         nN = self.nNode
-        ns, ne = np.zeros((6, nN)), np.zeros((6, nN))
-        ep, mi, tx, inc = np.zeros(nN), np.zeros(nN), np.zeros(nN), np.zeros(nN)
-        self._chk(self._fn("node_output")(self._h, _pf(ns), _pf(ne), _pf(ep), None if raw else _pf(mi), _pf(tx),
-                                          _pf(inc), C.c_int32(1 if raw else 0)))
-        out = dict(node_stress=np.ascontiguousarray(ns.T), node_strain=np.ascontiguousarray(ne.T),
-                   node_eq_plastic_strain=ep, node_triax_stress=tx, inc_num=inc)
+        out = out or {}
+
+        def buf(key, shape):
+            a = out.get(key)
+            if a is None:
+                return np.zeros(shape)
+            if a.dtype != np.float64 or a.shape != shape or not a.flags.c_contiguous:
+                raise ValueError(f"node_output: out[{key!r}] must be C-contiguous float64 {shape}")
+            return a
+        ns, ne = buf("node_stress", (6, nN)), buf("node_strain", (6, nN))
+        ep, tx, inc = buf("node_eq_plastic_strain", (nN,)), buf("node_triax_stress", (nN,)), buf("inc_num", (nN,))
+        mi = None if raw else buf("node_mises_stress", (nN,))
+        self._chk(self._fn("node_output")(self._h, _pf(ns), _pf(ne), _pf(ep), _pf(mi), _pf(tx), _pf(inc),
+                                          C.c_int32(1 if raw else 0)))
+        copy = (lambda a: a) if out else np.ascontiguousarray
+        res = dict(node_stress=copy(ns.T), node_strain=copy(ne.T), node_eq_plastic_strain=ep, node_triax_stress=tx,
+                   inc_num=inc)
         if not raw:
-            out["node_mises_stress"] = mi
-        return out
+            res["node_mises_stress"] = mi
+        return res
 
     def deleted_ids(self) -> np.ndarray:
         n = c_i64(0)

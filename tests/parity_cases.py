@@ -111,6 +111,11 @@ def case_node_output(engine_cls):
     raw = g.node_output(raw=True)
     assert np.array_equal(raw["node_stress"] / raw["inc_num"][:, None], b["node_stress"])
     assert "node_mises_stress" not in raw
+    nN = st.model.nNode
+    bufs = dict(node_stress=np.empty((6, nN)), node_mises_stress=np.empty(nN))      # caller-owned (e.g. pinned) buffers
+    c = g.node_output(out=bufs)
+    assert np.shares_memory(c["node_stress"], bufs["node_stress"]) and c["node_mises_stress"] is bufs["node_mises_stress"]
+    assert np.array_equal(c["node_stress"], b["node_stress"]) and np.array_equal(c["node_mises_stress"], b["node_mises_stress"])
     o.step(1, 200)                                    # with deletions (zeroed stress of dead elements is averaged in)
     nd = g.step(1, 200)
     assert nd > 0
