@@ -307,6 +307,7 @@ def main():
             out_frame = ("disp", "velo", "element_flag")
             h2d = sum(pinned[k].numel() * 8 for k in upl)
             d2h = sum(pinned[k].numel() * 8 for k in out_frame + nodal)
+            eng.node_output(raw=raw, out={k: hv[k] for k in nodal})     # untimed: allocates the engine's work buffers
             barrier()
             w0 = time.perf_counter()
             eng.upload_state(disp=hv["disp"], disp_pre=hv["disp_pre"], velo=hv["velo"], Q=hv["Q"],

@@ -98,6 +98,10 @@ struct hk_engine {
     // multi-GPU erosion: instance tables are GLOBAL; these map global (1-based) ids to engine-local 0-based ids or -1
     std::vector<int> g_node_map, g_elem_map;
     std::vector<int64_t> g_einst;  // instance of every GLOBAL element
+    // hk_node_output work buffers, allocated at the first call and kept (cudaMalloc/cudaFree of ~4 GB per frame costs
+    // more than the averaging itself)
+    double* no_emean = nullptr;    // [14][nEp]
+    double* no_out = nullptr;      // [16][nNode]
     int64_t begun_t = -1;          // step opened by hk_step_begin
     // special nodes (host mirror)
     std::vector<int> spec_idx_h;
@@ -1005,11 +1009,12 @@ int HKAPI(node_output)(hk_engine* e, double* node_stress, double* node_strain, d
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     const HkDev& d = e->d;
     if (!e->triax_current) { hk_launch_triax(d, e->stream); e->triax_current = true; }
-    double* emean = nullptr;
-    double* out = nullptr;
-    int rc = dalloc(e, &emean, (size_t)14 * d.nEp);
-    if (!rc) rc = dalloc(e, &out, (size_t)16 * d.nNode);
-    if (rc) { dfree(e, emean); dfree(e, out); return rc; }
+    int rc = 0;
+    if (!e->no_emean) rc = dalloc(e, &e->no_emean, (size_t)14 * d.nEp);
+    if (!rc && !e->no_out) rc = dalloc(e, &e->no_out, (size_t)16 * d.nNode);
+    if (rc) return rc;
+    double* emean = e->no_emean;
+    double* out = e->no_out;
     hk_launch_element_means(d, emean, e->stream);
     hk_launch_node_means(d, emean, out, raw ? 1 : 0, e->stream);
     e->n_launch += 2;
@@ -1022,8 +1027,6 @@ int HKAPI(node_output)(hk_engine* e, double* node_stress, double* node_strain, d
     if (node_triax_stress) err |= hkp::d2h(node_triax_stress, out + 14 * d.nNode, nb, e->stream);
     if (inc_num) err |= hkp::d2h(inc_num, out + 15 * d.nNode, nb, e->stream);
     err |= hkp::sync(e->stream);
-    dfree(e, emean);
-    dfree(e, out);
     if (err) return fail(e, HK_ERR_CUDA, "hk_node_output: copy failed");
     CK(hkp::last_error());
     return HK_OK;

@@ -156,7 +156,8 @@ int hk_download_ex(hk_engine* e, double* disp_pre, double* Q, double* external_f
  *   node_triax_stress f64 (nNode); inc_num f64 (nNode) = number of incident elements (J2:3456-3460).
  * raw != 0: sums are NOT divided by inc_num and node_mises_stress is not written — for partitioned meshes, where
  * the host adds the neighbours' sums of the interface nodes first.  Moves 15 doubles per node to the host instead
- * of 112 per element. */
+ * of 112 per element.  The first call allocates 14 doubles per element + 16 per node of device work space, which the
+ * engine keeps until hk_destroy. */
 int hk_node_output(hk_engine* e, double* node_stress, double* node_strain, double* node_eq_plastic_strain,
                    double* node_mises_stress, double* node_triax_stress, double* inc_num, int32_t raw);
 
