@@ -29,7 +29,7 @@ ALG_BYTES_NODAL = 224          # nodal update, per node-step
 ALG_BYTES_STEP = 2128          # total per element-step (nN/nE -> 1)
 
 
-def make_deck(workload, nz_override=None):
+def make_deck(workload, nz_override=None, strain_per_step=None):
     from hakai_fem_b200.mesh import StretchDeck, steel
     if workload == "W16":
         n = (252, 252, 252)
@@ -44,7 +44,8 @@ def make_deck(workload, nz_override=None):
     if nz_override:
         n = (n[0], n[1], nz_override)
     jitter = 0.0 if workload == "B1" else 0.05
-    return StretchDeck(n[0], n[1], n[2], h=1.0, material=steel(), jitter=jitter, n_steps=1.0e6)
+    kw = {} if strain_per_step is None else dict(strain_per_step=strain_per_step)
+    return StretchDeck(n[0], n[1], n[2], h=1.0, material=steel(), jitter=jitter, n_steps=1.0e6, **kw)
 
 
 def prepare_setup(deck):
@@ -156,6 +157,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", default="S1")
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--strain-per-step", type=float, default=None,
+                    help="override the deck's stretch rate (1e-6: purely elastic run, SURVEY §8d)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -180,7 +183,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from hakai_fem_b200.multi import slab_deck, SlabRunner
-    deck = make_deck(args.workload)
+    deck = make_deck(args.workload, strain_per_step=args.strain_per_step)
     stream = torch.cuda.current_stream()
     if world > 1:
         # weak scaling (config W): the global mesh is nx x ny x (nz*world), split in z; every rank builds only its slab
@@ -269,6 +272,14 @@ def main():
                 "nodal_kernel": {"achieved": ALG_BYTES_NODAL * nN / (nd_ms * 1e-3) / 1e9, "avg_launch_ms": nd_ms},
                 "whole_step": {"achieved": ALG_BYTES_STEP * nE / (ms / args.steps * 1e-3) / 1e9,
                                "frac": ALG_BYTES_STEP * nE / (ms / args.steps * 1e-3) / 1e9 / peak}}
+
+    fp_path = os.path.join(ROOT, "profiles", "r1_fp64_ops.json")
+    if os.path.exists(fp_path) and kname == "hk_element_tmem_kernel":
+        # secondary bound: FP64 issue.  Executed flops per element from the committed ncu instruction counts (plastic
+        # regime, which is what the default deck is in after warm-up) x the live launch rate of this run
+        fl = json.load(open(fp_path))["per_element"]["plastic"]["flops"]
+        roofline["fp64"] = {"flops_per_element": fl, "achieved_tflops": fl * nE / (el_ms * 1e-3) / 1e12,
+                            "source": "profiles/r1_fp64_ops.json (ncu instruction counts)"}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
     e2e = None
