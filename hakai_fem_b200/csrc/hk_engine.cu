@@ -95,6 +95,7 @@ struct hk_engine {
     int* d_node_list[3] = {nullptr, nullptr, nullptr};
     long long* d_import_src = nullptr;
     bool contact_done = false;     // hk_contact_enqueue already ran the contact pass of the next step
+    bool frame_next = false;       // hk_mark_frame: the next asynchronous step stores integ_triax_stress
     // multi-GPU erosion: instance tables are GLOBAL; these map global (1-based) ids to engine-local 0-based ids or -1
     std::vector<int> g_node_map, g_elem_map;
     std::vector<int64_t> g_einst;  // instance of every GLOBAL element
@@ -823,6 +824,7 @@ int HKAPI(finalize)(hk_engine* e) {
 // phase 0: whole step; phase 1: everything that does not need the halo (contact + nodal update of non-interface
 // nodes); phase 2: the rest (received partials, interface nodes, element kernel).
 static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end, int phase) {
+    if (phase != 1 && e->frame_next && n_steps > 0) { frame_at_end = true; e->frame_next = false; }
     const HkDev& d = e->d;
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
@@ -899,6 +901,15 @@ int HKAPI(step_enqueue)(hk_engine* e, int64_t t_first, int64_t n_steps) {
 
 // split step for the multi-GPU driver: hk_step_begin(t) runs what does not depend on the halo (so it overlaps the
 // NCCL exchange), hk_step_finish(t) the rest.  hk_step_begin + hk_step_finish == hk_step_enqueue(t, 1).
+// The asynchronous forms imply no output frame.  hk_mark_frame says the last step of the NEXT hk_step_enqueue /
+// hk_step_finish call is followed by one: that step stores integ_triax_stress as computed inside it (J2:677),
+// i.e. before the fracture pass zeroes the stress of the elements it deletes (what a frame of the reference shows).
+int HKAPI(mark_frame)(hk_engine* e) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    e->frame_next = true;
+    return HK_OK;
+}
+
 int HKAPI(step_begin)(hk_engine* e, int64_t t) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     if (e->begun_t >= 0) return fail(e, HK_ERR_STATE, "hk_step_begin called twice without hk_step_finish");

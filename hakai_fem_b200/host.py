@@ -193,11 +193,115 @@ def hakai(fname, outdir="temp", engine_cls=None, output_num=100, write_frames=Tr
     return eng, frames
 
 
+def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, output_num=100, write_frames=True,
+                      verbose=True, vtk_format="ascii", **params):
+    """hakai(fname) on several GPUs: one process per GPU inside an initialised torch.distributed group
+    (`torchrun --nproc-per-node N -m hakai_fem_b200.host deck.inp`).  Every rank reads the deck, keeps its element
+    block (multi.partition_model) and steps it with force halos / contact exchange (multi.SlabRunner); at a frame
+    the ranks send disp, velo, flags and their undivided nodal sums (`hk_node_output`, raw) to rank 0, which adds
+    the shares of interface nodes, divides by the incidence count (J2:3456-3469) and writes the same VTK file as
+    the single-GPU driver.  Returns (runner, frames); frames is empty on ranks > 0."""
+    import torch
+    import torch.distributed as dist
+    from .multi import partition_model, SlabRunner
+    rank, world = dist.get_rank(), dist.get_world_size()
+    # frames travel as pickled host arrays: keep them off the GPU / NCCL (a gloo side group when the main one is NCCL)
+    obj_group = dist.new_group(backend="gloo") if dist.get_backend() == "nccl" else None
+    if engine_cls is None:
+        from .engine import Engine
+        torch_device = torch.device("cuda", torch.cuda.current_device())
+        stream = torch.cuda.current_stream()
+
+        def engine_cls(**p):                                    # engine on torch's stream: ordered with the NCCL calls
+            e = Engine(**p)
+            e.set_stream(stream.cuda_stream)
+            return e
+        params.setdefault("device", torch_device.index)
+    log = print if (verbose and rank == 0) else (lambda *a, **k: None)
+    model = read_inp_file(fname)
+    setup = prepare(model)
+    log("nNode:", model.nNode, " nElement:", model.nElement, " contact_flag:", model.contact_flag, " ranks:", world)
+    dom = partition_model(setup, world)[rank]
+    runner = SlabRunner.from_domain(engine_cls, dom, torch_device, world, **params)
+    eng = runner.engine
+    n_held = len(np.unique(dom.setup.model.elementmat))         # local ids 1..n_held are nodes of own elements
+    g_nodes = dom.node_l2g[:n_held] - 1
+    n_total = int(math.floor(setup.time_num))
+    d_out = int(math.floor(setup.time_num / output_num))
+    frames = []
+
+    def frame(index):
+        d = eng.download(fields=("disp", "velo", "element_flag"))
+        nd = eng.node_output(raw=True)
+        part = dict(nodes=g_nodes, elems=dom.elem_l2g - 1, flag=d["element_flag"],
+                    disp=d["disp"].reshape(-1, 3)[:n_held], velo=d["velo"].reshape(-1, 3)[:n_held],
+                    **{k: nd[k][:n_held] for k in ("node_stress", "node_strain", "node_eq_plastic_strain",
+                                                    "node_triax_stress", "inc_num")})
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(part, parts, dst=0, group=obj_group)
+        if rank != 0:
+            return
+        nN = model.nNode
+        disp, velo = np.zeros((nN, 3)), np.zeros((nN, 3))
+        flag = np.zeros(model.nElement, np.int64)
+        acc = dict(node_stress=np.zeros((nN, 6)), node_strain=np.zeros((nN, 6)), node_eq_plastic_strain=np.zeros(nN),
+                   node_triax_stress=np.zeros(nN), inc_num=np.zeros(nN))
+        for p in reversed(parts):                               # lowest rank last: the owner's copy of shared nodes wins
+            disp[p["nodes"]] = p["disp"]
+            velo[p["nodes"]] = p["velo"]
+            flag[p["elems"]] = p["flag"]
+        for p in parts:                                         # ascending rank = ascending element blocks
+            for k in acc:
+                acc[k][p["nodes"]] += p[k]
+        inc = acc.pop("inc_num")
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ns, ne = acc["node_stress"] / inc[:, None], acc["node_strain"] / inc[:, None]
+            ep, tx = acc["node_eq_plastic_strain"] / inc, acc["node_triax_stress"] / inc
+        ox, oy, oz, txy, tyz, txz = (ns[:, i] for i in range(6))
+        mises = np.sqrt(0.5 * ((ox - oy) ** 2 + (oy - oz) ** 2 + (ox - oz) ** 2 + 6 * (txy ** 2 + tyz ** 2 + txz ** 2)))
+        nodal = dict(node_stress=ns, node_strain=ne, node_eq_plastic_strain=ep, node_mises_stress=mises,
+                     node_triax_stress=tx)
+        frames.append(write_vtk(outdir, index, model.coordmat, model.elementmat, flag, disp.reshape(-1),
+                                velo.reshape(-1), nodal, binary=(vtk_format == "binary")))
+    if write_frames:
+        frame(0)
+    t0 = time.perf_counter()
+    t, i_out = 0, 1
+    n_deleted = 0
+    while t < n_total:
+        n = min(d_out - t % d_out, n_total - t) if d_out > 0 else n_total - t
+        nd_local = runner.run(t + 1, n, frame_at_end=write_frames and d_out > 0 and (t + n) % d_out == 0)
+        t += n
+        tot = torch.tensor([nd_local], dtype=torch.int64, device=torch_device)
+        dist.all_reduce(tot)
+        if int(tot.item()):
+            n_deleted += int(tot.item())
+            log("Element deleted:", model.nElement - n_deleted, "/", model.nElement)
+        if write_frames and d_out > 0 and t % d_out == 0:
+            frame(i_out)
+            i_out += 1
+        log("\r%.4e / %.4e     " % (t * setup.d_time, model.end_time), end="")
+    log("\n%.3f seconds for %d steps on %d ranks" % (time.perf_counter() - t0, n_total, world))
+    return runner, frames
+
+
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     if not argv:
-        raise SystemExit("usage: python -m hakai_fem_b200.host deck.inp [outdir]")
-    hakai(argv[0], argv[1] if len(argv) > 1 else "temp")
+        raise SystemExit("usage: [torchrun --nproc-per-node N -m | python -m] hakai_fem_b200.host deck.inp [outdir]")
+    outdir = argv[1] if len(argv) > 1 else "temp"
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:              # launched by torchrun: one rank per GPU
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        try:
+            hakai_distributed(argv[0], outdir)
+        finally:
+            dist.destroy_process_group()
+    else:
+        hakai(argv[0], outdir)
 
 
 if __name__ == "__main__":

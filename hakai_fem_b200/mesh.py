@@ -186,12 +186,14 @@ class ImpactDeck:
     d_time: float = 1.0e-08
     n_steps: float = 99.5
     name: str = "impact"
+    plate_ductile: Optional[list] = None      # rows [eps_f, triax, rate] replacing alum's table (brittle plates in tests)
 
     def materials(self):
         alum = Material(name="alum", density=2800., young=7e+10, poisson=0.33)
         alum.plastic = np.array([[1.6e+8, 0.], [3.4e+8, 0.3]])
         alum.Hd = (alum.plastic[1:, 0] - alum.plastic[:-1, 0]) / (alum.plastic[1:, 1] - alum.plastic[:-1, 1])
-        alum.ductile = np.array([[1.0, 0., 30.], [0.7, 0.4, 30.]])
+        alum.ductile = np.array([[1.0, 0., 30.], [0.7, 0.4, 30.]] if self.plate_ductile is None else self.plate_ductile,
+                                dtype=np.float64)
         alum.fracture_flag = 1
         lead = Material(name="lead", density=11340., young=1.4e+10, poisson=0.425)
         return [alum, lead]
@@ -235,3 +237,51 @@ class ImpactDeck:
                      element_material=np.concatenate([np.full(m1, 1, np.int64), np.full(m2, 2, np.int64)]),
                      element_instance=np.concatenate([np.full(m1, 1, np.int64), np.full(m2, 2, np.int64)]),
                      d_time=self.d_time, end_time=end_time, mass_scaling=1.0, contact_flag=1)
+
+    def write_inp(self, path: str):
+        """The same model as an Abaqus deck in the dialect of HAKAI-v0.0.0/input/bullet-impact.inp (two parts, two
+        instances, assembly-level node set for the clamped plate edges, part-level `generate` sets, `*Contact` +
+        `*Contact Inclusions, ALL EXTERIOR`), so that the reference and `read_inp_file` see the arrays of build_model()."""
+        m = self.build_model()
+        mats = {x.name: x for x in m.MATERIAL}
+        with open(path, "w") as f:
+            w = f.write
+            w("*Heading\n** synthetic impact deck %s plate %s proj %s\n" % (self.name, self.plate, self.proj))
+            for part in m.PART:
+                w("*Part, name=%s\n*Node\n" % part.name)
+                for n in range(part.nNode):
+                    c = part.coordmat[:, n]
+                    w("%7d, %s, %s, %s\n" % (n + 1, repr(float(c[0])), repr(float(c[1])), repr(float(c[2]))))
+                w("*Element, type=C3D8R\n")
+                for e in range(part.nElement):
+                    w("%d, " % (e + 1) + ", ".join(str(int(v)) for v in part.elementmat[:, e]) + "\n")
+                w("*Nset, nset=Set-all, generate\n  1, %d, 1\n" % part.nNode)
+                w("*Elset, elset=Set-all, generate\n 1, %d, 1\n" % part.nElement)
+                w("*Solid Section, elset=Set-all, material=%s\n,\n*End Part\n**\n" % part.material_name)
+            px, py, pz = self.plate
+            qx, qy, _ = self.proj
+            h = self.h
+            w("*Assembly, name=Assembly\n**\n*Instance, name=plate-1, part=plate\n*End Instance\n**\n")
+            w("*Instance, name=proj-1, part=proj\n%s, %s, %s\n*End Instance\n**\n" % (
+                repr(float((px - qx) * h / 2.0)), repr(float((py - qy) * h / 2.0)), repr(float(pz * h + self.gap * h))))
+            edge = (m.BC[0].dof[0][: len(m.BC[0].dof[0]) // 3] + 2) // 3
+            w("*Nset, nset=edge, instance=plate-1\n")
+            for i in range(0, len(edge), 16):
+                w(", ".join(str(int(v)) for v in edge[i:i + 16]) + "\n")
+            w("*End Assembly\n**\n")
+            for name in ("alum", "lead"):
+                x = mats[name]
+                w("*Material, name=%s\n*Density\n %s,\n*Elastic\n%s, %s\n" % (name, repr(x.density), repr(x.young), repr(x.poisson)))
+                if x.plastic.shape[0]:
+                    w("*Plastic\n")
+                    for r in x.plastic:
+                        w(" %s, %s\n" % (repr(float(r[0])), repr(float(r[1]))))
+                if x.ductile.shape[0]:
+                    w("*Damage Initiation, criterion=DUCTILE\n")
+                    for r in x.ductile:
+                        w(" %s, %s, %s\n" % (repr(float(r[0])), repr(float(r[1])), repr(float(r[2]))))
+            w("**\n*Boundary\nedge, ENCASTRE\n")
+            w("**\n*Initial Conditions, type=VELOCITY\nproj-1.Set-all, 3, %s\n" % repr(float(self.v0)))
+            w("**\n*Contact, op=NEW\n*Contact Inclusions, ALL EXTERIOR\n")
+            w("**\n*Step, name=Step-1, nlgeom=YES\n*Dynamic, Explicit\n%s, %s\n**\n*End Step\n" % (
+                repr(self.d_time), repr(float(self.n_steps * self.d_time))))

@@ -375,12 +375,15 @@ class SlabRunner:
                                           else np.zeros(0, np.int64))
         return n
 
-    def run(self, t_first: int, n_steps: int) -> int:
-        """Enqueues pack -> exchange -> step for every step without blocking the host, then synchronises once."""
+    def run(self, t_first: int, n_steps: int, frame_at_end: bool = False) -> int:
+        """Enqueues pack -> exchange -> step for every step without blocking the host, then synchronises once.
+        frame_at_end: an output frame follows (the last step stores integ_triax_stress, hk_mark_frame)."""
         import time as _time
         _t0 = _time.perf_counter()
         n_del = 0
         for t in range(t_first, t_first + n_steps):
+            if frame_at_end and t == t_first + n_steps - 1:
+                self.engine.mark_frame()
             if self.contact is not None:
                 self.contact.run()
             if self.halo.neighbors:

@@ -208,6 +208,13 @@ int hk_set_stream(hk_engine* e, void* cuda_stream);
 int hk_set_halo(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr, const int64_t* nodes);
 int hk_halo_bind(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_dev);
 int hk_halo_pack(hk_engine* e);
+/* The asynchronous step calls imply no output frame, so they do not store integ_triax_stress (hk_download and
+ * hk_node_output then derive it from the current stress).  hk_mark_frame announces that the last step of the NEXT
+ * hk_step_enqueue / hk_step_finish call is followed by a frame: that step stores the triaxiality computed inside it
+ * (J2:677) — for elements deleted in that very step this is the value from before their stress is zeroed, as in
+ * a frame written by the reference. */
+int hk_mark_frame(hk_engine* e);
+
 /* Split form of hk_step_enqueue(e, t, 1) that overlaps the exchange with compute:
  *     hk_halo_pack -> start send/recv -> hk_step_begin(t) [contact, nodal update of all non-interface nodes]
  *                  -> wait send/recv  -> hk_step_finish(t) [add partials, interface nodes, element kernel] */

@@ -1080,6 +1080,7 @@ int hko_apply_deleted(hk_engine* e, int64_t n, const int64_t* ids) {           /
     for (int64_t g : v) e->deleted_all.push_back(g);
     return HK_OK;
 }
+int hko_mark_frame(hk_engine* e) { return e && e->finalized ? HK_OK : fail(e, HK_ERR_STATE, "engine not finalised"); }   // triax is always stored
 int hko_step_begin(hk_engine* e, int64_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_step_finish(hk_engine* e, int64_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 

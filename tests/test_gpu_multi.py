@@ -98,3 +98,57 @@ def test_ranks_match_single_domain_oracle(mode, world):
         assert any(r["n_surf"] > r["n_surf0"] for _, r in res), "contact surface never grew"
     else:
         assert sum(r["nd"] for _, r in res) == nd_ref > 0
+
+
+def _worker_host(rank, world, port, deck_path, outdir, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hakai_fem_b200.host import hakai_distributed
+        _, frames = hakai_distributed(deck_path, outdir, output_num=6, verbose=False)      # CUDA engine, NCCL
+        q.put((rank, len(frames)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_distributed_host_driver_frames_match_oracle_frames(world, tmp_path):
+    """The `torchrun -m hakai_fem_b200.host deck.inp` path (partition, NCCL exchanges, rank-0 frame assembly from the
+    device-side nodal sums) against the single-domain driver running the CPU oracle on the same deck."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from hakai_fem_b200.host import hakai
+    from hakai_fem_b200.mesh import ImpactDeck
+    from oracle.oracle_engine import OracleEngine
+    from .test_multi_gloo import _vtk_sections
+    deck_path = str(tmp_path / "deck.inp")
+    ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0, n_steps=120,
+               plate_ductile=[[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]]).write_inp(deck_path)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_host, args=(r, world, port, deck_path, str(tmp_path / "multi"), q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    eng, ref = hakai(deck_path, str(tmp_path / "single"), engine_cls=OracleEngine, output_num=6, verbose=False)
+    assert len(eng.deleted_ids()) > 0 and res[0] == len(ref) == 7
+    for f in ref:
+        a = _vtk_sections(f)
+        b = _vtk_sections(os.path.join(str(tmp_path / "multi"), os.path.basename(f)))
+        assert list(a) == list(b)
+        for k in a:
+            assert a[k].shape == b[k].shape, (os.path.basename(f), k)          # same live cells: same deleted set
+            if k in ("CELLS", "CELL_TYPES", "POINTS"):
+                assert np.array_equal(a[k], b[k]), (os.path.basename(f), k)
+            elif k != "TRIAX_STRESS":                            # a ratio that is rounding noise while the plate is at rest
+                scale = max(np.abs(a[k]).max(), 1e-300)
+                assert np.allclose(a[k], b[k], rtol=0, atol=1e-5 * scale), (os.path.basename(f), k, scale)

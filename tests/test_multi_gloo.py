@@ -296,3 +296,81 @@ def test_erosion_across_ranks_matches_single_domain(world):
         assert np.array_equal(res[r]["flag"], ref["element_flag"][e])
         ep = ref["integ_eq_plastic_strain"].reshape(-1, 8)[e].reshape(-1)
         assert np.abs(res[r]["eps"] - ep).max() <= 1e-7 * max(np.abs(ep).max(), 1e-30)
+
+
+def _vtk_sections(path):
+    """ASCII legacy VTK -> {section name: flat array}"""
+    out, name = {}, None
+    for line in open(path):
+        w = line.split()
+        if not w:
+            continue
+        if w[0] in ("POINTS", "CELLS", "CELL_TYPES"):
+            name = w[0]
+            out[name] = []
+        elif w[0] in ("SCALARS", "VECTORS"):
+            name = w[1]
+            out[name] = []
+        elif w[0] in ("LOOKUP_TABLE", "POINT_DATA", "#", "Test", "ASCII", "DATASET"):
+            continue
+        elif name is not None:
+            out[name].extend(float(v) for v in w)
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def _worker_host(rank, world, port, deck_path, outdir, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.host import hakai_distributed
+        from tests.emu.emu_engine import EmuEngine
+        runner, frames = hakai_distributed(deck_path, outdir, engine_cls=EmuEngine, torch_device="cpu", output_num=6,
+                                           verbose=False)
+        q.put((rank, len(frames)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["fracture", "impact_erosion"])
+def test_distributed_host_driver_writes_the_single_domain_frames(kind, tmp_path):
+    """`torchrun -m hakai_fem_b200.host deck.inp` path: partitioned run + rank-0 assembly of the frames (nodal sums of
+    interface nodes added across ranks) against the single-domain driver on the same deck."""
+    from hakai_fem_b200.host import hakai
+    from hakai_fem_b200.mesh import ImpactDeck, StretchDeck, steel
+    from tests.emu.emu_engine import EmuEngine
+    deck_path = str(tmp_path / "deck.inp")
+    if kind == "fracture":
+        StretchDeck(4, 3, 8, jitter=0.05, strain_per_step=8e-4, n_steps=120,
+                    material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]])).write_inp(deck_path)
+    else:
+        ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0, n_steps=120,
+                   plate_ductile=[[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]]).write_inp(deck_path)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000) + (0 if kind == "fracture" else 1)
+    procs = [ctx.Process(target=_worker_host, args=(r, world, port, deck_path, str(tmp_path / "multi"), q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    eng, ref = hakai(deck_path, str(tmp_path / "single"), engine_cls=EmuEngine, output_num=6, verbose=False)
+    assert len(eng.deleted_ids()) > 0, "nothing deleted: CELLS would not be exercised"
+    assert res[0] == len(ref) == 7 and res[1] == 0
+    for f in ref:
+        a = _vtk_sections(f)
+        b = _vtk_sections(os.path.join(str(tmp_path / "multi"), os.path.basename(f)))
+        assert list(a) == list(b) and len(a) == 22
+        for k in a:
+            assert a[k].shape == b[k].shape, (os.path.basename(f), k)          # same live-cell list
+            if k in ("CELLS", "CELL_TYPES", "POINTS"):
+                assert np.array_equal(a[k], b[k]), (os.path.basename(f), k)
+            else:                                                   # %1.6e text of values equal to ~1e-9 relative
+                scale = max(np.abs(a[k]).max(), 1e-300)
+                assert np.allclose(a[k], b[k], rtol=0, atol=3e-6 * scale), (os.path.basename(f), k, scale)
