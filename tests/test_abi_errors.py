@@ -73,3 +73,32 @@ def test_finalize_twice_and_halo_multi_step_rejected():
     e.step(1, 1)
     with pytest.raises(HakaiError):
         e.step(2, 2)                                             # with halos: one step per exchange
+
+
+def test_restart_and_multi_domain_hooks_are_checked():
+    st = prepare(StretchDeck(2, 2, 2).build_model())
+    e = EmuEngine(d_time=st.d_time)
+    for call in (lambda: e.node_output(), lambda: e.mark_frame(), lambda: e.apply_deleted([1]),
+                 lambda: e.set_global_maps([1], [1], [1])):
+        with pytest.raises(HakaiError):
+            call()                                               # not finalised
+    e = configure_engine(EmuEngine, st)
+    nE, nN = st.model.nElement, st.model.nNode
+    with pytest.raises(HakaiError):
+        e.apply_deleted([nE + 1])                                # local id out of range
+    with pytest.raises(HakaiError):
+        e.apply_deleted([0])
+    e.apply_deleted([2])                                         # restart hook: recorded as already deleted
+    assert list(e.deleted_ids()) == [2] and e.sync() == 0
+    with pytest.raises(HakaiError):
+        e.set_global_maps(np.full(3, nN + 1), np.ones(2), np.ones(2))       # local node id beyond the mesh
+    with pytest.raises(HakaiError):
+        e.set_global_maps(np.ones(3), np.full(2, nE + 1), np.ones(2))
+    e.set_global_maps(np.arange(1, nN + 1), np.arange(1, nE + 1), np.ones(nE))
+    with pytest.raises(HakaiError):
+        e.apply_deleted([nE + 1])                                # now a GLOBAL id: still range-checked
+    with pytest.raises(ValueError):
+        e.node_output(out=dict(node_stress=np.zeros((nN, 6))))   # wrong layout: (6, nNode) expected
+    e.mark_frame()
+    e.step_enqueue(1, 1)
+    assert e.sync() == 0

@@ -134,3 +134,28 @@ def test_written_deck_equals_direct_arrays(tmp_path):
     assert all(np.array_equal(x, y) for x, y in zip(a.BC[0].dof, b.BC[0].dof))
     assert a.IC[0].value == b.IC[0].value and all(np.array_equal(x, y) for x, y in zip(a.IC[0].dof, b.IC[0].dof))
     assert np.array_equal(a.BC[0].amplitude.time, b.BC[0].amplitude.time)
+
+
+def test_written_impact_deck_equals_direct_arrays(tmp_path):
+    """ImpactDeck.write_inp (two parts, translated instance, assembly-level set, *Contact ... ALL EXTERIOR) read back
+    by the readInpFile mirror gives the arrays of build_model(), down to the contact surfaces and the lumped mass."""
+    from hakai_fem_b200.mesh import ImpactDeck
+    from hakai_fem_b200.model_setup import prepare
+    deck = ImpactDeck(plate=(6, 5, 2), proj=(2, 3, 2), v0=-300.0, plate_ductile=[[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]])
+    path = tmp_path / "impact.inp"
+    deck.write_inp(str(path))
+    a, b = read_inp_file(str(path)), deck.build_model()
+    assert (a.nNode, a.nElement, a.contact_flag, a.d_time, a.end_time) == (b.nNode, b.nElement, 1, b.d_time, b.end_time)
+    assert np.array_equal(a.coordmat, b.coordmat) and np.array_equal(a.elementmat, b.elementmat)
+    assert np.array_equal(a.element_material, b.element_material)
+    assert np.array_equal(a.element_instance, b.element_instance)
+    assert [m.name for m in a.MATERIAL] == ["alum", "lead"]
+    assert np.array_equal(a.MATERIAL[0].ductile, b.MATERIAL[0].ductile)
+    assert np.array_equal(np.sort(np.concatenate(a.BC[0].dof)), np.sort(np.concatenate(b.BC[0].dof)))
+    assert a.IC[0].value == b.IC[0].value and np.array_equal(a.IC[0].dof[0], b.IC[0].dof[0])
+    sa, sb = prepare(a), prepare(b)
+    assert np.array_equal(sa.diag_M, sb.diag_M) and len(sa.CT) == len(sb.CT) == 2
+    for x, y in zip(sa.CT, sb.CT):
+        assert (x.i_instance, x.j_instance, x.young) == (y.i_instance, y.j_instance, y.young)
+        assert np.array_equal(x.c_triangles, y.c_triangles) and np.array_equal(x.c_nodes_i, y.c_nodes_i)
+        assert np.array_equal(x.c_nodes_j, y.c_nodes_j) and np.array_equal(x.c_triangles_eleid, y.c_triangles_eleid)
