@@ -52,6 +52,16 @@ def block_arrays(nx: int, ny: int, nz: int, h: float = 1.0, origin=(0.0, 0.0, 0.
     return coord, em
 
 
+def _write_nodes_elements(f, coord: np.ndarray, em: np.ndarray):
+    """`*Node` / `*Element` blocks; %.17g round-trips every double exactly."""
+    nN, nE = coord.shape[1], em.shape[1]
+    f.write("*Node\n")
+    ids = np.arange(1, nN + 1, dtype=np.float64)[:, None]
+    np.savetxt(f, np.concatenate([ids, coord.T], axis=1), fmt=["%7d", "%.17g", "%.17g", "%.17g"], delimiter=", ")
+    f.write("*Element, type=C3D8R\n")
+    np.savetxt(f, np.concatenate([np.arange(1, nE + 1, dtype=np.int64)[:, None], em.T], axis=1), fmt="%d", delimiter=", ")
+
+
 @dataclass
 class StretchDeck:
     """Uniform-stretch brick: z-layer initial velocities v = rate*z and amplitude-driven end layers."""
@@ -130,12 +140,8 @@ class StretchDeck:
         with open(path, "w") as f:
             w = f.write
             w("*Heading\n** synthetic stretch deck %s %dx%dx%d\n" % (self.name, self.nx, self.ny, self.nz))
-            w("*Part, name=Part-1\n*Node\n")
-            for n in range(nN):
-                w("%7d, %s, %s, %s\n" % (n + 1, repr(float(coord[0, n])), repr(float(coord[1, n])), repr(float(coord[2, n]))))
-            w("*Element, type=C3D8R\n")
-            for e in range(nE):
-                w("%d, " % (e + 1) + ", ".join(str(int(v)) for v in em[:, e]) + "\n")
+            w("*Part, name=Part-1\n")
+            _write_nodes_elements(f, coord, em)
             w("*Nset, nset=Set-all, generate\n  1, %d, 1\n" % nN)
             w("*Elset, elset=Set-all, generate\n 1, %d, 1\n" % nE)
             w("*Solid Section, elset=Set-all, material=%s\n,\n*End Part\n" % m.name)
@@ -248,13 +254,8 @@ class ImpactDeck:
             w = f.write
             w("*Heading\n** synthetic impact deck %s plate %s proj %s\n" % (self.name, self.plate, self.proj))
             for part in m.PART:
-                w("*Part, name=%s\n*Node\n" % part.name)
-                for n in range(part.nNode):
-                    c = part.coordmat[:, n]
-                    w("%7d, %s, %s, %s\n" % (n + 1, repr(float(c[0])), repr(float(c[1])), repr(float(c[2]))))
-                w("*Element, type=C3D8R\n")
-                for e in range(part.nElement):
-                    w("%d, " % (e + 1) + ", ".join(str(int(v)) for v in part.elementmat[:, e]) + "\n")
+                w("*Part, name=%s\n" % part.name)
+                _write_nodes_elements(f, part.coordmat, part.elementmat)
                 w("*Nset, nset=Set-all, generate\n  1, %d, 1\n" % part.nNode)
                 w("*Elset, elset=Set-all, generate\n 1, %d, 1\n" % part.nElement)
                 w("*Solid Section, elset=Set-all, material=%s\n,\n*End Part\n**\n" % part.material_name)
