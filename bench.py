@@ -108,6 +108,12 @@ def cpu_oracle_rate(sample_workload, warmup, steps, threads=None):
     deck = make_deck(sample_workload)
     st = prepare_setup(deck)
     eng = configure_engine(OracleEngine, st)
+    if threads:                 # torchrun exports OMP_NUM_THREADS=1 and libgomp may have read it already: set it directly
+        try:
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+        except OSError:
+            pass
     eng.step(1, warmup)
     t0 = time.perf_counter()
     eng.step(warmup + 1, steps)
