@@ -202,6 +202,46 @@ def case_contact_erosion(engine_cls, n_steps=400):
     util.assert_states_close(a, b, 1e-7, ("disp", "integ_eq_plastic_strain", "element_flag"), "erosion")
 
 
+def case_bc_edge_cases(engine_cls):
+    """Boundary-condition corners of J2:585-617: a multi-segment amplitude table, times outside every segment (the
+    search falls back to segment 1 and extrapolates it), a BC without amplitude, later BCs overriding earlier ones on
+    the same dof, an empty dof list — and hk_step with n_steps = 0."""
+    from hakai_fem_b200.inp import Amplitude, BC
+    deck = util.distorted_block(nx=3, ny=3, nz=4, jitter=0.1)
+    model = deck.build_model()
+    per = 4 * 4
+    top = np.arange(4 * per + 1, 5 * per + 1, dtype=np.int64)
+    bottom = np.arange(1, per + 1, dtype=np.int64)
+    dt = model.d_time
+    amp = Amplitude(name="kink", time=np.array([0.0, 40 * dt, 80 * dt]), value=np.array([0.0, 1.0, 0.25]))
+    b1 = BC(Nset_name="top", amp_name="kink", amplitude=amp)
+    b1.dof, b1.value = [top * 3, top * 3 - 2], [0.02, 0.005]
+    b2 = BC(Nset_name="bottom")                                  # no amplitude: amp = 1
+    b2.dof, b2.value = [bottom * 3, bottom * 3 - 1, np.zeros(0, np.int64)], [0.0, 0.0, 7.0]
+    b3 = BC(Nset_name="override", amp_name="kink", amplitude=amp)
+    b3.dof, b3.value = [top[:4] * 3 - 2], [-0.01]                # same dofs as part of b1's second list: the later BC wins
+    model.BC = [b1, b2, b3]
+    model.IC = []
+    st = prepare(model)
+    o, g = util.make_pair(st, engine_cls, OracleEngine)
+    assert o.step(1, 0) == 0 and g.step(1, 0) == 0               # nothing happens, nothing breaks
+    a, b = util.full_state(o), util.full_state(g)
+    assert np.array_equal(a["disp"], b["disp"]) and not a["disp"].any()
+    t = 0
+    for n in (39, 2, 38, 2, 40):                                 # across the kink (40), the table end (80) and beyond
+        o.step(t + 1, n)
+        g.step(t + 1, n)
+        t += n
+        a, b = util.full_state(o), util.full_state(g)
+        util.assert_states_close(a, b, 1e-10, STATE_KEYS, f"bc edge step {t}")
+        assert np.array_equal(a["disp"][top * 3 - 1], b["disp"][top * 3 - 1])          # prescribed values: bit-equal
+    # past the table end the reference extrapolates SEGMENT 1 (time_index stays 1, J2:588-600): amp(t) = t / (40 dt)
+    want = 0.02 * (t * dt) / (40 * dt)
+    assert np.allclose(b["disp"][top * 3 - 1], want, rtol=1e-14)
+    assert np.allclose(b["disp"][top[:4] * 3 - 3], -0.01 * (t * dt) / (40 * dt), rtol=1e-14)
+    assert np.allclose(b["disp"][top[4:] * 3 - 3], 0.005 * (t * dt) / (40 * dt), rtol=1e-14)
+
+
 # ---------------------------------------------------------------- checkpoint / resume (hakai_fem_b200/checkpoint.py)
 def erosion_setup():
     model = ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0).build_model()

@@ -33,6 +33,10 @@ def test_contact_single_step_exact():
     pc.case_contact_single_step(EmuEngine)
 
 
+def test_bc_edge_cases():
+    pc.case_bc_edge_cases(EmuEngine)
+
+
 def test_node_output():
     pc.case_node_output(EmuEngine)
 

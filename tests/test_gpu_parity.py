@@ -37,6 +37,10 @@ def test_contact_single_step_exact():
     pc.case_contact_single_step(Engine)
 
 
+def test_bc_edge_cases():
+    pc.case_bc_edge_cases(Engine)
+
+
 def test_node_output():
     pc.case_node_output(Engine)
 
