@@ -21,6 +21,8 @@ reference; conversion to 0-based happens once, inside the engine's ``hk_set_*`` 
 """
 from __future__ import annotations
 
+import bisect
+
 import math
 from dataclasses import dataclass, field
 from typing import List
@@ -194,6 +196,12 @@ def _read_table(lines, start, ncol, dtype):
     rows = end - start - 1
     if rows == 0:
         return np.zeros((0, ncol), dtype)
+    try:                                                        # regular table: NumPy's C parser (same correctly
+        arr = np.loadtxt(lines[start + 1:end], delimiter=",", dtype=np.float64, ndmin=2)    # rounded doubles)
+        if arr.shape[1] == len(_fields(lines[start + 1])) and np.all(np.isfinite(arr)):
+            return arr
+    except ValueError:                                          # ragged rows / trailing commas: the general path
+        pass
     txt = ",".join(_nosp(l).rstrip(",") for l in lines[start + 1:end])
     flat = np.array(txt.split(","), dtype=object)
     per = len(_fields(lines[start + 1]))
@@ -212,16 +220,22 @@ def read_inp_file(fname: str) -> Model:
 
 def parse_inp_lines(lines: List[str]) -> Model:
     n = len(lines)
+    # every keyword test below looks for a token starting with '*': scan only the lines that contain one (a 16 M-
+    # element deck has 3e7 data lines and a few hundred keyword lines; readInpFile re-scans the whole file per keyword)
+    star = [i for i, l in enumerate(lines) if "*" in l]
+
+    def star_from(i0):
+        return star[bisect.bisect_left(star, i0):]
 
     # --- Part ---  (:165-308)
-    part_index = [i for i in range(n) if "*Part, name=" in lines[i]]
+    part_index = [i for i in star if "*Part, name=" in lines[i]]
     PART: List[Part] = []
     for pi in part_index:
         p = Part()
         p.name = _after(_fields(lines[pi])[1], "name=")
 
         index = 0
-        for i in range(pi, n):
+        for i in star_from(pi):
             if "*Node" in lines[i]:
                 index = i
                 break
@@ -230,7 +244,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
         p.coordmat = np.ascontiguousarray(tab[:, 1:4].astype(np.float64).T)
 
         index = 0
-        for i in range(pi, n):
+        for i in star_from(pi):
             if "*Element" in lines[i]:
                 index = i
                 break
@@ -238,7 +252,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
         p.nElement = tab.shape[0]
         p.elementmat = np.ascontiguousarray(tab[:, 1:9].astype(np.int64).T)
 
-        for i in range(pi, n):
+        for i in star_from(pi):
             if "*Nset" in lines[i] and "generate" in lines[i]:
                 ns = Nset()
                 ns.name = _after(_fields(lines[i])[1], "nset=")
@@ -248,7 +262,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
             if "*End Part" in lines[i]:
                 break
 
-        for i in range(pi, n):
+        for i in star_from(pi):
             if "*Solid Section" in lines[i]:
                 for tok in _fields(lines[i]):
                     if "material=" in tok:
@@ -260,7 +274,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- Instance ---  (:311-362)
     INSTANCE: List[Instance] = []
-    for ii in [i for i in range(n) if "*Instance" in lines[i]]:
+    for ii in [i for i in star if "*Instance" in lines[i]]:
         ins = Instance()
         ff = _fields(lines[ii])
         ins.name = _after(ff[1], "name=")
@@ -286,7 +300,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- Nset (assembly level) ---  (:365-432)
     NSET: List[Nset] = []
-    for idx in [i for i in range(n) if "*Nset" in lines[i] and "instance=" in lines[i]]:
+    for idx in [i for i in star if "*Nset" in lines[i] and "instance=" in lines[i]]:
         ns = Nset()
         ff = _fields(lines[idx])
         ns.name = _after(ff[1], "nset=")
@@ -306,7 +320,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- Elset ---  (:435-514)
     ELSET: List[Elset] = []
-    for idx in [i for i in range(n) if "*Elset" in lines[i] and "instance=" in lines[i]]:
+    for idx in [i for i in star if "*Elset" in lines[i] and "instance=" in lines[i]]:
         es = Elset()
         ff = _fields(lines[idx])
         es.name = _after(ff[1], "elset=")
@@ -331,7 +345,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- Surface ---  (:517-563)
     SURFACE: List[Surface] = []
-    for idx in [i for i in range(n) if "*Surface," in lines[i]]:
+    for idx in [i for i in star if "*Surface," in lines[i]]:
         sf = Surface()
         sf.name = _after(_fields(lines[idx])[2], "name=")
         a = []
@@ -387,7 +401,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- Amplitude ---  (:624-668)
     AMPLITUDE: List[Amplitude] = []
-    for idx in [i for i in range(n) if "*Amplitude" in lines[i]]:
+    for idx in [i for i in star if "*Amplitude" in lines[i]]:
         am = Amplitude()
         am.name = _after(_fields(lines[idx])[1], "name=")
         for i in range(idx + 1, n):
@@ -401,7 +415,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- Material ---  (:671-793)
     MATERIAL: List[Material] = []
-    for idx in [i for i in range(n) if "*Material" in lines[i]]:
+    for idx in [i for i in star if "*Material" in lines[i]]:
         mt = Material()
         mt.name = _after(_fields(lines[idx])[1], "name=")
         plastic_index = -1
@@ -461,14 +475,14 @@ def parse_inp_lines(lines: List[str]) -> Model:
     # --- Step / mass scaling ---  (:816-840)
     d_time = 0.0
     end_time = 0.0
-    for i in range(n):
+    for i in star:
         if "*Dynamic, Explicit" in lines[i]:
             ss = _fields(lines[i + 1])
             d_time = float(ss[0])
             end_time = float(ss[1])
             break
     mass_scaling = 1.0
-    for i in range(n):
+    for i in star:
         if "*Fixed Mass Scaling" in lines[i]:
             mass_scaling = float(_after(_fields(lines[i])[1], "factor="))
             break
@@ -502,7 +516,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- BC ---  (:843-957)
     BCs: List[BC] = []
-    for idx in [i for i in range(n) if "*Boundary" in lines[i]]:
+    for idx in [i for i in star if "*Boundary" in lines[i]]:
         bc = BC()
         ff = _fields(lines[idx])
         if len(ff) == 2 and "amplitude=" in ff[1]:
@@ -536,7 +550,7 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- Initial conditions ---  (:960-1043)
     ICs: List[IC] = []
-    for idx in [i for i in range(n) if "*Initial Conditions" in lines[i]]:
+    for idx in [i for i in star if "*Initial Conditions" in lines[i]]:
         ic = IC()
         ic.type = _after(_fields(lines[idx])[1], "type=")
         for i in range(idx + 1, n):
@@ -552,16 +566,16 @@ def parse_inp_lines(lines: List[str]) -> Model:
 
     # --- Contact ---  (:1046-1102)
     contact_flag = 0
-    for i in range(n):
+    for i in star:
         if "*Contact" in lines[i]:
             contact_flag = 1
             break
-    for i in range(n):
+    for i in star:
         if "*Contact Inclusions" in lines[i] and "HAKAIoption=self-contact" in lines[i]:
             contact_flag = 2
             break
     CPs: List[CP] = []
-    for idx in [i for i in range(n) if "*Contact Pair," in lines[i]]:
+    for idx in [i for i in star if "*Contact Pair," in lines[i]]:
         cp = CP()
         cp.name = _after(_fields(lines[idx])[3], "cpset=")
         ss = _fields(lines[idx + 1])
