@@ -11,11 +11,11 @@ Materials are the blocks of HAKAI-v0.0.0/input/Tensile5e.inp (mm-t-s units).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 
-from .inp import (Model, Part, Instance, Material, Amplitude, BC, IC, Nset)
+from .inp import Model, Part, Instance, Material, Amplitude, BC, IC
 
 STEEL_PLASTIC = np.array([[755., 0.], [809., 0.01], [829., 0.02], [842., 0.1], [895., 0.15],
                           [922., 0.4], [953., 1.], [1100., 4.]])

@@ -23,7 +23,7 @@ from typing import List
 import numpy as np
 
 from . import inp as I
-from .model_setup import Setup, prepare, configure_engine, lumped_mass, element_volumes, element_sizes
+from .model_setup import Setup, configure_engine
 
 
 @dataclass

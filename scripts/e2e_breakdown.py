@@ -3,7 +3,6 @@ import sys
 import time
 import os
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
