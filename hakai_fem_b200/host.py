@@ -221,7 +221,7 @@ def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, 
     model = read_inp_file(fname)
     setup = prepare(model)
     log("nNode:", model.nNode, " nElement:", model.nElement, " contact_flag:", model.contact_flag, " ranks:", world)
-    dom = partition_model(setup, world)[rank]
+    dom = partition_model(setup, world, only_rank=rank)[rank]
     runner = SlabRunner.from_domain(engine_cls, dom, torch_device, world, **params)
     eng = runner.engine
     n_held = len(np.unique(dom.setup.model.elementmat))         # local ids 1..n_held are nodes of own elements

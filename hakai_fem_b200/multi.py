@@ -88,14 +88,15 @@ def build_contact_lists(surf, owner, g2l, n_held, rank, n_ranks, erosion=None) -
     return ContactLists(g2l[export_lists[rank]], g2l[ghost], src, loc, maxlen, erosion)
 
 
-def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
+def partition_model(setup: Setup, n_ranks: int, only_rank: int = None) -> List[LocalDomain]:
     """Splits a (small) global model into contiguous element blocks.  Used by the tests and for general
     decks; the 16 M/GPU bench builds each slab directly (slab_deck) without materialising the global mesh.
 
     With contact, every rank receives the GLOBAL contact node lists (nodes it does not hold are appended as ghost
     nodes that no element references) and the master triangles of its own elements.  If a material can fail, the
     ghost set is every node of the instances in contact (any of them may become exposed) and the rank gets the
-    global instance face tables + ErosionMaps."""
+    global instance face tables + ErosionMaps.  only_rank: build just that rank's LocalDomain (the other list
+    entries are None) — what a rank of a distributed run needs."""
     m = setup.model
     nE = m.nElement
     bounds = [(nE * r) // n_ranks for r in range(n_ranks + 1)]
@@ -124,6 +125,9 @@ def partition_model(setup: Setup, n_ranks: int) -> List[LocalDomain]:
                 [surf] + [np.arange(m.INSTANCE[i - 1].node_offset + 1,
                                     m.INSTANCE[i - 1].node_offset + m.INSTANCE[i - 1].nNode + 1) for i in inst]))
     for r in range(n_ranks):
+        if only_rank is not None and r != only_rank:
+            doms.append(None)
+            continue
         el, nodes_own = locals_[r]
         ghosts = np.setdiff1d(candidates, nodes_own) if m.contact_flag else np.zeros(0, np.int64)
         nodes = np.concatenate([nodes_own, ghosts])              # local numbering: own nodes, then ghosts
