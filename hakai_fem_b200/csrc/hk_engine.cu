@@ -1320,6 +1320,22 @@ int HKAPI(contact_import)(hk_engine* e, const void* in_dev, int64_t n_ranks) {
     return HK_OK;
 }
 
+int HKAPI(contact_export_limbs)(hk_engine* e, void* out_dev) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    hk_launch_cacc_export_limbs(e->d, e->d_node_list[2], (long long)e->node_list[2].size(), (long long*)out_dev, e->stream);
+    e->n_launch += 1;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(contact_import_limbs)(hk_engine* e, const void* in_dev) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    hk_launch_cacc_import_limbs(e->d, e->d_node_list[2], (long long)e->node_list[2].size(), (const long long*)in_dev, e->stream);
+    e->n_launch += 1;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
 int HKAPI(set_stream)(hk_engine* e, void* cuda_stream) {
     if (!e) return HK_ERR_ARG;
 #ifndef HK_EMU

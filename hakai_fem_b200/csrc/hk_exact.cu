@@ -591,6 +591,43 @@ void hk_launch_cacc_import(const HkDev& dd, const int* nodes, long long n, const
     });
 }
 
+// The same exchange as a plain integer all-reduce: each 128-bit accumulator X (two's complement, mod 2^128) travels as
+// three limbs X[0:43], X[43:86], X[86:128] in int64 lanes.  The lane-wise sums over R ranks stay below R * 2^43 (no
+// overflow for R < 2^20), and S0 + S1*2^43 + S2*2^86 mod 2^128 is the exact sum of the X — no carry is ever lost.
+void hk_launch_cacc_export_limbs(const HkDev& dd, const int* nodes, long long n, long long* out, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 3, s, HK_LAMBDA(long long j) {
+        const long long i = j / 3;
+        const int c = (int)(j - 3 * i);
+        const int slot = d.spec[d.spec_idx[nodes[i]]].contact_slot;
+        const unsigned long long lo = d.cacc[6ll * slot + 2 * c], hi = d.cacc[6ll * slot + 2 * c + 1];
+        const unsigned long long m43 = (1ull << 43) - 1;
+        out[9 * i + 3 * c + 0] = (long long)(lo & m43);
+        out[9 * i + 3 * c + 1] = (long long)(((lo >> 43) | (hi << 21)) & m43);      // bits 43..85
+        out[9 * i + 3 * c + 2] = (long long)(hi >> 22);                             // bits 86..127
+    });
+}
+void hk_launch_cacc_import_limbs(const HkDev& dd, const int* nodes, long long n, const long long* in, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 3, s, HK_LAMBDA(long long j) {
+        const long long i = j / 3;
+        const int c = (int)(j - 3 * i);
+        const unsigned long long s0 = (unsigned long long)in[9 * i + 3 * c + 0];
+        const unsigned long long s1 = (unsigned long long)in[9 * i + 3 * c + 1];
+        const unsigned long long s2 = (unsigned long long)in[9 * i + 3 * c + 2];
+        // X = s0 + s1 * 2^43 + s2 * 2^86  (mod 2^128), 128-bit adds with carry
+        unsigned long long lo = s0, hi = 0ull;
+        const unsigned long long a_lo = s1 << 43, a_hi = s1 >> 21;
+        unsigned long long nlo = lo + a_lo;
+        hi += a_hi + (nlo < lo ? 1ull : 0ull);
+        lo = nlo;
+        hi += s2 << 22;
+        const int slot = d.spec[d.spec_idx[nodes[i]]].contact_slot;
+        d.cacc[6ll * slot + 2 * c] = lo;
+        d.cacc[6ll * slot + 2 * c + 1] = hi;
+    });
+}
+
 // external_force of the last step (J2:497-538): zero plus the rounded contact sums
 void hk_launch_external_force(const HkDev& dd, double* F_out, int lsb_exp, int contact_on, cudaStream_t s) {
     const HkDev d = dd;

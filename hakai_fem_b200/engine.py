@@ -42,7 +42,7 @@ EXPORTS = [
     "deleted_ids", "contact_pair_info", "counters", "profile", "profile_read", "set_stream",
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
-    "set_global_maps", "apply_deleted", "node_output", "mark_frame",
+    "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
 ]
 
 
@@ -335,6 +335,12 @@ class EngineBase:
 
     def contact_import(self, in_ptr: int, n_ranks: int):
         self._chk(self._fn("contact_import")(self._h, C.c_void_p(in_ptr), c_i64(n_ranks)))
+
+    def contact_export_limbs(self, out_ptr: int):
+        self._chk(self._fn("contact_export_limbs")(self._h, C.c_void_p(out_ptr)))
+
+    def contact_import_limbs(self, in_ptr: int):
+        self._chk(self._fn("contact_import_limbs")(self._h, C.c_void_p(in_ptr)))
 
     def mark_frame(self):
         """The next asynchronous step is followed by an output frame (stores integ_triax_stress)."""

@@ -256,7 +256,13 @@ def exchange_sum(values_per_nbr, neighbors, device):
 class ContactExchanger:
     """All-gather of contact-surface node {position, velocity} and of the fixed-point force accumulators."""
 
-    def __init__(self, engine, lists: ContactLists, world: int, device, rank=None, node_l2g=None, n_pairs=0):
+    def __init__(self, engine, lists: ContactLists, world: int, device, rank=None, node_l2g=None, n_pairs=0,
+                 force_exchange="allgather"):
+        """force_exchange: "allgather" (6 x u64 per surface node from every rank, summed on import) or "allreduce"
+        (three 43-bit limbs per accumulator in int64 lanes, one SUM all-reduce: world/1.5 times fewer bytes)."""
+        if force_exchange not in ("allgather", "allreduce"):
+            raise ValueError("force_exchange: allgather | allreduce")
+        self.force_exchange = force_exchange
         self.engine, self.world, self.device = engine, world, device
         self.rank, self.node_l2g, self.n_pairs = rank, node_l2g, n_pairs
         self.erosion = lists.erosion
@@ -276,8 +282,11 @@ class ContactExchanger:
         self.send_nodes = torch.zeros(lists.maxlen * 6, dtype=torch.float64, device=device)
         self.all_nodes = torch.zeros(world * lists.maxlen * 6, dtype=torch.float64, device=device)
         n_surf = len(lists.surface_nodes)
-        self.send_acc = torch.zeros(n_surf * 6, dtype=torch.int64, device=device)
-        self.all_acc = torch.zeros(world * n_surf * 6, dtype=torch.int64, device=device)
+        if self.force_exchange == "allreduce":
+            self.limbs = torch.zeros(n_surf * 9, dtype=torch.int64, device=device)
+        else:
+            self.send_acc = torch.zeros(n_surf * 6, dtype=torch.int64, device=device)
+            self.all_acc = torch.zeros(world * n_surf * 6, dtype=torch.int64, device=device)
         engine.set_node_list(0, lists.export_nodes)
         engine.set_node_list(1, lists.import_nodes)
         engine.set_node_list(2, lists.surface_nodes)
@@ -321,9 +330,14 @@ class ContactExchanger:
         eng.nodes_import(self.all_nodes.data_ptr(), self.lists.import_src if self._first else None)
         self._first = False
         eng.contact_enqueue()
-        eng.contact_export(self.send_acc.data_ptr())
-        dist.all_gather(list(self.all_acc.chunk(self.world)), self.send_acc)
-        eng.contact_import(self.all_acc.data_ptr(), self.world)
+        if self.force_exchange == "allreduce":
+            eng.contact_export_limbs(self.limbs.data_ptr())
+            dist.all_reduce(self.limbs, op=dist.ReduceOp.SUM)
+            eng.contact_import_limbs(self.limbs.data_ptr())
+        else:
+            eng.contact_export(self.send_acc.data_ptr())
+            dist.all_gather(list(self.all_acc.chunk(self.world)), self.send_acc)
+            eng.contact_import(self.all_acc.data_ptr(), self.world)
 
 
 class SlabRunner:
@@ -331,7 +345,7 @@ class SlabRunner:
     host-compiled kernel build, whose "device" pointers are host pointers."""
 
     def __init__(self, engine_cls, setup: Setup, neighbors, halo_nodes, torch_device, sum_mass=False, contact=None,
-                 world=1, rank=None, node_l2g=None, elem_l2g=None, **params):
+                 world=1, rank=None, node_l2g=None, elem_l2g=None, force_exchange="allgather", **params):
         self.setup = setup
         if sum_mass and neighbors:
             # interface nodes: add the neighbour's partial lumped mass (J2:201-215 summed over ALL elements)
@@ -349,7 +363,8 @@ class SlabRunner:
             return eng
         self.engine = configure_engine(with_halo, setup, **params)
         self.halo = HaloExchanger(self.engine, neighbors, halo_nodes, torch_device)
-        self.contact = (ContactExchanger(self.engine, contact, world, torch_device, rank, node_l2g, len(setup.CT))
+        self.contact = (ContactExchanger(self.engine, contact, world, torch_device, rank, node_l2g, len(setup.CT),
+                                         force_exchange)
                         if contact is not None else None)
         self.erosion = self.contact is not None and self.contact.erosion is not None
         if self.erosion and elem_l2g is None:
@@ -358,9 +373,10 @@ class SlabRunner:
         self.nElement = model.nElement
 
     @classmethod
-    def from_domain(cls, engine_cls, dom: LocalDomain, torch_device, world, **params):
+    def from_domain(cls, engine_cls, dom: LocalDomain, torch_device, world, force_exchange="allgather", **params):
         return cls(engine_cls, dom.setup, dom.neighbors, dom.halo_nodes, torch_device, contact=dom.contact,
-                   world=world, rank=dom.rank, node_l2g=dom.node_l2g, elem_l2g=dom.elem_l2g, **params)
+                   world=world, rank=dom.rank, node_l2g=dom.node_l2g, elem_l2g=dom.elem_l2g,
+                   force_exchange=force_exchange, **params)
 
     def _after_step(self) -> int:
         """Erosion across ranks: one host sync per step (the deleted set decides the next step's contact surface)."""

@@ -240,6 +240,11 @@ int hk_nodes_import(hk_engine* e, const void* in_dev, const int64_t* src_index /
 int hk_contact_enqueue(hk_engine* e);                             /* contact pass of the NEXT step, now     */
 int hk_contact_export(hk_engine* e, void* out_dev);               /* list 2 -> 6 uint64 per node             */
 int hk_contact_import(hk_engine* e, const void* in_dev, int64_t n_ranks);   /* sum of n_ranks records per node */
+/* The same exchange for a plain integer all-reduce (ncclAllReduce, ncclInt64, ncclSum) instead of an all-gather: every
+ * 128-bit accumulator travels as three 43-bit limbs in int64 lanes — 9 x int64 per surface node, summed lane-wise by
+ * the collective, recombined exactly (mod 2^128) on import; valid for fewer than 2^20 ranks. */
+int hk_contact_export_limbs(hk_engine* e, void* out_dev);      /* 9 x i64 per surface node */
+int hk_contact_import_limbs(hk_engine* e, const void* in_dev); /* lane-wise sums over all ranks */
 /* Erosion of contact surfaces across ranks (add_surface_triangle, J2:767-804, 2167-2245).  The instance face tables
  * given to hk_add_instance are then the GLOBAL ones; the maps translate global 1-based ids to this rank's local
  * 1-based ids (0 = not present / not owned).  After every step the host all-gathers the freshly deleted GLOBAL

@@ -374,3 +374,81 @@ def test_distributed_host_driver_writes_the_single_domain_frames(kind, tmp_path)
             else:                                                   # %1.6e text of values equal to ~1e-9 relative
                 scale = max(np.abs(a[k]).max(), 1e-300)
                 assert np.allclose(a[k], b[k], rtol=0, atol=3e-6 * scale), (os.path.basename(f), k, scale)
+
+
+def _worker_force_exchange(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.model_setup import prepare
+        from hakai_fem_b200.multi import partition_model, SlabRunner
+        from hakai_fem_b200.mesh import ImpactDeck
+        from tests.emu.emu_engine import EmuEngine
+        out = {}
+        for mode in ("allgather", "allreduce"):
+            gsetup = prepare(ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3)).build_model())
+            dom = partition_model(gsetup, world, only_rank=rank)[rank]
+            run = SlabRunner.from_domain(EmuEngine, dom, "cpu", world, force_exchange=mode, contact_myu=0.25)
+            run.run(1, 60)
+            d = run.engine.download()
+            x = run.engine.download_ex(fields=("external_force",))
+            out[mode] = dict(disp=d["disp"], velo=d["velo"], eps=d["integ_eq_plastic_strain"], ext=x["external_force"],
+                             hits=int(run.engine.counters()[1]))
+        q.put((rank, out))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_contact_force_exchange_by_limb_allreduce_is_bit_identical():
+    """The 128-bit accumulators as three 43-bit limbs through ONE integer all-reduce give exactly the state the
+    all-gather + 128-bit sum gives (positive and negative forces, carries across limbs)."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_force_exchange, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sum(res[r]["allgather"]["hits"] for r in range(world)) > 0
+    for r in range(world):
+        a, b = res[r]["allgather"], res[r]["allreduce"]
+        assert np.abs(a["ext"]).max() > 0 and (a["ext"] < 0).any() and (a["ext"] > 0).any()
+        for k in ("disp", "velo", "eps", "ext"):
+            assert np.array_equal(a[k], b[k]), (r, k)
+        assert a["hits"] == b["hits"]
+
+
+def test_limb_split_and_recombine_formulas_are_exact_mod_2_128():
+    """The bit manipulation of hk_launch_cacc_export_limbs / _import_limbs (hk_exact.cu), restated with Python integers
+    masked to 64 bits, over random 128-bit two's-complement values and up to 4096 ranks."""
+    import random
+    rnd = random.Random(5)
+    M64, M43 = (1 << 64) - 1, (1 << 43) - 1
+
+    def export(x):
+        lo, hi = x & M64, (x >> 64) & M64
+        return [lo & M43, ((lo >> 43) | ((hi << 21) & M64)) & M43, hi >> 22]
+
+    def recombine(s0, s1, s2):
+        lo, hi = s0 & M64, 0
+        a_lo, a_hi = (s1 << 43) & M64, s1 >> 21
+        nlo = (lo + a_lo) & M64
+        hi = (hi + a_hi + (1 if nlo < lo else 0)) & M64
+        lo = nlo
+        hi = (hi + ((s2 << 22) & M64)) & M64
+        return lo | (hi << 64)
+    for ranks in (1, 2, 3, 8, 4096):
+        for _ in range(200):
+            vals = [rnd.choice([rnd.getrandbits(128), (1 << 128) - rnd.getrandbits(70), rnd.getrandbits(50), (1 << 128) - 1, 0])
+                    for _ in range(ranks)]
+            limbs = [export(v) for v in vals]
+            sums = [sum(l[i] for l in limbs) for i in range(3)]
+            assert all(0 <= s < (1 << 63) for s in sums)               # fits the int64 lanes of the all-reduce
+            assert recombine(*sums) == sum(vals) % (1 << 128)
