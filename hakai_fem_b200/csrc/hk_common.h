@@ -126,6 +126,8 @@ void hk_launch_nodes_export(const HkDev& d, const int* nodes, long long n, doubl
 void hk_launch_nodes_import(const HkDev& d, const int* nodes, const long long* src, long long n, const double* in, cudaStream_t s);
 void hk_launch_cacc_export(const HkDev& d, const int* nodes, long long n, unsigned long long* out, cudaStream_t s);
 void hk_launch_cacc_import(const HkDev& d, const int* nodes, long long n, const unsigned long long* in, long long n_ranks, cudaStream_t s);
+void hk_launch_state_export(const HkDev& d, const int* nodes, long long n, double* out, cudaStream_t s);
+void hk_launch_state_import(const HkDev& d, const int* nodes, long long n, const double* in, double d_time, cudaStream_t s);
 void hk_launch_cacc_export_limbs(const HkDev& d, const int* nodes, long long n, long long* out, cudaStream_t s);
 void hk_launch_cacc_import_limbs(const HkDev& d, const int* nodes, long long n, const long long* in, cudaStream_t s);
 // halo: partial internal force of `n` listed nodes -> out[3*i..] ; recv sums -> d.halo_recv

@@ -91,8 +91,10 @@ struct hk_engine {
     std::vector<HaloNbr> halo;
     int n_halo_nodes = 0;
     int* d_halo_list = nullptr;    // node id of every halo slot (nodal kernel mode 2)
-    std::vector<int> node_list[3]; // multi-GPU contact: 0 own-export, 1 ghost-import, 2 surface nodes (force exchange)
-    int* d_node_list[3] = {nullptr, nullptr, nullptr};
+    // multi-GPU node lists: contact 0 own-export, 1 ghost-import, 2 surface nodes (force exchange);
+    // ghost-element mode 3 state-export, 4 state-import
+    std::vector<int> node_list[5];
+    int* d_node_list[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     long long* d_import_src = nullptr;
     bool contact_done = false;     // hk_contact_enqueue already ran the contact pass of the next step
     bool frame_next = false;       // hk_mark_frame: the next asynchronous step stores integ_triax_stress
@@ -1212,7 +1214,7 @@ int HKAPI(halo_pack)(hk_engine* e) {
 
 int HKAPI(set_node_list)(hk_engine* e, int32_t which, int64_t n, const int64_t* nodes) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
-    if (which < 0 || which > 2) return fail(e, HK_ERR_ARG, "bad list id");
+    if (which < 0 || which > 4) return fail(e, HK_ERR_ARG, "bad list id");
     std::vector<int>& L = e->node_list[which];
     L.resize(n);
     for (int64_t i = 0; i < n; ++i) {
@@ -1250,6 +1252,24 @@ int HKAPI(nodes_import)(hk_engine* e, const void* in_dev, const int64_t* src_ind
     }
     if (n && !e->d_import_src) return fail(e, HK_ERR_STATE, "hk_nodes_import: source index never given");
     hk_launch_nodes_import(e->d, e->d_node_list[1], e->d_import_src, (long long)n, (const double*)in_dev, e->stream);
+    e->n_launch += 1;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+// ghost-element partitions (bit-identical results for any number of ranks): displacement state of listed nodes
+int HKAPI(state_export)(hk_engine* e, void* out_dev) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    hk_launch_state_export(e->d, e->d_node_list[3], (long long)e->node_list[3].size(), (double*)out_dev, e->stream);
+    e->n_launch += 1;
+    CK(hkp::last_error());
+    return HK_OK;
+}
+
+int HKAPI(state_import)(hk_engine* e, const void* in_dev) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    hk_launch_state_import(e->d, e->d_node_list[4], (long long)e->node_list[4].size(), (const double*)in_dev,
+                           e->prm.d_time, e->stream);
     e->n_launch += 1;
     CK(hkp::last_error());
     return HK_OK;

@@ -562,6 +562,34 @@ void hk_launch_nodes_import(const HkDev& dd, const int* nodes, const long long* 
         if (c < 3) d.rec[6 * nd + c] = v; else d.velo[3 * nd + c - 3] = v;
     });
 }
+// ghost-element partitions: {disp, disp_pre} of the listed nodes -> out (6 doubles per node); the import overwrites a
+// ghost node's whole kinematic state with the owner's values, rebuilding position / d_disp / velo by the same
+// expressions as the nodal kernel (J2:625-652), so the copy is bit-identical to the owner's node
+void hk_launch_state_export(const HkDev& dd, const int* nodes, long long n, double* out, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 6, s, HK_LAMBDA(long long j) {
+        const long long i = j / 6;
+        const int c = (int)(j - 6 * i);
+        const long long nd = nodes[i];
+        out[j] = c < 3 ? d.u[3 * nd + c] : d.u_pre[3 * nd + c - 3];
+    });
+}
+void hk_launch_state_import(const HkDev& dd, const int* nodes, long long n, const double* in, double d_time, cudaStream_t s) {
+    const HkDev d = dd;
+    hk_parallel_for(n * 3, s, HK_LAMBDA(long long j) {
+        const long long i = j / 3;
+        const int c = (int)(j - 3 * i);
+        const long long nd = nodes[i];
+        const double un = in[6 * i + c], up = in[6 * i + 3 + c];
+        const double dd_ = un - up;
+        d.u[3 * nd + c] = un;
+        d.u_pre[3 * nd + c] = up;
+        d.rec[6 * nd + c] = d.X[3 * nd + c] + un;
+        d.rec[6 * nd + 3 + c] = dd_;
+        d.velo[3 * nd + c] = dd_ / d_time;
+    });
+}
+
 // contact accumulators of the listed nodes -> out (6 x u64 per node); import = exact 128-bit sum over n_ranks records
 void hk_launch_cacc_export(const HkDev& dd, const int* nodes, long long n, unsigned long long* out, cudaStream_t s) {
     const HkDev d = dd;

@@ -43,6 +43,7 @@ EXPORTS = [
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
     "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
+    "state_export", "state_import",
 ]
 
 
@@ -335,6 +336,12 @@ class EngineBase:
 
     def contact_import(self, in_ptr: int, n_ranks: int):
         self._chk(self._fn("contact_import")(self._h, C.c_void_p(in_ptr), c_i64(n_ranks)))
+
+    def state_export(self, out_ptr: int):
+        self._chk(self._fn("state_export")(self._h, C.c_void_p(out_ptr)))
+
+    def state_import(self, in_ptr: int):
+        self._chk(self._fn("state_import")(self._h, C.c_void_p(in_ptr)))
 
     def contact_export_limbs(self, out_ptr: int):
         self._chk(self._fn("contact_export_limbs")(self._h, C.c_void_p(out_ptr)))

@@ -194,16 +194,21 @@ def hakai(fname, outdir="temp", engine_cls=None, output_num=100, write_frames=Tr
 
 
 def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, output_num=100, write_frames=True,
-                      verbose=True, vtk_format="ascii", **params):
+                      verbose=True, vtk_format="ascii", partition="halo", **params):
     """hakai(fname) on several GPUs: one process per GPU inside an initialised torch.distributed group
     (`torchrun --nproc-per-node N -m hakai_fem_b200.host deck.inp`).  Every rank reads the deck, keeps its element
     block (multi.partition_model) and steps it with force halos / contact exchange (multi.SlabRunner); at a frame
     the ranks send disp, velo, flags and their undivided nodal sums (`hk_node_output`, raw) to rank 0, which adds
     the shares of interface nodes, divides by the incidence count (J2:3456-3469) and writes the same VTK file as
-    the single-GPU driver.  Returns (runner, frames); frames is empty on ranks > 0."""
+    the single-GPU driver.  partition="ghost" uses ghost-element partitions instead (multi.partition_model_ghost: no
+    contact decks): every rank then holds complete nodal sums for the nodes of its own elements, the run and the
+    frames are bit-identical to the single-GPU run for any number of ranks.
+    Returns (runner, frames); frames is empty on ranks > 0."""
+    if partition not in ("halo", "ghost"):
+        raise ValueError("partition: halo | ghost")
     import torch
     import torch.distributed as dist
-    from .multi import partition_model, SlabRunner
+    from .multi import partition_model, SlabRunner, partition_model_ghost, GhostRunner
     rank, world = dist.get_rank(), dist.get_world_size()
     # frames travel as pickled host arrays: keep them off the GPU / NCCL (a gloo side group when the main one is NCCL)
     obj_group = dist.new_group(backend="gloo") if dist.get_backend() == "nccl" else None
@@ -221,22 +226,29 @@ def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, 
     model = read_inp_file(fname)
     setup = prepare(model)
     log("nNode:", model.nNode, " nElement:", model.nElement, " contact_flag:", model.contact_flag, " ranks:", world)
-    dom = partition_model(setup, world, only_rank=rank)[rank]
-    runner = SlabRunner.from_domain(engine_cls, dom, torch_device, world, **params)
+    ghost = partition == "ghost"
+    if ghost:
+        dom = partition_model_ghost(setup, world, only_rank=rank)[rank]
+        runner = GhostRunner(engine_cls, dom, torch_device, **params)
+        sel_n, sel_e = np.flatnonzero(dom.own_node), np.flatnonzero(dom.own_elem)
+    else:
+        dom = partition_model(setup, world, only_rank=rank)[rank]
+        runner = SlabRunner.from_domain(engine_cls, dom, torch_device, world, **params)
+        n_held = len(np.unique(dom.setup.model.elementmat))     # local ids 1..n_held are nodes of own elements
+        sel_n, sel_e = np.arange(n_held), np.arange(dom.setup.model.nElement)
     eng = runner.engine
-    n_held = len(np.unique(dom.setup.model.elementmat))         # local ids 1..n_held are nodes of own elements
-    g_nodes = dom.node_l2g[:n_held] - 1
+    g_nodes = dom.node_l2g[sel_n] - 1
     n_total = int(math.floor(setup.time_num))
     d_out = int(math.floor(setup.time_num / output_num))
     frames = []
 
     def frame(index):
         d = eng.download(fields=("disp", "velo", "element_flag"))
-        nd = eng.node_output(raw=True)
-        part = dict(nodes=g_nodes, elems=dom.elem_l2g - 1, flag=d["element_flag"],
-                    disp=d["disp"].reshape(-1, 3)[:n_held], velo=d["velo"].reshape(-1, 3)[:n_held],
-                    **{k: nd[k][:n_held] for k in ("node_stress", "node_strain", "node_eq_plastic_strain",
-                                                    "node_triax_stress", "inc_num")})
+        nd = eng.node_output(raw=True)      # ghost partitions: the sums of own nodes are already complete (and in
+        part = dict(nodes=g_nodes, elems=dom.elem_l2g[sel_e] - 1, flag=d["element_flag"][sel_e],       # global order)
+                    disp=d["disp"].reshape(-1, 3)[sel_n], velo=d["velo"].reshape(-1, 3)[sel_n],
+                    **{k: nd[k][sel_n] for k in ("node_stress", "node_strain", "node_eq_plastic_strain",
+                                                  "node_triax_stress", "inc_num")})
         parts = [None] * world if rank == 0 else None
         dist.gather_object(part, parts, dst=0, group=obj_group)
         if rank != 0:
@@ -250,9 +262,12 @@ def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, 
             disp[p["nodes"]] = p["disp"]
             velo[p["nodes"]] = p["velo"]
             flag[p["elems"]] = p["flag"]
-        for p in parts:                                         # ascending rank = ascending element blocks
+        for p in (reversed(parts) if ghost else parts):         # halo: ascending rank = ascending element blocks
             for k in acc:
-                acc[k][p["nodes"]] += p[k]
+                if ghost:
+                    acc[k][p["nodes"]] = p[k]                   # complete sums: copy (lowest rank last, as for disp)
+                else:
+                    acc[k][p["nodes"]] += p[k]
         inc = acc.pop("inc_num")
         with np.errstate(divide="ignore", invalid="ignore"):
             ns, ne = acc["node_stress"] / inc[:, None], acc["node_strain"] / inc[:, None]

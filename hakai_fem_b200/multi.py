@@ -417,3 +417,128 @@ class SlabRunner:
                 n_del += self._after_step()
         self.last_enqueue_s = _time.perf_counter() - _t0      # host time to enqueue (diagnostic)
         return n_del + self.engine.sync()
+
+
+# ------------------------------------------------------------------ ghost-element partitions (partition-independent bits)
+@dataclass
+class GhostDomain:
+    """Element block of a rank plus one layer of ghost elements (every element sharing a node with the block)."""
+    rank: int
+    setup: Setup                       # local model: own + ghost elements in ascending global order, global lumped mass
+    node_l2g: np.ndarray               # local -> global node id (1-based values, ascending)
+    elem_l2g: np.ndarray               # local -> global element id (1-based values, ascending)
+    own_elem: np.ndarray               # bool per local element: in this rank's block (ghost copies are recomputed)
+    own_node: np.ndarray               # bool per local node: node of an own element (complete force sum locally)
+    neighbors: List[int] = field(default_factory=list)
+    send_nodes: List[np.ndarray] = field(default_factory=list)     # local 1-based ids per neighbour (ascending global)
+    recv_nodes: List[np.ndarray] = field(default_factory=list)
+
+
+def partition_model_ghost(setup: Setup, n_ranks: int, only_rank: int = None) -> List[GhostDomain]:
+    """SURVEY §8e's optional mode.  Every node of a rank's own elements has ALL its incident elements on the rank
+    (own or ghost), listed in ascending global order, so its internal-force sum is the single-domain sum bit for bit;
+    the outer nodes of the ghost layer are overwritten each step with the state computed by a rank that owns them.
+    Results do not depend on the number of ranks.  Contact decks are not supported in this mode."""
+    m = setup.model
+    if m.contact_flag:
+        raise ValueError("ghost-element partitions do not support contact decks; use partition_model")
+    nE = m.nElement
+    bounds = [(nE * r) // n_ranks for r in range(n_ranks + 1)]
+    holds = np.zeros((n_ranks, m.nNode + 1), bool)              # node of an OWN element of rank r
+    for r in range(n_ranks):
+        holds[r, np.unique(m.elementmat[:, bounds[r]:bounds[r + 1]])] = True
+    owner = np.argmax(holds, axis=0)                            # lowest rank that computes the node completely
+    local_el, ghost_nodes = [], []
+    for r in range(n_ranks):
+        el = np.flatnonzero(holds[r][m.elementmat].any(axis=0))                # own block + ghost layer, ascending
+        nodes = np.unique(m.elementmat[:, el])
+        local_el.append((el, nodes))
+        ghost_nodes.append(nodes[~holds[r, nodes]])
+    doms = []
+    for r in range(n_ranks):
+        if only_rank is not None and r != only_rank:
+            doms.append(None)
+            continue
+        el, nodes = local_el[r]
+        g2l = np.zeros(m.nNode + 1, np.int64)
+        g2l[nodes] = np.arange(1, len(nodes) + 1)
+        lm = copy.copy(m)
+        lm.nNode, lm.nElement = len(nodes), len(el)
+        lm.coordmat = np.ascontiguousarray(m.coordmat[:, nodes - 1])
+        lm.elementmat = np.ascontiguousarray(g2l[m.elementmat[:, el]])
+        lm.element_material = m.element_material[el]
+        lm.element_instance = np.ones(len(el), np.int64)
+        lm.BC, lm.IC, lm.INSTANCE = [], [], []
+        for bc in m.BC:
+            nb = I.BC(Nset_name=bc.Nset_name, amp_name=bc.amp_name, amplitude=bc.amplitude)
+            nb.dof, nb.value = _restrict_dofs(bc.dof, bc.value, g2l)
+            lm.BC.append(nb)
+        for ic in m.IC:
+            ni = I.IC(Nset_name=ic.Nset_name, type=ic.type)
+            ni.dof, ni.value = _restrict_dofs(ic.dof, ic.value, g2l)
+            lm.IC.append(ni)
+        lst = Setup(lm, setup.d_time, setup.time_num, setup.elementVolume[el],
+                    np.repeat(setup.diag_M.reshape(-1, 3)[nodes - 1, 0], 3), setup.elementMinSize, setup.elementMaxSize)
+        dom = GhostDomain(r, lst, nodes, el + 1, (el >= bounds[r]) & (el < bounds[r + 1]), holds[r, nodes])
+        for q in range(n_ranks):
+            if q == r:
+                continue
+            recv = ghost_nodes[r][owner[ghost_nodes[r]] == q]               # q computes them, I copy them
+            send = ghost_nodes[q][owner[ghost_nodes[q]] == r]               # I compute them, q copies them
+            if len(recv) or len(send):
+                dom.neighbors.append(q)
+                dom.recv_nodes.append(g2l[recv])
+                dom.send_nodes.append(g2l[send])
+        doms.append(dom)
+    return doms
+
+
+class GhostRunner:
+    """Engine + state exchange of one rank of a ghost-element partition: per step
+    hk_step_begin (nodal update) -> hk_state_export -> send/recv -> hk_state_import -> hk_step_finish (elements)."""
+
+    def __init__(self, engine_cls, dom: GhostDomain, torch_device, **params):
+        import torch
+        self.dom = dom
+        self.engine = configure_engine(engine_cls, dom.setup, **params)
+        cat = lambda lists: np.concatenate(lists) if lists else np.zeros(0, np.int64)
+        self.engine.set_node_list(3, cat(dom.send_nodes))
+        self.engine.set_node_list(4, cat(dom.recv_nodes))
+        self.send = torch.zeros(6 * sum(len(x) for x in dom.send_nodes), dtype=torch.float64, device=torch_device)
+        self.recv = torch.zeros(6 * sum(len(x) for x in dom.recv_nodes), dtype=torch.float64, device=torch_device)
+        so = np.cumsum([0] + [6 * len(x) for x in dom.send_nodes])
+        ro = np.cumsum([0] + [6 * len(x) for x in dom.recv_nodes])
+        self.send_parts = [self.send[so[i]:so[i + 1]] for i in range(len(dom.neighbors))]
+        self.recv_parts = [self.recv[ro[i]:ro[i + 1]] for i in range(len(dom.neighbors))]
+        self.n_reported = 0
+
+    def run(self, t_first: int, n_steps: int, frame_at_end: bool = False) -> int:
+        """Returns the number of OWN elements deleted in these steps (ghost copies delete in step but are not counted)."""
+        import torch.distributed as dist
+        eng = self.engine
+        for t in range(t_first, t_first + n_steps):
+            if frame_at_end and t == t_first + n_steps - 1:
+                eng.mark_frame()
+            eng.step_begin(t)
+            if self.dom.neighbors:
+                eng.state_export(self.send.data_ptr())
+                ops = []
+                for i, nb in enumerate(self.dom.neighbors):
+                    if len(self.send_parts[i]):
+                        ops.append(dist.P2POp(dist.isend, self.send_parts[i], nb))
+                    if len(self.recv_parts[i]):
+                        ops.append(dist.P2POp(dist.irecv, self.recv_parts[i], nb))
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                eng.state_import(self.recv.data_ptr())
+            eng.step_finish(t)
+        eng.sync()
+        ids = eng.deleted_ids()
+        fresh = ids[self.n_reported:]
+        self.n_reported = len(ids)
+        return int(self.dom.own_elem[fresh - 1].sum())
+
+    def deleted_global_ids(self) -> np.ndarray:
+        """Global ids of the OWN elements deleted so far, in deletion order."""
+        ids = self.engine.deleted_ids()
+        return self.dom.elem_l2g[ids[self.dom.own_elem[ids - 1]] - 1]

@@ -233,13 +233,23 @@ int hk_step_finish(hk_engine* e, int64_t t);
  * then the usual (halo) step, which skips its own contact pass once.
  *   list ids: LOCAL 1-based node ids; buffers: DEVICE memory owned by the caller.
  *   export/import node record: 6 doubles {x,y,z,vx,vy,vz}; accumulator record: 6 x uint64 per node. */
-int hk_set_node_list(hk_engine* e, int32_t which /* 0 own-export, 1 ghost-import, 2 surface (force exchange) */,
+int hk_set_node_list(hk_engine* e, int32_t which /* 0 own-export, 1 ghost-import, 2 surface (force exchange),
+                                                    3 state-export, 4 state-import (ghost-element partitions) */,
                      int64_t n, const int64_t* nodes);
 int hk_nodes_export(hk_engine* e, void* out_dev);                 /* list 0 -> 6 doubles per node            */
 int hk_nodes_import(hk_engine* e, const void* in_dev, const int64_t* src_index /* host, n(list 1) */);
 int hk_contact_enqueue(hk_engine* e);                             /* contact pass of the NEXT step, now     */
 int hk_contact_export(hk_engine* e, void* out_dev);               /* list 2 -> 6 uint64 per node             */
 int hk_contact_import(hk_engine* e, const void* in_dev, int64_t n_ranks);   /* sum of n_ranks records per node */
+/* Ghost-element partitions (optional mode): a rank holds its element block PLUS every element that shares
+ * a node with it, so all nodes of its own elements see their complete force sum locally, in the global ascending
+ * element order — results are bit-identical for any number of ranks and no force halo is needed.  What is
+ * exchanged instead is the displacement state of the outer nodes of the ghost layer, once per step between the nodal
+ * update and the element kernel:   hk_step_begin(t) -> hk_state_export (list 3: 6 doubles {disp, disp_pre} per node)
+ * -> send/recv -> hk_state_import (list 4, same record order) -> hk_step_finish(t).   No hk_set_halo in this mode. */
+int hk_state_export(hk_engine* e, void* out_dev);
+int hk_state_import(hk_engine* e, const void* in_dev);
+
 /* The same exchange for a plain integer all-reduce (ncclAllReduce, ncclInt64, ncclSum) instead of an all-gather: every
  * 128-bit accumulator travels as three 43-bit limbs in int64 lanes — 9 x int64 per surface node, summed lane-wise by
  * the collective, recombined exactly (mod 2^128) on import; valid for fewer than 2^20 ranks. */

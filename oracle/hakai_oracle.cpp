@@ -1071,6 +1071,8 @@ int hko_nodes_import(hk_engine* e, const void*, const int64_t*) { return fail(e,
 int hko_contact_enqueue(hk_engine* e) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_contact_export(hk_engine* e, void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_contact_import(hk_engine* e, const void*, int64_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_state_export(hk_engine* e, void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_state_import(hk_engine* e, const void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_contact_export_limbs(hk_engine* e, void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_contact_import_limbs(hk_engine* e, const void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_set_global_maps(hk_engine* e, int64_t, const int64_t*, int64_t, const int64_t*, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }

@@ -318,7 +318,7 @@ def _vtk_sections(path):
     return {k: np.array(v) for k, v in out.items()}
 
 
-def _worker_host(rank, world, port, deck_path, outdir, q):
+def _worker_host(rank, world, port, deck_path, outdir, q, partition="halo"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -327,7 +327,7 @@ def _worker_host(rank, world, port, deck_path, outdir, q):
         from hakai_fem_b200.host import hakai_distributed
         from tests.emu.emu_engine import EmuEngine
         runner, frames = hakai_distributed(deck_path, outdir, engine_cls=EmuEngine, torch_device="cpu", output_num=6,
-                                           verbose=False)
+                                           verbose=False, partition=partition)
         q.put((rank, len(frames)))
         dist.barrier()
     finally:
@@ -452,3 +452,98 @@ def test_limb_split_and_recombine_formulas_are_exact_mod_2_128():
             sums = [sum(l[i] for l in limbs) for i in range(3)]
             assert all(0 <= s < (1 << 63) for s in sums)               # fits the int64 lanes of the all-reduce
             assert recombine(*sums) == sum(vals) % (1 << 128)
+
+
+def _worker_ghost(rank, world, port, exact, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.model_setup import prepare
+        from hakai_fem_b200.multi import partition_model_ghost, GhostRunner
+        from hakai_fem_b200.mesh import StretchDeck, steel
+        from tests.emu.emu_engine import EmuEngine
+        deck = StretchDeck(5, 4, 9, jitter=0.1, strain_per_step=8e-4,
+                           material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]))
+        dom = partition_model_ghost(prepare(deck.build_model()), world, only_rank=rank)[rank]
+        run = GhostRunner(EmuEngine, dom, "cpu", element_mode=1 if exact else 0)
+        nd = run.run(1, 60) + run.run(61, 30)
+        d = run.engine.download()
+        x = run.engine.download_ex(fields=("Q", "integ_yield_stress"))
+        own_n = np.flatnonzero(dom.own_node)
+        own_e = np.flatnonzero(dom.own_elem)
+        ip = (own_e[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        q.put((rank, dict(nodes=dom.node_l2g[own_n] - 1, elems=dom.elem_l2g[own_e] - 1, nd=nd,
+                          disp=d["disp"].reshape(-1, 3)[own_n], Q=x["Q"].reshape(-1, 3)[own_n],
+                          stress=d["integ_stress"][:, ip], eps=d["integ_eq_plastic_strain"][ip],
+                          flag=d["element_flag"][own_e], deleted=run.deleted_global_ids(),
+                          n_ghost_el=int((~dom.own_elem).sum()), n_ghost_nodes=int((~dom.own_node).sum()))))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,exact", [(2, False), (3, False), (3, True)])
+def test_ghost_element_partition_is_bit_identical_to_single_domain(world, exact):
+    """SURVEY 8e optional mode: with a ghost-element layer the partitioned run reproduces the single-domain run of the
+    same kernels BIT FOR BIT for any number of ranks; with element_mode=1 that single-domain run is the oracle's."""
+    from hakai_fem_b200.model_setup import prepare, configure_engine
+    from hakai_fem_b200.mesh import StretchDeck, steel
+    from oracle.oracle_engine import OracleEngine
+    from tests.emu.emu_engine import EmuEngine
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 2000) + 2 * world + int(exact)
+    procs = [ctx.Process(target=_worker_ghost, args=(r, world, port, exact, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    deck = StretchDeck(5, 4, 9, jitter=0.1, strain_per_step=8e-4,
+                       material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]))
+    st = prepare(deck.build_model())
+    ref_eng = configure_engine(OracleEngine, st) if exact else configure_engine(EmuEngine, st)
+    nd_ref = ref_eng.step(1, 90)
+    ref = ref_eng.download()
+    refx = ref_eng.download_ex(fields=("Q",))
+    assert nd_ref > 0, "nothing deleted: the fracture path would not be exercised"
+    assert sum(res[r]["nd"] for r in range(world)) == nd_ref
+    assert np.array_equal(np.sort(np.concatenate([res[r]["deleted"] for r in range(world)])), np.sort(ref_eng.deleted_ids()))
+    for r in range(world):
+        a = res[r]
+        assert a["n_ghost_el"] > 0 and a["n_ghost_nodes"] > 0
+        ip = (a["elems"][:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        assert np.array_equal(a["disp"], ref["disp"].reshape(-1, 3)[a["nodes"]]), r
+        assert np.array_equal(a["Q"], refx["Q"].reshape(-1, 3)[a["nodes"]]), r
+        assert np.array_equal(a["stress"], ref["integ_stress"][:, ip]), r
+        assert np.array_equal(a["eps"], ref["integ_eq_plastic_strain"][ip]), r
+        assert np.array_equal(a["flag"], ref["element_flag"][a["elems"]]), r
+
+
+def test_distributed_host_driver_with_ghost_partitions_writes_identical_files(tmp_path):
+    """partition="ghost": the frames of a 3-rank run are byte-for-byte the single-domain frames."""
+    from hakai_fem_b200.host import hakai
+    from hakai_fem_b200.mesh import StretchDeck, steel
+    from tests.emu.emu_engine import EmuEngine
+    deck_path = str(tmp_path / "deck.inp")
+    StretchDeck(4, 3, 8, jitter=0.05, strain_per_step=8e-4, n_steps=120,
+                material=steel("steel_Ductile", ductile=[[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]])).write_inp(deck_path)
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30300 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_host, args=(r, world, port, deck_path, str(tmp_path / "multi"), q, "ghost"))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    eng, ref = hakai(deck_path, str(tmp_path / "single"), engine_cls=EmuEngine, output_num=6, verbose=False)
+    assert len(eng.deleted_ids()) > 0 and res[0] == len(ref) == 7
+    for f in ref:
+        assert open(f).read() == open(os.path.join(str(tmp_path / "multi"), os.path.basename(f))).read(), f
