@@ -201,7 +201,7 @@ def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, 
     the ranks send disp, velo, flags and their undivided nodal sums (`hk_node_output`, raw) to rank 0, which adds
     the shares of interface nodes, divides by the incidence count (J2:3456-3469) and writes the same VTK file as
     the single-GPU driver.  partition="ghost" uses ghost-element partitions instead (multi.partition_model_ghost: no
-    contact decks): every rank then holds complete nodal sums for the nodes of its own elements, the run and the
+    cross-rank summation order anywhere): every rank then holds complete nodal sums for the nodes of its own elements, the run and the
     frames are bit-identical to the single-GPU run for any number of ranks.
     Returns (runner, frames); frames is empty on ranks > 0."""
     if partition not in ("halo", "ghost"):
@@ -229,7 +229,7 @@ def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, 
     ghost = partition == "ghost"
     if ghost:
         dom = partition_model_ghost(setup, world, only_rank=rank)[rank]
-        runner = GhostRunner(engine_cls, dom, torch_device, **params)
+        runner = GhostRunner(engine_cls, dom, torch_device, world=world, **params)
         sel_n, sel_e = np.flatnonzero(dom.own_node), np.flatnonzero(dom.own_elem)
     else:
         dom = partition_model(setup, world, only_rank=rank)[rank]

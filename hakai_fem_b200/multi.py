@@ -88,6 +88,25 @@ def build_contact_lists(surf, owner, g2l, n_held, rank, n_ranks, erosion=None) -
     return ContactLists(g2l[export_lists[rank]], g2l[ghost], src, loc, maxlen, erosion)
 
 
+def _contact_candidates(setup: Setup):
+    """(surface nodes now, nodes that may ever join the surface, erosion possible?) — global 1-based ids."""
+    m = setup.model
+    surf = np.zeros(0, np.int64)
+    if not m.contact_flag:
+        return surf, surf, False
+    surf = np.unique(np.concatenate([np.concatenate([ct.c_nodes_i, ct.c_nodes_j, ct.c_triangles.reshape(-1)])
+                                     for ct in setup.CT]))
+    candidates = surf
+    erosion = (any(mat.ductile.shape[0] > 0 for mat in m.MATERIAL)
+               and any(len(ins.surfaces) > 0 for ins in m.INSTANCE))
+    if erosion:
+        inst = sorted({i for ct in setup.CT for i in (ct.i_instance, ct.j_instance)})
+        candidates = np.unique(np.concatenate(
+            [surf] + [np.arange(m.INSTANCE[i - 1].node_offset + 1,
+                                m.INSTANCE[i - 1].node_offset + m.INSTANCE[i - 1].nNode + 1) for i in inst]))
+    return surf, candidates, erosion
+
+
 def partition_model(setup: Setup, n_ranks: int, only_rank: int = None) -> List[LocalDomain]:
     """Splits a (small) global model into contiguous element blocks.  Used by the tests and for general
     decks; the 16 M/GPU bench builds each slab directly (slab_deck) without materialising the global mesh.
@@ -110,20 +129,7 @@ def partition_model(setup: Setup, n_ranks: int, only_rank: int = None) -> List[L
         holds[r, nodes] = True
         locals_.append((el, nodes))
     first_holder = np.argmax(holds, axis=0)
-    surf = np.zeros(0, np.int64)
-    candidates = surf
-    erosion = False
-    if m.contact_flag:
-        surf = np.unique(np.concatenate([np.concatenate([ct.c_nodes_i, ct.c_nodes_j, ct.c_triangles.reshape(-1)])
-                                         for ct in setup.CT]))
-        candidates = surf
-        erosion = (any(mat.ductile.shape[0] > 0 for mat in m.MATERIAL)
-                   and any(len(ins.surfaces) > 0 for ins in m.INSTANCE))
-        if erosion:
-            inst = sorted({i for ct in setup.CT for i in (ct.i_instance, ct.j_instance)})
-            candidates = np.unique(np.concatenate(
-                [surf] + [np.arange(m.INSTANCE[i - 1].node_offset + 1,
-                                    m.INSTANCE[i - 1].node_offset + m.INSTANCE[i - 1].nNode + 1) for i in inst]))
+    surf, candidates, erosion = _contact_candidates(setup)
     for r in range(n_ranks):
         if only_rank is not None and r != only_rank:
             doms.append(None)
@@ -149,7 +155,7 @@ def partition_model(setup: Setup, n_ranks: int, only_rank: int = None) -> List[L
             ni = I.IC(Nset_name=ic.Nset_name, type=ic.type)
             ni.dof, ni.value = _restrict_dofs(ic.dof, ic.value, g2l)
             lm.IC.append(ni)
-        lst = Setup(lm, setup.d_time, setup.time_num, setup.elementVolume[el],
+        lst = Setup(lm, setup.d_time, setup.time_num, (None if setup.elementVolume is None else setup.elementVolume[el]),
                     np.repeat(setup.diag_M.reshape(-1, 3)[nodes - 1, 0], 3),     # global (summed) mass
                     setup.elementMinSize, setup.elementMaxSize)
         dom = LocalDomain(r, lst, nodes, el + 1)
@@ -432,16 +438,19 @@ class GhostDomain:
     neighbors: List[int] = field(default_factory=list)
     send_nodes: List[np.ndarray] = field(default_factory=list)     # local 1-based ids per neighbour (ascending global)
     recv_nodes: List[np.ndarray] = field(default_factory=list)
+    contact: object = None             # ContactLists when the model has contact (master triangles of OWN elements only)
 
 
 def partition_model_ghost(setup: Setup, n_ranks: int, only_rank: int = None) -> List[GhostDomain]:
     """SURVEY §8e's optional mode.  Every node of a rank's own elements has ALL its incident elements on the rank
     (own or ghost), listed in ascending global order, so its internal-force sum is the single-domain sum bit for bit;
     the outer nodes of the ghost layer are overwritten each step with the state computed by a rank that owns them.
-    Results do not depend on the number of ranks.  Contact decks are not supported in this mode."""
+    Results do not depend on the number of ranks.
+    Contact works as in partition_model (global slave lists, ghost copies of remote surface nodes appended after the
+    element-layer nodes, exact integer force sums over ranks — order independent, hence also partition independent);
+    a master triangle is processed by the rank that OWNS its element, never by a rank holding it as a ghost."""
     m = setup.model
-    if m.contact_flag:
-        raise ValueError("ghost-element partitions do not support contact decks; use partition_model")
+    surf, candidates, erosion = _contact_candidates(setup)
     nE = m.nElement
     bounds = [(nE * r) // n_ranks for r in range(n_ranks + 1)]
     holds = np.zeros((n_ranks, m.nNode + 1), bool)              # node of an OWN element of rank r
@@ -459,7 +468,9 @@ def partition_model_ghost(setup: Setup, n_ranks: int, only_rank: int = None) -> 
         if only_rank is not None and r != only_rank:
             doms.append(None)
             continue
-        el, nodes = local_el[r]
+        el, layer_nodes = local_el[r]
+        n_layer = len(layer_nodes)                              # nodes of local (own + ghost) elements come first ...
+        nodes = np.concatenate([layer_nodes, np.setdiff1d(candidates, layer_nodes)])    # ... then contact-only ghosts
         g2l = np.zeros(m.nNode + 1, np.int64)
         g2l[nodes] = np.arange(1, len(nodes) + 1)
         lm = copy.copy(m)
@@ -477,9 +488,24 @@ def partition_model_ghost(setup: Setup, n_ranks: int, only_rank: int = None) -> 
             ni = I.IC(Nset_name=ic.Nset_name, type=ic.type)
             ni.dof, ni.value = _restrict_dofs(ic.dof, ic.value, g2l)
             lm.IC.append(ni)
-        lst = Setup(lm, setup.d_time, setup.time_num, setup.elementVolume[el],
+        lst = Setup(lm, setup.d_time, setup.time_num, (None if setup.elementVolume is None else setup.elementVolume[el]),
                     np.repeat(setup.diag_M.reshape(-1, 3)[nodes - 1, 0], 3), setup.elementMinSize, setup.elementMaxSize)
-        dom = GhostDomain(r, lst, nodes, el + 1, (el >= bounds[r]) & (el < bounds[r + 1]), holds[r, nodes])
+        own_elem = (el >= bounds[r]) & (el < bounds[r + 1])
+        dom = GhostDomain(r, lst, nodes, el + 1, own_elem, holds[r, nodes])
+        if m.contact_flag:
+            from .model_setup import ContactTriangle
+            e_g2l = np.zeros(nE + 1, np.int64)                  # global element -> local id, OWN elements only
+            e_g2l[el[own_elem] + 1] = np.flatnonzero(own_elem) + 1
+            maps = None
+            if erosion:
+                lm.INSTANCE = [copy.copy(ins) for ins in m.INSTANCE]
+                maps = ErosionMaps(g2l[1:].copy(), e_g2l[1:].copy(), np.asarray(m.element_instance, np.int64),
+                                   owner.astype(np.int64), n_layer)
+            for ct in setup.CT:
+                mine = e_g2l[ct.c_triangles_eleid] > 0
+                lst.CT.append(ContactTriangle(ct.i_instance, ct.j_instance, g2l[ct.c_nodes_i], g2l[ct.c_nodes_j],
+                                              g2l[ct.c_triangles[mine]], e_g2l[ct.c_triangles_eleid[mine]], ct.young))
+            dom.contact = build_contact_lists(surf, owner, g2l, n_layer, r, n_ranks, maps)
         for q in range(n_ranks):
             if q == r:
                 continue
@@ -497,10 +523,17 @@ class GhostRunner:
     """Engine + state exchange of one rank of a ghost-element partition: per step
     hk_step_begin (nodal update) -> hk_state_export -> send/recv -> hk_state_import -> hk_step_finish (elements)."""
 
-    def __init__(self, engine_cls, dom: GhostDomain, torch_device, **params):
+    def __init__(self, engine_cls, dom: GhostDomain, torch_device, world=None, force_exchange="allgather", **params):
         import torch
         self.dom = dom
         self.engine = configure_engine(engine_cls, dom.setup, **params)
+        self.contact = None
+        if dom.contact is not None:
+            if world is None:
+                raise ValueError("contact decks: pass world")
+            self.contact = ContactExchanger(self.engine, dom.contact, world, torch_device, dom.rank, dom.node_l2g,
+                                            len(dom.setup.CT), force_exchange)
+        self.erosion = self.contact is not None and self.contact.erosion is not None
         cat = lambda lists: np.concatenate(lists) if lists else np.zeros(0, np.int64)
         self.engine.set_node_list(3, cat(dom.send_nodes))
         self.engine.set_node_list(4, cat(dom.recv_nodes))
@@ -511,6 +544,7 @@ class GhostRunner:
         self.send_parts = [self.send[so[i]:so[i + 1]] for i in range(len(dom.neighbors))]
         self.recv_parts = [self.recv[ro[i]:ro[i + 1]] for i in range(len(dom.neighbors))]
         self.n_reported = 0
+        self._seen_erosion = 0
 
     def run(self, t_first: int, n_steps: int, frame_at_end: bool = False) -> int:
         """Returns the number of OWN elements deleted in these steps (ghost copies delete in step but are not counted)."""
@@ -519,6 +553,8 @@ class GhostRunner:
         for t in range(t_first, t_first + n_steps):
             if frame_at_end and t == t_first + n_steps - 1:
                 eng.mark_frame()
+            if self.contact is not None:
+                self.contact.run()          # ghost-layer nodes are current (state_import of the previous step)
             eng.step_begin(t)
             if self.dom.neighbors:
                 eng.state_export(self.send.data_ptr())
@@ -532,6 +568,11 @@ class GhostRunner:
                     req.wait()
                 eng.state_import(self.recv.data_ptr())
             eng.step_finish(t)
+            if self.erosion:                # every rank replays the same ascending list of freshly deleted GLOBAL ids
+                eng.sync()
+                ids = eng.deleted_ids()[self._seen_erosion:]
+                self._seen_erosion += len(ids)
+                self.contact.exchange_deleted(self.dom.elem_l2g[ids[self.dom.own_elem[ids - 1]] - 1])
         eng.sync()
         ids = eng.deleted_ids()
         fresh = ids[self.n_reported:]

@@ -547,3 +547,82 @@ def test_distributed_host_driver_with_ghost_partitions_writes_identical_files(tm
     assert len(eng.deleted_ids()) > 0 and res[0] == len(ref) == 7
     for f in ref:
         assert open(f).read() == open(os.path.join(str(tmp_path / "multi"), os.path.basename(f))).read(), f
+
+
+def _ghost_contact_setup(kind):
+    from hakai_fem_b200.model_setup import prepare
+    from hakai_fem_b200.mesh import ImpactDeck
+    if kind == "crash_tube":                                     # the reference's self-contact deck (tie-sensitive)
+        from tests import util
+        return util.deck_setup("crash_tube"), 400
+    if kind == "erosion":
+        return prepare(ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0,
+                                  plate_ductile=[[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]]).build_model()), 120
+    return prepare(ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3)).build_model()), 60
+
+
+def _worker_ghost_contact(rank, world, port, kind, exact, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.multi import partition_model_ghost, GhostRunner
+        from tests.emu.emu_engine import EmuEngine
+        st, n_steps = _ghost_contact_setup(kind)
+        dom = partition_model_ghost(st, world, only_rank=rank)[rank]
+        run = GhostRunner(EmuEngine, dom, "cpu", world=world, force_exchange="allreduce" if kind == "impact" else "allgather",
+                          element_mode=1 if exact else 0)
+        nd = run.run(1, n_steps)
+        d = run.engine.download()
+        x = run.engine.download_ex(fields=("external_force",))
+        own_n, own_e = np.flatnonzero(dom.own_node), np.flatnonzero(dom.own_elem)
+        ip = (own_e[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        q.put((rank, dict(nodes=dom.node_l2g[own_n] - 1, elems=dom.elem_l2g[own_e] - 1, nd=nd,
+                          disp=d["disp"].reshape(-1, 3)[own_n], velo=d["velo"].reshape(-1, 3)[own_n],
+                          ext=x["external_force"].reshape(-1, 3)[own_n], eps=d["integ_eq_plastic_strain"][ip],
+                          stress=d["integ_stress"][:, ip], flag=d["element_flag"][own_e],
+                          deleted=run.deleted_global_ids(), hits=int(run.engine.counters()[1]),
+                          n_ghost_el=int((~dom.own_elem).sum()))))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,world,exact", [("impact", 2, False), ("erosion", 3, False), ("crash_tube", 2, True)])
+def test_ghost_partition_with_contact_is_bit_identical(kind, world, exact):
+    """Contact decks on ghost-element partitions: exact (order-independent) contact sums + complete local element sums
+    => bit-identical to the single-domain run for any rank count; with element_mode=1 bit-identical to the ORACLE, even
+    on the reference's tie-sensitive self-contact deck."""
+    from hakai_fem_b200.model_setup import configure_engine
+    from oracle.oracle_engine import OracleEngine
+    from tests.emu.emu_engine import EmuEngine
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + (os.getpid() % 2000) + ("impact", "erosion", "crash_tube").index(kind)
+    procs = [ctx.Process(target=_worker_ghost_contact, args=(r, world, port, kind, exact, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=400) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    st, n_steps = _ghost_contact_setup(kind)
+    ref_eng = configure_engine(OracleEngine if exact else EmuEngine, st)
+    nd_ref = ref_eng.step(1, n_steps)
+    ref = ref_eng.download()
+    refx = ref_eng.download_ex(fields=("external_force",))
+    assert ref_eng.counters()[1] > 0, "no contact: vacuous"
+    assert sum(res[r]["hits"] for r in range(world)) == ref_eng.counters()[1], "every hit found by exactly one rank"
+    assert sum(res[r]["nd"] for r in range(world)) == nd_ref
+    if kind == "erosion":
+        assert nd_ref > 10
+    assert np.array_equal(np.sort(np.concatenate([res[r]["deleted"] for r in range(world)])), np.sort(ref_eng.deleted_ids()))
+    for r in range(world):
+        a = res[r]
+        ip = (a["elems"][:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        for k, want in (("disp", ref["disp"].reshape(-1, 3)[a["nodes"]]), ("velo", ref["velo"].reshape(-1, 3)[a["nodes"]]),
+                        ("ext", refx["external_force"].reshape(-1, 3)[a["nodes"]]),
+                        ("eps", ref["integ_eq_plastic_strain"][ip]), ("stress", ref["integ_stress"][:, ip]),
+                        ("flag", ref["element_flag"][a["elems"]])):
+            assert np.array_equal(a[k], want), (kind, r, k)
