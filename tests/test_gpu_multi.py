@@ -152,3 +152,71 @@ def test_distributed_host_driver_frames_match_oracle_frames(world, tmp_path):
             elif k != "TRIAX_STRESS":                            # a ratio that is rounding noise while the plate is at rest
                 scale = max(np.abs(a[k]).max(), 1e-300)
                 assert np.allclose(a[k], b[k], rtol=0, atol=1e-5 * scale), (os.path.basename(f), k, scale)
+
+
+# ---- built and verified on CPU ranks (tests/test_multi_gloo.py) but not yet run over NCCL: opt in with HK_RUN_UNVALIDATED=1
+_UNVALIDATED = os.environ.get("HK_RUN_UNVALIDATED") != "1"
+
+
+def _worker_ghost(rank, world, port, kind, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hakai_fem_b200.engine import Engine
+        from hakai_fem_b200.multi import partition_model_ghost, GhostRunner
+        gsetup, prm, n_steps = _global_setup(kind)
+        dom = partition_model_ghost(gsetup, world, only_rank=rank)[rank]
+        stream = torch.cuda.current_stream()
+
+        def make(**p):
+            e = Engine(**p)
+            e.set_stream(stream.cuda_stream)
+            return e
+        run = GhostRunner(make, dom, torch.device("cuda", rank), world=world, device=rank,
+                          force_exchange="allreduce" if kind == "contact" else "allgather", **prm)
+        nd = run.run(1, n_steps)
+        d = run.engine.download()
+        own_n, own_e = np.flatnonzero(dom.own_node), np.flatnonzero(dom.own_elem)
+        ip = (own_e[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        q.put((rank, dict(nodes=dom.node_l2g[own_n] - 1, elems=dom.elem_l2g[own_e] - 1, nd=nd,
+                          disp=d["disp"].reshape(-1, 3)[own_n], eps=d["integ_eq_plastic_strain"][ip],
+                          flag=d["element_flag"][own_e], deleted=run.deleted_global_ids())))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_UNVALIDATED, reason="ghost-element partitions over NCCL: set HK_RUN_UNVALIDATED=1")
+@pytest.mark.parametrize("kind", ["fracture", "contact", "erosion"])
+def test_ghost_partitions_are_bit_identical_to_one_gpu(kind):
+    """Two GPUs with ghost-element partitions vs ONE GPU running the same CUDA kernels: array_equal on every field."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from hakai_fem_b200.engine import Engine
+    from hakai_fem_b200.model_setup import configure_engine
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 2000) + ("fracture", "contact", "erosion").index(kind)
+    procs = [ctx.Process(target=_worker_ghost, args=(r, world, port, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    gsetup, prm, n_steps = _global_setup(kind)
+    one = configure_engine(Engine, gsetup, **prm)
+    nd_ref = one.step(1, n_steps)
+    ref = one.download()
+    assert sum(res[r]["nd"] for r in range(world)) == nd_ref
+    assert np.array_equal(np.sort(np.concatenate([res[r]["deleted"] for r in range(world)])), np.sort(one.deleted_ids()))
+    for r in range(world):
+        a = res[r]
+        ip = (a["elems"][:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        assert np.array_equal(a["disp"], ref["disp"].reshape(-1, 3)[a["nodes"]]), (kind, r)
+        assert np.array_equal(a["eps"], ref["integ_eq_plastic_strain"][ip]), (kind, r)
+        assert np.array_equal(a["flag"], ref["element_flag"][a["elems"]]), (kind, r)
