@@ -353,9 +353,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         rate, nEs, dtc = cpu_oracle_rate(args.cpu_sample, 2, args.cpu_steps, threads=cores)
+        rate1, _, dt1 = cpu_oracle_rate(args.cpu_sample, 1, 2, threads=1)      # also OMP_NUM_THREADS=1
         cpu = {"value": rate, "unit": "element-steps/s", "cores": cores, "kind": "port",
                "sample": f"{args.cpu_sample}: {nEs} elements of the same deck recipe, 2 warm-up + {args.cpu_steps} timed "
-                         f"steps ({dtc:.1f} s), OpenMP C++ oracle, {cores} threads"}
+                         f"steps ({dtc:.1f} s), OpenMP C++ oracle, {cores} threads",
+               "single_thread": {"value": rate1, "cores": 1, "sample": f"same sample, 1 warm-up + 2 timed steps ({dt1:.1f} s)"}}
 
     if rank == 0:
         line = {
