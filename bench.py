@@ -1,14 +1,20 @@
 #!/usr/bin/env python
 """bench.py — element-steps/s of the HAKAI time-step engine on B200 (BASELINE.json's metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W16|B1|...] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W16|F16D|I8|B1|...] [--impl reference]
 
-A "step" is one explicit time step (contact-free hot path: nodal gather/update/BC/kinematics kernel +
-hex8 elastoplastic element kernel) of the synthetic uniform-stretch deck of SURVEY §8(d):
-  W16 (default): 252x252x252 = 16 003 008 hex per GPU, elastoplastic steel, jittered interior nodes — the mesh
-      the north star's roofline target is quoted on and the per-GPU shard of the weak-scaling config.
-  B1: the 50x50x400 1 M-hex bar (BASELINE configs[1]).
-State (>= 14 GB at W16) is far larger than L2, so no L2 flush is needed between steps.
+A "step" is one explicit time step of the hot path (contact kernels when the deck has contact, nodal
+gather/update/BC/kinematics kernel, hex8 elastoplastic element kernel, deletion flush) on a synthetic deck of
+SURVEY §8(d):
+  W16 (default): 252x252x252 = 16 003 008 hex per GPU, elastoplastic steel, uniform stretch, jittered interior nodes —
+      the mesh the north star's roofline target is quoted on and the per-GPU shard of the weak-scaling config.
+  F16D: the same block with the ductile-damage table [0.03 0 30; 0.02 0.3 30] (BASELINE configs[2]): the timed window
+      starts just before the first deletion and the live-element count falls inside it.
+  I8:   two-instance impact, 400x400x48 plate + 68^3 projectile, frictionless penalty contact (BASELINE configs[3]).
+  B1:   the 50x50x400 1 M-hex bar (BASELINE configs[1]).
+Whatever --warmup says, the engine is advanced UNTIMED until the deck is in the regime the metric is quoted on (every
+Gauss point yielding; F16D: deletion imminent; I8: bodies in contact) — `config.regime` records it.
+State (>= 7 GB) is far larger than L2, so no L2 flush is needed between steps.
 Prints ONE JSON line (see DESIGN.md §6 for every key).
 """
 import argparse
@@ -27,34 +33,50 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_ELEMENT = 1904       # element kernel, per element-step
 ALG_BYTES_NODAL = 224          # nodal update, per node-step
 ALG_BYTES_STEP = 2128          # total per element-step (nN/nE -> 1)
+DUCTILE_ROWS = [[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]
 
 
-def make_deck(workload, nz_override=None, strain_per_step=None):
-    from hakai_fem_b200.mesh import StretchDeck, steel
-    if workload == "W16":
+def make_deck(workload, strain_per_step=None):
+    """-> (deck, kind) with kind in stretch | ductile | impact."""
+    from hakai_fem_b200.mesh import StretchDeck, ImpactDeck, steel
+    kw = {} if strain_per_step is None else dict(strain_per_step=strain_per_step)
+    if workload in ("I8", "I1", "I0"):          # I1 / I0: 1 M / 125 k-element cuts of I8 (CPU samples, debugging)
+        plate, proj = {"I8": ((400, 400, 48), (68, 68, 68)), "I1": ((200, 200, 24), (34, 34, 34)),
+                       "I0": ((100, 100, 12), (17, 17, 17))}[workload]
+        return ImpactDeck(plate=plate, proj=proj), "impact"
+    ductile = workload.endswith("D")
+    base = workload[:-1] if ductile else workload
+    if base in ("W16", "F16"):
         n = (252, 252, 252)
-    elif workload == "B1":
+    elif base == "B1":
         n = (50, 50, 400)
-    elif workload == "S1":      # 1 M-element slab of W16 (CPU sample)
+    elif base == "S1":          # 1 M-element slab of W16 (CPU sample)
         n = (252, 252, 16)
-    elif workload.startswith("N"):   # Nnx,ny,nz
-        n = tuple(int(v) for v in workload[1:].split(","))
+    elif base.startswith("N"):   # Nnx,ny,nz
+        n = tuple(int(v) for v in base[1:].split(","))
     else:
         raise SystemExit(f"unknown workload {workload}")
-    if nz_override:
-        n = (n[0], n[1], nz_override)
-    jitter = 0.0 if workload == "B1" else 0.05
-    kw = {} if strain_per_step is None else dict(strain_per_step=strain_per_step)
-    return StretchDeck(n[0], n[1], n[2], h=1.0, material=steel(), jitter=jitter, n_steps=1.0e6, **kw)
+    mat = steel("steel_Ductile", ductile=DUCTILE_ROWS) if ductile else steel()
+    jitter = 0.0 if base == "B1" else 0.05
+    return (StretchDeck(n[0], n[1], n[2], h=1.0, material=mat, jitter=jitter, n_steps=1.0e6, jitter_by_layer=True, **kw),
+            "ductile" if ductile else "stretch")
 
 
 def prepare_setup(deck):
     from hakai_fem_b200.model_setup import prepare
     model = deck.build_model()
     vol = None
-    if deck.jitter == 0.0:
+    if getattr(deck, "jitter", None) == 0.0:
         vol = np.full(model.nElement, deck.h ** 3)
     return prepare(model, elementVolume=vol)
+
+
+def deck_text(deck, kind):
+    if kind == "impact":
+        return (f"impact: plate {deck.plate[0]}x{deck.plate[1]}x{deck.plate[2]} (alum, elastoplastic + ductile) + projectile "
+                f"{deck.proj[0]}x{deck.proj[1]}x{deck.proj[2]} (lead) at {deck.v0:g} m/s, frictionless penalty contact")
+    return (f"{deck.nx}x{deck.ny}x{deck.nz} hex8, steel {'elastoplastic + ductile damage' if kind == 'ductile' else 'elastoplastic'}"
+            f", uniform stretch {deck.strain_per_step:g}/step, jitter {deck.jitter}")
 
 
 class ClockSampler(threading.Thread):
@@ -99,21 +121,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def cpu_sample_for(workload):
+    if workload.startswith("I"):
+        return "I0"
+    return "S1D" if workload.endswith("D") else "S1"
+
+
 def cpu_oracle_rate(sample_workload, warmup, steps, threads=None):
     """Times the CPU oracle (C++ restatement of HAKAI_j.jl's loop, OpenMP) on a bounded sample."""
     from hakai_fem_b200.model_setup import configure_engine
     from oracle.oracle_engine import OracleEngine
     if threads:
         os.environ["OMP_NUM_THREADS"] = str(threads)
-    deck = make_deck(sample_workload)
+    deck, kind = make_deck(sample_workload)
     st = prepare_setup(deck)
-    eng = configure_engine(OracleEngine, st)
+    prm = dict(contact_myu=0.0) if kind == "impact" else {}
+    eng = configure_engine(OracleEngine, st, **prm)
     if threads:                 # torchrun exports OMP_NUM_THREADS=1 and libgomp may have read it already: set it directly
         try:
             import ctypes
             ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
         except OSError:
             pass
+    if kind == "impact":
+        warmup = max(warmup, 12)        # the 0.1 h gap closes after 10 steps: time steps that do contact work
     eng.step(1, warmup)
     t0 = time.perf_counter()
     eng.step(warmup + 1, steps)
@@ -129,7 +160,7 @@ def run_reference(args, emit):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample
+    sample = args.cpu_sample or cpu_sample_for(args.workload)
     rate, nE, dt = cpu_oracle_rate(sample, args.warmup, args.steps, threads=cores)
     line = {
         "impl": "reference", "metric": "element-steps/sec (hex8 elastoplastic)", "value": rate,
@@ -139,8 +170,8 @@ def run_reference(args, emit):
         "config": {"workload": args.workload, "sample": sample, "elements_in_sample": nE},
         "cpu_baseline": {"value": rate, "unit": "element-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{sample}: {nE} elements of the same deck recipe, {args.warmup} warm-up + "
-                                   f"{args.steps} timed steps, OpenMP oracle (HAKAI_j.jl restated in C++), "
-                                   f"{cores} threads"},
+                                   f"{args.steps} timed steps, OpenMP oracle (our C++ restatement of HAKAI_j.jl; Julia is "
+                                   f"not installed), {cores} threads"},
         "e2e": {"value": rate, "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -161,12 +192,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="W16")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-sample", default="S1")
+    ap.add_argument("--cpu-sample", default=None)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--strain-per-step", type=float, default=None,
-                    help="override the deck's stretch rate (1e-6: purely elastic run, SURVEY §8d)")
+                    help="override the deck's stretch rate (1e-6: purely elastic run, SURVEY §8d; disables the regime gate)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the partition parity check")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -177,7 +209,6 @@ def main():
     import torch
     import torch.distributed as dist
     from hakai_fem_b200.engine import Engine
-    from hakai_fem_b200.model_setup import configure_engine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,63 +218,122 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+
+    pcheck = None
+    if world > 1 and not args.no_parity:
+        from hakai_fem_b200.multi import slab_parity_check
+
+        def make_checked(**p):
+            e_ = Engine(**p)
+            e_.set_stream(stream.cuda_stream)
+            return e_
+        pcheck = slab_parity_check(make_checked, torch.device("cuda", local_rank), rank, world, device=local_rank)
+        if rank == 0:
+            print(f"[parity_check] {pcheck}", file=sys.stderr)
 
     from hakai_fem_b200.multi import slab_deck, SlabRunner
-    deck = make_deck(args.workload, strain_per_step=args.strain_per_step)
-    stream = torch.cuda.current_stream()
+    deck, kind = make_deck(args.workload, strain_per_step=args.strain_per_step)
     if world > 1:
+        if kind == "impact":
+            raise SystemExit("workload I8 is a single-GPU bench line (multi-GPU contact: tests/test_gpu_multi.py)")
         # weak scaling (config W): the global mesh is nx x ny x (nz*world), split in z; every rank builds only its slab
         deck, nbrs, halos = slab_deck(deck, rank, world)
     else:
         nbrs, halos = [], []
     st = prepare_setup(deck)
     nE, nN = st.model.nElement, st.model.nNode
+    prm = dict(contact_myu=0.0) if kind == "impact" else {}        # north star: frictionless
 
     def make_engine(**p):
         e_ = Engine(**p)
         e_.set_stream(stream.cuda_stream)
         return e_
-    runner = SlabRunner(make_engine, st, nbrs, halos, torch.device("cuda", local_rank), sum_mass=True, device=local_rank)
+    runner = SlabRunner(make_engine, st, nbrs, halos, torch.device("cuda", local_rank), sum_mass=True, device=local_rank, **prm)
     eng = runner.engine
 
     def run_steps(t0, n):
         if world > 1:
-            runner.run(t0, n)          # halo pack -> NCCL send/recv -> hk_step, every step
-        else:
-            eng.step(t0, n)
+            return runner.run(t0, n)          # halo pack -> NCCL send/recv -> hk_step, every step
+        return eng.step(t0, n)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ---------------------------------------------------------------
+    def all_ranks(flag):
+        if world == 1:
+            return bool(flag)
+        t_ = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+        return bool(t_.item())
+
+    # ---- untimed advance into the regime the metric is quoted on ----------------------------------------------------
     run_steps(1, args.warmup)
+    t_next = args.warmup + 1
+    regime, extra = "as given (--strain-per-step override)", 0
+    if args.strain_per_step is None:
+        if kind == "impact":
+            regime = "in contact"
+            ready = lambda: int(eng.counters()[1]) > 0
+        elif kind == "ductile":
+            regime = "plastic, first deletion imminent"
+            eps_f = min(r[0] for r in DUCTILE_ROWS)
+            ready = lambda: (lambda s: s["live_elements"] < nE or s["eps_max"] >= eps_f - 3.0 * deck.strain_per_step)(eng.state_summary())
+        else:
+            regime = "plastic (every Gauss point yielding)"
+            ready = lambda: (lambda s: s["yielded_points"] == 8 * s["live_elements"])(eng.state_summary())
+        chunk = 1 if kind == "ductile" else 4
+        while not all_ranks(ready()) and extra < 400:
+            run_steps(t_next, chunk)
+            t_next += chunk
+            extra += chunk
+    s_start = eng.state_summary()
+
+    # ---- device-resident throughput ---------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_wait = time.time()
     while not sampler.rows and time.time() - t_wait < 3.0:      # first nvidia-smi sample before timing starts
         time.sleep(0.05)
-    l0 = int(eng.counters()[3])
+    c0 = eng.counters()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    run_steps(args.warmup + 1, args.steps)
+    live_steps, live = 0, s_start["live_elements"]
+    per_step_deleted = []
+    if kind == "ductile" and world == 1:
+        for t in range(t_next, t_next + args.steps):      # one call per step: the live count after every step is known
+            live_steps += live
+            eng.step_enqueue(t, 1)
+            nd = eng.sync()
+            live -= nd
+            per_step_deleted.append(int(nd))
+    else:
+        run_steps(t_next, args.steps)
+        live_steps = live * args.steps
     ev1.record(stream)
     barrier()
+    t_next += args.steps
     ms = ev0.elapsed_time(ev1)
     print(f"[rank {rank}] host enqueue time of the timed steps: {getattr(runner, 'last_enqueue_s', 0.0) * 1e3:.1f} ms "
           f"of {ms:.1f} ms", file=sys.stderr)
     clocks = sampler.stop()
-    launches = int(eng.counters()[3]) - l0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    c1 = eng.counters()
+    launches = int(c1[3] - c0[3])
+    s_end = eng.state_summary()
+    t = torch.tensor([ms, float(live_steps)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = nE * world * args.steps / (ms * 1e-3)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, live_steps = float(tm[0].item()), float(t[1].item())
+    else:
+        ms = float(t[0].item())
+    value = live_steps / (ms * 1e-3)        # live element-steps of all ranks / max-over-ranks device time
 
     # ---- per-kernel timing (CUDA events on the engine's stream around every launch) -------------------
-    t_next = args.warmup + args.steps + 1
     eng.profile(True)
     n_prof = min(args.steps, 10)
     run_steps(t_next, n_prof)
@@ -251,13 +341,16 @@ def main():
     kms, kn = eng.profile_read()
     eng.profile(False)
     el_ms = kms[2] / max(kn[2], 1)
-    nd_ms = kms[1] / max(kn[1], 1)
+    nd_ms = kms[1] / max(n_prof, 1)          # per step (with halos the nodal update is two launches per step)
+    ct_ms = kms[0] / max(n_prof, 1)
+    ot_ms = kms[3] / max(n_prof, 1)
     per_rank = None
     if world > 1:          # kernel times of every rank: the exchange makes the slowest GPU set the pace
-        tk = torch.tensor([el_ms, nd_ms * max(kn[1], 1) / max(kn[2], 1)], dtype=torch.float64, device="cuda")
+        tk = torch.tensor([el_ms, nd_ms, ot_ms], dtype=torch.float64, device="cuda")
         allk = [torch.zeros_like(tk) for _ in range(world)]
         dist.all_gather(allk, tk)
-        per_rank = [{"rank": i, "element_ms": float(a[0]), "nodal_ms_per_step": float(a[1])} for i, a in enumerate(allk)]
+        per_rank = {"element_ms": [round(float(a[0]), 4) for a in allk], "nodal_ms_per_step": [round(float(a[1]), 4) for a in allk],
+                    "halo_unpack_ms_per_step": [round(float(a[2]), 4) for a in allk]}
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
@@ -265,27 +358,38 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     achieved = ALG_BYTES_ELEMENT * nE / (el_ms * 1e-3) / 1e9
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tr_path):      # dram__bytes_read+write per element from the committed ncu --set full capture
-        traffic = json.load(open(tr_path))["element_kernel_dram_bytes_per_element"] * nE
-    variant = int(os.environ.get("HK_ELEMENT_VARIANT", "11"))
-    kname = ("hk_element_simple_kernel" if os.environ.get("HK_ELEMENT_KERNEL") == "simple"
-             else "hk_element_tmem_kernel" if variant >= 10 else "hk_element_tma_kernel")
+    traffic, traffic_src = None, None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        tr_path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tr_path):      # dram__bytes_read+write per element from the committed ncu --set full capture
+            tj = json.load(open(tr_path))
+            traffic = tj["element_kernel_dram_bytes_per_element"] * nE
+            traffic_src = (f"profiles/{name}: ncu --set full on a {tj.get('mesh', '4 M-element')} mesh, per-element bytes "
+                           f"scaled to this run's element count — a committed measurement, not taken in this run")
+            break
+    kname = "hk_element_simple_kernel" if os.environ.get("HK_ELEMENT_KERNEL") == "simple" else "hk_element_ring_kernel"
+    step_ms = ms / args.steps
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_ELEMENT * nE, "avg_launch_ms": el_ms,
-                "nodal_kernel": {"achieved": ALG_BYTES_NODAL * nN / (nd_ms * 1e-3) / 1e9, "avg_launch_ms": nd_ms},
-                "whole_step": {"achieved": ALG_BYTES_STEP * nE / (ms / args.steps * 1e-3) / 1e9,
-                               "frac": ALG_BYTES_STEP * nE / (ms / args.steps * 1e-3) / 1e9 / peak}}
-
+                "nodal_kernel": {"achieved": ALG_BYTES_NODAL * nN / (nd_ms * 1e-3) / 1e9, "ms_per_step": nd_ms},
+                "whole_step": {"achieved": ALG_BYTES_STEP * nE / (step_ms * 1e-3) / 1e9,
+                               "frac": ALG_BYTES_STEP * nE / (step_ms * 1e-3) / 1e9 / peak,
+                               "note": "2128 B x ALL elements of the mesh (deleted ones still stream through the kernels)"}}
     fp_path = os.path.join(ROOT, "profiles", "r1_fp64_ops.json")
-    if os.path.exists(fp_path) and kname == "hk_element_tmem_kernel":
-        # secondary bound: FP64 issue.  Executed flops per element from the committed ncu instruction counts (plastic
-        # regime, which is what the default deck is in after warm-up) x the live launch rate of this run
+    if os.path.exists(fp_path):
+        # secondary bound: FP64 issue.  Executed flops per element from the committed ncu instruction counts of the
+        # plastic regime (the regime gate above guarantees it) x the live launch rate of this run
         fl = json.load(open(fp_path))["per_element"]["plastic"]["flops"]
         roofline["fp64"] = {"flops_per_element": fl, "achieved_tflops": fl * nE / (el_ms * 1e-3) / 1e12,
-                            "source": "profiles/r1_fp64_ops.json (ncu instruction counts)"}
+                            "source": "profiles/r1_fp64_ops.json (ncu instruction counts, same Gauss-point math)"}
+    contact = None
+    if kind == "impact":
+        contact = {"ms_per_step": ct_ms, "hits_per_step": float(c1[1] - c0[1]) / args.steps,
+                   "tests_per_step": float(c1[2] - c0[2]) / args.steps,
+                   "pairs": [dict(nn_i=len(c.c_nodes_i), nn_j=len(c.c_nodes_j), nTri=len(c.c_triangles)) for c in st.CT],
+                   "fixed_point_overflows": int(c1[5]),
+                   "kernels": "hk_contact_{reset,bbox,cells,narrow}_kernel per ordered pair + accumulator memset"}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
     e2e = None
@@ -325,52 +429,83 @@ def main():
             h2d = sum(pinned[k].numel() * 8 for k in upl)
             d2h = sum(pinned[k].numel() * 8 for k in out_frame + nodal)
             eng.node_output(raw=raw, out={k: hv[k] for k in nodal})     # untimed: allocates the engine's work buffers
+
+            def frame_out():
+                eng.download(fields=out_frame, out={k: hv[k] for k in out_frame})
+                eng.node_output(raw=raw, out={k: hv[k] for k in nodal})
             barrier()
             w0 = time.perf_counter()
             eng.upload_state(disp=hv["disp"], disp_pre=hv["disp_pre"], velo=hv["velo"], Q=hv["Q"],
                              integ_stress=hv["integ_stress"].T, integ_strain=hv["integ_strain"].T,
                              integ_eq_plastic_strain=hv["integ_eq_plastic_strain"],
                              integ_yield_stress=hv["integ_yield_stress"])
+            w_up = time.perf_counter() - w0
             run_steps(t_next, args.steps)
-            eng.download(fields=out_frame, out={k: hv[k] for k in out_frame})
-            eng.node_output(raw=raw, out={k: hv[k] for k in nodal})
+            t_next += args.steps
+            w_st = time.perf_counter() - w0 - w_up
+            frame_out()
             barrier()
             w = time.perf_counter() - w0
-            tw = torch.tensor([w], dtype=torch.float64, device="cuda")
+            # the drop-in loop itself (J2:487-951 with write_vtk every d_out steps): state stays on the device, the
+            # host receives one frame per d_out = `steps` steps
+            barrier()
+            w1 = time.perf_counter()
+            run_steps(t_next, args.steps)
+            t_next += args.steps
+            frame_out()
+            barrier()
+            wl = time.perf_counter() - w1
+            tw = torch.tensor([w, wl], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-            w = float(tw.item())
+            w, wl = float(tw[0].item()), float(tw[1].item())
             e2e = {"value": nE * world * args.steps / w, "unit": "element-steps/s",
                    "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+                   "seconds": {"upload": w_up, "steps": w_st, "frame": w - w_up - w_st},
                    "what": f"hk_upload_state (pinned host arrays, all loop state) + {args.steps} steps + one output "
                            f"frame (hk_download of disp, velo, element_flag + hk_node_output: the nodal averages "
                            f"write_vtk needs, computed on the device) per rank through the C ABI; wall clock, max "
-                           f"over ranks"}
+                           f"over ranks",
+                   "frame_loop": {"value": nE * world * args.steps / wl, "unit": "element-steps/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": d2h / args.steps,
+                                  "what": f"the drop-in loop: {args.steps} steps (d_out) + one output frame to host "
+                                          f"buffers, state resident on the device; wall clock, max over ranks"}}
             del pinned, hv
 
     # ---- CPU baseline (oracle port on the host cores, bounded sample) ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        rate, nEs, dtc = cpu_oracle_rate(args.cpu_sample, 2, args.cpu_steps, threads=cores)
-        rate1, _, dt1 = cpu_oracle_rate(args.cpu_sample, 1, 2, threads=1)      # also OMP_NUM_THREADS=1
+        sample = args.cpu_sample or cpu_sample_for(args.workload)
+        rate, nEs, dtc = cpu_oracle_rate(sample, 2, args.cpu_steps, threads=cores)
+        rate1, _, dt1 = cpu_oracle_rate(sample, 1, 2, threads=1)      # also OMP_NUM_THREADS=1
         cpu = {"value": rate, "unit": "element-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_sample}: {nEs} elements of the same deck recipe, 2 warm-up + {args.cpu_steps} timed "
-                         f"steps ({dtc:.1f} s), OpenMP C++ oracle, {cores} threads",
+               "sample": f"{sample}: {nEs} elements of the same deck recipe, 2 warm-up + {args.cpu_steps} timed "
+                         f"steps ({dtc:.1f} s), OpenMP C++ oracle (our restatement of HAKAI_j.jl, not Julia), {cores} threads",
                "single_thread": {"value": rate1, "cores": 1, "sample": f"same sample, 1 warm-up + 2 timed steps ({dt1:.1f} s)"}}
 
     if rank == 0:
+        cfg = {"workload": args.workload, "elements_per_gpu": nE, "nodes_per_gpu": nN, "deck": deck_text(deck, kind),
+               "regime": regime, "untimed_steps_before_timing": args.warmup + extra,
+               "eps_at_start": [s_start["eps_min"], s_start["eps_max"]],
+               "live_elements_start": s_start["live_elements"], "live_elements_end": s_end["live_elements"],
+               "l2": "state >> L2 (inputs larger than L2), no flush", "parallelism": f"z-slab x{world}",
+               "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step}
+        if per_step_deleted:
+            cfg["deleted_per_step"] = per_step_deleted
         line = {
             "metric": "element-steps/sec (hex8 elastoplastic)", "value": value, "unit": "element-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "elements_per_gpu": nE, "nodes_per_gpu": nN,
-                       "deck": f"{deck.nx}x{deck.ny}x{deck.nz} hex8, steel elastoplastic, uniform stretch "
-                               f"{deck.strain_per_step:g}/step, jitter {deck.jitter}",
-                       "l2": "state >> L2 (inputs larger than L2), no flush", "parallelism": f"z-slab x{world}",
-                       "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step, "per_rank_kernel_ms": per_rank},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks,
         }
+        if contact is not None:
+            line["contact"] = contact
+        if per_rank is not None:
+            line["per_rank_kernel_ms"] = per_rank
+        if pcheck is not None:
+            line["parity_check"] = pcheck
         emit(line)
     eng.close()
     if world > 1:

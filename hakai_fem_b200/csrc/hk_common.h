@@ -72,6 +72,8 @@ struct HkDev {
                           // 12 eps (integ_eq_plastic_strain), 13 yield (integ_yield_stress): the 14 rows x TL
                           // elements of one Gauss point of one tile are ONE contiguous burst (14*TL*8 bytes)
     int element_mode;     // hk_params.element_mode (1: reference-order kernel)
+    int variant;          // element-kernel variant (hk_element.cu: kVariants; 1 = simple kernel)
+    int n_sm;             // multiprocessors of the engine's device (grid of the persistent kernels)
     int TL;               // layout tile = elements per tile of the element kernel in use; nEp % TL == 0
     double* triax;        // [8][nEp]   integ_triax_stress (written on request)
     double* Qe;           // [24][nEp]
@@ -117,7 +119,7 @@ struct HkContactParams {
 void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double dt2, double dt2p,
                      int lsb_exp, int contact_on, int use_Q0, int mode, const int* list, long long n_list,
                      cudaStream_t s);
-void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s);
+int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s);   // 0 or a CUDA error code
 void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s);
 void hk_launch_velo_from_rec(const HkDev& d, double d_time, cudaStream_t s);
 void hk_launch_gather_Q(const HkDev& d, double* Q_out, cudaStream_t s);
@@ -143,7 +145,10 @@ void hk_launch_ip_to_aos(const HkDev& d, double* aos, int row0, int ncomp, long 
 void hk_launch_triax_to_aos(const HkDev& d, double* aos, long long e0, long long ne, cudaStream_t s);
 void hk_launch_element_means(const HkDev& d, double* emean, cudaStream_t s);                 // [14][nEp]
 void hk_launch_node_means(const HkDev& d, const double* emean, double* out, int raw, cudaStream_t s);   // [16][nNode]
+void hk_launch_state_summary(const HkDev& d, unsigned long long* out4, cudaStream_t s);   // out4 preset {0,~0,0,0}
+double hk_decode_double(unsigned long long order_encoded);
 void hk_upload_pusai(const double* P);
 void hk_launch_element_exact(const HkDev& d, long long step, int write_triax, cudaStream_t s);
-long long hk_element_tile();   // nEp must be a multiple of this
+int hk_element_variant_from_env();        // HK_ELEMENT_VARIANT / HK_ELEMENT_KERNEL (A/B switches), else the default
+long long hk_element_tile(int variant);   // nEp must be a multiple of this
 void hk_launch_external_force(const HkDev& d, double* F_out, int lsb_exp, int contact_on, cudaStream_t s);

@@ -6,22 +6,13 @@
 // return, state update, nodal force, triaxiality, ductile-damage deletion.  The math (trilinear mode
 // form) is in hk_element_math.h.
 //
-// Two kernels share that math:
-//   hk_element_tma_kernel   (default) persistent CTAs of 128 threads = tiles of 128 elements.  The ip state
-//       of a tile (14 rows x 1 KB per Gauss point) is streamed through a shared-memory ring by the TMA
-//       (cp.async.bulk global->shared with mbarrier completion, shared->global bulk stores), so HBM sees
-//       only 1 KB bursts, no state load ever stalls a math warp's scoreboard, and registers hold only
-//       the element's geometry modes and force accumulators.
-//   hk_element_simple_kernel  thread per element with plain coalesced loads (HK_ELEMENT_KERNEL=simple),
-//       kept as the A/B baseline for the profiles.
+// Kernels sharing that math:
+//   hk_element_ring_kernel   (default) persistent CTAs; ip state streamed through shared-memory rings by the TMA
+//       (cp.async.bulk + mbarrier), element state parked in tensor memory, phase-shifted consumer groups — see the
+//       comment above the kernel.
+//   hk_element_simple_kernel  thread per element with plain coalesced loads (HK_ELEMENT_KERNEL=simple): the A/B
+//       baseline of the profiles and the body the host-compiled debugging build runs.
 #include "hk_element_math.h"
-
-// HK_ELEMENT_VARIANT: >= 10 TMEM kernel (tile 352), < 10 TMA kernel variants (tile 224); default 11
-static int element_variant() {
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("HK_ELEMENT_VARIANT"); variant = v ? atoi(v) : 11; }
-    return variant;
-}
 
 struct ElemArgs {
     HkDev d;
@@ -177,19 +168,29 @@ __global__ void __launch_bounds__(128, 2) hk_element_simple_kernel(ElemArgs A) {
     if (e < A.d.nElement) element_body_simple(A, e);
 }
 
-// ---- TMA-staged kernel --------------------------------------------------------------------------------------
-// One persistent CTA per SM: HK_TILE consumer threads (one element each) + one producer warp.  The producer's
-// lane 0 drives the TMA: bulk loads of the next Gauss points' state rows into a ring of shared-memory stages
-// (completion on `full` mbarriers) and bulk stores of finished stages back to HBM (after all consumers arrived
-// on the stage's `done` mbarrier).  Consumers never execute a global load or store for ip state and never meet
-// at a CTA-wide barrier.
-#ifndef HK_TILE
-#define HK_TILE 224                       // elements per tile = consumer threads per CTA (7 warps + 1 producer warp = 256 threads -> 255 regs)
-#endif
+// ---- ring kernel: TMA-staged ip state, TMEM-parked element state, phase-shifted consumer groups ---------------
+// One persistent CTA per SM.  The CTA holds NG independent consumer groups of WG warps (one element per thread, tile =
+// WG*32 elements) and one producer warp per group.  Per group:
+//   * the producer's lane 0 streams the tile's ip state through a ring of S shared-memory stages: ONE
+//     cp.async.bulk (TMA, SASS UBLKCP) of 14 rows x tile doubles per (tile, Gauss point) with mbarrier completion
+//     (`full`), and one bulk store of the updated block after the group's warps arrived on the stage's `done`
+//     barrier.  Consumers never issue a global load/store for ip state and never meet at a CTA-wide barrier.
+//   * CP = 1: the producer also brings the NEXT tile's connectivity (8 x tile int32) into a double-buffered
+//     shared-memory block while the current tile is being processed, so the node gather of a tile starts with its
+//     node ids already on chip (the dependent DRAM round trip conn -> node record is gone from the prologue).
+//   * all per-element state that must survive the Gauss-point loop (geometry modes X, displacement modes U, the 36
+//     force-mode accumulators M: 78 doubles) lives in tensor memory, one TMEM lane per thread (hk_tmem.h), so
+//     registers hold only one Gauss point's temporaries.
+// Why groups: a tile has a prologue (gather 8 node records, Hadamard transforms, closed-form B-bar sums) and an
+// epilogue (force modes -> 24 nodal forces, Qe stores) during which its ring does not drain.  With ONE group the whole
+// SM pauses for ~3 us of every ~21 us tile (round 1: 0.71 of the copy roofline, and the same 6.1 ms with the math
+// deleted).  Two groups run half a tile out of phase — group 1 starts after group 0 has finished 4 Gauss points —
+// so one group's prologue/epilogue overlaps the other's Gauss-point loop and the SM's DRAM streams never all pause.
+// Every lane runs the full math (dead or padded elements get a unit cube with zero displacement, which leaves their
+// state rows bit-unchanged), so the warp-collective tcgen05.ld/st never execute under divergence.
 #define HK_ROWS 14                        // state rows per Gauss point: stress 6, strain 6, eps, yield
-#define HK_STAGE_DOUBLES (HK_ROWS * HK_TILE)
-#define HK_CTA_THREADS (HK_TILE + 32)
 #define HK_SMEM_MATS 8                    // materials whose hardening tables are cached in shared memory
+#define HK_TCOLS 168                      // TMEM columns per thread: X [0,42) U [48,90) M [96,168)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -228,9 +229,6 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, u
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -238,169 +236,12 @@ template <int N>
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void modes_store(const HexModes& m, double* p) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        p[(0 + c) * HK_TILE] = m.c0[c];  p[(3 + c) * HK_TILE] = m.c1[c];  p[(6 + c) * HK_TILE] = m.c2[c];
-        p[(9 + c) * HK_TILE] = m.h01[c]; p[(12 + c) * HK_TILE] = m.h02[c]; p[(15 + c) * HK_TILE] = m.h12[c];
-        p[(18 + c) * HK_TILE] = m.h012[c];
-    }
-}
-__device__ __forceinline__ void modes_load(HexModes& m, const double* p) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        m.c0[c] = p[(0 + c) * HK_TILE];  m.c1[c] = p[(3 + c) * HK_TILE];  m.c2[c] = p[(6 + c) * HK_TILE];
-        m.h01[c] = p[(9 + c) * HK_TILE]; m.h02[c] = p[(12 + c) * HK_TILE]; m.h12[c] = p[(15 + c) * HK_TILE];
-        m.h012[c] = p[(18 + c) * HK_TILE];
-    }
-}
-
 // global address of the state of Gauss point k of the tile starting at element e0: 14 rows x TL doubles, contiguous
 __device__ __forceinline__ double* stage_base(const HkDev& d, int k, long long e0) {
     return d.ips + ((e0 / d.TL) * 8 + k) * 14 * d.TL;
 }
 
-// MODES: 0 = geometry/displacement modes in registers, 1 = displacement modes U in shared memory,
-//        2 = X and U in shared memory (thread-private columns; frees registers so ptxas can overlap more math)
-//   PF: > 0 = the producer also issues cp.async.bulk.prefetch.L2 for the work item PF stages beyond the ring, so
-//        the depth of DRAM prefetch is no longer bounded by shared-memory capacity
-template <int STAGES, int MODES, int PF>
-__global__ void __launch_bounds__(HK_CTA_THREADS, 1) hk_element_tma_kernel(ElemArgs A) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* stage_buf = reinterpret_cast<double*>(smem_raw);
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(stage_buf + STAGES * HK_STAGE_DOUBLES);
-    unsigned long long* done = full + STAGES;
-    double* mat_tab = reinterpret_cast<double*>(done + STAGES);   // [HK_SMEM_MATS][2][HK_MAX_TABLE]
-    double* modes_buf = mat_tab + HK_SMEM_MATS * 2 * HK_MAX_TABLE;   // [42][HK_TILE] (MODES > 0)
-    const HkDev& d = A.d;
-    const int tid = threadIdx.x;
-    const long long n_tiles = d.nEp / HK_TILE;
-    const long long first = blockIdx.x;
-    const long long my_tiles = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
-    const long long total_q = my_tiles * 8;                 // (tile, gauss point) work items of this CTA
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], HK_TILE); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    const bool tabs_in_smem = d.n_mat <= HK_SMEM_MATS;
-    if (tabs_in_smem)
-        for (int i = tid; i < d.n_mat * 2 * HK_MAX_TABLE; i += HK_CTA_THREADS) {
-            const int m = i / (2 * HK_MAX_TABLE), r = i % (2 * HK_MAX_TABLE);
-            mat_tab[i] = r < HK_MAX_TABLE ? d.mats[m].plastic_e[r] : d.mats[m].Hd[r - HK_MAX_TABLE];
-        }
-    __syncthreads();
-
-    if (tid >= HK_TILE) {
-        // ===== producer warp =====
-        if (tid != HK_TILE) return;
-        auto issue_load = [&](long long q) {
-            const int st = (int)(q % STAGES);
-            const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
-            const int k = (int)(q & 7);
-            double* dst = stage_buf + st * HK_STAGE_DOUBLES;
-            mbar_expect_tx(&full[st], HK_ROWS * HK_TILE * 8);
-            tma_load_1d(dst, stage_base(d, k, e0), HK_ROWS * HK_TILE * 8, &full[st]);
-            if (PF > 0 && q + PF < total_q) {
-                const long long qp = q + PF;
-                const long long ep0 = (first + (qp >> 3) * gridDim.x) * HK_TILE;
-                tma_prefetch_l2(stage_base(d, (int)(qp & 7), ep0), HK_ROWS * HK_TILE * 8);
-            }
-        };
-        for (long long q = 0; q < STAGES && q < total_q; ++q) issue_load(q);
-        for (long long q = 0; q < total_q; ++q) {
-            const int st = (int)(q % STAGES);
-            mbar_wait(&done[st], (unsigned)((q / STAGES) & 1));      // every consumer finished item q
-            const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE;
-            const int k = (int)(q & 7);
-            const double* src = stage_buf + st * HK_STAGE_DOUBLES;
-            tma_store_1d(stage_base(d, k, e0), src, HK_ROWS * HK_TILE * 8);
-            tma_commit();
-            // refill the stage whose store group was committed one round ago (it has been read by now)
-            const long long qn = q - 1 + STAGES;
-            if (q >= 1 && qn < total_q) {
-                tma_wait_read<1>();
-                issue_load(qn);
-            }
-        }
-        tma_wait_all<0>();
-        return;
-    }
-
-    // ===== consumers: one element per thread =====
-    long long q = 0;
-    for (long long it = 0; it < my_tiles; ++it) {
-        const long long e0 = (first + it * gridDim.x) * HK_TILE;
-        const long long e = e0 + tid;
-        const bool live = !element_dead(d, e);              // padded elements carry flag 2
-        HexModes X, U;
-        ElemAcc acc;
-        double V = 1.0, trbar = 0.0;
-        const HkMaterialDev* Mt = &d.mats[0];
-        MatLite ML = mat_lite(Mt);
-        acc_init(acc);
-        if (live) {
-            const int mi = d.mat[e];
-            Mt = &d.mats[mi];
-            ML = mat_lite(Mt);
-            ML.fast = A.fast;
-            if (tabs_in_smem) { ML.pe = mat_tab + mi * 2 * HK_MAX_TABLE; ML.hd = ML.pe + HK_MAX_TABLE; }
-            element_gather(d, e, X, U);
-            double G[3][3][3];
-            adj_mode_sums(X, G);
-            element_volume_terms(X, U, G, V, trbar);
-            if (MODES >= 1) modes_store(U, modes_buf + tid);
-            if (MODES >= 2) modes_store(X, modes_buf + 21 * HK_TILE + tid);
-        }
-        const bool need_triax = A.write_triax || Mt->nd > 0;
-#pragma unroll 1
-        for (int k = 0; k < 8; ++k, ++q) {
-            const int st = (int)(q % STAGES);
-            double* sb = stage_buf + st * HK_STAGE_DOUBLES + tid;
-            mbar_wait(&full[st], (unsigned)((q / STAGES) & 1));
-            if (live) {
-                double sv[14];
-#pragma unroll
-                for (int r = 0; r < HK_ROWS; ++r) sv[r] = sb[r * HK_TILE];
-                if (MODES >= 1) modes_load(U, modes_buf + tid);
-                if (MODES >= 2) modes_load(X, modes_buf + 21 * HK_TILE + tid);
-                const double tx = gauss_point(X, U, ML, k, trbar, sv, acc, need_triax);
-#pragma unroll
-                for (int r = 0; r < HK_ROWS; ++r) sb[r * HK_TILE] = sv[r];
-                if (A.write_triax) d.triax[(long long)k * d.nEp + e] = tx;
-            }
-            fence_async_smem();                              // generic-proxy smem writes -> visible to the TMA
-            mbar_arrive(&done[st]);
-        }
-        if (live) {
-            if (MODES >= 2) modes_load(X, modes_buf + 21 * HK_TILE + tid);
-            element_finish(A, e, X, acc, V);
-            if (ductile_check(*Mt, acc.v_e, acc.t_e)) {
-                // the state rows of this element are still in flight in bulk stores: only mark it here,
-                // hk_launch_flush_deleted zeroes stress/strain after this kernel (stream order)
-                d.flag[e] = 3;
-                const int slot = hk_atomic_add_i32(d.del_count, 1);
-                if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
-            }
-        }
-    }
-}
-#endif
-
-#ifndef HK_EMU
 #include "hk_tmem.h"
-// ---- TMEM kernel ----------------------------------------------------------------------------------------------
-// Same ring and producer as hk_element_tma_kernel, but ALL per-element state that must survive the Gauss-point
-// loop (geometry modes X, displacement modes U, the 36 force-mode accumulators M: 78 doubles) lives in tensor
-// memory, one TMEM lane per thread (hk_tmem.h).  Registers then hold only the temporaries of one Gauss point, so
-// the CTA grows from 7 to 11 consumer warps per SM (352 elements per tile) — the kernel is issue/latency bound,
-// not bandwidth bound (profiles/), so warps are what it needs.  Every lane runs the full math (dead or padded
-// elements get a unit cube with zero displacement, which leaves their state rows bit-unchanged), so the
-// warp-collective tcgen05.ld/st never execute under divergence.
-#define HK_TILE_T 352
-#define HK_CTA_T (HK_TILE_T + 32)
-#define HK_STAGE_T (HK_ROWS * HK_TILE_T)
-#define HK_TCOLS 168                      // columns per thread: X [0,42) U [48,90) M [96,168)
 
 __device__ __forceinline__ void tmem_store_modes(uint32_t t, const HexModes& m) {
     double v[24];
@@ -430,23 +271,50 @@ __device__ __forceinline__ void tmem_load_modes(uint32_t t, HexModes& m) {
     }
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A) {
+// node records of the 8 nodes listed in shared memory (conn block [8][TLD] of the tile) -> modes
+template <int TLD>
+__device__ __forceinline__ void element_gather_ids(const HkDev& d, const int* ids, HexModes& X, HexModes& U) {
+    double x[8][3], du[8][3];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const long long n = ids[a * TLD];
+        const double2* r = reinterpret_cast<const double2*>(d.rec + 6 * n);
+        const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+        x[a][0] = r0.x; x[a][1] = r0.y; x[a][2] = r1.x;
+        du[a][0] = r1.y; du[a][1] = r2.x; du[a][2] = r2.y;
+    }
+    hex_modes(x, X);
+    hex_modes(du, U);
+}
+
+template <int NG, int WG, int S, int CP>
+struct RingCfg {
+    static constexpr int TLD = WG * 32;                        // elements per tile
+    static constexpr int STAGE = HK_ROWS * TLD;                // doubles per stage
+    static constexpr int THREADS = (NG * WG + NG) * 32;        // consumers + one producer warp per group
+    static constexpr int SMEM = NG * S * STAGE * 8 + (2 * NG * S + 2 * NG) * 8 + HK_SMEM_MATS * 2 * HK_MAX_TABLE * 8 +
+                                (CP ? NG * 2 * 8 * TLD * 4 : 0) + 64;
+};
+
+template <int NG, int WG, int S, int CP>
+__global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel(ElemArgs A) {
+    using Cfg = RingCfg<NG, WG, S, CP>;
+    constexpr int TLD = Cfg::TLD, STAGE = Cfg::STAGE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* stage_buf = reinterpret_cast<double*>(smem_raw);
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(stage_buf + STAGES * HK_STAGE_T);
-    unsigned long long* done = full + STAGES;
-    double* mat_tab = reinterpret_cast<double*>(done + STAGES);
-    uint32_t* tbase_s = reinterpret_cast<uint32_t*>(mat_tab + HK_SMEM_MATS * 2 * HK_MAX_TABLE);
+    double* stage_buf = reinterpret_cast<double*>(smem_raw);                                  // [NG][S][STAGE]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(stage_buf + NG * S * STAGE);   // [NG][S]
+    unsigned long long* done = full + NG * S;                                                 // [NG][S]
+    unsigned long long* cfull = done + NG * S;                                                // [NG][2]
+    double* mat_tab = reinterpret_cast<double*>(cfull + NG * 2);
+    int* conn_buf = reinterpret_cast<int*>(mat_tab + HK_SMEM_MATS * 2 * HK_MAX_TABLE);        // [NG][2][8][TLD]
+    uint32_t* tbase_s = reinterpret_cast<uint32_t*>(conn_buf + (CP ? NG * 2 * 8 * TLD : 0));
     const HkDev& d = A.d;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const long long n_tiles = d.nEp / HK_TILE_T;
-    const long long first = blockIdx.x;
-    const long long my_tiles = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
-    const long long total_q = my_tiles * 8;
+    const long long n_tiles = d.nEp / TLD;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], HK_TILE_T); }
+        for (int s = 0; s < NG * S; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], WG); }
+        for (int s = 0; s < NG * 2; ++s) mbar_init(&cfull[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -455,7 +323,7 @@ __global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A
     }
     const bool tabs_in_smem = d.n_mat <= HK_SMEM_MATS;
     if (tabs_in_smem)
-        for (int i = tid; i < d.n_mat * 2 * HK_MAX_TABLE; i += HK_CTA_T) {
+        for (int i = tid; i < d.n_mat * 2 * HK_MAX_TABLE; i += Cfg::THREADS) {
             const int m = i / (2 * HK_MAX_TABLE), r = i % (2 * HK_MAX_TABLE);
             mat_tab[i] = r < HK_MAX_TABLE ? d.mats[m].plastic_e[r] : d.mats[m].Hd[r - HK_MAX_TABLE];
         }
@@ -464,27 +332,48 @@ __global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tbase = *tbase_s;
 
-    if (tid >= HK_TILE_T) {
-        // ===== producer warp (same protocol as hk_element_tma_kernel) =====
-        if (tid == HK_TILE_T) {
-            auto issue_load = [&](long long q) {
-                const int st = (int)(q % STAGES);
-                const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE_T;
-                const int k = (int)(q & 7);
-                double* dst = stage_buf + st * HK_STAGE_T;
-                mbar_expect_tx(&full[st], HK_ROWS * HK_TILE_T * 8);
-                tma_load_1d(dst, stage_base(d, k, e0), HK_ROWS * HK_TILE_T * 8, &full[st]);
+    // group of this warp, its virtual CTA id and its share of the tiles (round-robin over all groups of the grid)
+    const int g = warp < NG * WG ? warp / WG : warp - NG * WG;
+    const long long n_v = (long long)gridDim.x * NG;
+    const long long vcta = (long long)blockIdx.x * NG + g;
+    const long long my_tiles = vcta < n_tiles ? (n_tiles - vcta + n_v - 1) / n_v : 0;
+    const long long total_q = my_tiles * 8;                 // (tile, Gauss point) work items of this group
+    double* gstage = stage_buf + (long long)g * S * STAGE;
+    unsigned long long* gfull = full + g * S;
+    unsigned long long* gdone = done + g * S;
+    unsigned long long* gcfull = cfull + g * 2;
+    int* gconn = conn_buf + (CP ? g * 2 * 8 * TLD : 0);
+
+    if (warp >= NG * WG) {
+        // ===== producer warp of group g =====
+        if ((tid & 31) == 0) {
+            auto issue_conn = [&](long long it) {             // connectivity of this group's tile number `it`
+                if (!CP || it >= my_tiles) return;
+                const long long e0 = (vcta + it * n_v) * TLD;
+                unsigned long long* bar = &gcfull[it & 1];
+                mbar_expect_tx(bar, 8 * TLD * 4);
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    tma_load_1d(gconn + ((it & 1) * 8 + a) * TLD, d.conn + (long long)a * d.nEp + e0, TLD * 4, bar);
             };
-            for (long long q = 0; q < STAGES && q < total_q; ++q) issue_load(q);
+            auto issue_load = [&](long long q) {
+                const int st = (int)(q % S);
+                const long long e0 = (vcta + (q >> 3) * n_v) * TLD;
+                mbar_expect_tx(&gfull[st], STAGE * 8);
+                tma_load_1d(gstage + st * STAGE, stage_base(d, (int)(q & 7), e0), STAGE * 8, &gfull[st]);
+            };
+            issue_conn(0);
+            for (long long q = 0; q < S && q < total_q; ++q) issue_load(q);
             for (long long q = 0; q < total_q; ++q) {
-                const int st = (int)(q % STAGES);
-                mbar_wait(&done[st], (unsigned)((q / STAGES) & 1));
-                const long long e0 = (first + (q >> 3) * gridDim.x) * HK_TILE_T;
-                const int k = (int)(q & 7);
-                const double* src = stage_buf + st * HK_STAGE_T;
-                tma_store_1d(stage_base(d, k, e0), src, HK_ROWS * HK_TILE_T * 8);
+                const int st = (int)(q % S);
+                mbar_wait(&gdone[st], (unsigned)((q / S) & 1));      // every warp of the group finished item q
+                const long long e0 = (vcta + (q >> 3) * n_v) * TLD;
+                tma_store_1d(stage_base(d, (int)(q & 7), e0), gstage + st * STAGE, STAGE * 8);
                 tma_commit();
-                const long long qn = q - 1 + STAGES;
+                // the group is past the prologue of tile q/8: the buffer of tile q/8 - 1 is free for tile q/8 + 1
+                if ((q & 7) == 0) issue_conn((q >> 3) + 1);
+                // refill the stage whose store group was committed one round ago (it has been read by now)
+                const long long qn = q - 1 + S;
                 if (q >= 1 && qn < total_q) {
                     tma_wait_read<1>();
                     issue_load(qn);
@@ -494,21 +383,30 @@ __global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A
         }
     } else {
         // ===== consumers =====
+        const int gt = tid - g * TLD;                          // thread within the group = element within the tile
         const uint32_t tcol = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * HK_TCOLS);
         const uint32_t tX = tcol, tU = tcol + 48, tM = tcol + 96;
+        // phase shift: group g > 0 starts when group 0 has finished g*8/NG Gauss points of its first tile
+        if (NG > 1 && g > 0) {
+            const long long tiles0 = (long long)blockIdx.x * NG < n_tiles ? 1 : 0;
+            const int item = g * 8 / NG - 1;
+            if (tiles0 && item < S) mbar_wait(&done[item], 0u);
+        }
         long long q = 0;
         for (long long it = 0; it < my_tiles; ++it) {
-            const long long e0 = (first + it * gridDim.x) * HK_TILE_T;
-            const long long e = e0 + tid;
+            const long long e0 = (vcta + it * n_v) * TLD;
+            const long long e = e0 + gt;
             const bool live = !element_dead(d, e);
             const HkMaterialDev* Mt = &d.mats[0];
             double V = 0.125, trbar = 0.0;
             int mi = 0;
+            if (CP) mbar_wait(&gcfull[it & 1], (unsigned)((it >> 1) & 1));
             {
                 HexModes X, U;
                 if (live) {
                     mi = d.mat[e];
-                    element_gather(d, e, X, U);
+                    if (CP) element_gather_ids<TLD>(d, gconn + (it & 1) * 8 * TLD + gt, X, U);
+                    else element_gather(d, e, X, U);
                 } else {                                     // unit cube at rest: finite math, state rows unchanged
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -539,17 +437,20 @@ __global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A
             int negj = 0;
 #pragma unroll 1
             for (int k = 0; k < 8; ++k, ++q) {
-                const int st = (int)(q % STAGES);
-                double* sb = stage_buf + st * HK_STAGE_T + tid;
-                mbar_wait(&full[st], (unsigned)((q / STAGES) & 1));
+                const int st = (int)(q % S);
+                double* sb = gstage + st * STAGE + gt;
+                mbar_wait(&gfull[st], (unsigned)((q / S) & 1));
                 __syncwarp();
-                if (A.fast == 2) {                           // experiment: memory pipeline only (no math)
+#ifdef HK_PROFILE_NOMATH                                     // profiling builds only: memory pipeline without the math
+                {
 #pragma unroll
-                    for (int r = 0; r < HK_ROWS; ++r) sb[r * HK_TILE_T] = sb[r * HK_TILE_T] + 0.0;
+                    for (int r = 0; r < HK_ROWS; ++r) sb[r * TLD] = sb[r * TLD] + 0.0;
                     fence_async_smem();
-                    mbar_arrive(&done[st]);
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&gdone[st]);
                     continue;
                 }
+#endif
                 const double s0 = (k & 4) ? 1.0 : -1.0, s1 = (k & 2) ? 1.0 : -1.0, s2 = (k & 1) ? 1.0 : -1.0;
                 double Aj[3][3], det;
                 {
@@ -565,26 +466,28 @@ __global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A
                     tmem_load_modes(tU, U);
                     gp_strain(U, Aj, idet, trbar, s0, s1, s2, de);
                 }
-                GpStress g;
+                GpStress gs;
                 {
                     double sv[14];
 #pragma unroll
-                    for (int r = 0; r < HK_ROWS; ++r) sv[r] = sb[r * HK_TILE_T];
-                    gp_stress(ML, sv, de, need_triax, g);
+                    for (int r = 0; r < HK_ROWS; ++r) sv[r] = sb[r * TLD];
+                    gp_stress(ML, sv, de, need_triax, gs);
 #pragma unroll
-                    for (int r = 0; r < HK_ROWS; ++r) sb[r * HK_TILE_T] = sv[r];
+                    for (int r = 0; r < HK_ROWS; ++r) sb[r * TLD] = sv[r];
                 }
-                pdet += g.mean * det;
-                v_e += g.ep;
-                t_e += g.tx;
-                if (A.write_triax && live) d.triax[(long long)k * d.nEp + e] = g.tx;
+                fence_async_smem();                          // generic-proxy smem writes -> visible to the TMA
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&gdone[st]);   // the stage can go back to HBM while the forces are formed
+                pdet += gs.mean * det;
+                v_e += gs.ep;
+                t_e += gs.tx;
+                if (A.write_triax && live) d.triax[(long long)k * d.nEp + e] = gs.tx;
                 const double sa[3] = {s1, s0, s0};
                 const double sb_[3] = {s2, s2, s1};
-                __syncwarp();
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     double T[3];
-                    gp_T(g, Aj[r], T);
+                    gp_T(gs, Aj[r], T);
                     uint32_t w[24];
                     tmem_ld_x8(tM + 24 * r, w);
                     tmem_ld_x8(tM + 24 * r + 8, w + 8);
@@ -604,8 +507,6 @@ __global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A
                     tmem_st_doubles<4>(tM + 24 * r + 16, mo + 8);
                 }
                 tmem_wait_st();
-                fence_async_smem();
-                mbar_arrive(&done[st]);
             }
             // ---- element epilogue: forces from the modes parked in TMEM
             __syncwarp();
@@ -631,7 +532,9 @@ __global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A
             if (live) {
                 element_finish(A, e, X, acc, V);
                 if (ductile_check(*Mt, acc.v_e, acc.t_e)) {
-                    d.flag[e] = 3;                           // zeroed by hk_launch_flush_deleted (stream order)
+                    // the state rows of this element are still in flight in bulk stores: only mark it here,
+                    // hk_launch_flush_deleted zeroes stress/strain after this kernel (stream order)
+                    d.flag[e] = 3;
                     const int slot = hk_atomic_add_i32(d.del_count, 1);
                     if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
                 }
@@ -643,80 +546,63 @@ __global__ void __launch_bounds__(HK_CTA_T, 1) hk_element_tmem_kernel(ElemArgs A
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
 }
 
-template <int STAGES>
-static void launch_tmem(const ElemArgs& A, int n_sm, cudaStream_t s) {
-    const int smem_bytes = STAGES * HK_STAGE_T * 8 + 2 * STAGES * 8 + HK_SMEM_MATS * 2 * HK_MAX_TABLE * 8 + 64;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(hk_element_tmem_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        configured = true;
-    }
-    const long long n_tiles = A.d.nEp / HK_TILE_T;
+template <int NG, int WG, int S, int CP>
+static int launch_ring(const ElemArgs& A, int n_sm, cudaStream_t s) {
+    using Cfg = RingCfg<NG, WG, S, CP>;
+    static_assert(Cfg::SMEM <= 227 * 1024, "ring does not fit in shared memory");
+    static_assert(((NG * WG + 3) / 4) * HK_TCOLS <= 512, "TMEM columns");
+    cudaError_t rc = cudaFuncSetAttribute(hk_element_ring_kernel<NG, WG, S, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::SMEM);               // per device: cheap, so set on every launch
+    if (rc != cudaSuccess) return (int)rc;
+    const long long n_tiles = A.d.nEp / Cfg::TLD;
     long long grid = n_sm;
-    if (grid > n_tiles) grid = n_tiles;
-    hk_element_tmem_kernel<STAGES><<<(unsigned)grid, HK_CTA_T, smem_bytes, s>>>(A);
+    if (grid * NG > n_tiles) grid = (n_tiles + NG - 1) / NG;
+    hk_element_ring_kernel<NG, WG, S, CP><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, s>>>(A);
+    return 0;
 }
 #endif
 
-#ifndef HK_EMU
-template <int STAGES, int MODES, int PF>
-static void launch_tma(const ElemArgs& A, unsigned grid, cudaStream_t s) {
-    const int smem_bytes = STAGES * HK_STAGE_DOUBLES * 8 + 2 * STAGES * 8 + HK_SMEM_MATS * 2 * HK_MAX_TABLE * 8 +
-                           21 * MODES * HK_TILE * 8 + 64;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(hk_element_tma_kernel<STAGES, MODES, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        configured = true;
-    }
-    hk_element_tma_kernel<STAGES, MODES, PF><<<grid, HK_CTA_THREADS, smem_bytes, s>>>(A);
+// element-kernel variant table (A/B history: profiles/r2_element_kernel_variants.md).  variant = groups, warps per
+// group, ring stages per group, connectivity prefetch
+struct RingVariant { int id, ng, wg, stages, cp; };
+static const RingVariant kVariants[] = {
+    {11, 1, 11, 4, 0},      // round-1 kernel: one group of 11 warps (tile 352)
+    {12, 1, 11, 4, 1},
+    {20, 2, 5, 4, 1},
+    {21, 2, 5, 5, 1},       // default
+    {22, 2, 5, 6, 0},
+    {23, 2, 5, 5, 0},
+};
+#define HK_DEFAULT_VARIANT 21
+
+int hk_element_variant_from_env() {
+    const char* v = getenv("HK_ELEMENT_VARIANT");
+    int id = v ? atoi(v) : HK_DEFAULT_VARIANT;
+    if (const char* k = getenv("HK_ELEMENT_KERNEL")) if (strcmp(k, "simple") == 0) return 1;
+    for (const RingVariant& r : kVariants) if (r.id == id) return id;
+    return HK_DEFAULT_VARIANT;
 }
-#endif
 
-static int g_elem_kernel = -1;   // 0 tma, 1 simple
-
-void hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s) {
-    if (d.element_mode == 1) { hk_launch_element_exact(d, step, write_triax, s); return; }
-    static int fast = -1;
-    if (fast < 0) { const char* f = getenv("HK_ELEMENT_FASTMATH"); fast = f ? atoi(f) : 1; }
-    ElemArgs A{d, step, write_triax, fast};
+int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s) {
+    if (d.element_mode == 1) { hk_launch_element_exact(d, step, write_triax, s); return 0; }
+    ElemArgs A{d, step, write_triax, 1};
 #ifndef HK_EMU
-    if (g_elem_kernel < 0) {
-        const char* env = getenv("HK_ELEMENT_KERNEL");
-        g_elem_kernel = (env && strcmp(env, "simple") == 0) ? 1 : 0;
-    }
-    if (g_elem_kernel == 1) {
-        const int block = 128;
-        hk_element_simple_kernel<<<(unsigned)((d.nElement + block - 1) / block), block, 0, s>>>(A);
-        return;
-    }
-    static int n_sm = 0, variant = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        variant = element_variant();
-    }
-    const long long n_tiles = d.nEp / HK_TILE;
-    long long grid = (long long)n_sm;
-    if (grid > n_tiles) grid = n_tiles;
-    if (variant >= 10) {                                 // TMEM kernels (tile 352)
-        switch (variant) {
-            case 10: launch_tmem<5>(A, n_sm, s); break;
-            case 12: launch_tmem<3>(A, n_sm, s); break;
-            default: launch_tmem<4>(A, n_sm, s); break;        // 11: measured best
+    switch (d.variant) {
+        case 1: {
+            const int block = 128;
+            hk_element_simple_kernel<<<(unsigned)((d.nElement + block - 1) / block), block, 0, s>>>(A);
+            return 0;
         }
-        return;
-    }
-    switch (variant) {                                   // A/B history: profiles/r1_element_kernel_variants.md
-        case 0: launch_tma<8, 0, 0>(A, (unsigned)grid, s); break;
-        case 2: launch_tma<6, 2, 0>(A, (unsigned)grid, s); break;
-        case 3: launch_tma<7, 1, 0>(A, (unsigned)grid, s); break;
-        case 4: launch_tma<6, 1, 8>(A, (unsigned)grid, s); break;
-        case 5: launch_tma<4, 1, 0>(A, (unsigned)grid, s); break;
-        default: launch_tma<6, 1, 0>(A, (unsigned)grid, s); break;   // measured best
+        case 11: return launch_ring<1, 11, 4, 0>(A, d.n_sm, s);
+        case 12: return launch_ring<1, 11, 4, 1>(A, d.n_sm, s);
+        case 20: return launch_ring<2, 5, 4, 1>(A, d.n_sm, s);
+        case 22: return launch_ring<2, 5, 6, 0>(A, d.n_sm, s);
+        case 23: return launch_ring<2, 5, 5, 0>(A, d.n_sm, s);
+        default: return launch_ring<2, 5, 5, 1>(A, d.n_sm, s);
     }
 #else
     for (long long e = 0; e < d.nElement; ++e) element_body_simple(A, e);
+    return 0;
 #endif
 }
 
@@ -762,10 +648,12 @@ void hk_launch_element_volume(const HkDev& dd, double* V_out, cudaStream_t s) {
 }
 
 
-long long hk_element_tile() {      // layout tile TL of the ip state = tile of the element kernel that will run
+long long hk_element_tile(int variant) {      // layout tile TL of the ip state = tile of the element kernel that will run
 #ifndef HK_EMU
-    return element_variant() >= 10 ? HK_TILE_T : HK_TILE;
+    for (const RingVariant& r : kVariants) if (r.id == variant) return r.wg * 32;
+    return 128;                                // simple kernel: any multiple of its block works
 #else
+    (void)variant;
     return 32;
 #endif
 }

@@ -105,6 +105,7 @@ struct hk_engine {
     // more than the averaging itself)
     double* no_emean = nullptr;    // [14][nEp]
     double* no_out = nullptr;      // [16][nNode]
+    unsigned long long* d_summary = nullptr;   // hk_state_summary scratch
     int64_t begun_t = -1;          // step opened by hk_step_begin
     // special nodes (host mirror)
     std::vector<int> spec_idx_h;
@@ -592,9 +593,14 @@ int HKAPI(finalize)(hk_engine* e) {
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
     if (e->nNode == 0) return fail(e, HK_ERR_STATE, "hk_set_mesh not called");
     const int64_t nN = e->nNode, nE = e->nElement;
-    const int64_t tile = hk_element_tile();
-    const int64_t nEp = (nE + tile - 1) / tile * tile;   // whole tiles for hk_element_tma_kernel
     HkDev& d = e->d;
+    d.variant = hk_element_variant_from_env();
+    d.n_sm = 1;
+#ifndef HK_EMU
+    CK(cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, e->prm.device));
+#endif
+    const int64_t tile = hk_element_tile(d.variant);
+    const int64_t nEp = (nE + tile - 1) / tile * tile;   // whole tiles for the element kernel
     d.nNode = nN; d.nElement = nE; d.nEp = nEp;
     d.element_mode = e->prm.element_mode;
     const double dt = e->prm.d_time;
@@ -866,7 +872,7 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
         prof_end(e);
         e->use_Q0 = 0;
         prof_begin(e, 2);
-        hk_launch_element(d, t, (frame_at_end && t == t_first + n_steps - 1) ? 1 : 0, e->stream);
+        CK(hk_launch_element(d, t, (frame_at_end && t == t_first + n_steps - 1) ? 1 : 0, e->stream));
         prof_end(e);
         e->n_launch += 2;
         if (e->any_ductile) { hk_launch_flush_deleted(d, e->stream); e->n_launch += 1; }
@@ -1163,6 +1169,24 @@ int HKAPI(counters)(hk_engine* e, int64_t out[8]) {
     out[5] = (int64_t)c[3];
     out[6] = 0;
     out[7] = 0;
+    return HK_OK;
+}
+
+int HKAPI(state_summary)(hk_engine* e, double out[8]) {
+    if (!e || !e->finalized || !out) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (!e->d_summary) { int rc = dalloc(e, &e->d_summary, (size_t)4); if (rc) return rc; }
+    const unsigned long long init[4] = {0ull, ~0ull, 0ull, 0ull};
+    unsigned long long got[4];
+    CK(hkp::h2d(e->d_summary, init, sizeof(init), e->stream));
+    hk_launch_state_summary(e->d, e->d_summary, e->stream);
+    e->n_launch += 1;
+    CK(hkp::d2h(got, e->d_summary, sizeof(got), e->stream));
+    CK(hkp::last_error());
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+    out[0] = (double)got[0];
+    out[1] = got[0] ? hk_decode_double(got[1]) : 0.0;
+    out[2] = got[0] ? hk_decode_double(got[2]) : 0.0;
+    out[3] = (double)got[3];
     return HK_OK;
 }
 

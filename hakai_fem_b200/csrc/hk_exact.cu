@@ -700,6 +700,64 @@ void hk_launch_triax_to_aos(const HkDev& dd, double* aos, long long e0, long lon
     });
 }
 
+// ------------------------------------------------------------------ state summary (hk_state_summary)
+// out[0] live elements, out[1] / out[2] order-encoded min / max of integ_eq_plastic_strain over the Gauss points of
+// live elements, out[3] Gauss points of live elements with eps > 0.  `out` must be initialised {0, ~0, 0, 0}.
+HK_HD void summary_element(const HkDev& d, long long e, unsigned long long& live, unsigned long long& mn,
+                           unsigned long long& mx, unsigned long long& npl) {
+    live = 0ull; mn = ~0ull; mx = 0ull; npl = 0ull;
+    if (e >= d.nElement || d.flag[e] != 1) return;
+    live = 1ull;
+    for (int k = 0; k < 8; ++k) {
+        const double ep = d.ips[hk_ip(d, 12, k, e)];
+        const unsigned long long en = enc_double(ep);
+        mn = en < mn ? en : mn;
+        mx = en > mx ? en : mx;
+        npl += ep > 0.0 ? 1ull : 0ull;
+    }
+}
+#ifndef HK_EMU
+__global__ void __launch_bounds__(256) hk_state_summary_kernel(HkDev d, unsigned long long* out) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned long long live = 0ull, mn = ~0ull, mx = 0ull, npl = 0ull;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < d.nElement; e += (long long)gridDim.x * blockDim.x) {
+        unsigned long long l, a, b, c;
+        summary_element(d, e, l, a, b, c);
+        live += l; npl += c;
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    for (int off = 16; off; off >>= 1) {
+        live += __shfl_xor_sync(FULL, live, off);
+        npl += __shfl_xor_sync(FULL, npl, off);
+        const unsigned long long a = __shfl_xor_sync(FULL, mn, off), b = __shfl_xor_sync(FULL, mx, off);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (live) atomicAdd(&out[0], live);
+        if (npl) atomicAdd(&out[3], npl);
+        atomicMin(&out[1], mn);
+        atomicMax(&out[2], mx);
+    }
+}
+#endif
+void hk_launch_state_summary(const HkDev& d, unsigned long long* out, cudaStream_t s) {
+#ifndef HK_EMU
+    const int grid = d.n_sm > 0 ? d.n_sm * 8 : 256;
+    hk_state_summary_kernel<<<grid, 256, 0, s>>>(d, out);
+#else
+    for (long long e = 0; e < d.nElement; ++e) {
+        unsigned long long l, a, b, c;
+        summary_element(d, e, l, a, b, c);
+        out[0] += l; out[3] += c;
+        if (a < out[1]) out[1] = a;
+        if (b > out[2]) out[2] = b;
+    }
+#endif
+}
+double hk_decode_double(unsigned long long v) { return dec_double(v); }
+
 // ------------------------------------------------------------------ cal_node_stress_strain on the device (J2:3408-3486)
 // element means (J2:3428-3440): rows 0-5 stress, 6-11 strain, 12 eps, 13 triax; the 8 Gauss points are summed in order
 void hk_launch_element_means(const HkDev& dd, double* emean, cudaStream_t s) {

@@ -43,7 +43,7 @@ EXPORTS = [
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
     "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
-    "state_export", "state_import",
+    "state_export", "state_import", "state_summary",
 ]
 
 
@@ -294,6 +294,12 @@ class EngineBase:
         out = np.zeros(8, np.int64)
         self._chk(self._fn("counters")(self._h, _pi(out)))
         return out
+
+    def state_summary(self) -> dict:
+        """Device-side reduction: live elements, min / max eq. plastic strain of live Gauss points, yielded points."""
+        out = np.zeros(8)
+        self._chk(self._fn("state_summary")(self._h, _pf(out)))
+        return dict(live_elements=int(out[0]), eps_min=float(out[1]), eps_max=float(out[2]), yielded_points=int(out[3]))
 
     def profile(self, enable: bool = True):
         self._chk(self._fn("profile")(self._h, C.c_int32(1 if enable else 0)))

@@ -78,6 +78,9 @@ class StretchDeck:
     name: str = "stretch"
     layer_offset: int = 0                 # multi-GPU slabs: this block starts at global element layer `layer_offset`
     global_nz: Optional[int] = None       # ... of a global mesh with `global_nz` element layers (None: nz)
+    jitter_by_layer: bool = False         # noise seeded per GLOBAL node layer ([seed, layer]) instead of one stream over
+                                          # the whole array: a z-slab of a larger mesh then carries exactly the nodes the
+                                          # single-domain mesh has (the weak-scaling decks and their parity twin)
 
     def _layers(self):
         per = (self.nx + 1) * (self.ny + 1)
@@ -86,13 +89,21 @@ class StretchDeck:
     def coord_elem(self):
         coord, em = block_arrays(self.nx, self.ny, self.nz, self.h, origin=(0.0, 0.0, self.layer_offset * self.h))
         if self.jitter > 0:
-            rng = np.random.default_rng(self.seed)
             nnx, nny, nnz = self.nx + 1, self.ny + 1, self.nz + 1
+            gnz = self.global_nz if self.global_nz is not None else self.nz
             ii = np.tile(np.arange(nnx), nny * nnz)
             jj = np.tile(np.repeat(np.arange(nny), nnx), nnz)
-            kk = np.repeat(np.arange(nnz), nnx * nny)
-            interior = (ii > 0) & (ii < nnx - 1) & (jj > 0) & (jj < nny - 1) & (kk > 0) & (kk < nnz - 1)
-            noise = rng.uniform(-self.jitter * self.h, self.jitter * self.h, size=coord.shape)
+            kk = np.repeat(np.arange(nnz), nnx * nny) + self.layer_offset        # GLOBAL node layer
+            interior = (ii > 0) & (ii < nnx - 1) & (jj > 0) & (jj < nny - 1) & (kk > 0) & (kk < gnz)
+            amp = self.jitter * self.h
+            if self.jitter_by_layer:
+                per = nnx * nny
+                noise = np.empty(coord.shape)
+                for k in range(nnz):
+                    rng = np.random.default_rng([self.seed, k + self.layer_offset])
+                    noise[:, k * per:(k + 1) * per] = rng.uniform(-amp, amp, size=(3, per))
+            else:
+                noise = np.random.default_rng(self.seed).uniform(-amp, amp, size=coord.shape)
             coord = coord + noise * interior[None, :]
         return coord, em
 

@@ -60,9 +60,9 @@ def lumped_mass(model: Model, elementVolume: np.ndarray) -> np.ndarray:
     """diag_M (J2:201-215): rho*V/8 to each of the 8 nodes, same value on the 3 dofs, times mass_scaling."""
     dens = np.array([m.density for m in model.MATERIAL])
     node_mass = dens[model.element_material - 1] * elementVolume / 8.0
-    m = np.zeros(model.nNode)
-    for i in range(8):
-        m += np.bincount(model.elementmat[i] - 1, weights=node_mass, minlength=model.nNode)
+    # the reference adds element by element, node by node (J2:201-209): bincount accumulates in input order, so an
+    # element-major / node-minor index stream reproduces that summation order (and its rounding) exactly
+    m = np.bincount(model.elementmat.T.reshape(-1) - 1, weights=np.repeat(node_mass, 8), minlength=model.nNode)
     return np.repeat(m, 3) * model.mass_scaling
 
 

@@ -193,7 +193,7 @@ def slab_deck(deck, rank: int, world: int):
     local = copy.copy(deck)
     local.layer_offset = rank * deck.nz
     local.global_nz = deck.nz * world
-    local.seed = deck.seed + rank
+    local.jitter_by_layer = True          # noise is a function of the GLOBAL node layer: the slabs tile one global mesh
     per = (deck.nx + 1) * (deck.ny + 1)
     nbrs, halos = [], []
     if rank > 0:
@@ -203,6 +203,59 @@ def slab_deck(deck, rank: int, world: int):
         nbrs.append(rank + 1)
         halos.append(np.arange(deck.nz * per + 1, (deck.nz + 1) * per + 1, dtype=np.int64))
     return local, nbrs, halos
+
+
+def slab_parity_check(make_engine, torch_device, rank: int, world: int, n_steps: int = 32, nx: int = 24, ny: int = 24,
+                      nz_per_rank: int = 8, **params):
+    """Checks the z-slab / force-halo path against an unpartitioned run of the SAME mesh and the same kernels.
+
+    A small GLOBAL deck (nx x ny x nz_per_rank*world ductile block, jitter seeded per global node layer, stretched fast
+    enough that elements delete within `n_steps`) is stepped by `world` ranks through slab_deck + SlabRunner (pack ->
+    send/recv -> split step); rank 0 also runs the whole mesh on one engine.  Returns on rank 0 (None elsewhere):
+    max relative field error, whether the deleted-element sets and the element flags are identical, and whether the
+    node layer shared by two ranks is bit-identical on both.  bench.py runs it at N > 1 before anything is timed."""
+    import torch.distributed as dist
+    from .mesh import StretchDeck, steel
+    from .model_setup import prepare
+    rows = [[0.03, 0.0, 30.0], [0.02, 0.3, 30.0]]
+    mk = lambda nz: StretchDeck(nx, ny, nz, material=steel("steel_Ductile", ductile=rows), jitter=0.05,
+                                strain_per_step=1.0e-3, jitter_by_layer=True)
+    fields = ("disp", "integ_eq_plastic_strain", "integ_stress", "element_flag")
+    deck, nbrs, halos = slab_deck(mk(nz_per_rank), rank, world)
+    runner = SlabRunner(make_engine, prepare(deck.build_model()), nbrs, halos, torch_device, sum_mass=True, **params)
+    runner.run(1, n_steps)
+    d = runner.engine.download(fields=fields)
+    mine = dict(disp=d["disp"], eps=d["integ_eq_plastic_strain"], stress=np.ascontiguousarray(d["integ_stress"]),
+                flag=d["element_flag"], deleted=np.sort(runner.engine.deleted_ids()))
+    runner.engine.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    if rank != 0:
+        return None
+    g = configure_engine(make_engine, prepare(mk(nz_per_rank * world).build_model()), **params)
+    g.step(1, n_steps)
+    ref = g.download(fields=fields)
+    ref_del = np.sort(g.deleted_ids())
+    g.close()
+    per, nEl = (nx + 1) * (ny + 1), nx * ny * nz_per_rank
+    err, flags_equal, bitwise, got_del = 0.0, True, True, []
+    rs = np.asarray(ref["integ_stress"])
+    su, se, ss = np.abs(ref["disp"]).max(), max(ref["integ_eq_plastic_strain"].max(), 1e-300), max(np.abs(rs).max(), 1e-300)
+    for r, p in enumerate(parts):
+        n0, e0 = r * nz_per_rank * per, r * nEl
+        err = max(err, np.abs(p["disp"] - ref["disp"][3 * n0:3 * (n0 + (nz_per_rank + 1) * per)]).max() / su)
+        err = max(err, np.abs(p["eps"] - ref["integ_eq_plastic_strain"][8 * e0:8 * (e0 + nEl)]).max() / se)
+        err = max(err, np.abs(p["stress"] - rs[:, 8 * e0:8 * (e0 + nEl)]).max() / ss)
+        flags_equal = flags_equal and np.array_equal(p["flag"], ref["element_flag"][e0:e0 + nEl])
+        got_del.append(p["deleted"] + e0)
+        if r + 1 < world:        # last node layer of rank r == first node layer of rank r+1
+            bitwise = bitwise and np.array_equal(p["disp"][3 * nz_per_rank * per:], parts[r + 1]["disp"][:3 * per])
+    del_equal = bool(np.array_equal(np.sort(np.concatenate(got_del)), ref_del)) and flags_equal
+    return {"n_ranks": world, "deck": f"{nx}x{ny}x{nz_per_rank * world} ductile block, {n_steps} steps, {world} slabs over "
+                                      f"the halo exchange vs the same mesh unpartitioned on one engine",
+            "max_rel_err": float(err), "deleted_equal": del_equal, "n_deleted": int(len(ref_del)),
+            "interface_bitwise": bool(bitwise),
+            "ok": bool(err <= 1e-10 and del_equal and bitwise and 0 < len(ref_del))}
 
 
 class HaloExchanger:
@@ -263,7 +316,7 @@ class ContactExchanger:
     """All-gather of contact-surface node {position, velocity} and of the fixed-point force accumulators."""
 
     def __init__(self, engine, lists: ContactLists, world: int, device, rank=None, node_l2g=None, n_pairs=0,
-                 force_exchange="allgather"):
+                 force_exchange="allreduce"):
         """force_exchange: "allgather" (6 x u64 per surface node from every rank, summed on import) or "allreduce"
         (three 43-bit limbs per accumulator in int64 lanes, one SUM all-reduce: world/1.5 times fewer bytes)."""
         if force_exchange not in ("allgather", "allreduce"):
@@ -351,7 +404,7 @@ class SlabRunner:
     host-compiled kernel build, whose "device" pointers are host pointers."""
 
     def __init__(self, engine_cls, setup: Setup, neighbors, halo_nodes, torch_device, sum_mass=False, contact=None,
-                 world=1, rank=None, node_l2g=None, elem_l2g=None, force_exchange="allgather", **params):
+                 world=1, rank=None, node_l2g=None, elem_l2g=None, force_exchange="allreduce", **params):
         self.setup = setup
         if sum_mass and neighbors:
             # interface nodes: add the neighbour's partial lumped mass (J2:201-215 summed over ALL elements)
@@ -379,7 +432,7 @@ class SlabRunner:
         self.nElement = model.nElement
 
     @classmethod
-    def from_domain(cls, engine_cls, dom: LocalDomain, torch_device, world, force_exchange="allgather", **params):
+    def from_domain(cls, engine_cls, dom: LocalDomain, torch_device, world, force_exchange="allreduce", **params):
         return cls(engine_cls, dom.setup, dom.neighbors, dom.halo_nodes, torch_device, contact=dom.contact,
                    world=world, rank=dom.rank, node_l2g=dom.node_l2g, elem_l2g=dom.elem_l2g,
                    force_exchange=force_exchange, **params)
@@ -523,7 +576,7 @@ class GhostRunner:
     """Engine + state exchange of one rank of a ghost-element partition: per step
     hk_step_begin (nodal update) -> hk_state_export -> send/recv -> hk_state_import -> hk_step_finish (elements)."""
 
-    def __init__(self, engine_cls, dom: GhostDomain, torch_device, world=None, force_exchange="allgather", **params):
+    def __init__(self, engine_cls, dom: GhostDomain, torch_device, world=None, force_exchange="allreduce", **params):
         import torch
         self.dom = dom
         self.engine = configure_engine(engine_cls, dom.setup, **params)

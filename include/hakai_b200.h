@@ -181,6 +181,12 @@ int hk_contact_pair_info(hk_engine* e, int64_t c, int64_t* nn_i, int64_t* nn_j, 
  * [2] contact candidate tests, [3] kernel launches, [4] steps run. */
 int hk_counters(hk_engine* e, int64_t out[8]);
 
+/* Cheap summary of the element state, reduced on the device (32 bytes cross the bus): what a driver needs to
+ * know the regime it is timing and how many elements are still alive, without downloading nip doubles.
+ *   out[0] live elements (element_flag == 1, J2:733); out[1] / out[2] min / max of integ_eq_plastic_strain over the
+ *   Gauss points of live elements; out[3] number of those Gauss points with eps > 0; out[4..7] = 0 (reserved). */
+int hk_state_summary(hk_engine* e, double out[8]);
+
 /* Per-kernel device timing with CUDA events on the engine's stream.
  *   kind: 0 contact, 1 nodal update (+assembly gather, BC, kinematics), 2 element, 3 other.
  * hk_profile(e, 1) enables/reset; hk_profile_read returns total ms and launch count per kind. */

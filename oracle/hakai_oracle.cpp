@@ -1055,6 +1055,25 @@ int hko_counters(hk_engine* e, int64_t out[8]) {
     return HK_OK;
 }
 
+// hk_state_summary twin: plain loops over the reference's arrays
+int hko_state_summary(hk_engine* e, double out[8]) {
+    if (!e || !e->finalized || !out) return fail(e, HK_ERR_STATE, "engine not finalised");
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+    bool any = false;
+    for (int64_t el = 0; el < e->nElement; ++el) {
+        if (e->element_flag[el] != 1) continue;
+        out[0] += 1.0;
+        for (int k = 0; k < 8; ++k) {
+            const double ep = e->integ_eq_plastic_strain[el * 8 + k];
+            if (!any || ep < out[1]) out[1] = ep;
+            if (!any || ep > out[2]) out[2] = ep;
+            any = true;
+            if (ep > 0.0) out[3] += 1.0;
+        }
+    }
+    return HK_OK;
+}
+
 int hko_profile(hk_engine*, int32_t) { return HK_OK; }
 int hko_profile_read(hk_engine*, double ms[4], int64_t launches[4]) {
     for (int i = 0; i < 4; ++i) { ms[i] = 0; launches[i] = 0; }

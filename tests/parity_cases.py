@@ -93,6 +93,31 @@ def case_fracture_block(engine_cls, n_steps=260):
     util.assert_states_close(a, b, 1e-8, STATE_KEYS, "fracture block")
 
 
+def case_state_summary(engine_cls):
+    """hk_state_summary (device-side reduction) against the oracle's plain loops and against the downloaded arrays,
+    before yield, in the plastic regime and after deletions."""
+    deck = util.distorted_block(nx=5, ny=4, nz=6, jitter=0.05, ductile=True, strain_per_step=4e-4)
+    st = prepare(deck.build_model())
+    o, g = util.make_pair(st, engine_cls, OracleEngine)
+    s0 = g.state_summary()
+    assert s0 == dict(live_elements=st.model.nElement, eps_min=0.0, eps_max=0.0, yielded_points=0)
+    t = 0
+    for n in (30, 120, 110):
+        o.step(t + 1, n)
+        g.step(t + 1, n)
+        t += n
+        a, b = o.state_summary(), g.state_summary()
+        d = g.download(fields=("integ_eq_plastic_strain", "element_flag"))
+        live = np.repeat(d["element_flag"] == 1, 8)
+        eps = d["integ_eq_plastic_strain"][live]
+        assert b["live_elements"] == int((d["element_flag"] == 1).sum()) == a["live_elements"]
+        assert b["eps_min"] == eps.min() and b["eps_max"] == eps.max() and b["yielded_points"] == int((eps > 0).sum())
+        assert a["yielded_points"] == b["yielded_points"]
+        assert abs(a["eps_max"] - b["eps_max"]) <= 1e-9 * max(a["eps_max"], 1e-30)
+    assert b["live_elements"] < st.model.nElement, "deck did not delete anything: test is vacuous"
+    assert b["eps_min"] > 0
+
+
 def case_node_output(engine_cls):
     """hk_node_output = cal_node_stress_strain (J2:3408-3486) on the device: bit-identical to the oracle's loop on an
     identical ip state (same summation orders), equal to the NumPy host twin up to summation order, and consistent

@@ -37,6 +37,10 @@ def test_bc_edge_cases():
     pc.case_bc_edge_cases(EmuEngine)
 
 
+def test_state_summary():
+    pc.case_state_summary(EmuEngine)
+
+
 def test_node_output():
     pc.case_node_output(EmuEngine)
 

@@ -154,9 +154,7 @@ def test_distributed_host_driver_frames_match_oracle_frames(world, tmp_path):
                 assert np.allclose(a[k], b[k], rtol=0, atol=1e-5 * scale), (os.path.basename(f), k, scale)
 
 
-# ---- built and verified on CPU ranks (tests/test_multi_gloo.py) but not yet run over NCCL: opt in with HK_RUN_UNVALIDATED=1
-_UNVALIDATED = os.environ.get("HK_RUN_UNVALIDATED") != "1"
-
+# ---- ghost-element partitions (first run over NCCL in round 2: profiles/r2_multi_nccl_n2.log)
 
 def _worker_ghost(rank, world, port, kind, q):
     sys.path.insert(0, ROOT)
@@ -189,7 +187,6 @@ def _worker_ghost(rank, world, port, kind, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_UNVALIDATED, reason="ghost-element partitions over NCCL: set HK_RUN_UNVALIDATED=1")
 @pytest.mark.parametrize("kind", ["fracture", "contact", "erosion"])
 def test_ghost_partitions_are_bit_identical_to_one_gpu(kind):
     """Two GPUs with ghost-element partitions vs ONE GPU running the same CUDA kernels: array_equal on every field."""

@@ -41,6 +41,10 @@ def test_bc_edge_cases():
     pc.case_bc_edge_cases(Engine)
 
 
+def test_state_summary():
+    pc.case_state_summary(Engine)
+
+
 def test_node_output():
     pc.case_node_output(Engine)
 

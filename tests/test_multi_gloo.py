@@ -626,3 +626,57 @@ def test_ghost_partition_with_contact_is_bit_identical(kind, world, exact):
                         ("eps", ref["integ_eq_plastic_strain"][ip]), ("stress", ref["integ_stress"][:, ip]),
                         ("flag", ref["element_flag"][a["elems"]])):
             assert np.array_equal(a[k], want), (kind, r, k)
+
+
+# ---- bench.py's N > 1 parity check (slab_parity_check) on CPU ranks ------------------------------------------------
+def _worker_parity_check(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.multi import slab_parity_check
+        from tests.emu.emu_engine import EmuEngine
+        res = slab_parity_check(EmuEngine, "cpu", rank, world, n_steps=30, nx=6, ny=5, nz_per_rank=3)
+        q.put((rank, res))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_parity_check_green_on_cpu_ranks(world):
+    """The check bench.py emits as `parity_check` at N > 1: slabs of ONE global jittered mesh (global-layer seeds) over
+    the halo exchange vs the same mesh unpartitioned — deleted set identical, fields <= 1e-10, shared layers bitwise."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_parity_check, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    r0 = res[0]
+    assert all(res[r] is None for r in range(1, world))
+    assert r0["ok"], r0
+    assert r0["n_ranks"] == world and r0["n_deleted"] > 0 and r0["interface_bitwise"] and r0["max_rel_err"] <= 1e-10
+
+
+def test_slab_jitter_is_a_function_of_the_global_layer():
+    """slab_deck: the slabs of an N-rank run tile exactly the mesh a single domain would build (per-rank
+    seeds and unjittered interface planes made the weak-scaling mesh one no single-domain run computes)."""
+    from hakai_fem_b200.mesh import StretchDeck
+    from hakai_fem_b200.multi import slab_deck
+    deck = StretchDeck(5, 4, 3, jitter=0.07, jitter_by_layer=True)
+    world = 3
+    whole, _ = StretchDeck(5, 4, 3 * world, jitter=0.07, jitter_by_layer=True).coord_elem()
+    per = 6 * 5
+    for r in range(world):
+        local, nbrs, halos = slab_deck(deck, r, world)
+        c, _ = local.coord_elem()
+        assert np.array_equal(c, whole[:, r * 3 * per:(r * 3 + 4) * per])
+    inner = whole[:, 3 * per:4 * per]                         # an interface plane: interior nodes ARE jittered
+    base, _ = StretchDeck(5, 4, 3 * world).coord_elem()
+    assert np.any(inner != base[:, 3 * per:4 * per])
