@@ -94,20 +94,50 @@ HK_HD long long hk_ip(const HkDev& d, int row, int k, long long e) {
     return ((t * 8 + k) * 14 + row) * d.TL + j;
 }
 
+struct HkPairDyn {               // current sizes of a pair's lists: device-resident, because exposed faces are
+    int nn_i, nn_j, nTri;        // appended on the device (hk_erode_kernel) without the host knowing
+    int n_bucket;                // power of two >= 2*nn_i (<= cap_bucket)
+};
+
 struct HkPairDev {               // one ordered contact pair (ContactTriangle, J2:72-78)
-    int nn_i, nn_j, nTri;
+    int i_instance, j_instance;  // 1-based instance ids (J2:272-354)
     int self;                    // i_instance == j_instance
+    int cap_i, cap_j, cap_tri, cap_bucket;   // allocated lengths (== initial sizes when the surface cannot erode)
     int* nodes_i;                // 0-based node ids (c_nodes_i)
     int* nodes_j;
     int* t0; int* t1; int* t2;   // c_triangles columns, 0-based node ids
     int* tele;                   // c_triangles_eleid, 0-based
     double young;
+    HkPairDyn* dyn;
+    unsigned char* in_i;         // [nNode] membership of c_nodes_i / c_nodes_j (erodible pairs only, else NULL)
+    unsigned char* in_j;
     // per-step work
     unsigned long long* bbox;    // 12 order-encoded doubles: min_i[3] max_i[3] min_j[3] max_j[3]
-    int* cell_i;                 // [3][nn_i] cell coordinates of the i nodes
-    int* head;                   // [n_bucket] bucket heads (linked lists), -1 = empty
-    int* next;                   // [nn_i]
-    int n_bucket;                // power of two
+    int* cell_i;                 // [3][cap_i] cell coordinates of the i nodes
+    int* head;                   // [cap_bucket] bucket heads (linked lists), -1 = empty
+    int* next;                   // [cap_i]
+};
+
+// exposed-face update on the device (A10, J2:767-804 + add_surface_triangle J2:2167-2245): static per-instance tables
+struct HkInstDev {
+    long long element_offset, nElement;   // engine elements [element_offset, element_offset + nElement)
+    int* surf;                   // [4][F] oriented face nodes (J2:1946-1992) as engine node ids (0-based), F = 6*nElement
+    int* feleid;                 // [F] engine element (0-based) of every face
+    int* twin;                   // [F] first face (in face-id order) of ANOTHER element with the same node set, or -1
+};
+
+struct HkErodeDev {              // everything hk_erode_kernel needs
+    int n_inst, n_pair;
+    HkInstDev* inst;
+    HkPairDev* pairs;            // device copy of the pair descriptors
+    unsigned short* einst;       // [nElement] 1-based instance of every element (0: none)
+    int* fresh;                  // elements deleted in the step that just ran, ascending id
+    int* fresh_count;
+    int* block_count;            // per 1024-element block: elements marked for deletion in this step
+    int* n_spec;                 // special-node table length / capacity, contact slots / capacity
+    int* n_slots;
+    int spec_cap, slot_cap;
+    int* overflow;               // set when a capacity would be exceeded (checked at hk_sync)
 };
 
 struct HkContactParams {
@@ -121,9 +151,12 @@ void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double 
                      cudaStream_t s);
 int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s);   // 0 or a CUDA error code
 void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s);
+// deletion pass of a step: elements the element kernel marked (flag 3) are listed in ascending id order (er != NULL),
+// their stress/strain zeroed (J2:742-756), and the faces they expose join the contact surfaces (er != NULL)
+void hk_launch_deletion_pass(const HkDev& d, const HkErodeDev* er, cudaStream_t s, long long* n_launch);
+void hk_launch_cacc_zero(const HkDev& d, const int* n_slots, int slot_cap, cudaStream_t s);
 void hk_launch_velo_from_rec(const HkDev& d, double d_time, cudaStream_t s);
 void hk_launch_gather_Q(const HkDev& d, double* Q_out, cudaStream_t s);
-void hk_launch_flush_deleted(const HkDev& d, cudaStream_t s);
 void hk_launch_nodes_export(const HkDev& d, const int* nodes, long long n, double* out, cudaStream_t s);
 void hk_launch_nodes_import(const HkDev& d, const int* nodes, const long long* src, long long n, const double* in, cudaStream_t s);
 void hk_launch_cacc_export(const HkDev& d, const int* nodes, long long n, unsigned long long* out, cudaStream_t s);

@@ -115,12 +115,12 @@ HK_D void element_finish(const ElemArgs& A, long long e, const HexModes& X, cons
     if (acc.negj) hk_atomic_add_u64(&d.counters[0], (unsigned long long)acc.negj);
 }
 
+// deletion (J2:733-756): the element is only MARKED here (flag 3) and logged; hk_launch_deletion_pass, which follows
+// every element kernel in stream order, zeroes its stress/strain (in the ring kernels the rows are still in flight in
+// bulk stores at this point), lists the step's deletions in ascending order and updates the contact surfaces
 HK_D void element_delete(const ElemArgs& A, long long e) {
     const HkDev& d = A.d;
-    d.flag[e] = 0;
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k)
-        for (int r = 0; r < 12; ++r) d.ips[hk_ip(d, r, k, e)] = 0.0;
+    d.flag[e] = 3;
     const int slot = hk_atomic_add_i32(d.del_count, 1);
     if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
 }
@@ -531,13 +531,7 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
             tmem_load_modes(tX, X);
             if (live) {
                 element_finish(A, e, X, acc, V);
-                if (ductile_check(*Mt, acc.v_e, acc.t_e)) {
-                    // the state rows of this element are still in flight in bulk stores: only mark it here,
-                    // hk_launch_flush_deleted zeroes stress/strain after this kernel (stream order)
-                    d.flag[e] = 3;
-                    const int slot = hk_atomic_add_i32(d.del_count, 1);
-                    if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
-                }
+                if (ductile_check(*Mt, acc.v_e, acc.t_e)) element_delete(A, e);
             }
         }
     }
@@ -604,17 +598,6 @@ int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStrea
     for (long long e = 0; e < d.nElement; ++e) element_body_simple(A, e);
     return 0;
 #endif
-}
-
-// zero stress/strain of elements the TMA kernel marked for deletion (flag 3 -> 0), J2:742-756
-void hk_launch_flush_deleted(const HkDev& dd, cudaStream_t s) {
-    const HkDev d = dd;
-    hk_parallel_for(d.nElement, s, HK_LAMBDA(long long e) {
-        if (d.flag[e] != 3) return;
-        for (int k = 0; k < 8; ++k)
-            for (int r = 0; r < 12; ++r) d.ips[hk_ip(d, r, k, e)] = 0.0;
-        d.flag[e] = 0;
-    });
 }
 
 // integ_triax_stress recomputed from the current stress (used when no step has written it yet)

@@ -47,11 +47,16 @@ struct InstanceH {
 };
 struct PairH {
     int64_t i_instance, j_instance;
-    std::vector<int> nodes_i, nodes_j, t0, t1, t2, tele;   // 0-based
+    std::vector<int> nodes_i, nodes_j, t0, t1, t2, tele;   // 0-based; mirror of the device lists (see contact_refresh_host)
     std::unordered_set<int> set_i, set_j;
     double young;
     HkPairDev dev;
     bool dev_valid = false;
+};
+struct InstDevH {                   // device tables of one instance for hk_erode_kernel
+    int* surf = nullptr;
+    int* feleid = nullptr;
+    int* twin = nullptr;
 };
 struct HaloNbr {
     std::vector<int> nodes;        // local 0-based node ids
@@ -96,6 +101,13 @@ struct hk_engine {
     std::vector<int> node_list[5];
     int* d_node_list[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     long long* d_import_src = nullptr;
+    // exposed-face update on the device (single-domain engines whose contact surfaces can erode)
+    bool dev_erosion = false;      // tables built, hk_erode_kernel runs after every step
+    bool erosion_checked = false;  // decided at the first step (multi-GPU drivers call hk_set_global_maps after finalize)
+    bool contact_host_stale = false;   // device lists may have grown since the host mirrors were read
+    std::vector<char> inst_erodes; // per instance: has surfaces and an element whose material can fail
+    std::vector<InstDevH> inst_dev;
+    HkErodeDev er;
     bool contact_done = false;     // hk_contact_enqueue already ran the contact pass of the next step
     bool frame_next = false;       // hk_mark_frame: the next asynchronous step stores integ_triax_stress
     // multi-GPU erosion: instance tables are GLOBAL; these map global (1-based) ids to engine-local 0-based ids or -1
@@ -221,38 +233,64 @@ static void cal_Pusai_hexa(double P[8][3][8]) {
 }
 
 // --------------------------------------------------------------------------------- contact pair device arrays
+static bool inst_can_erode(const hk_engine* e, int64_t inst) {
+    return e->dev_erosion && inst >= 1 && inst <= (int64_t)e->inst_erodes.size() && e->inst_erodes[inst - 1];
+}
+
+// (re)creates the device arrays of a pair from the host mirrors.  With device-side erosion the lists are allocated at
+// their worst-case length (every node of an eroding instance exposed, two triangles per face of its elements), so
+// hk_erode_kernel can append without the host.
 static int pair_upload(hk_engine* e, PairH& p) {
     HkPairDev& D = p.dev;
     if (p.dev_valid) {
         dfree(e, D.nodes_i); dfree(e, D.nodes_j); dfree(e, D.t0); dfree(e, D.t1); dfree(e, D.t2); dfree(e, D.tele);
-        dfree(e, D.bbox); dfree(e, D.cell_i); dfree(e, D.head); dfree(e, D.next);
+        dfree(e, D.bbox); dfree(e, D.cell_i); dfree(e, D.head); dfree(e, D.next); dfree(e, D.dyn);
+        dfree(e, D.in_i); dfree(e, D.in_j);
         p.dev_valid = false;
     }
-    D.nn_i = (int)p.nodes_i.size();
-    D.nn_j = (int)p.nodes_j.size();
-    D.nTri = (int)p.t0.size();
+    std::memset(&D, 0, sizeof(D));
+    const int nn_i = (int)p.nodes_i.size(), nn_j = (int)p.nodes_j.size(), nTri = (int)p.t0.size();
+    D.i_instance = (int)p.i_instance; D.j_instance = (int)p.j_instance;
     D.self = p.i_instance == p.j_instance;
     D.young = p.young;
-    int nb = 64;
-    while (nb < 2 * D.nn_i) nb <<= 1;
-    D.n_bucket = nb;
+    const bool ei = inst_can_erode(e, p.i_instance), ej = inst_can_erode(e, p.j_instance);
+    long long cap_i = nn_i, cap_j = nn_j, cap_tri = nTri;
+    if (ei) cap_i += e->instances[p.i_instance - 1].nNode;
+    if (ej && !D.self) { cap_j += e->instances[p.j_instance - 1].nNode; cap_tri += 12 * e->instances[p.j_instance - 1].nElement; }
+    if (cap_i >= (1ll << 30) || cap_j >= (1ll << 30) || cap_tri >= (1ll << 31) - 1) return fail(e, HK_ERR_UNSUPPORTED, "contact pair too large");
+    D.cap_i = (int)cap_i; D.cap_j = (int)cap_j; D.cap_tri = (int)cap_tri;
+    auto pow2 = [](long long n) { int nb = 64; while (nb < 2 * n) nb <<= 1; return nb; };
+    D.cap_bucket = pow2(cap_i);
     int rc;
-    if ((rc = dalloc(e, &D.nodes_i, (size_t)D.nn_i))) return rc;
-    if ((rc = dalloc(e, &D.nodes_j, (size_t)D.nn_j))) return rc;
-    if ((rc = dalloc(e, &D.t0, (size_t)D.nTri))) return rc;
-    if ((rc = dalloc(e, &D.t1, (size_t)D.nTri))) return rc;
-    if ((rc = dalloc(e, &D.t2, (size_t)D.nTri))) return rc;
-    if ((rc = dalloc(e, &D.tele, (size_t)D.nTri))) return rc;
+    if ((rc = dalloc(e, &D.nodes_i, (size_t)D.cap_i))) return rc;
+    if ((rc = dalloc(e, &D.nodes_j, (size_t)D.cap_j))) return rc;
+    if ((rc = dalloc(e, &D.t0, (size_t)D.cap_tri))) return rc;
+    if ((rc = dalloc(e, &D.t1, (size_t)D.cap_tri))) return rc;
+    if ((rc = dalloc(e, &D.t2, (size_t)D.cap_tri))) return rc;
+    if ((rc = dalloc(e, &D.tele, (size_t)D.cap_tri))) return rc;
     if ((rc = dalloc(e, &D.bbox, (size_t)12))) return rc;
-    if ((rc = dalloc(e, &D.cell_i, (size_t)3 * D.nn_i))) return rc;
-    if ((rc = dalloc(e, &D.head, (size_t)nb))) return rc;
-    if ((rc = dalloc(e, &D.next, (size_t)D.nn_i))) return rc;
+    if ((rc = dalloc(e, &D.cell_i, (size_t)3 * D.cap_i))) return rc;
+    if ((rc = dalloc(e, &D.head, (size_t)D.cap_bucket))) return rc;
+    if ((rc = dalloc(e, &D.next, (size_t)D.cap_i))) return rc;
+    if ((rc = dalloc(e, &D.dyn, (size_t)1))) return rc;
     if ((rc = upload(e, D.nodes_i, p.nodes_i))) return rc;
     if ((rc = upload(e, D.nodes_j, p.nodes_j))) return rc;
     if ((rc = upload(e, D.t0, p.t0))) return rc;
     if ((rc = upload(e, D.t1, p.t1))) return rc;
     if ((rc = upload(e, D.t2, p.t2))) return rc;
     if ((rc = upload(e, D.tele, p.tele))) return rc;
+    const HkPairDyn dyn = {nn_i, nn_j, nTri, pow2(nn_i)};
+    CK(hkp::h2d(D.dyn, &dyn, sizeof(dyn), e->stream));
+    if (ei || ej) {                                   // membership bytes for the device-side `unique!` (J2:786, 791)
+        std::vector<unsigned char> in(e->nNode, 0);
+        for (int n : p.nodes_i) in[n] = 1;
+        if ((rc = dalloc(e, &D.in_i, (size_t)e->nNode))) return rc;
+        if ((rc = upload(e, D.in_i, in))) return rc;
+        std::fill(in.begin(), in.end(), 0);
+        for (int n : p.nodes_j) in[n] = 1;
+        if ((rc = dalloc(e, &D.in_j, (size_t)e->nNode))) return rc;
+        if ((rc = upload(e, D.in_j, in))) return rc;
+    }
     p.dev_valid = true;
     return 0;
 }
@@ -302,8 +340,15 @@ static int spec_upload(hk_engine* e, const std::vector<int>* touched_nodes) {
         rc = upload(e, e->d.spec_idx, e->spec_idx_h);
         if (rc) return rc;
     }
+    if (e->dev_erosion) {                     // lengths live on the device in this mode
+        const int ns_h = (int)e->spec_h.size(), nl_h = e->n_contact_slots;
+        CK(hkp::h2d(e->er.n_spec, &ns_h, sizeof(int), e->stream));
+        CK(hkp::h2d(e->er.n_slots, &nl_h, sizeof(int), e->stream));
+    }
     return 0;
 }
+
+static int erosion_upload_descriptors(hk_engine* e);
 
 // --------------------------------------------------------------------------------- exposed faces (A10)
 static void build_face_table(InstanceH& I) {
@@ -394,14 +439,209 @@ static int update_surfaces(hk_engine* e, const std::vector<int64_t>& deleted) {
             }
         }
     }
+    bool any_changed = false;
     for (size_t c = 0; c < e->pairs.size(); ++c)
-        if (changed[c]) { int rc = pair_upload(e, e->pairs[c]); if (rc) return rc; }
+        if (changed[c]) { int rc = pair_upload(e, e->pairs[c]); if (rc) return rc; any_changed = true; }
     if (!touched.empty()) { int rc = spec_upload(e, &touched); if (rc) return rc; }
+    if (any_changed && e->dev_erosion) { int rc = erosion_upload_descriptors(e); if (rc) return rc; }
+    return 0;
+}
+
+// ---- exposed faces on the device --------------------------------------------------------------------------------
+// twin[f]: the face add_surface_triangle (J2:2167-2245) would find for face f of a deleted element — the first face, in
+// face-id order, of ANOTHER element with the same node set — or -1.  Sort-based: faces are ordered by (hash of the
+// sorted node 4-tuple, face id); equal tuples are adjacent, hash collisions are resolved by comparing the tuples.
+static void build_twin_table(const InstanceH& I, std::vector<int>& twin) {
+    const int64_t F = 6 * I.nElement;
+    struct Rec { uint64_t key; int64_t face; };
+    std::vector<Rec> rec(F);
+    std::vector<std::array<int64_t, 4>> tup(F);
+    for (int64_t j = 0; j < F; ++j) {
+        std::array<int64_t, 4> k = {I.surfaces[j], I.surfaces[j + F], I.surfaces[j + 2 * F], I.surfaces[j + 3 * F]};
+        std::sort(k.begin(), k.end());
+        tup[j] = k;
+        uint64_t h = 0x9e3779b97f4a7c15ull;
+        for (int a = 0; a < 4; ++a) { h ^= (uint64_t)k[a] + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); h *= 0xff51afd7ed558ccdull; }
+        rec[j] = {h, j};
+    }
+    std::sort(rec.begin(), rec.end(), [](const Rec& a, const Rec& b) { return a.key != b.key ? a.key < b.key : a.face < b.face; });
+    twin.assign(F, -1);
+    for (int64_t lo = 0; lo < F;) {
+        int64_t hi = lo + 1;
+        while (hi < F && rec[hi].key == rec[lo].key) ++hi;
+        if (hi - lo > 1)
+            for (int64_t a = lo; a < hi; ++a) {
+                const int64_t f = rec[a].face;
+                for (int64_t b = lo; b < hi; ++b) {           // ascending face id
+                    const int64_t k = rec[b].face;
+                    if (I.eleid[k] == I.eleid[f] || tup[k] != tup[f]) continue;
+                    twin[f] = (int)k;
+                    break;
+                }
+            }
+        lo = hi;
+    }
+}
+
+static int erosion_upload_descriptors(hk_engine* e) {
+    std::vector<HkPairDev> pd;
+    for (const PairH& p : e->pairs) pd.push_back(p.dev);
+    return upload(e, e->er.pairs, pd);
+}
+
+// Decided at the first step: a single-domain engine (no hk_set_global_maps) with contact and a material that can fail
+// keeps its contact surfaces current on the device.  Builds the per-instance twin tables, re-creates the pair lists
+// at worst-case capacity and moves the special-node / accumulator bookkeeping to device counters.
+static int ensure_erosion(hk_engine* e) {
+    if (e->erosion_checked) return 0;
+    e->erosion_checked = true;
+    const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
+    if (!contact_on || !e->any_ductile || !e->g_node_map.empty()) return 0;
+    const size_t nI = e->instances.size();
+    if (nI == 0 || nI >= 65535) return 0;
+    std::vector<char> used(nI, 0);
+    for (const PairH& p : e->pairs) {
+        if (p.i_instance >= 1 && p.i_instance <= (int64_t)nI) used[p.i_instance - 1] = 1;
+        if (p.j_instance >= 1 && p.j_instance <= (int64_t)nI) used[p.j_instance - 1] = 1;
+    }
+    e->inst_erodes.assign(nI, 0);
+    bool any = false;
+    for (int64_t el = 0; el < e->nElement; ++el) {
+        const int64_t inst = e->einst[el];
+        if (inst < 1 || inst > (int64_t)nI || !used[inst - 1] || e->instances[inst - 1].surfaces.empty()) continue;
+        if (e->materials[e->emat[el]].nd > 0) { e->inst_erodes[inst - 1] = 1; any = true; }
+    }
+    if (!any) return 0;
+    int rc;
+    HkErodeDev& E = e->er;
+    std::memset(&E, 0, sizeof(E));
+    E.n_inst = (int)nI;
+    E.n_pair = (int)e->pairs.size();
+    e->inst_dev.assign(nI, InstDevH());
+    std::vector<HkInstDev> idv(nI);
+    long long extra_nodes = 0;
+    for (size_t i = 0; i < nI; ++i) {
+        const InstanceH& I = e->instances[i];
+        HkInstDev& D = idv[i];
+        std::memset(&D, 0, sizeof(D));
+        D.element_offset = I.element_offset;
+        D.nElement = I.nElement;
+        if (!e->inst_erodes[i]) continue;
+        if (I.element_offset < 0 || I.element_offset + I.nElement > e->nElement || I.node_offset < 0 ||
+            I.node_offset + I.nNode > e->nNode)
+            return fail(e, HK_ERR_ARG, "instance range outside the mesh");
+        const int64_t F = 6 * I.nElement;
+        std::vector<int> twin, surf((size_t)4 * F), fele(F);
+        build_twin_table(I, twin);
+        for (int64_t j = 0; j < 4 * F; ++j) {
+            const int64_t v = I.surfaces[j];
+            if (v < 1 || v > I.nNode) return fail(e, HK_ERR_ARG, "instance face node out of range");
+            surf[j] = (int)(v + I.node_offset - 1);
+        }
+        for (int64_t j = 0; j < F; ++j) {
+            const int64_t v = I.eleid[j];
+            if (v < 1 || v > I.nElement) return fail(e, HK_ERR_ARG, "instance face element out of range");
+            fele[j] = (int)(v + I.element_offset - 1);
+        }
+        InstDevH& H = e->inst_dev[i];
+        if ((rc = dalloc(e, &H.surf, surf.size()))) return rc;
+        if ((rc = dalloc(e, &H.feleid, fele.size()))) return rc;
+        if ((rc = dalloc(e, &H.twin, twin.size()))) return rc;
+        if ((rc = upload(e, H.surf, surf))) return rc;
+        if ((rc = upload(e, H.feleid, fele))) return rc;
+        if ((rc = upload(e, H.twin, twin))) return rc;
+        D.surf = H.surf; D.feleid = H.feleid; D.twin = H.twin;
+        extra_nodes += I.nNode;
+    }
+    if ((rc = dalloc(e, &E.inst, nI))) return rc;
+    if ((rc = upload(e, E.inst, idv))) return rc;
+    {
+        std::vector<unsigned short> ei(e->nElement);
+        for (int64_t el = 0; el < e->nElement; ++el) {
+            const int64_t v = e->einst[el];
+            ei[el] = (unsigned short)((v >= 1 && v <= (int64_t)nI) ? v : 0);
+        }
+        if ((rc = dalloc(e, &E.einst, ei.size()))) return rc;
+        if ((rc = upload(e, E.einst, ei))) return rc;
+    }
+    if ((rc = dalloc(e, &E.fresh, (size_t)e->nElement))) return rc;
+    if ((rc = dalloc(e, &E.fresh_count, (size_t)1))) return rc;
+    if ((rc = dalloc(e, &E.block_count, (size_t)((e->nElement + 1023) / 1024)))) return rc;
+    if ((rc = dalloc(e, &E.n_spec, (size_t)1))) return rc;
+    if ((rc = dalloc(e, &E.n_slots, (size_t)1))) return rc;
+    if ((rc = dalloc(e, &E.overflow, (size_t)1))) return rc;
+    if ((rc = dalloc(e, &E.pairs, e->pairs.size()))) return rc;
+    CK(hkp::dev_memset(E.fresh_count, 0, sizeof(int), e->stream));
+    CK(hkp::dev_memset(E.overflow, 0, sizeof(int), e->stream));
+    // special-node table and accumulators at worst-case capacity, lengths on the device from now on
+    e->dev_erosion = true;
+    E.spec_cap = (int)std::min<long long>((long long)e->spec_h.size() + extra_nodes, e->nNode);
+    E.slot_cap = (int)std::min<long long>((long long)e->n_contact_slots + extra_nodes, e->nNode);
+    {
+        HkSpecialNode* ns = nullptr;
+        unsigned long long* nc = nullptr;
+        if ((rc = dalloc(e, &ns, (size_t)E.spec_cap))) return rc;
+        if ((rc = dalloc(e, &nc, (size_t)E.slot_cap * 6))) return rc;
+        dfree(e, e->d.spec);
+        dfree(e, e->d.cacc);
+        e->d.spec = ns; e->d.cacc = nc;
+        e->spec_cap = (size_t)E.spec_cap;
+        e->cacc_cap = (size_t)E.slot_cap;
+        if ((rc = upload(e, e->d.spec, e->spec_h))) return rc;
+        CK(hkp::dev_memset(e->d.cacc, 0, (size_t)E.slot_cap * 6 * sizeof(unsigned long long), e->stream));
+        const int ns_h = (int)e->spec_h.size(), nl_h = e->n_contact_slots;
+        CK(hkp::h2d(E.n_spec, &ns_h, sizeof(int), e->stream));
+        CK(hkp::h2d(E.n_slots, &nl_h, sizeof(int), e->stream));
+    }
+    for (PairH& p : e->pairs) if ((rc = pair_upload(e, p))) return rc;
+    return erosion_upload_descriptors(e);
+}
+
+// Host mirrors of everything hk_erode_kernel may have grown: pair lists, special-node table, slot count.
+static int contact_refresh_host(hk_engine* e) {
+    if (!e->dev_erosion || !e->contact_host_stale) return 0;
+    CK(hkp::sync(e->stream));
+    bool grew = false;
+    for (PairH& p : e->pairs) {
+        HkPairDyn dyn;
+        CK(hkp::d2h(&dyn, p.dev.dyn, sizeof(dyn), e->stream));
+        auto tail = [&](std::vector<int>& v, const int* dev, int n) -> int {
+            const size_t old = v.size();
+            if ((size_t)n <= old) return 0;
+            v.resize(n);
+            grew = true;
+            return hkp::d2h(v.data() + old, dev + old, ((size_t)n - old) * sizeof(int), e->stream);
+        };
+        const size_t oi = p.nodes_i.size(), oj = p.nodes_j.size();
+        CK(tail(p.nodes_i, p.dev.nodes_i, dyn.nn_i));
+        CK(tail(p.nodes_j, p.dev.nodes_j, dyn.nn_j));
+        CK(tail(p.t0, p.dev.t0, dyn.nTri));
+        CK(tail(p.t1, p.dev.t1, dyn.nTri));
+        CK(tail(p.t2, p.dev.t2, dyn.nTri));
+        CK(tail(p.tele, p.dev.tele, dyn.nTri));
+        for (size_t k = oi; k < p.nodes_i.size(); ++k) p.set_i.insert(p.nodes_i[k]);
+        for (size_t k = oj; k < p.nodes_j.size(); ++k) p.set_j.insert(p.nodes_j[k]);
+    }
+    if (grew) {
+        int ns = 0, nl = 0;
+        CK(hkp::d2h(&ns, e->er.n_spec, sizeof(int), e->stream));
+        CK(hkp::d2h(&nl, e->er.n_slots, sizeof(int), e->stream));
+        e->spec_h.resize(ns);
+        CK(hkp::d2h(e->spec_h.data(), e->d.spec, (size_t)ns * sizeof(HkSpecialNode), e->stream));
+        CK(hkp::d2h(e->spec_idx_h.data(), e->d.spec_idx, e->spec_idx_h.size() * sizeof(int), e->stream));
+        e->n_contact_slots = nl;
+    }
+    e->contact_host_stale = false;
     return 0;
 }
 
 // fetch deletion log entries [del_seen, count) -> sorted (step, id), appended to deleted_all
 static int fetch_deleted(hk_engine* e, std::vector<int64_t>* fresh) {
+    if (e->dev_erosion) {
+        int ovf = 0;
+        CK(hkp::d2h(&ovf, e->er.overflow, sizeof(int), e->stream));
+        if (ovf) return fail(e, HK_ERR_STATE, "contact surface grew beyond its device capacity");
+    }
     int count = 0;
     CK(hkp::d2h(&count, e->d.del_count, sizeof(int), e->stream));
     if (count > e->d.del_cap) count = e->d.del_cap;
@@ -833,14 +1073,16 @@ int HKAPI(finalize)(hk_engine* e) {
 // nodes); phase 2: the rest (received partials, interface nodes, element kernel).
 static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end, int phase) {
     if (phase != 1 && e->frame_next && n_steps > 0) { frame_at_end = true; e->frame_next = false; }
-    const HkDev& d = e->d;
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
+    if (n_steps > 0) { int rc = ensure_erosion(e); if (rc) return rc; }
+    const HkDev& d = e->d;
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
         if (phase != 2 && contact_on && e->contact_done) {
             e->contact_done = false;             // done by hk_contact_enqueue (+ force exchange) for this step
         } else if (phase != 2 && contact_on) {
             prof_begin(e, 0);
-            CK(hkp::dev_memset(d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
+            if (e->dev_erosion) hk_launch_cacc_zero(d, e->er.n_slots, e->er.slot_cap, e->stream);
+            else CK(hkp::dev_memset(d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
             for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 4; }
             prof_end(e);
         }
@@ -875,14 +1117,17 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
         CK(hk_launch_element(d, t, (frame_at_end && t == t_first + n_steps - 1) ? 1 : 0, e->stream));
         prof_end(e);
         e->n_launch += 2;
-        if (e->any_ductile) { hk_launch_flush_deleted(d, e->stream); e->n_launch += 1; }
-        e->n_steps += 1;
-        if (contact_on && e->any_ductile && e->g_node_map.empty()) {      // multi-GPU: the host drives hk_apply_deleted
-            std::vector<int64_t> fresh;
-            int rc = fetch_deleted(e, &fresh);
-            if (rc) return rc;
-            if (!fresh.empty()) { rc = update_surfaces(e, fresh); if (rc) return rc; }
+        if (e->any_ductile) {
+            // marked elements: stress/strain zeroed; with contact their exposed faces join the surfaces ON THE DEVICE
+            // (multi-GPU engines: the host driver replays the all-gathered ids through hk_apply_deleted instead)
+            prof_begin(e, 3);
+            long long nl = 0;
+            hk_launch_deletion_pass(d, e->dev_erosion ? &e->er : nullptr, e->stream, &nl);
+            e->n_launch += nl;
+            prof_end(e);
+            if (e->dev_erosion) e->contact_host_stale = true;
         }
+        e->n_steps += 1;
     }
     if (n_steps > 0 && phase != 1) {
         e->velo_current = contact_on;
@@ -1140,6 +1385,7 @@ int HKAPI(deleted_ids)(hk_engine* e, int64_t* ids, int64_t cap, int64_t* n_out) 
 int HKAPI(contact_pair_info)(hk_engine* e, int64_t c, int64_t* nn_i, int64_t* nn_j, int64_t* nTri, int64_t* c_nodes_i,
                              int64_t* c_nodes_j, int64_t* c_triangles, int64_t* c_triangles_eleid) {
     if (!e || c < 0 || c >= (int64_t)e->pairs.size()) return fail(e, HK_ERR_ARG, "bad contact pair index");
+    { int rc = contact_refresh_host(e); if (rc) return rc; }
     const PairH& p = e->pairs[c];
     const int64_t nt = (int64_t)p.t0.size();
     if (nn_i) *nn_i = (int64_t)p.nodes_i.size();
@@ -1239,6 +1485,7 @@ int HKAPI(halo_pack)(hk_engine* e) {
 int HKAPI(set_node_list)(hk_engine* e, int32_t which, int64_t n, const int64_t* nodes) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     if (which < 0 || which > 4) return fail(e, HK_ERR_ARG, "bad list id");
+    { int rc = contact_refresh_host(e); if (rc) return rc; }
     std::vector<int>& L = e->node_list[which];
     L.resize(n);
     for (int64_t i = 0; i < n; ++i) {
@@ -1324,7 +1571,10 @@ int HKAPI(apply_deleted)(hk_engine* e, int64_t n, const int64_t* global_ids) {
     std::vector<int64_t> ids(global_ids, global_ids + n);
     for (int64_t g : ids)
         if (g < 1 || g > limit) return fail(e, HK_ERR_ARG, "element id out of range");
-    int rc = update_surfaces(e, ids);
+    int rc = global ? 0 : ensure_erosion(e);          // restart hook: the replay and later steps share one set of lists
+    if (rc) return rc;
+    if ((rc = contact_refresh_host(e))) return rc;
+    rc = update_surfaces(e, ids);
     if (rc) return rc;
     if (!global) {                       // restart of a single-domain run: the replayed ids are part of the history
         e->deleted_all.insert(e->deleted_all.end(), ids.begin(), ids.end());
@@ -1338,8 +1588,10 @@ int HKAPI(contact_enqueue)(hk_engine* e) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     if (!contact_on) return HK_OK;
+    { int rc = ensure_erosion(e); if (rc) return rc; }
     prof_begin(e, 0);
-    CK(hkp::dev_memset(e->d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
+    if (e->dev_erosion) hk_launch_cacc_zero(e->d, e->er.n_slots, e->er.slot_cap, e->stream);
+    else CK(hkp::dev_memset(e->d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
     for (PairH& p : e->pairs) { hk_launch_contact(e->d, p.dev, e->cp, e->stream); e->n_launch += 4; }
     prof_end(e);
     e->contact_done = true;

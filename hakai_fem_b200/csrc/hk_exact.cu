@@ -244,8 +244,8 @@ struct ContactArgs {
 #ifdef HK_EMU
 HK_HD void contact_bbox_body(const ContactArgs& A, long long t) {
     const HkPairDev& p = A.p;
-    const bool is_i = t < p.nn_i;
-    const int node = is_i ? p.nodes_i[t] : p.nodes_j[t - p.nn_i];
+    const bool is_i = t < p.dyn->nn_i;
+    const int node = is_i ? p.nodes_i[t] : p.nodes_j[t - p.dyn->nn_i];
     unsigned long long* bb = p.bbox + (is_i ? 0 : 6);
     for (int a = 0; a < 3; ++a) {
         unsigned long long e = enc_double(A.d.rec[6ll * node + a]);
@@ -287,9 +287,9 @@ HK_D void contact_cells_body(const ContactArgs& A, long long k) {
     int c[3];
     for (int a = 0; a < 3; ++a) c[a] = (int)ceil((A.d.rec[6ll * node + a] - b.all_min[a]) / ddiv);
     p.cell_i[k] = c[0];
-    p.cell_i[p.nn_i + k] = c[1];
-    p.cell_i[2ll * p.nn_i + k] = c[2];
-    unsigned h = cell_hash(c[0], c[1], c[2]) & (unsigned)(p.n_bucket - 1);
+    p.cell_i[p.cap_i + k] = c[1];
+    p.cell_i[2ll * p.cap_i + k] = c[2];
+    unsigned h = cell_hash(c[0], c[1], c[2]) & (unsigned)(p.dyn->n_bucket - 1);
     p.next[k] = hk_atomic_exch_i32(&p.head[h], (int)k);
 }
 
@@ -352,13 +352,14 @@ HK_D void contact_tri_body(const ContactArgs& A, long long j) {
         for (int q = 0; q < 8; ++q) en[q] = d.conn[(long long)q * d.nEp + eleid];
 
     unsigned long long n_tests = 0, n_hits = 0;
+    const unsigned bucket_mask = (unsigned)(p.dyn->n_bucket - 1);
     for (int dz = -1; dz <= 1; ++dz)
         for (int dy = -1; dy <= 1; ++dy)
             for (int dx = -1; dx <= 1; ++dx) {
                 const int ccx = cj[0] + dx, ccy = cj[1] + dy, ccz = cj[2] + dz;
-                const unsigned h = cell_hash(ccx, ccy, ccz) & (unsigned)(p.n_bucket - 1);
+                const unsigned h = cell_hash(ccx, ccy, ccz) & bucket_mask;
                 for (int k = p.head[h]; k >= 0; k = p.next[k]) {
-                    if (p.cell_i[k] != ccx || p.cell_i[p.nn_i + k] != ccy || p.cell_i[2ll * p.nn_i + k] != ccz) continue;
+                    if (p.cell_i[k] != ccx || p.cell_i[p.cap_i + k] != ccy || p.cell_i[2ll * p.cap_i + k] != ccz) continue;
                     const int i = p.nodes_i[k];
                     if (p.self) {
                         bool own = false;
@@ -415,71 +416,265 @@ HK_D void contact_tri_body(const ContactArgs& A, long long j) {
 }
 
 #ifndef HK_EMU
+// All contact kernels are grid-stride over list lengths that live on the device (HkPairDyn): the lists grow when
+// deleted elements expose new faces (hk_erode_kernel), and the host never has to know by how much.
 __global__ void hk_contact_bbox_kernel(ContactArgs A) {
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n = (long long)A.p.nn_i + A.p.nn_j;
-    // warp-level min/max first, one atomic set per (warp, side)
+    const long long nn_i = A.p.dyn->nn_i;
+    const long long n = nn_i + A.p.dyn->nn_j;
     const unsigned FULL = 0xffffffffu;
-    const bool valid = t < n;
-    const bool is_i = valid && t < A.p.nn_i;
-    unsigned long long mn[3], mx[3];
-    for (int a = 0; a < 3; ++a) { mn[a] = ~0ull; mx[a] = 0ull; }
-    if (valid) {
-        const int node = is_i ? A.p.nodes_i[t] : A.p.nodes_j[t - A.p.nn_i];
-        for (int a = 0; a < 3; ++a) mn[a] = mx[a] = enc_double(A.d.rec[6ll * node + a]);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long mn[2][3], mx[2][3];           // [side][axis] running min / max of this thread
+    for (int sd = 0; sd < 2; ++sd)
+        for (int a = 0; a < 3; ++a) { mn[sd][a] = ~0ull; mx[sd][a] = 0ull; }
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += stride) {
+        const int sd = t < nn_i ? 0 : 1;
+        const int node = sd == 0 ? A.p.nodes_i[t] : A.p.nodes_j[t - nn_i];
+        for (int a = 0; a < 3; ++a) {
+            const unsigned long long en = enc_double(A.d.rec[6ll * node + a]);
+            mn[sd][a] = en < mn[sd][a] ? en : mn[sd][a];
+            mx[sd][a] = en > mx[sd][a] ? en : mx[sd][a];
+        }
     }
-    // a warp may straddle the i/j boundary: reduce the two sides separately
-    for (int side = 0; side < 2; ++side) {
-        const bool mine = valid && (is_i == (side == 0));
-        const unsigned m = __ballot_sync(FULL, mine);
-        if (!m) continue;
-        unsigned long long smn[3], smx[3];
-        for (int a = 0; a < 3; ++a) { smn[a] = mine ? mn[a] : ~0ull; smx[a] = mine ? mx[a] : 0ull; }
+    // warp-level min/max (warp-shuffle reduction), then one atomic set per (warp, side)
+    for (int sd = 0; sd < 2; ++sd) {
         for (int off = 16; off; off >>= 1)
             for (int a = 0; a < 3; ++a) {
-                unsigned long long o1 = __shfl_xor_sync(FULL, smn[a], off);
-                unsigned long long o2 = __shfl_xor_sync(FULL, smx[a], off);
-                smn[a] = o1 < smn[a] ? o1 : smn[a];
-                smx[a] = o2 > smx[a] ? o2 : smx[a];
+                const unsigned long long o1 = __shfl_xor_sync(FULL, mn[sd][a], off);
+                const unsigned long long o2 = __shfl_xor_sync(FULL, mx[sd][a], off);
+                mn[sd][a] = o1 < mn[sd][a] ? o1 : mn[sd][a];
+                mx[sd][a] = o2 > mx[sd][a] ? o2 : mx[sd][a];
             }
-        if ((threadIdx.x & 31) == 0) {
-            unsigned long long* bb = A.p.bbox + (side == 0 ? 0 : 6);
-            for (int a = 0; a < 3; ++a) { atomicMin(&bb[a], smn[a]); atomicMax(&bb[3 + a], smx[a]); }
+        if ((threadIdx.x & 31) == 0 && mn[sd][0] != ~0ull) {
+            unsigned long long* bb = A.p.bbox + (sd == 0 ? 0 : 6);
+            for (int a = 0; a < 3; ++a) { atomicMin(&bb[a], mn[sd][a]); atomicMax(&bb[3 + a], mx[sd][a]); }
         }
     }
 }
 __global__ void hk_contact_cells_kernel(ContactArgs A) {
-    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (k < A.p.nn_i) contact_cells_body(A, k);
+    const long long n = A.p.dyn->nn_i, stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += stride) contact_cells_body(A, k);
 }
 __global__ void __launch_bounds__(128) hk_contact_narrow_kernel(ContactArgs A) {
-    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (j < A.p.nTri) contact_tri_body(A, j);
+    const long long n = A.p.dyn->nTri, stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += stride) contact_tri_body(A, j);
 }
 __global__ void hk_contact_reset_kernel(HkPairDev p) {
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t < p.n_bucket) p.head[t] = -1;
-    if (t < 12) p.bbox[t] = ((t % 6) < 3) ? ~0ull : 0ull;
+    const long long n = p.dyn->n_bucket, stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += stride) p.head[t] = -1;
+    if (blockIdx.x == 0 && threadIdx.x < 12) p.bbox[threadIdx.x] = ((threadIdx.x % 6) < 3) ? ~0ull : 0ull;
+}
+static unsigned contact_grid(long long cap, int block, int n_sm) {
+    long long g = (cap + block - 1) / block, mx = (long long)(n_sm > 0 ? n_sm : 148) * 32;
+    if (g > mx) g = mx;                     // larger lists: grid-stride
+    return (unsigned)(g < 1 ? 1 : g);
 }
 #endif
 
 void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s) {
-    if (p.nn_i == 0 || p.nn_j == 0 || p.nTri == 0) return;
+    if (p.cap_i == 0 || p.cap_j == 0 || p.cap_tri == 0) return;
     ContactArgs A{d, p, cp};
 #ifndef HK_EMU
-    const int B = 128;
-    long long nr = p.n_bucket > 12 ? p.n_bucket : 12;
-    hk_contact_reset_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(p);
-    long long nb = (long long)p.nn_i + p.nn_j;
-    hk_contact_bbox_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(A);
-    hk_contact_cells_kernel<<<(unsigned)((p.nn_i + 255) / 256), 256, 0, s>>>(A);
-    hk_contact_narrow_kernel<<<(unsigned)((p.nTri + B - 1) / B), B, 0, s>>>(A);
+    hk_contact_reset_kernel<<<contact_grid(p.cap_bucket, 256, d.n_sm), 256, 0, s>>>(p);
+    hk_contact_bbox_kernel<<<contact_grid((long long)p.cap_i + p.cap_j, 256, d.n_sm), 256, 0, s>>>(A);
+    hk_contact_cells_kernel<<<contact_grid(p.cap_i, 256, d.n_sm), 256, 0, s>>>(A);
+    hk_contact_narrow_kernel<<<contact_grid(p.cap_tri, 128, d.n_sm), 128, 0, s>>>(A);
 #else
-    for (int t = 0; t < p.n_bucket; ++t) p.head[t] = -1;
+    for (int t = 0; t < p.dyn->n_bucket; ++t) p.head[t] = -1;
     for (int t = 0; t < 12; ++t) p.bbox[t] = ((t % 6) < 3) ? ~0ull : 0ull;
-    for (long long t = 0; t < (long long)p.nn_i + p.nn_j; ++t) contact_bbox_body(A, t);
-    for (long long k = 0; k < p.nn_i; ++k) contact_cells_body(A, k);
-    for (long long j = 0; j < p.nTri; ++j) contact_tri_body(A, j);
+    for (long long t = 0; t < (long long)p.dyn->nn_i + p.dyn->nn_j; ++t) contact_bbox_body(A, t);
+    for (long long k = 0; k < p.dyn->nn_i; ++k) contact_cells_body(A, k);
+    for (long long j = 0; j < p.dyn->nTri; ++j) contact_tri_body(A, j);
+#endif
+}
+
+// zero the contact-force accumulators in use (their number grows on the device with the contact surface)
+void hk_launch_cacc_zero(const HkDev& dd, const int* n_slots, int slot_cap, cudaStream_t s) {
+    const HkDev d = dd;
+#ifndef HK_EMU
+    const long long cap = (long long)slot_cap * 6;
+    long long grid = (cap + 255) / 256, mx = (long long)(d.n_sm > 0 ? d.n_sm : 148) * 16;
+    if (grid > mx) grid = mx;
+    if (grid < 1) return;
+    hk_generic_kernel<<<(unsigned)grid, 256, 0, s>>>(grid * 256, HK_LAMBDA(long long t) {
+        const long long n = (long long)(*n_slots) * 6, stride = (long long)gridDim.x * blockDim.x;
+        for (long long i = t; i < n; i += stride) d.cacc[i] = 0ull;
+    });
+#else
+    (void)slot_cap; (void)s;
+    for (long long i = 0; i < (long long)(*n_slots) * 6; ++i) d.cacc[i] = 0ull;
+#endif
+}
+
+// ------------------------------------------------------------------ deletion pass + exposed faces on the device (A9/A10)
+// Step 1 (count): per block of HK_DEL_BLOCK elements, how many the element kernel marked for deletion (flag 3).
+// Step 2 (emit):  blocks holding marks write their elements to `fresh` in ASCENDING id order (offset = sum of the
+//                 counts of the blocks before: read only by the few blocks that have marks), zero stress/strain
+//                 (J2:742-756) and set flag 0.
+// Step 3 (erode): ONE thread replays the reference's serial loop J2:767-804 over `fresh`: for each face of a deleted
+//                 element the twin face (precomputed at hk_finalize) becomes two master triangles of every pair whose
+//                 j instance is the element's instance, and its nodes join c_nodes_i / c_nodes_j, in the reference's
+//                 order.  Deletions per step are few, the replay is inherently ordered, and nothing leaves the device.
+#define HK_DEL_BLOCK 1024
+
+HK_HD void flush_element(const HkDev& d, long long e) {
+    for (int k = 0; k < 8; ++k)
+        for (int r = 0; r < 12; ++r) d.ips[hk_ip(d, r, k, e)] = 0.0;
+    d.flag[e] = 0;
+}
+
+HK_HD void erode_contact_slot(const HkDev& d, const HkErodeDev& E, int node) {
+    int si = d.spec_idx[node];
+    if (si < 0) {
+        if (*E.n_spec >= E.spec_cap) { *E.overflow = 1; return; }
+        si = (*E.n_spec)++;
+        HkSpecialNode sn;
+        sn.bc_entry[0] = sn.bc_entry[1] = sn.bc_entry[2] = -1;
+        sn.contact_slot = -1; sn.halo_slot = -1; sn.pad = 0;
+        d.spec[si] = sn;
+        d.spec_idx[node] = si;
+    }
+    if (d.spec[si].contact_slot < 0) {
+        if (*E.n_slots >= E.slot_cap) { *E.overflow = 1; return; }
+        d.spec[si].contact_slot = (*E.n_slots)++;
+    }
+}
+
+// add_surface_triangle (J2:2167-2245) + the pair loop J2:778-801 for ONE deleted element
+HK_HD void erode_element(const HkDev& d, const HkErodeDev& E, int e) {
+    const int inst = E.einst[e];
+    if (inst < 1 || inst > E.n_inst) return;
+    const HkInstDev& I = E.inst[inst - 1];
+    if (!I.twin) return;
+    const long long F = 6 * I.nElement;
+    int tri[36], tele[12], nodes[24];
+    int nt = 0, nn = 0;
+    for (int j = 0; j < 6; ++j) {
+        const long long k = I.twin[6 * (e - I.element_offset) + j];
+        if (k < 0) continue;
+        const int s0 = I.surf[k], s1 = I.surf[k + F], s2 = I.surf[k + 2 * F], s3 = I.surf[k + 3 * F];
+        tri[3 * nt] = s0; tri[3 * nt + 1] = s1; tri[3 * nt + 2] = s2; tele[nt++] = I.feleid[k];
+        tri[3 * nt] = s2; tri[3 * nt + 1] = s3; tri[3 * nt + 2] = s0; tele[nt++] = I.feleid[k];
+        const int q[4] = {s0, s1, s2, s3};
+        for (int a = 0; a < 4; ++a) {                 // sorted unique insert (`nodes = unique(sort(tri))`)
+            int pos = 0;
+            while (pos < nn && nodes[pos] < q[a]) ++pos;
+            if (pos < nn && nodes[pos] == q[a]) continue;
+            for (int m = nn; m > pos; --m) nodes[m] = nodes[m - 1];
+            nodes[pos] = q[a];
+            ++nn;
+        }
+    }
+    if (nt == 0) return;
+    for (int c = 0; c < E.n_pair; ++c) {
+        const HkPairDev& p = E.pairs[c];
+        if (!p.in_i) continue;                        // this pair's surface cannot erode
+        HkPairDyn& D = *p.dyn;
+        if (p.i_instance == inst) {                   // J2:784-787
+            for (int m = 0; m < nn; ++m) {
+                const int g = nodes[m];
+                if (p.in_i[g]) continue;
+                if (D.nn_i >= p.cap_i) { *E.overflow = 1; continue; }
+                p.in_i[g] = 1;
+                p.nodes_i[D.nn_i++] = g;
+                erode_contact_slot(d, E, g);
+            }
+            while (D.n_bucket < 2 * D.nn_i && D.n_bucket < p.cap_bucket) D.n_bucket <<= 1;
+        } else if (p.j_instance == inst) {            // J2:789-797
+            for (int m = 0; m < nn; ++m) {
+                const int g = nodes[m];
+                if (p.in_j[g]) continue;
+                if (D.nn_j >= p.cap_j) { *E.overflow = 1; continue; }
+                p.in_j[g] = 1;
+                p.nodes_j[D.nn_j++] = g;
+                erode_contact_slot(d, E, g);
+            }
+            for (int r = 0; r < nt; ++r) {
+                if (D.nTri >= p.cap_tri) { *E.overflow = 1; break; }
+                const int o = D.nTri++;
+                p.t0[o] = tri[3 * r]; p.t1[o] = tri[3 * r + 1]; p.t2[o] = tri[3 * r + 2]; p.tele[o] = tele[r];
+            }
+        }
+    }
+}
+
+#ifndef HK_EMU
+__global__ void __launch_bounds__(256) hk_delete_count_kernel(HkDev d, HkErodeDev E) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const long long e0 = (long long)blockIdx.x * HK_DEL_BLOCK;
+    int mine = 0;
+    for (int i = threadIdx.x; i < HK_DEL_BLOCK; i += 256) {
+        const long long e = e0 + i;
+        if (e < d.nElement && d.flag[e] == 3) ++mine;
+    }
+    if (mine) atomicAdd(&cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) E.block_count[blockIdx.x] = cnt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *E.fresh_count = 0;
+}
+__global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, HkErodeDev E) {
+    const int mycount = E.block_count[blockIdx.x];
+    if (mycount == 0) return;
+    __shared__ int base, warp_tot[8];
+    __shared__ int red[256];
+    int part = 0;                                     // offset: marks in all blocks before this one
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 256) part += E.block_count[b];
+    red[threadIdx.x] = part;
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) base = red[0];
+    __syncthreads();
+    const long long e0 = (long long)blockIdx.x * HK_DEL_BLOCK;
+    int run = base;
+    for (int chunk = 0; chunk < HK_DEL_BLOCK; chunk += 256) {      // ordered compaction, 256 elements at a time
+        const long long e = e0 + chunk + threadIdx.x;
+        const bool m = e < d.nElement && d.flag[e] == 3;
+        const unsigned bal = __ballot_sync(0xffffffffu, m);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) warp_tot[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int i = 0; i < 8; ++i) { if (i < w) before += warp_tot[i]; total += warp_tot[i]; }
+        if (m) {
+            E.fresh[run + before + __popc(bal & ((1u << lane) - 1u))] = (int)e;
+            flush_element(d, e);
+        }
+        run += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(E.fresh_count, mycount);
+}
+__global__ void hk_erode_kernel(HkDev d, HkErodeDev E) {
+    const int n = *E.fresh_count;
+    for (int i = 0; i < n; ++i) erode_element(d, E, E.fresh[i]);
+}
+#endif
+
+void hk_launch_deletion_pass(const HkDev& dd, const HkErodeDev* er, cudaStream_t s, long long* n_launch) {
+    const HkDev d = dd;
+    if (!er) {                                       // no contact surface to update: zero the marked elements, any order
+        hk_parallel_for(d.nElement, s, HK_LAMBDA(long long e) { if (d.flag[e] == 3) flush_element(d, e); });
+        if (n_launch) *n_launch += 1;
+        return;
+    }
+    const HkErodeDev E = *er;
+#ifndef HK_EMU
+    const unsigned nb = (unsigned)((d.nElement + HK_DEL_BLOCK - 1) / HK_DEL_BLOCK);
+    hk_delete_count_kernel<<<nb, 256, 0, s>>>(d, E);
+    hk_delete_emit_kernel<<<nb, 256, 0, s>>>(d, E);
+    hk_erode_kernel<<<1, 1, 0, s>>>(d, E);
+    if (n_launch) *n_launch += 3;
+#else
+    (void)s; (void)n_launch;
+    int n = 0;
+    for (long long e = 0; e < d.nElement; ++e)
+        if (d.flag[e] == 3) { E.fresh[n++] = (int)e; flush_element(d, e); }
+    *E.fresh_count = n;
+    for (int i = 0; i < n; ++i) erode_element(d, E, E.fresh[i]);
 #endif
 }
 
@@ -999,9 +1194,7 @@ HK_D void element_body_exact(const ExactArgs& A, long long e) {
                     break;
                 }
             if (v_e >= fr_e) {
-                d.flag[e] = 0;
-                for (int k = 0; k < 8; ++k)
-                    for (int r = 0; r < 12; ++r) d.ips[hk_ip(d, r, k, e)] = 0.0;
+                d.flag[e] = 3;                     // zeroed by hk_launch_deletion_pass (stream order)
                 const int slot = hk_atomic_add_i32(d.del_count, 1);
                 if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
             }
