@@ -301,20 +301,16 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    live_steps, live = 0, s_start["live_elements"]
-    per_step_deleted = []
-    if kind == "ductile" and world == 1:
-        for t in range(t_next, t_next + args.steps):      # one call per step: the live count after every step is known
-            live_steps += live
-            eng.step_enqueue(t, 1)
-            nd = eng.sync()
-            live -= nd
-            per_step_deleted.append(int(nd))
-    else:
-        run_steps(t_next, args.steps)
-        live_steps = live * args.steps
+    run_steps(t_next, args.steps)
     ev1.record(stream)
     barrier()
+    # live element-steps: elements alive at the start of each timed step.  The steps were enqueued in ONE call; the step
+    # of every deletion comes from the engine's deletion log afterwards (hk_deleted_steps)
+    dsteps = eng.deleted_steps()
+    per_step_deleted = np.bincount(dsteps[dsteps >= t_next] - t_next, minlength=args.steps)[:args.steps]
+    live_before = s_start["live_elements"] - np.concatenate([[0], np.cumsum(per_step_deleted)[:-1]])
+    live_steps = int(live_before.sum())
+    per_step_deleted = [int(v) for v in per_step_deleted] if kind == "ductile" else []
     t_next += args.steps
     ms = ev0.elapsed_time(ev1)
     print(f"[rank {rank}] host enqueue time of the timed steps: {getattr(runner, 'last_enqueue_s', 0.0) * 1e3:.1f} ms "

@@ -72,6 +72,8 @@ struct HkDev {
                           // 12 eps (integ_eq_plastic_strain), 13 yield (integ_yield_stress): the 14 rows x TL
                           // elements of one Gauss point of one tile are ONE contiguous burst (14*TL*8 bytes)
     int element_mode;     // hk_params.element_mode (1: reference-order kernel)
+    int blocked;          // layout of Qe / conn, see hk_qe / hk_cn
+    int experiment;       // HK_EXPERIMENT (profiling builds only): 1 = "red"
     int variant;          // element-kernel variant (hk_element.cu: kVariants; 1 = simple kernel)
     int n_sm;             // multiprocessors of the engine's device (grid of the persistent kernels)
     int TL;               // layout tile = elements per tile of the element kernel in use; nEp % TL == 0
@@ -86,6 +88,20 @@ struct HkDev {
     unsigned long long* cacc;
     double* halo_recv;    // [n_halo*3]
 };
+
+// index of (row r of 24, element e) in HkDev::Qe and of (local node a, element e) in HkDev::conn.  blocked != 0: both are
+// tile-blocked like the ip state ([tile][24][TL], [tile][8][TL]) so that everything one tile of the element kernel
+// reads or writes is a handful of contiguous bursts; blocked == 0: plain SoA [24][nEp], [8][nEp] (round-1 layout, A/B)
+HK_HD long long hk_qe(const HkDev& d, int r, long long e) {
+    if (!d.blocked) return (long long)r * d.nEp + e;
+    const long long t = e / d.TL;
+    return (t * 24 + r) * d.TL + (e - t * d.TL);
+}
+HK_HD long long hk_cn(const HkDev& d, int a, long long e) {
+    if (!d.blocked) return (long long)a * d.nEp + e;
+    const long long t = e / d.TL;
+    return (t * 8 + a) * d.TL + (e - t * d.TL);
+}
 
 // index of (row, gauss point k, element e) in HkDev::ips
 HK_HD long long hk_ip(const HkDev& d, int row, int k, long long e) {
@@ -143,12 +159,19 @@ struct HkErodeDev {              // everything hk_erode_kernel needs
 struct HkContactParams {
     double d_lim, myu, kc_o, kc_s, cr_o, cr_s, ddiv_o, ddiv_s, d_time;
     int lsb_exp;                 // fixed-point LSB = 2^lsb_exp
+    // v0.0.1 penetration-rate clamp (hk_params.contact_dmax_clamp; J1:2756, 2898, 618): per contact slot the largest
+    // (clamped) penetration of this / the previous step, and d_max = max_n |d_disp_n| of the previous step as the bit
+    // pattern of a non-negative double (so that an integer atomicMax orders it)
+    int clamp;
+    double* dnode;
+    const double* dnode_pre;
+    const unsigned long long* dmax;
 };
 
 // launchers (hk_exact.cu: built with -fmad=false; hk_element.cu: FMA allowed)
 void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double dt2, double dt2p,
                      int lsb_exp, int contact_on, int use_Q0, int mode, const int* list, long long n_list,
-                     cudaStream_t s);
+                     unsigned long long* dmax_out, cudaStream_t s);   // dmax_out: NULL or max |d_disp| accumulator
 int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s);   // 0 or a CUDA error code
 void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s);
 // deletion pass of a step: elements the element kernel marked (flag 3) are listed in ascending id order (er != NULL),

@@ -20,6 +20,12 @@ struct ElemArgs {
     int write_triax;
     int fast;          // MatLite::fast
 };
+#ifndef HK_EMU
+#define HK_EXPERIMENT_RED 1      /* round-2 A/B only (HK_EXPERIMENT=red): cost of assembling by integer RED; not a product path */
+#endif
+#ifdef HK_EXPERIMENT_RED
+__device__ __forceinline__ bool getenv_red(const ElemArgs& A) { return A.fast == 3; }
+#endif
 
 HK_HD MatLite mat_lite(const HkMaterialDev* m) {
     MatLite l;
@@ -43,7 +49,7 @@ HK_D bool element_dead(const HkDev& d, long long e) {
     if (fl == 1) return false;
     if (fl == 0) {      // deleted during the previous step: its last force has been consumed, clear it
 #pragma unroll
-        for (int r = 0; r < 24; ++r) d.Qe[(long long)r * d.nEp + e] = 0.0;
+        for (int r = 0; r < 24; ++r) d.Qe[hk_qe(d, r, e)] = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) d.triax[(long long)k * d.nEp + e] = 0.0;   // zero stress -> triax 0 (J2:1012)
         d.flag[e] = 2;
@@ -55,7 +61,7 @@ HK_D void element_gather(const HkDev& d, long long e, HexModes& X, HexModes& U) 
     double x[8][3], du[8][3];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-        const long long n = d.conn[(long long)a * d.nEp + e];
+        const long long n = d.conn[hk_cn(d, a, e)];
 #if defined(__CUDA_ARCH__)
         const double2* r = reinterpret_cast<const double2*>(d.rec + 6 * n);
         const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
@@ -111,7 +117,7 @@ HK_D void element_finish(const ElemArgs& A, long long e, const HexModes& X, cons
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) d.Qe[(long long)(a * 3 + c) * d.nEp + e] = f[a][c];
+        for (int c = 0; c < 3; ++c) d.Qe[hk_qe(d, a * 3 + c, e)] = f[a][c];
     if (acc.negj) hk_atomic_add_u64(&d.counters[0], (unsigned long long)acc.negj);
 }
 
@@ -352,9 +358,13 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
                 const long long e0 = (vcta + it * n_v) * TLD;
                 unsigned long long* bar = &gcfull[it & 1];
                 mbar_expect_tx(bar, 8 * TLD * 4);
+                if (d.blocked) {                              // [tile][8][TL]: the tile's connectivity is ONE burst
+                    tma_load_1d(gconn + (it & 1) * 8 * TLD, d.conn + e0 * 8, 8 * TLD * 4, bar);
+                } else {
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
-                    tma_load_1d(gconn + ((it & 1) * 8 + a) * TLD, d.conn + (long long)a * d.nEp + e0, TLD * 4, bar);
+                    for (int a = 0; a < 8; ++a)
+                        tma_load_1d(gconn + ((it & 1) * 8 + a) * TLD, d.conn + (long long)a * d.nEp + e0, TLD * 4, bar);
+                }
             };
             auto issue_load = [&](long long q) {
                 const int st = (int)(q % S);
@@ -530,6 +540,23 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
             HexModes X;
             tmem_load_modes(tX, X);
             if (live) {
+#ifdef HK_EXPERIMENT_RED
+                if (CP && getenv_red(A)) {                   // experiment: fixed-point RED assembly instead of the Qe stores
+                    double G[3][3][3];
+                    adj_mode_sums(X, G);
+                    double f[8][3];
+                    element_forces(acc, G, acc.pdet / V, f);
+                    const int* ids = gconn + (it & 1) * 8 * TLD + gt;
+                    unsigned long long* Qf = reinterpret_cast<unsigned long long*>(d.Q0);
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        const long long n = ids[a * TLD];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            atomicAdd(&Qf[3 * n + c], (unsigned long long)__double2ll_rn(f[a][c] * 1.099511627776e12));
+                    }
+                } else
+#endif
                 element_finish(A, e, X, acc, V);
                 if (ductile_check(*Mt, acc.v_e, acc.t_e)) element_delete(A, e);
             }
@@ -562,12 +589,12 @@ struct RingVariant { int id, ng, wg, stages, cp; };
 static const RingVariant kVariants[] = {
     {11, 1, 11, 4, 0},      // round-1 kernel: one group of 11 warps (tile 352)
     {12, 1, 11, 4, 1},
-    {20, 2, 5, 4, 1},
-    {21, 2, 5, 5, 1},       // default
+    {20, 2, 5, 4, 1},       // default
+    {21, 2, 5, 5, 1},
     {22, 2, 5, 6, 0},
     {23, 2, 5, 5, 0},
 };
-#define HK_DEFAULT_VARIANT 21
+#define HK_DEFAULT_VARIANT 20
 
 int hk_element_variant_from_env() {
     const char* v = getenv("HK_ELEMENT_VARIANT");
@@ -581,6 +608,9 @@ int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStrea
     if (d.element_mode == 1) { hk_launch_element_exact(d, step, write_triax, s); return 0; }
     ElemArgs A{d, step, write_triax, 1};
 #ifndef HK_EMU
+#ifdef HK_EXPERIMENT_RED
+    if (d.experiment == 1) A.fast = 3;
+#endif
     switch (d.variant) {
         case 1: {
             const int block = 128;
@@ -619,7 +649,7 @@ void hk_launch_element_volume(const HkDev& dd, double* V_out, cudaStream_t s) {
     hk_parallel_for(d.nElement, s, HK_LAMBDA(long long e) {
         double x[8][3];
         for (int a = 0; a < 8; ++a) {
-            const long long n = d.conn[(long long)a * d.nEp + e];
+            const long long n = d.conn[hk_cn(d, a, e)];
             for (int c = 0; c < 3; ++c) x[a][c] = d.rec[6 * n + c];
         }
         HexModes X;

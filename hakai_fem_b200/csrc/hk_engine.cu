@@ -108,6 +108,11 @@ struct hk_engine {
     std::vector<char> inst_erodes; // per instance: has surfaces and an element whose material can fail
     std::vector<InstDevH> inst_dev;
     HkErodeDev er;
+    // v0.0.1 penetration clamp: d_node ping-pong [2][slot capacity], d_max ping-pong [2] (bit patterns), current index
+    double* d_dnode = nullptr;
+    unsigned long long* d_dmax = nullptr;
+    size_t dnode_cap = 0;
+    int clamp_cur = 0;
     bool contact_done = false;     // hk_contact_enqueue already ran the contact pass of the next step
     bool frame_next = false;       // hk_mark_frame: the next asynchronous step stores integ_triax_stress
     // multi-GPU erosion: instance tables are GLOBAL; these map global (1-based) ids to engine-local 0-based ids or -1
@@ -135,6 +140,7 @@ struct hk_engine {
     double* staging = nullptr;     // device staging for layout transposes
     size_t staging_doubles = 0;
     std::vector<int64_t> deleted_all;
+    std::vector<int64_t> deleted_step;          // step t of every entry of deleted_all (0: replayed by hk_apply_deleted)
     size_t deleted_reported = 0;
     int del_seen = 0;
     int64_t n_launch = 0, n_steps = 0;
@@ -652,6 +658,7 @@ static int fetch_deleted(hk_engine* e, std::vector<int64_t>* fresh) {
     for (long long v : ent) {
         int64_t id = (int64_t)(v & 0xffffffffll) + 1;
         e->deleted_all.push_back(id);
+        e->deleted_step.push_back((int64_t)(v >> 32));
         if (fresh) fresh->push_back(id);
     }
     e->del_seen = count;
@@ -835,6 +842,8 @@ int HKAPI(finalize)(hk_engine* e) {
     const int64_t nN = e->nNode, nE = e->nElement;
     HkDev& d = e->d;
     d.variant = hk_element_variant_from_env();
+    { const char* b = getenv("HK_LAYOUT_BLOCKED"); d.blocked = b ? atoi(b) : 1; }
+    { const char* x = getenv("HK_EXPERIMENT"); d.experiment = (x && strcmp(x, "red") == 0) ? 1 : 0; }
     d.n_sm = 1;
 #ifndef HK_EMU
     CK(cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, e->prm.device));
@@ -968,8 +977,9 @@ int HKAPI(finalize)(hk_engine* e) {
     // ---- elements
     {
         std::vector<int> conn_soa((size_t)8 * nEp, 0);
+        d.nEp = nEp; d.TL = (int)tile;                      // hk_cn needs them
         for (int64_t el = 0; el < nE; ++el)
-            for (int a = 0; a < 8; ++a) conn_soa[(size_t)a * nEp + el] = e->conn[8 * el + a];
+            for (int a = 0; a < 8; ++a) conn_soa[(size_t)hk_cn(d, a, el)] = e->conn[8 * el + a];
         if ((rc = dalloc(e, &d.conn, conn_soa.size()))) return rc;
         if ((rc = upload(e, d.conn, conn_soa))) return rc;
         std::vector<unsigned char> fl(nEp, 2);
@@ -1023,6 +1033,7 @@ int HKAPI(finalize)(hk_engine* e) {
         cp.ddiv_o = e->prm.element_max_size * e->prm.contact_ddiv_other;          // J2:2331
         cp.ddiv_s = e->prm.element_max_size * e->prm.contact_ddiv_self;           // J2:2333
         cp.d_time = dt;
+        cp.clamp = 0; cp.dnode = nullptr; cp.dnode_pre = nullptr; cp.dmax = nullptr;
         double ymax = 0;
         for (const PairH& p : e->pairs) ymax = std::max(ymax, p.young);
         const double nominal = ymax * e->prm.element_max_size * cp.d_lim * std::max(cp.kc_o, cp.kc_s);
@@ -1067,6 +1078,38 @@ int HKAPI(finalize)(hk_engine* e) {
     return HK_OK;
 }
 
+// contact pass of one step (A11 + the accumulator reset of A2): all ordered pairs on the engine's stream
+static int contact_pass(hk_engine* e) {
+    const HkDev& d = e->d;
+    prof_begin(e, 0);
+    if (e->dev_erosion) hk_launch_cacc_zero(d, e->er.n_slots, e->er.slot_cap, e->stream);
+    else CK(hkp::dev_memset(d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
+    if (e->prm.contact_dmax_clamp) {              // v0.0.1 clamp: d_node .= 0 (J1:492); d_node_pre / d_max are last step's
+        if (e->dnode_cap < e->cacc_cap) {
+            dfree(e, e->d_dnode);
+            e->d_dnode = nullptr;
+            int rc = dalloc(e, &e->d_dnode, 2 * e->cacc_cap);
+            if (rc) return rc;
+            e->dnode_cap = e->cacc_cap;
+            CK(hkp::dev_memset(e->d_dnode, 0, 2 * e->dnode_cap * sizeof(double), e->stream));
+        }
+        if (!e->d_dmax) {
+            int rc = dalloc(e, &e->d_dmax, (size_t)2);
+            if (rc) return rc;
+            CK(hkp::dev_memset(e->d_dmax, 0, 2 * sizeof(unsigned long long), e->stream));      // d_max = 0.0, J1:413
+        }
+        const int cur = e->clamp_cur;
+        e->cp.clamp = 1;
+        e->cp.dnode = e->d_dnode + (size_t)cur * e->dnode_cap;
+        e->cp.dnode_pre = e->d_dnode + (size_t)(1 - cur) * e->dnode_cap;
+        e->cp.dmax = e->d_dmax + cur;
+        CK(hkp::dev_memset(e->cp.dnode, 0, e->dnode_cap * sizeof(double), e->stream));
+    }
+    for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 4; }
+    prof_end(e);
+    return 0;
+}
+
 // enqueue the kernels of steps t_first .. t_first+n_steps-1 on the engine's stream (no host synchronisation
 // unless contact surfaces may change: exposed faces must be in place before the next contact pass).
 // phase 0: whole step; phase 1: everything that does not need the halo (contact + nodal update of non-interface
@@ -1074,22 +1117,26 @@ int HKAPI(finalize)(hk_engine* e) {
 static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end, int phase) {
     if (phase != 1 && e->frame_next && n_steps > 0) { frame_at_end = true; e->frame_next = false; }
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
+    if (e->prm.contact_dmax_clamp && (!e->halo.empty() || !e->g_node_map.empty()))
+        return fail(e, HK_ERR_UNSUPPORTED, "contact_dmax_clamp: d_max is a global maximum; single-domain engines only");
     if (n_steps > 0) { int rc = ensure_erosion(e); if (rc) return rc; }
     const HkDev& d = e->d;
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
         if (phase != 2 && contact_on && e->contact_done) {
             e->contact_done = false;             // done by hk_contact_enqueue (+ force exchange) for this step
         } else if (phase != 2 && contact_on) {
-            prof_begin(e, 0);
-            if (e->dev_erosion) hk_launch_cacc_zero(d, e->er.n_slots, e->er.slot_cap, e->stream);
-            else CK(hkp::dev_memset(d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
-            for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 4; }
-            prof_end(e);
+            int rc = contact_pass(e);
+            if (rc) return rc;
+        }
+        unsigned long long* dmax_out = nullptr;       // clamp: this step's max |d_disp| becomes the next step's d_max
+        if (contact_on && e->prm.contact_dmax_clamp && e->d_dmax) {
+            dmax_out = e->d_dmax + (1 - e->clamp_cur);
+            if (phase != 2) CK(hkp::dev_memset(dmax_out, 0, sizeof(unsigned long long), e->stream));
         }
         if (phase == 1) {
             prof_begin(e, 1);
             hk_launch_nodal(d, (double)t * e->prm.d_time, e->prm.d_time, e->dt2, e->dt2p, e->cp.lsb_exp,
-                            contact_on ? 1 : 0, e->use_Q0, 1, nullptr, 0, e->stream);
+                            contact_on ? 1 : 0, e->use_Q0, 1, nullptr, 0, dmax_out, e->stream);
             prof_end(e);
             e->n_launch += 1;
             continue;
@@ -1107,10 +1154,10 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
         prof_begin(e, 1);
         if (phase == 2)
             hk_launch_nodal(d, (double)t * e->prm.d_time, e->prm.d_time, e->dt2, e->dt2p, e->cp.lsb_exp,
-                            contact_on ? 1 : 0, e->use_Q0, 2, e->d_halo_list, e->n_halo_nodes, e->stream);
+                            contact_on ? 1 : 0, e->use_Q0, 2, e->d_halo_list, e->n_halo_nodes, dmax_out, e->stream);
         else
             hk_launch_nodal(d, (double)t * e->prm.d_time, e->prm.d_time, e->dt2, e->dt2p, e->cp.lsb_exp,
-                            contact_on ? 1 : 0, e->use_Q0, 0, nullptr, 0, e->stream);
+                            contact_on ? 1 : 0, e->use_Q0, 0, nullptr, 0, dmax_out, e->stream);
         prof_end(e);
         e->use_Q0 = 0;
         prof_begin(e, 2);
@@ -1128,6 +1175,7 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
             if (e->dev_erosion) e->contact_host_stale = true;
         }
         e->n_steps += 1;
+        if (contact_on && e->prm.contact_dmax_clamp) e->clamp_cur = 1 - e->clamp_cur;
     }
     if (n_steps > 0 && phase != 1) {
         e->velo_current = contact_on;
@@ -1140,6 +1188,7 @@ static int step_enqueue_impl(hk_engine* e, int64_t t_first, int64_t n_steps, boo
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     if (n_steps < 0 || t_first < 0 || t_first + n_steps >= (1ll << 31)) return fail(e, HK_ERR_ARG, "bad step range");
     if (!e->halo.empty() && n_steps > 1) return fail(e, HK_ERR_ARG, "with halos, exchange and step one step at a time");
+
     int rc = enqueue_steps(e, t_first, n_steps, frame_at_end, 0);
     if (rc) return rc;
     CK(hkp::last_error());
@@ -1382,6 +1431,14 @@ int HKAPI(deleted_ids)(hk_engine* e, int64_t* ids, int64_t cap, int64_t* n_out) 
     return HK_OK;
 }
 
+int HKAPI(deleted_steps)(hk_engine* e, int64_t* steps, int64_t cap, int64_t* n_out) {
+    if (!e) return HK_ERR_ARG;
+    const int64_t n = (int64_t)e->deleted_step.size();
+    if (n_out) *n_out = n;
+    if (steps) for (int64_t i = 0; i < std::min(n, cap); ++i) steps[i] = e->deleted_step[i];
+    return HK_OK;
+}
+
 int HKAPI(contact_pair_info)(hk_engine* e, int64_t c, int64_t* nn_i, int64_t* nn_j, int64_t* nTri, int64_t* c_nodes_i,
                              int64_t* c_nodes_j, int64_t* c_triangles, int64_t* c_triangles_eleid) {
     if (!e || c < 0 || c >= (int64_t)e->pairs.size()) return fail(e, HK_ERR_ARG, "bad contact pair index");
@@ -1578,6 +1635,7 @@ int HKAPI(apply_deleted)(hk_engine* e, int64_t n, const int64_t* global_ids) {
     if (rc) return rc;
     if (!global) {                       // restart of a single-domain run: the replayed ids are part of the history
         e->deleted_all.insert(e->deleted_all.end(), ids.begin(), ids.end());
+        e->deleted_step.insert(e->deleted_step.end(), ids.size(), 0);
         e->deleted_reported = e->deleted_all.size();
     }
     CK(hkp::sync(e->stream));
@@ -1589,11 +1647,7 @@ int HKAPI(contact_enqueue)(hk_engine* e) {
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     if (!contact_on) return HK_OK;
     { int rc = ensure_erosion(e); if (rc) return rc; }
-    prof_begin(e, 0);
-    if (e->dev_erosion) hk_launch_cacc_zero(e->d, e->er.n_slots, e->er.slot_cap, e->stream);
-    else CK(hkp::dev_memset(e->d.cacc, 0, (size_t)e->n_contact_slots * 6 * sizeof(unsigned long long), e->stream));
-    for (PairH& p : e->pairs) { hk_launch_contact(e->d, p.dev, e->cp, e->stream); e->n_launch += 4; }
-    prof_end(e);
+    { int rc = contact_pass(e); if (rc) return rc; }
     e->contact_done = true;
     CK(hkp::last_error());
     return HK_OK;

@@ -92,6 +92,7 @@ struct NodalArgs {
     int mode;                 // 0: every node; 1: all but the halo (interface) nodes; 2: only the nodes in `list`
     const int* list;
     long long n_list;
+    unsigned long long* dmax_out;   // clamp mode: bit pattern of max_n sqrt(dx^2+dy^2+dz^2) of d_disp (J1:611-618)
 };
 
 HK_HD double eval_amp(const HkDev& d, int amp_id, double current_time) {   // J2:586-600
@@ -136,7 +137,7 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
             const long long e = ok ? (ent[w] >> 3) : 0;
             const int a = ok ? (ent[w] & 7) : 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[w][c] = ok ? HK_LDG(&d.Qe[(long long)(a * 3 + c) * d.nEp + e]) : 0.0;
+            for (int c = 0; c < 3; ++c) v[w][c] = ok ? HK_LDG(&d.Qe[hk_qe(d, a * 3 + c, e)]) : 0.0;
         }
 #pragma unroll
         for (int w = 0; w < 8; ++w) { q0 += v[w][0]; q1 += v[w][1]; q2 += v[w][2]; }
@@ -145,9 +146,9 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
             if (en < 0) break;
             const long long e = en >> 3;
             const int a = en & 7;
-            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
-            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
-            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+            q0 += d.Qe[hk_qe(d, a * 3 + 0, e)];
+            q1 += d.Qe[hk_qe(d, a * 3 + 1, e)];
+            q2 += d.Qe[hk_qe(d, a * 3 + 2, e)];
         }
     }
     double F[3] = {0.0, 0.0, 0.0};
@@ -196,6 +197,14 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
         d.u[i] = un[c];
         if (A.contact_on) d.velo[i] = dd[c] / A.d_time;   // velo, J2:628
     }
+    if (A.dmax_out) {                            // d_disp_norm, J1:611-616; the max over nodes is order independent
+        const double nrm = sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+        unsigned long long bits;
+        memcpy(&bits, &nrm, 8);
+#if defined(__CUDA_ARCH__) || defined(HK_EMU)
+        if (bits > *A.dmax_out) hk_atomic_max_u64(A.dmax_out, bits);       // racy pre-check only skips losers
+#endif
+    }
     // node record {position (J2:650-652), d_disp}: 48 contiguous bytes
 #if defined(__CUDA_ARCH__)
     double2* r = reinterpret_cast<double2*>(d.rec + 6 * n);
@@ -219,8 +228,9 @@ __global__ void __launch_bounds__(256) hk_nodal_kernel(NodalArgs A) {
 #endif
 
 void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double dt2, double dt2p, int lsb_exp,
-                     int contact_on, int use_Q0, int mode, const int* list, long long n_list, cudaStream_t s) {
-    NodalArgs A{d, current_time, d_time, dt2, dt2p, lsb_exp, contact_on, use_Q0, mode, list, n_list};
+                     int contact_on, int use_Q0, int mode, const int* list, long long n_list, unsigned long long* dmax_out,
+                     cudaStream_t s) {
+    NodalArgs A{d, current_time, d_time, dt2, dt2p, lsb_exp, contact_on, use_Q0, mode, list, n_list, dmax_out};
     const long long n = mode == 2 ? n_list : d.nNode;
     if (n <= 0) return;
 #ifndef HK_EMU
@@ -349,7 +359,7 @@ HK_D void contact_tri_body(const ContactArgs& A, long long j) {
 
     int en[8];
     if (p.self)
-        for (int q = 0; q < 8; ++q) en[q] = d.conn[(long long)q * d.nEp + eleid];
+        for (int q = 0; q < 8; ++q) en[q] = d.conn[hk_cn(d, q, eleid)];
 
     unsigned long long n_tests = 0, n_hits = 0;
     const unsigned bucket_mask = (unsigned)(p.dyn->n_bucket - 1);
@@ -378,6 +388,15 @@ HK_D void contact_tri_body(const ContactArgs& A, long long j) {
                     const double dd = (im31 * bx + im32 * by + im33 * bz) / detA;
                     if (0.0 <= x1 && 0.0 <= x2 && x1 + x2 <= 1.0 && dd > 0.0 && dd <= cp.d_lim) {
                         ++n_hits;
+                        const int slot_i = d.spec[d.spec_idx[i]].contact_slot;
+                        double dcl = dd;
+                        if (cp.clamp) {                           // J1:2756-2758
+                            double dmax;
+                            const unsigned long long mb = *cp.dmax;
+                            memcpy(&dmax, &mb, 8);
+                            const double pre = cp.dnode_pre[slot_i];
+                            if (dcl - pre > dmax) dcl = pre + dmax;
+                        }
                         const double vx = d.velo[3ll * i] - d.velo[3ll * j0];
                         const double vy = d.velo[3ll * i + 1] - d.velo[3ll * j0 + 1];
                         const double vz = d.velo[3ll * i + 2] - d.velo[3ll * j0 + 2];
@@ -385,7 +404,7 @@ HK_D void contact_tri_body(const ContactArgs& A, long long j) {
                         double vex = 0.0, vey = 0.0, vez = 0.0;
                         if (mag_v > 0.0) { vex = vx / mag_v; vey = vy / mag_v; vez = vz / mag_v; }
                         const double k_ = p.young * S / Lmax * kc;
-                        const double F = k_ * dd;
+                        const double F = k_ * dcl;
                         double fx = F * nx, fy = F * ny, fz = F * nz;
                         // damping: diag_M[i] is indexed with the NODE id in the reference (J2:2593)
                         const double C = 2 * sqrt(d.mass[i / 3] * k_) * Cr;
@@ -399,9 +418,11 @@ HK_D void contact_tri_body(const ContactArgs& A, long long j) {
                         const double f[3] = {fx, fy, fz};
                         const double f3[3] = {-fx / 3.0, -fy / 3.0, -fz / 3.0};
                         unsigned long long* ovf = &d.counters[3];
-                        {
-                            const int slot = d.spec[d.spec_idx[i]].contact_slot;
-                            for (int c = 0; c < 3; ++c) fx_atomic_add(d.cacc + 6ll * slot + 2 * c, f[c], cp.lsb_exp, ovf);
+                        for (int c = 0; c < 3; ++c) fx_atomic_add(d.cacc + 6ll * slot_i + 2 * c, f[c], cp.lsb_exp, ovf);
+                        if (cp.clamp) {                           // d_node[i] = max(d_node[i], d), J1:2898-2900
+                            unsigned long long bits;
+                            memcpy(&bits, &dcl, 8);
+                            hk_atomic_max_u64(reinterpret_cast<unsigned long long*>(cp.dnode + slot_i), bits);
                         }
                         const int jn[3] = {j0, j1, j2};
                         for (int q = 0; q < 3; ++q) {
@@ -698,9 +719,9 @@ void hk_launch_gather_Q(const HkDev& dd, double* Q_out, cudaStream_t s) {
             if (ent < 0) break;
             long long e = ent >> 3;
             int a = ent & 7;
-            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
-            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
-            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+            q0 += d.Qe[hk_qe(d, a * 3 + 0, e)];
+            q1 += d.Qe[hk_qe(d, a * 3 + 1, e)];
+            q2 += d.Qe[hk_qe(d, a * 3 + 2, e)];
         }
         Q_out[3 * n] = q0; Q_out[3 * n + 1] = q1; Q_out[3 * n + 2] = q2;
     });
@@ -717,9 +738,9 @@ void hk_launch_halo_pack(const HkDev& dd, const int* nodes, long long n, double*
             if (ent < 0) break;
             const long long e = ent >> 3;
             const int a = ent & 7;
-            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
-            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
-            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+            q0 += d.Qe[hk_qe(d, a * 3 + 0, e)];
+            q1 += d.Qe[hk_qe(d, a * 3 + 1, e)];
+            q2 += d.Qe[hk_qe(d, a * 3 + 2, e)];
         }
         out[3 * i] = q0; out[3 * i + 1] = q1; out[3 * i + 2] = q2;
     });
@@ -1050,7 +1071,7 @@ HK_D void element_body_exact(const ExactArgs& A, long long e) {
     const unsigned char fl = d.flag[e];
     if (fl != 1) {
         if (fl == 0) {
-            for (int r = 0; r < 24; ++r) d.Qe[(long long)r * d.nEp + e] = 0.0;
+            for (int r = 0; r < 24; ++r) d.Qe[hk_qe(d, r, e)] = 0.0;
             for (int k = 0; k < 8; ++k) d.triax[(long long)k * d.nEp + e] = 0.0;
             d.flag[e] = 2;
         }
@@ -1065,7 +1086,7 @@ HK_D void element_body_exact(const ExactArgs& A, long long e) {
     Dm[3][3] = Dm[4][4] = Dm[5][5] = M.D44;
     double d_u[24], ep[3][8];
     for (int i = 0; i < 8; ++i) {
-        const long long n = d.conn[(long long)i * d.nEp + e];
+        const long long n = d.conn[hk_cn(d, i, e)];
         for (int c = 0; c < 3; ++c) { ep[c][i] = d.rec[6 * n + c]; d_u[i * 3 + c] = d.rec[6 * n + 3 + c]; }
     }
     // cal_BVbar_hexa
@@ -1180,7 +1201,7 @@ HK_D void element_body_exact(const ExactArgs& A, long long e) {
         v_e += ep_;
         t_e += tx;
     }
-    for (int j = 0; j < 24; ++j) d.Qe[(long long)j * d.nEp + e] = Qe[j];
+    for (int j = 0; j < 24; ++j) d.Qe[hk_qe(d, j, e)] = Qe[j];
     // fracture, J2:701-762
     if (M.nd > 0) {
         v_e /= 8;

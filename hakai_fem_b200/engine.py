@@ -33,6 +33,7 @@ class HkParams(C.Structure):
         ("contact_cr_other", c_f64), ("contact_cr_self", c_f64),
         ("contact_ddiv_other", c_f64), ("contact_ddiv_self", c_f64),
         ("deterministic", C.c_int32), ("element_mode", C.c_int32),
+        ("contact_dmax_clamp", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -43,7 +44,7 @@ EXPORTS = [
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
     "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
-    "state_export", "state_import", "state_summary",
+    "state_export", "state_import", "state_summary", "deleted_steps",
 ]
 
 
@@ -279,6 +280,15 @@ class EngineBase:
         if n.value:
             self._chk(self._fn("deleted_ids")(self._h, _pi(ids), c_i64(n.value), C.byref(n)))
         return ids
+
+    def deleted_steps(self) -> np.ndarray:
+        """Step in which each entry of deleted_ids() was deleted (0: replayed through apply_deleted)."""
+        n = c_i64(0)
+        self._chk(self._fn("deleted_steps")(self._h, None, c_i64(0), C.byref(n)))
+        st = np.zeros(n.value, np.int64)
+        if n.value:
+            self._chk(self._fn("deleted_steps")(self._h, _pi(st), c_i64(n.value), C.byref(n)))
+        return st
 
     def contact_pair(self, c: int):
         a, b, t = c_i64(0), c_i64(0), c_i64(0)

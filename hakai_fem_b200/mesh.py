@@ -204,6 +204,9 @@ class ImpactDeck:
     n_steps: float = 99.5
     name: str = "impact"
     plate_ductile: Optional[list] = None      # rows [eps_f, triax, rate] replacing alum's table (brittle plates in tests)
+    contact_pair: bool = False                # write_inp: `*Surface` element sets (top layer of the plate, bottom layer of
+                                              # the projectile) + `*Contact Pair` instead of `*Contact Inclusions, ALL
+                                              # EXTERIOR` (readInpFile_j.jl:1062-1103, HAKAI_j.jl:2094-2119)
 
     def materials(self):
         alum = Material(name="alum", density=2800., young=7e+10, poisson=0.33)
@@ -280,6 +283,12 @@ class ImpactDeck:
             w("*Nset, nset=edge, instance=plate-1\n")
             for i in range(0, len(edge), 16):
                 w(", ".join(str(int(v)) for v in edge[i:i + 16]) + "\n")
+            if self.contact_pair:
+                pz, qy = self.plate[2], self.proj[1]
+                w("*Elset, elset=_plate-top_S2, internal, instance=plate-1, generate\n %d, %d, 1\n" % ((pz - 1) * px * py + 1, pz * px * py))
+                w("*Surface, type=ELEMENT, name=plate-top\n_plate-top_S2, S2\n")
+                w("*Elset, elset=_proj-bottom_S1, internal, instance=proj-1, generate\n 1, %d, 1\n" % (qx * qy))
+                w("*Surface, type=ELEMENT, name=proj-bottom\n_proj-bottom_S1, S1\n")
             w("*End Assembly\n**\n")
             for name in ("alum", "lead"):
                 x = mats[name]
@@ -294,6 +303,10 @@ class ImpactDeck:
                         w(" %s, %s, %s\n" % (repr(float(r[0])), repr(float(r[1])), repr(float(r[2]))))
             w("**\n*Boundary\nedge, ENCASTRE\n")
             w("**\n*Initial Conditions, type=VELOCITY\nproj-1.Set-all, 3, %s\n" % repr(float(self.v0)))
-            w("**\n*Contact, op=NEW\n*Contact Inclusions, ALL EXTERIOR\n")
+            if self.contact_pair:
+                w("**\n*Surface Interaction, name=IntProp-1\n1.,\n")
+                w("*Contact Pair, interaction=IntProp-1, mechanical constraint=KINEMATIC, cpset=CP-1\nproj-bottom, plate-top\n")
+            else:
+                w("**\n*Contact, op=NEW\n*Contact Inclusions, ALL EXTERIOR\n")
             w("**\n*Step, name=Step-1, nlgeom=YES\n*Dynamic, Explicit\n%s, %s\n**\n*End Step\n" % (
                 repr(self.d_time), repr(float(self.n_steps * self.d_time))))

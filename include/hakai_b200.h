@@ -60,6 +60,12 @@ typedef struct hk_params {
                                      reference arithmetic.  1: reference-order kernel: the dense 6x24 Bfinal algebra of
                                      J2:1033-1371 in the reference's operation order without FMA — bit-identical to the
                                      CPU oracle (and ~10x slower); resolves contact ties like the reference          */
+    int32_t contact_dmax_clamp;   /* 0 (default, v0.0.2 behaviour): off.  1: v0.0.1's penetration-rate clamp — a slave node's
+                                     penetration may grow by at most d_max = max_n |d_disp_n| of the previous step:
+                                     if d - d_node_pre[i] > d_max: d = d_node_pre[i] + d_max
+                                     (HAKAI-v0.0.1/Julia/HAKAI_j.jl:2756, 3218; d_node J1:2898, d_max J1:618).  Single-domain
+                                     engines only                                                                       */
+    int32_t reserved0;            /* keep 0 */
 } hk_params;
 
 int hk_default_params(hk_params* p);
@@ -170,6 +176,11 @@ int hk_upload_state(hk_engine* e, const double* disp, const double* disp_pre, co
 /* Ids (1-based, deletion order: ascending step, ascending id within a step, J2:701-735) of
  * all elements deleted since hk_finalize.  Copies min(cap, n) ids; *n_out = total count. */
 int hk_deleted_ids(hk_engine* e, int64_t* ids, int64_t cap, int64_t* n_out);
+
+/* The step t (as passed to hk_step) in which each of those elements was deleted, aligned with hk_deleted_ids; 0 for
+ * ids replayed through hk_apply_deleted.  Lets a driver that enqueued many steps in one call reconstruct the
+ * live-element count of every step without synchronising in between. */
+int hk_deleted_steps(hk_engine* e, int64_t* steps, int64_t cap, int64_t* n_out);
 
 /* Current contact surface of pair c (0-based), after A10 updates (J2:767-804): sizes, or
  * arrays when non-NULL (caller sizes them from a first call). */

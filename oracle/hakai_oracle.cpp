@@ -92,10 +92,13 @@ struct hk_engine {
     std::vector<double> position, disp, disp_new, disp_pre, d_disp, velo, external_force, Q, Qe;
     std::vector<double> integ_stress, integ_strain, integ_eq_plastic_strain, integ_triax_stress,
         integ_yield_stress, elementVolume, d_disp_norm;
+    // v0.0.1 penetration-rate clamp (hk_params.contact_dmax_clamp): J1:413-415, 492, 513, 618
+    std::vector<double> d_node, d_node_pre;
+    double d_max = 0.0;
     std::vector<int64_t> element_flag;
     std::vector<f128> c_force3;             // (fn, Nth)
     int Nth = 1;
-    std::vector<int64_t> deleted_all;
+    std::vector<int64_t> deleted_all, deleted_step;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -476,6 +479,7 @@ static void cal_contact_force(hk_engine* E) {
     const double Cr_o = E->prm.contact_cr_other, Cr_s = E->prm.contact_cr_self;
     const int64_t fn = E->fn;
     int64_t hits = 0, tests = 0;
+    const bool clamp = E->prm.contact_dmax_clamp != 0;
 
     for (size_t c = 0; c < E->CT.size(); ++c) {
         const ContactTriangleO& ct = E->CT[c];
@@ -594,6 +598,7 @@ static void cal_contact_force(hk_engine* E) {
                 my3SolveAb(A11, A21, A31, A12, A22, A32, A13, A23, A33, bx, by, bz, x1, x2, d);
                 if (0.0 <= x1 && 0.0 <= x2 && x1 + x2 <= 1.0 && d > 0.0 && d <= d_lim) {
                     ++hits;
+                    if (clamp && d - E->d_node_pre[i - 1] > E->d_max) d = E->d_node_pre[i - 1] + E->d_max;   // J1:2756-2758
                     const double vx = velo[i * 3 - 3] - velo[j0 * 3 - 3];
                     const double vy = velo[i * 3 - 2] - velo[j0 * 3 - 2];
                     const double vz = velo[i * 3 - 1] - velo[j0 * 3 - 1];
@@ -620,6 +625,10 @@ static void cal_contact_force(hk_engine* E) {
                         cf[1 + (jn[q] - 1) * 3] += -fy / 3.0;
                         cf[2 + (jn[q] - 1) * 3] += -fz / 3.0;
                     }
+                    if (clamp) {                                             // J1:2898-2900 (a max: order independent)
+#pragma omp critical(hk_d_node)
+                        if (d > E->d_node[i - 1]) E->d_node[i - 1] = d;
+                    }
                 }
             }
         }
@@ -638,7 +647,9 @@ static void one_step(hk_engine* E, int64_t t, int64_t* n_deleted) {
 
     if (E->prm.contact_flag >= 1) {                                          // J2:500-548
         std::fill(E->c_force3.begin(), E->c_force3.end(), (f128)0);
+        if (E->prm.contact_dmax_clamp) std::fill(E->d_node.begin(), E->d_node.end(), 0.0);      // J1:492
         cal_contact_force(E);
+        if (E->prm.contact_dmax_clamp) E->d_node_pre = E->d_node;                              // J1:512-514
         if (E->Nth > 1) {
 #pragma omp parallel for schedule(static)
             for (int64_t i = 0; i < fn; ++i)
@@ -694,6 +705,11 @@ static void one_step(hk_engine* E, int64_t t, int64_t* n_deleted) {
         E->position[1 + 3 * i] = E->coordmat[1 + 3 * i] + E->disp[i * 3 + 1];
         E->position[2 + 3 * i] = E->coordmat[2 + 3 * i] + E->disp[i * 3 + 2];
     }
+    if (E->prm.contact_dmax_clamp) {                                         // d_max = maximum(d_disp_norm), J1:618
+        double m = E->d_disp_norm[0];
+        for (int64_t i = 1; i < nNode; ++i) m = E->d_disp_norm[i] > m ? E->d_disp_norm[i] : m;
+        E->d_max = m;
+    }
 
     // internal force, J2:662-675
     std::fill(E->Qe.begin(), E->Qe.end(), 0.0);
@@ -746,7 +762,7 @@ static void one_step(hk_engine* E, int64_t t, int64_t* n_deleted) {
     }
 
     update_contact_surface(E, deleted_element);                              // J2:767-804
-    for (int64_t i : deleted_element) E->deleted_all.push_back(i);
+    for (int64_t i : deleted_element) { E->deleted_all.push_back(i); E->deleted_step.push_back(t); }
     if (n_deleted) *n_deleted += (int64_t)deleted_element.size();
     E->counters[4] += 1;
 }
@@ -916,6 +932,9 @@ int hko_finalize(hk_engine* e) {
     e->element_flag.assign(nE, 1);
     e->elementVolume.assign(nE, 0.0);
     e->d_disp_norm.assign(e->nNode, 0.0);
+    e->d_node.assign(e->nNode, 0.0);
+    e->d_node_pre.assign(e->nNode, 0.0);
+    e->d_max = 0.0;
     for (int64_t i = 0; i < nE; ++i) {                              // J2:456-465
         const Material& M = e->MATERIAL.at(e->element_material[i] - 1);
         if (M.npp > 0)
@@ -1032,6 +1051,14 @@ int hko_deleted_ids(hk_engine* e, int64_t* ids, int64_t cap, int64_t* n_out) {
     return HK_OK;
 }
 
+int hko_deleted_steps(hk_engine* e, int64_t* steps, int64_t cap, int64_t* n_out) {
+    if (!e) return HK_ERR_ARG;
+    int64_t n = (int64_t)e->deleted_step.size();
+    if (n_out) *n_out = n;
+    if (steps) for (int64_t i = 0; i < std::min(n, cap); ++i) steps[i] = e->deleted_step[i];
+    return HK_OK;
+}
+
 int hko_contact_pair_info(hk_engine* e, int64_t c, int64_t* nn_i, int64_t* nn_j, int64_t* nTri, int64_t* c_nodes_i,
                           int64_t* c_nodes_j, int64_t* c_triangles, int64_t* c_triangles_eleid) {
     if (!e || c < 0 || c >= (int64_t)e->CT.size()) return fail(e, HK_ERR_ARG, "bad contact pair index");
@@ -1100,7 +1127,7 @@ int hko_apply_deleted(hk_engine* e, int64_t n, const int64_t* ids) {           /
     std::vector<int64_t> v(ids, ids + n);
     for (int64_t g : v) if (g < 1 || g > e->nElement) return fail(e, HK_ERR_ARG, "element id out of range");
     update_contact_surface(e, v);
-    for (int64_t g : v) e->deleted_all.push_back(g);
+    for (int64_t g : v) { e->deleted_all.push_back(g); e->deleted_step.push_back(0); }
     return HK_OK;
 }
 int hko_mark_frame(hk_engine* e) { return e && e->finalized ? HK_OK : fail(e, HK_ERR_STATE, "engine not finalised"); }   // triax is always stored

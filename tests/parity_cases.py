@@ -91,6 +91,8 @@ def case_fracture_block(engine_cls, n_steps=260):
     assert seen > 3, "deck did not delete anything: test is vacuous"
     a, b = util.full_state(o), util.full_state(g)
     util.assert_states_close(a, b, 1e-8, STATE_KEYS, "fracture block")
+    so, sg = o.deleted_steps(), g.deleted_steps()          # the step of every deletion, aligned with deleted_ids
+    assert np.array_equal(so, sg) and len(sg) == seen and np.all(np.diff(sg) >= 0) and sg.min() >= 1 and sg.max() <= t
 
 
 def case_state_summary(engine_cls):
@@ -184,6 +186,32 @@ def case_contact(engine_cls, mu=0.25, n_steps=60):
     assert co[1] == cg[1] and co[1] > 0, f"hit counts differ: {co[1]} vs {cg[1]}"
 
 
+def case_contact_clamp(engine_cls, n_steps=60):
+    """v0.0.1's penetration-rate clamp (hk_params.contact_dmax_clamp; HAKAI-v0.0.1 HAKAI_j.jl:2756, 2898, 618): a slave
+    node's penetration may grow by at most d_max = max |d_disp| of the previous step.  Engine vs oracle with the clamp
+    on; and the clamp must actually bite (forces differ from the v0.0.2 run of the same deck)."""
+    st, prm = small_impact(0.25)
+    o, g = util.make_pair(st, engine_cls, OracleEngine, contact_dmax_clamp=1, **prm)
+    free = configure_engine(OracleEngine, st, **prm)
+    keys = tuple(k for k in STATE_KEYS if k != "integ_triax_stress") + ("external_force",)
+    t, differs = 0, False
+    for _ in range(n_steps // 4):
+        o.step(t + 1, 4)
+        g.step(t + 1, 4)
+        free.step(t + 1, 4)
+        t += 4
+        a, b = util.full_state(o), util.full_state(g)
+        util.assert_states_close(a, b, 1e-9, keys, f"clamp step {t}", floors=CONTACT_FLOORS)
+        f0 = free.download_ex(fields=("external_force",))["external_force"]
+        differs = differs or util.rel_err(f0, a["external_force"]) > 1e-3
+    assert o.counters()[1] == g.counters()[1] > 0
+    assert differs, "the clamp never changed a force: test is vacuous"
+    # one call for all steps (the d_node / d_max ping-pong is enqueued, not driven by host reads)
+    g2 = configure_engine(engine_cls, st, contact_dmax_clamp=1, **prm)
+    g2.step(1, t)
+    assert np.array_equal(g2.download()["disp"], b["disp"])
+
+
 def case_contact_single_step(engine_cls):
     """Contact force of ONE step from an identical penetrated state is bit-for-bit the oracle's
     (hk_exact.cu mirrors the reference's operation order; sums are exact)."""
@@ -238,6 +266,38 @@ def case_contact_erosion(engine_cls, n_steps=400):
     b2 = util.full_state(g2)
     for k in ("disp", "integ_eq_plastic_strain", "integ_stress", "element_flag", "external_force"):
         assert np.array_equal(b[k], b2[k]), f"one-call run: {k}"
+
+
+def case_contact_pair_surfaces(engine_cls, tmp_path):
+    """`*Contact Pair` between two `*Surface` element sets (readInpFile_j.jl:1062-1103; get_surface_triangle's elset
+    filter, HAKAI_j.jl:2094-2119) through the deck reader: the contact surfaces are the exterior faces of the plate's
+    top element layer and of the projectile's bottom layer only — fewer than ALL EXTERIOR — and the engine matches the
+    oracle on them (forces bit-exact per step, equal hit counts)."""
+    from hakai_fem_b200.inp import read_inp_file
+    kw = dict(plate=(16, 16, 3), proj=(5, 5, 5))
+    path = str(tmp_path / "pair.inp")
+    ImpactDeck(contact_pair=True, **kw).write_inp(path)
+    model = read_inp_file(path)
+    assert len(model.CP) == 1 and model.contact_flag == 1 and len(model.SURFACE) == 2
+    st = prepare(model)
+    st_all = prepare(ImpactDeck(**kw).build_model())
+    assert st.all_exterior_flag == 0 and st_all.all_exterior_flag == 1
+    assert [(c.i_instance, c.j_instance) for c in st.CT] == [(2, 1), (1, 2)]
+    n_tri = sorted(len(c.c_triangles_eleid) for c in st.CT)
+    assert n_tri == [2 * (5 * 5 + 4 * 5), 2 * (16 * 16 + 4 * 16)]          # top/bottom face + the layer's side faces
+    assert sum(n_tri) < sum(len(c.c_triangles_eleid) for c in st_all.CT)
+    o, g = util.make_pair(st, engine_cls, OracleEngine, contact_myu=0.25)
+    keys = tuple(k for k in STATE_KEYS if k != "integ_triax_stress") + ("external_force",)
+    for t0 in (1, 21, 41):
+        o.step(t0, 20)
+        g.step(t0, 20)
+        a, b = util.full_state(o), util.full_state(g)
+        util.assert_states_close(a, b, 1e-9, keys, f"contact pair step {t0 + 19}", floors=CONTACT_FLOORS)
+    assert o.counters()[1] == g.counters()[1] > 0
+    for c in range(2):
+        po, pg = o.contact_pair(c), g.contact_pair(c)
+        for k in po:
+            assert np.array_equal(po[k], pg[k]), (c, k)
 
 
 def case_bc_edge_cases(engine_cls):

@@ -29,8 +29,16 @@ def test_contact(mu):
     pc.case_contact(EmuEngine, mu)
 
 
+def test_contact_penetration_clamp():
+    pc.case_contact_clamp(EmuEngine)
+
+
 def test_contact_single_step_exact():
     pc.case_contact_single_step(EmuEngine)
+
+
+def test_contact_pair_surfaces(tmp_path):
+    pc.case_contact_pair_surfaces(EmuEngine, tmp_path)
 
 
 def test_bc_edge_cases():

@@ -33,8 +33,16 @@ def test_contact(mu):
     pc.case_contact(Engine, mu)
 
 
+def test_contact_penetration_clamp():
+    pc.case_contact_clamp(Engine)
+
+
 def test_contact_single_step_exact():
     pc.case_contact_single_step(Engine)
+
+
+def test_contact_pair_surfaces(tmp_path):
+    pc.case_contact_pair_surfaces(Engine, tmp_path)
 
 
 def test_bc_edge_cases():
