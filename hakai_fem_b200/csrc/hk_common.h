@@ -72,8 +72,6 @@ struct HkDev {
                           // 12 eps (integ_eq_plastic_strain), 13 yield (integ_yield_stress): the 14 rows x TL
                           // elements of one Gauss point of one tile are ONE contiguous burst (14*TL*8 bytes)
     int element_mode;     // hk_params.element_mode (1: reference-order kernel)
-    int blocked;          // layout of Qe / conn, see hk_qe / hk_cn
-    int experiment;       // HK_EXPERIMENT (profiling builds only): 1 = "red"
     int variant;          // element-kernel variant (hk_element.cu: kVariants; 1 = simple kernel)
     int n_sm;             // multiprocessors of the engine's device (grid of the persistent kernels)
     int TL;               // layout tile = elements per tile of the element kernel in use; nEp % TL == 0
@@ -88,20 +86,6 @@ struct HkDev {
     unsigned long long* cacc;
     double* halo_recv;    // [n_halo*3]
 };
-
-// index of (row r of 24, element e) in HkDev::Qe and of (local node a, element e) in HkDev::conn.  blocked != 0: both are
-// tile-blocked like the ip state ([tile][24][TL], [tile][8][TL]) so that everything one tile of the element kernel
-// reads or writes is a handful of contiguous bursts; blocked == 0: plain SoA [24][nEp], [8][nEp] (round-1 layout, A/B)
-HK_HD long long hk_qe(const HkDev& d, int r, long long e) {
-    if (!d.blocked) return (long long)r * d.nEp + e;
-    const long long t = e / d.TL;
-    return (t * 24 + r) * d.TL + (e - t * d.TL);
-}
-HK_HD long long hk_cn(const HkDev& d, int a, long long e) {
-    if (!d.blocked) return (long long)a * d.nEp + e;
-    const long long t = e / d.TL;
-    return (t * 8 + a) * d.TL + (e - t * d.TL);
-}
 
 // index of (row, gauss point k, element e) in HkDev::ips
 HK_HD long long hk_ip(const HkDev& d, int row, int k, long long e) {

@@ -20,13 +20,6 @@ struct ElemArgs {
     int write_triax;
     int fast;          // MatLite::fast
 };
-#ifndef HK_EMU
-#define HK_EXPERIMENT_RED 1      /* round-2 A/B only (HK_EXPERIMENT=red): cost of assembling by integer RED; not a product path */
-#endif
-#ifdef HK_EXPERIMENT_RED
-__device__ __forceinline__ bool getenv_red(const ElemArgs& A) { return A.fast == 3; }
-#endif
-
 HK_HD MatLite mat_lite(const HkMaterialDev* m) {
     MatLite l;
     l.D11 = m->D11; l.D12 = m->D12; l.D44 = m->D44; l.G3 = 3.0 * m->G; l.npp = m->npp;
@@ -44,12 +37,12 @@ HK_HD double triax_of(const double s[6]) {
 }
 
 // ---- pieces shared by both kernels ------------------------------------------------------------------
-HK_D bool element_dead(const HkDev& d, long long e) {
-    const unsigned char fl = d.flag[e];
+HK_D bool element_dead(const HkDev& d, long long e, int fl_known = -1) {
+    const unsigned char fl = fl_known >= 0 ? (unsigned char)fl_known : d.flag[e];   // ring kernels: flag already on chip
     if (fl == 1) return false;
     if (fl == 0) {      // deleted during the previous step: its last force has been consumed, clear it
 #pragma unroll
-        for (int r = 0; r < 24; ++r) d.Qe[hk_qe(d, r, e)] = 0.0;
+        for (int r = 0; r < 24; ++r) d.Qe[(long long)r * d.nEp + e] = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) d.triax[(long long)k * d.nEp + e] = 0.0;   // zero stress -> triax 0 (J2:1012)
         d.flag[e] = 2;
@@ -61,7 +54,7 @@ HK_D void element_gather(const HkDev& d, long long e, HexModes& X, HexModes& U) 
     double x[8][3], du[8][3];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-        const long long n = d.conn[hk_cn(d, a, e)];
+        const long long n = d.conn[(long long)a * d.nEp + e];
 #if defined(__CUDA_ARCH__)
         const double2* r = reinterpret_cast<const double2*>(d.rec + 6 * n);
         const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
@@ -117,7 +110,7 @@ HK_D void element_finish(const ElemArgs& A, long long e, const HexModes& X, cons
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) d.Qe[hk_qe(d, a * 3 + c, e)] = f[a][c];
+        for (int c = 0; c < 3; ++c) d.Qe[(long long)(a * 3 + c) * d.nEp + e] = f[a][c];
     if (acc.negj) hk_atomic_add_u64(&d.counters[0], (unsigned long long)acc.negj);
 }
 
@@ -299,7 +292,7 @@ struct RingCfg {
     static constexpr int STAGE = HK_ROWS * TLD;                // doubles per stage
     static constexpr int THREADS = (NG * WG + NG) * 32;        // consumers + one producer warp per group
     static constexpr int SMEM = NG * S * STAGE * 8 + (2 * NG * S + 2 * NG) * 8 + HK_SMEM_MATS * 2 * HK_MAX_TABLE * 8 +
-                                (CP ? NG * 2 * 8 * TLD * 4 : 0) + 64;
+                                (CP ? NG * 2 * 8 * TLD * 4 : 0) + (CP >= 2 ? NG * 2 * TLD * 4 : 0) + 64;
 };
 
 template <int NG, int WG, int S, int CP>
@@ -313,7 +306,9 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
     unsigned long long* cfull = done + NG * S;                                                // [NG][2]
     double* mat_tab = reinterpret_cast<double*>(cfull + NG * 2);
     int* conn_buf = reinterpret_cast<int*>(mat_tab + HK_SMEM_MATS * 2 * HK_MAX_TABLE);        // [NG][2][8][TLD]
-    uint32_t* tbase_s = reinterpret_cast<uint32_t*>(conn_buf + (CP ? NG * 2 * 8 * TLD : 0));
+    unsigned short* mat_buf = reinterpret_cast<unsigned short*>(conn_buf + (CP ? NG * 2 * 8 * TLD : 0));   // [NG][2][TLD]
+    unsigned char* flag_buf = reinterpret_cast<unsigned char*>(mat_buf + (CP >= 2 ? NG * 2 * TLD : 0));      // [NG][2][TLD]
+    uint32_t* tbase_s = reinterpret_cast<uint32_t*>(flag_buf + (CP >= 2 ? NG * 2 * TLD * 2 : 0));
     const HkDev& d = A.d;
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long n_tiles = d.nEp / TLD;
@@ -349,6 +344,8 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
     unsigned long long* gdone = done + g * S;
     unsigned long long* gcfull = cfull + g * 2;
     int* gconn = conn_buf + (CP ? g * 2 * 8 * TLD : 0);
+    unsigned short* gmat = mat_buf + (CP >= 2 ? g * 2 * TLD : 0);
+    unsigned char* gflag = flag_buf + (CP >= 2 ? g * 2 * TLD : 0);
 
     if (warp >= NG * WG) {
         // ===== producer warp of group g =====
@@ -357,13 +354,13 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
                 if (!CP || it >= my_tiles) return;
                 const long long e0 = (vcta + it * n_v) * TLD;
                 unsigned long long* bar = &gcfull[it & 1];
-                mbar_expect_tx(bar, 8 * TLD * 4);
-                if (d.blocked) {                              // [tile][8][TL]: the tile's connectivity is ONE burst
-                    tma_load_1d(gconn + (it & 1) * 8 * TLD, d.conn + e0 * 8, 8 * TLD * 4, bar);
-                } else {
+                mbar_expect_tx(bar, 8 * TLD * 4 + (CP >= 2 ? TLD * 3 : 0));
 #pragma unroll
-                    for (int a = 0; a < 8; ++a)
-                        tma_load_1d(gconn + ((it & 1) * 8 + a) * TLD, d.conn + (long long)a * d.nEp + e0, TLD * 4, bar);
+                for (int a = 0; a < 8; ++a)
+                    tma_load_1d(gconn + ((it & 1) * 8 + a) * TLD, d.conn + (long long)a * d.nEp + e0, TLD * 4, bar);
+                if (CP >= 2) {                                // material ids and element flags of the tile ride along
+                    tma_load_1d(gmat + (it & 1) * TLD, d.mat + e0, TLD * 2, bar);
+                    tma_load_1d(gflag + (it & 1) * TLD, d.flag + e0, TLD, bar);
                 }
             };
             auto issue_load = [&](long long q) {
@@ -399,22 +396,22 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
         // phase shift: group g > 0 starts when group 0 has finished g*8/NG Gauss points of its first tile
         if (NG > 1 && g > 0) {
             const long long tiles0 = (long long)blockIdx.x * NG < n_tiles ? 1 : 0;
-            const int item = g * 8 / NG - 1;
-            if (tiles0 && item < S) mbar_wait(&done[item], 0u);
+            const int item = g * 8 / NG - 1;                    // group 0's work item whose completion releases group g
+            if (tiles0) mbar_wait(&done[item % S], (unsigned)((item / S) & 1));
         }
         long long q = 0;
         for (long long it = 0; it < my_tiles; ++it) {
             const long long e0 = (vcta + it * n_v) * TLD;
             const long long e = e0 + gt;
-            const bool live = !element_dead(d, e);
+            if (CP) mbar_wait(&gcfull[it & 1], (unsigned)((it >> 1) & 1));
+            const bool live = !element_dead(d, e, CP >= 2 ? (int)gflag[(it & 1) * TLD + gt] : -1);
             const HkMaterialDev* Mt = &d.mats[0];
             double V = 0.125, trbar = 0.0;
             int mi = 0;
-            if (CP) mbar_wait(&gcfull[it & 1], (unsigned)((it >> 1) & 1));
             {
                 HexModes X, U;
                 if (live) {
-                    mi = d.mat[e];
+                    mi = CP >= 2 ? (int)gmat[(it & 1) * TLD + gt] : (int)d.mat[e];
                     if (CP) element_gather_ids<TLD>(d, gconn + (it & 1) * 8 * TLD + gt, X, U);
                     else element_gather(d, e, X, U);
                 } else {                                     // unit cube at rest: finite math, state rows unchanged
@@ -540,23 +537,6 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
             HexModes X;
             tmem_load_modes(tX, X);
             if (live) {
-#ifdef HK_EXPERIMENT_RED
-                if (CP && getenv_red(A)) {                   // experiment: fixed-point RED assembly instead of the Qe stores
-                    double G[3][3][3];
-                    adj_mode_sums(X, G);
-                    double f[8][3];
-                    element_forces(acc, G, acc.pdet / V, f);
-                    const int* ids = gconn + (it & 1) * 8 * TLD + gt;
-                    unsigned long long* Qf = reinterpret_cast<unsigned long long*>(d.Q0);
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) {
-                        const long long n = ids[a * TLD];
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            atomicAdd(&Qf[3 * n + c], (unsigned long long)__double2ll_rn(f[a][c] * 1.099511627776e12));
-                    }
-                } else
-#endif
                 element_finish(A, e, X, acc, V);
                 if (ductile_check(*Mt, acc.v_e, acc.t_e)) element_delete(A, e);
             }
@@ -589,12 +569,19 @@ struct RingVariant { int id, ng, wg, stages, cp; };
 static const RingVariant kVariants[] = {
     {11, 1, 11, 4, 0},      // round-1 kernel: one group of 11 warps (tile 352)
     {12, 1, 11, 4, 1},
-    {20, 2, 5, 4, 1},       // default
+    {20, 2, 5, 4, 1},
     {21, 2, 5, 5, 1},
     {22, 2, 5, 6, 0},
     {23, 2, 5, 5, 0},
+    {24, 2, 5, 3, 1},
+    {25, 2, 5, 4, 2},       // + material ids / flags prefetched with the connectivity
+    {26, 2, 5, 3, 2},
+    {13, 1, 11, 4, 2},      // default
+    {27, 3, 3, 4, 2},       // three groups of 3 warps (tile 96)
+    {28, 2, 6, 4, 2},       // 12 consumer warps at 144 registers
+    {29, 2, 6, 3, 2},
 };
-#define HK_DEFAULT_VARIANT 20
+#define HK_DEFAULT_VARIANT 13
 
 int hk_element_variant_from_env() {
     const char* v = getenv("HK_ELEMENT_VARIANT");
@@ -608,9 +595,6 @@ int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStrea
     if (d.element_mode == 1) { hk_launch_element_exact(d, step, write_triax, s); return 0; }
     ElemArgs A{d, step, write_triax, 1};
 #ifndef HK_EMU
-#ifdef HK_EXPERIMENT_RED
-    if (d.experiment == 1) A.fast = 3;
-#endif
     switch (d.variant) {
         case 1: {
             const int block = 128;
@@ -622,7 +606,14 @@ int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStrea
         case 20: return launch_ring<2, 5, 4, 1>(A, d.n_sm, s);
         case 22: return launch_ring<2, 5, 6, 0>(A, d.n_sm, s);
         case 23: return launch_ring<2, 5, 5, 0>(A, d.n_sm, s);
-        default: return launch_ring<2, 5, 5, 1>(A, d.n_sm, s);
+        case 24: return launch_ring<2, 5, 3, 1>(A, d.n_sm, s);
+        case 25: return launch_ring<2, 5, 4, 2>(A, d.n_sm, s);
+        case 26: return launch_ring<2, 5, 3, 2>(A, d.n_sm, s);
+        case 27: return launch_ring<3, 3, 4, 2>(A, d.n_sm, s);
+        case 28: return launch_ring<2, 6, 4, 2>(A, d.n_sm, s);
+        case 29: return launch_ring<2, 6, 3, 2>(A, d.n_sm, s);
+        case 21: return launch_ring<2, 5, 5, 1>(A, d.n_sm, s);
+        default: return launch_ring<1, 11, 4, 2>(A, d.n_sm, s);
     }
 #else
     for (long long e = 0; e < d.nElement; ++e) element_body_simple(A, e);
@@ -649,7 +640,7 @@ void hk_launch_element_volume(const HkDev& dd, double* V_out, cudaStream_t s) {
     hk_parallel_for(d.nElement, s, HK_LAMBDA(long long e) {
         double x[8][3];
         for (int a = 0; a < 8; ++a) {
-            const long long n = d.conn[hk_cn(d, a, e)];
+            const long long n = d.conn[(long long)a * d.nEp + e];
             for (int c = 0; c < 3; ++c) x[a][c] = d.rec[6 * n + c];
         }
         HexModes X;

@@ -842,8 +842,6 @@ int HKAPI(finalize)(hk_engine* e) {
     const int64_t nN = e->nNode, nE = e->nElement;
     HkDev& d = e->d;
     d.variant = hk_element_variant_from_env();
-    { const char* b = getenv("HK_LAYOUT_BLOCKED"); d.blocked = b ? atoi(b) : 1; }
-    { const char* x = getenv("HK_EXPERIMENT"); d.experiment = (x && strcmp(x, "red") == 0) ? 1 : 0; }
     d.n_sm = 1;
 #ifndef HK_EMU
     CK(cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, e->prm.device));
@@ -977,9 +975,8 @@ int HKAPI(finalize)(hk_engine* e) {
     // ---- elements
     {
         std::vector<int> conn_soa((size_t)8 * nEp, 0);
-        d.nEp = nEp; d.TL = (int)tile;                      // hk_cn needs them
         for (int64_t el = 0; el < nE; ++el)
-            for (int a = 0; a < 8; ++a) conn_soa[(size_t)hk_cn(d, a, el)] = e->conn[8 * el + a];
+            for (int a = 0; a < 8; ++a) conn_soa[(size_t)a * nEp + el] = e->conn[8 * el + a];
         if ((rc = dalloc(e, &d.conn, conn_soa.size()))) return rc;
         if ((rc = upload(e, d.conn, conn_soa))) return rc;
         std::vector<unsigned char> fl(nEp, 2);

@@ -137,7 +137,7 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
             const long long e = ok ? (ent[w] >> 3) : 0;
             const int a = ok ? (ent[w] & 7) : 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[w][c] = ok ? HK_LDG(&d.Qe[hk_qe(d, a * 3 + c, e)]) : 0.0;
+            for (int c = 0; c < 3; ++c) v[w][c] = ok ? HK_LDG(&d.Qe[(long long)(a * 3 + c) * d.nEp + e]) : 0.0;
         }
 #pragma unroll
         for (int w = 0; w < 8; ++w) { q0 += v[w][0]; q1 += v[w][1]; q2 += v[w][2]; }
@@ -146,9 +146,9 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
             if (en < 0) break;
             const long long e = en >> 3;
             const int a = en & 7;
-            q0 += d.Qe[hk_qe(d, a * 3 + 0, e)];
-            q1 += d.Qe[hk_qe(d, a * 3 + 1, e)];
-            q2 += d.Qe[hk_qe(d, a * 3 + 2, e)];
+            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
+            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
+            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
         }
     }
     double F[3] = {0.0, 0.0, 0.0};
@@ -359,7 +359,7 @@ HK_D void contact_tri_body(const ContactArgs& A, long long j) {
 
     int en[8];
     if (p.self)
-        for (int q = 0; q < 8; ++q) en[q] = d.conn[hk_cn(d, q, eleid)];
+        for (int q = 0; q < 8; ++q) en[q] = d.conn[(long long)q * d.nEp + eleid];
 
     unsigned long long n_tests = 0, n_hits = 0;
     const unsigned bucket_mask = (unsigned)(p.dyn->n_bucket - 1);
@@ -719,9 +719,9 @@ void hk_launch_gather_Q(const HkDev& dd, double* Q_out, cudaStream_t s) {
             if (ent < 0) break;
             long long e = ent >> 3;
             int a = ent & 7;
-            q0 += d.Qe[hk_qe(d, a * 3 + 0, e)];
-            q1 += d.Qe[hk_qe(d, a * 3 + 1, e)];
-            q2 += d.Qe[hk_qe(d, a * 3 + 2, e)];
+            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
+            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
+            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
         }
         Q_out[3 * n] = q0; Q_out[3 * n + 1] = q1; Q_out[3 * n + 2] = q2;
     });
@@ -738,9 +738,9 @@ void hk_launch_halo_pack(const HkDev& dd, const int* nodes, long long n, double*
             if (ent < 0) break;
             const long long e = ent >> 3;
             const int a = ent & 7;
-            q0 += d.Qe[hk_qe(d, a * 3 + 0, e)];
-            q1 += d.Qe[hk_qe(d, a * 3 + 1, e)];
-            q2 += d.Qe[hk_qe(d, a * 3 + 2, e)];
+            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
+            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
+            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
         }
         out[3 * i] = q0; out[3 * i + 1] = q1; out[3 * i + 2] = q2;
     });
@@ -1071,7 +1071,7 @@ HK_D void element_body_exact(const ExactArgs& A, long long e) {
     const unsigned char fl = d.flag[e];
     if (fl != 1) {
         if (fl == 0) {
-            for (int r = 0; r < 24; ++r) d.Qe[hk_qe(d, r, e)] = 0.0;
+            for (int r = 0; r < 24; ++r) d.Qe[(long long)r * d.nEp + e] = 0.0;
             for (int k = 0; k < 8; ++k) d.triax[(long long)k * d.nEp + e] = 0.0;
             d.flag[e] = 2;
         }
@@ -1086,7 +1086,7 @@ HK_D void element_body_exact(const ExactArgs& A, long long e) {
     Dm[3][3] = Dm[4][4] = Dm[5][5] = M.D44;
     double d_u[24], ep[3][8];
     for (int i = 0; i < 8; ++i) {
-        const long long n = d.conn[hk_cn(d, i, e)];
+        const long long n = d.conn[(long long)i * d.nEp + e];
         for (int c = 0; c < 3; ++c) { ep[c][i] = d.rec[6 * n + c]; d_u[i * 3 + c] = d.rec[6 * n + 3 + c]; }
     }
     // cal_BVbar_hexa
@@ -1201,7 +1201,7 @@ HK_D void element_body_exact(const ExactArgs& A, long long e) {
         v_e += ep_;
         t_e += tx;
     }
-    for (int j = 0; j < 24; ++j) d.Qe[hk_qe(d, j, e)] = Qe[j];
+    for (int j = 0; j < 24; ++j) d.Qe[(long long)j * d.nEp + e] = Qe[j];
     // fracture, J2:701-762
     if (M.nd > 0) {
         v_e /= 8;
