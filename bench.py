@@ -228,7 +228,8 @@ def main():
             e_ = Engine(**p)
             e_.set_stream(stream.cuda_stream)
             return e_
-        pcheck = slab_parity_check(make_checked, torch.device("cuda", local_rank), rank, world, device=local_rank)
+        pcheck = slab_parity_check(make_checked, torch.device("cuda", local_rank), rank, world, engine_comm=True,
+                                   device=local_rank)
         if rank == 0:
             print(f"[parity_check] {pcheck}", file=sys.stderr)
 
@@ -249,12 +250,14 @@ def main():
         e_ = Engine(**p)
         e_.set_stream(stream.cuda_stream)
         return e_
-    runner = SlabRunner(make_engine, st, nbrs, halos, torch.device("cuda", local_rank), sum_mass=True, device=local_rank, **prm)
+    # N > 1: the engine owns the NCCL communicator and runs pack -> send/recv -> step for all steps of a call by itself
+    runner = SlabRunner(make_engine, st, nbrs, halos, torch.device("cuda", local_rank), sum_mass=True, rank=rank,
+                        engine_comm=world > 1, device=local_rank, **prm)
     eng = runner.engine
 
     def run_steps(t0, n):
         if world > 1:
-            return runner.run(t0, n)          # halo pack -> NCCL send/recv -> hk_step, every step
+            return runner.run(t0, n)          # hk_step_enqueue(t0, n): pack -> ncclSend/Recv -> split step, n times, in the engine
         return eng.step(t0, n)
 
     def barrier():

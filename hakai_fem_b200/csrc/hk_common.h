@@ -172,9 +172,10 @@ void hk_launch_state_export(const HkDev& d, const int* nodes, long long n, doubl
 void hk_launch_state_import(const HkDev& d, const int* nodes, long long n, const double* in, double d_time, cudaStream_t s);
 void hk_launch_cacc_export_limbs(const HkDev& d, const int* nodes, long long n, long long* out, cudaStream_t s);
 void hk_launch_cacc_import_limbs(const HkDev& d, const int* nodes, long long n, const long long* in, cudaStream_t s);
-// halo: partial internal force of `n` listed nodes -> out[3*i..] ; recv sums -> d.halo_recv
-void hk_launch_halo_pack(const HkDev& d, const int* nodes, long long n, double* out, cudaStream_t s);
-void hk_launch_halo_accumulate(const HkDev& d, const int* slots, long long n, const double* recv, int first, cudaStream_t s);
+// halo (multi-GPU interface nodes): own partial forces, per-neighbour send blocks, rank-ordered total in d.halo_recv
+void hk_launch_halo_pack(const HkDev& d, const int* nodes, long long n, double* out, const double* Q0, cudaStream_t s);
+void hk_launch_halo_gather(const double* own, const int* slots, long long n, double* send, cudaStream_t s);
+void hk_launch_halo_accumulate(const HkDev& d, const int* slots, long long n, const double* recv, cudaStream_t s);
 void hk_launch_triax(const HkDev& d, cudaStream_t s);
 void hk_launch_element_volume(const HkDev& d, double* V_out, cudaStream_t s);
 // layout transposes between the reference's AoS (6,nip)/(nip) arrays and the SoA rows

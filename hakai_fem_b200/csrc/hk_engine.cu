@@ -65,8 +65,8 @@ struct HaloNbr {
     int* d_slots = nullptr;
     double* send = nullptr;        // caller-owned device buffers
     double* recv = nullptr;
-    std::vector<char> first;       // per entry: this neighbour is the first contributor of the slot
-    int* d_dummy = nullptr;
+    int64_t rank = -1;             // global rank of the neighbour (hk_set_halo_ranks); -1: unknown
+    bool own_buffers = false;      // send/recv allocated by the engine (hk_comm_init) rather than bound by the host
 };
 struct TimedEvent {
 #ifndef HK_EMU
@@ -96,6 +96,15 @@ struct hk_engine {
     std::vector<HaloNbr> halo;
     int n_halo_nodes = 0;
     int* d_halo_list = nullptr;    // node id of every halo slot (nodal kernel mode 2)
+    double* d_halo_own = nullptr;  // [n_halo*3] this rank's own partial force of every halo slot
+    int64_t my_rank = -1;          // global rank of this engine (hk_set_halo_ranks); -1: unknown
+    // NCCL inside the library (hk_comm_init): communicator, side stream for the exchange, ordering events
+    void* comm = nullptr;
+    int comm_world = 0;
+#ifndef HK_EMU
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_comm = nullptr;
+#endif
     // multi-GPU node lists: contact 0 own-export, 1 ghost-import, 2 surface nodes (force exchange);
     // ghost-element mode 3 state-export, 4 state-import
     std::vector<int> node_list[5];
@@ -665,6 +674,92 @@ static int fetch_deleted(hk_engine* e, std::vector<int64_t>* fresh) {
     return 0;
 }
 
+// --------------------------------------------------------------------------------- NCCL, loaded at run time
+// The engine owns its communicator.  libnccl is not a link-time dependency: the copy already loaded in the
+// process (e.g. by the host framework) is used when there is one, else libnccl.so.2 from the loader path.
+#ifndef HK_EMU
+#include <dlfcn.h>
+namespace {
+struct HkNcclId { char internal[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(HkNcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, HkNcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+NcclApi g_nccl;
+const int kNcclFloat64 = 8;          // ncclFloat64 (nccl.h)
+
+bool nccl_load() {
+    if (g_nccl.lib) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_nccl.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+    auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) g_nccl.err = std::string("libnccl lacks ") + n; return p; };
+    g_nccl.GetUniqueId = (int (*)(HkNcclId*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, HkNcclId, int))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.Send || !g_nccl.Recv ||
+        !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.GetErrorString)
+        return false;
+    g_nccl.lib = h;
+    return true;
+}
+}  // namespace
+#define NCK(call) do { int rn_ = (call); if (rn_) return fail(e, HK_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(rn_)); } while (0)
+#endif
+
+// own partial forces of all interface nodes -> d_halo_own, then one send block per neighbour
+static int halo_pack_all(hk_engine* e) {
+    if (e->halo.empty()) return 0;
+    hk_launch_halo_pack(e->d, e->d_halo_list, e->n_halo_nodes, e->d_halo_own, e->use_Q0 ? e->d.Q0 : nullptr, e->stream);
+    e->n_launch += 1;
+    for (HaloNbr& h : e->halo) {
+        if (!h.send) return fail(e, HK_ERR_STATE, "hk_halo_bind (or hk_comm_init) not called for every neighbour");
+        hk_launch_halo_gather(e->d_halo_own, h.d_slots, (long long)h.slots.size(), h.send, e->stream);
+        e->n_launch += 1;
+    }
+    return 0;
+}
+
+// received partials + this rank's own -> d.halo_recv, one holder at a time in ascending global-rank order (own first
+// when the ranks are unknown): every holder of an interface node then forms the same sum bit for bit, whatever the
+// number of holders
+static int halo_total(hk_engine* e) {
+    const HkDev& d = e->d;
+    CK(hkp::dev_memset(d.halo_recv, 0, sizeof(double) * 3 * e->n_halo_nodes, e->stream));
+    std::vector<size_t> order(e->halo.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return e->halo[a].rank < e->halo[b].rank; });
+    bool own_done = false;
+    auto add_own = [&]() {
+        hk_launch_halo_accumulate(d, nullptr, e->n_halo_nodes, e->d_halo_own, e->stream);
+        e->n_launch += 1;
+        own_done = true;
+    };
+    for (size_t i : order) {
+        HaloNbr& h = e->halo[i];
+        if (!h.recv) return fail(e, HK_ERR_STATE, "hk_halo_bind (or hk_comm_init) not called for every neighbour");
+        if (!own_done && (e->my_rank < 0 || h.rank > e->my_rank)) add_own();
+        hk_launch_halo_accumulate(d, h.d_slots, (long long)h.slots.size(), h.recv, e->stream);
+        e->n_launch += 1;
+    }
+    if (!own_done) add_own();
+    return 0;
+}
+
 // ================================================================================= exported ABI
 extern "C" {
 
@@ -717,6 +812,13 @@ int HKAPI(destroy)(hk_engine* e) {
     hkp::sync(e->stream);
     for (void* p : e->allocs) hkp::dev_free(p);
 #ifndef HK_EMU
+    if (e->comm) {
+        cudaStreamSynchronize(e->comm_stream);
+        g_nccl.CommDestroy(e->comm);
+        cudaStreamDestroy(e->comm_stream);
+        cudaEventDestroy(e->ev_pack);
+        cudaEventDestroy(e->ev_comm);
+    }
     if (e->own_stream) cudaStreamDestroy(e->stream);
 #endif
     delete e;
@@ -1063,6 +1165,7 @@ int HKAPI(finalize)(hk_engine* e) {
             if ((rc = dalloc(e, &e->d_halo_list, list.size()))) return rc;
             if ((rc = upload(e, e->d_halo_list, list))) return rc;
         }
+        if ((rc = dalloc(e, &e->d_halo_own, (size_t)3 * e->n_halo_nodes))) return rc;
         if ((rc = dalloc(e, &d.halo_recv, (size_t)3 * e->n_halo_nodes))) return rc;
         CK(hkp::dev_memset(d.halo_recv, 0, sizeof(double) * 3 * e->n_halo_nodes, e->stream));
     }
@@ -1138,14 +1241,10 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
             e->n_launch += 1;
             continue;
         }
-        if (!e->halo.empty()) {          // received partial forces -> halo_recv (fixed neighbour order)
+        if (!e->halo.empty()) {          // received partial forces + own -> halo_recv (ascending rank order)
             prof_begin(e, 3);
-            CK(hkp::dev_memset(d.halo_recv, 0, sizeof(double) * 3 * e->n_halo_nodes, e->stream));
-            for (HaloNbr& h : e->halo) {
-                if (!h.recv) return fail(e, HK_ERR_STATE, "hk_halo_bind not called for every neighbour");
-                hk_launch_halo_accumulate(d, h.d_slots, (long long)h.slots.size(), h.recv, 0, e->stream);
-                e->n_launch += 1;
-            }
+            int rc = halo_total(e);
+            if (rc) return rc;
             prof_end(e);
         }
         prof_begin(e, 1);
@@ -1181,10 +1280,50 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
     return HK_OK;
 }
 
+#ifndef HK_EMU
+// Multi-GPU steps with the engine's own communicator: per step
+//     pack (main stream) -> ncclSend/ncclRecv with every neighbour (side stream) || nodal update of the non-interface
+//     nodes (main stream) -> interface nodes, element kernel (main stream, after the exchange)
+// all enqueued for n_steps steps without the host looking at anything in between.
+static int comm_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end) {
+    if (e->frame_next && n_steps > 0) { frame_at_end = true; e->frame_next = false; }      // hk_mark_frame: LAST step
+    for (int64_t t = t_first; t < t_first + n_steps; ++t) {
+        int rc = halo_pack_all(e);
+        if (rc) return rc;
+        CK(cudaEventRecord(e->ev_pack, e->stream));
+        CK(cudaStreamWaitEvent(e->comm_stream, e->ev_pack, 0));
+        NCK(g_nccl.GroupStart());
+        for (HaloNbr& h : e->halo) {
+            NCK(g_nccl.Send(h.send, 3 * h.nodes.size(), kNcclFloat64, (int)h.rank, e->comm, e->comm_stream));
+            NCK(g_nccl.Recv(h.recv, 3 * h.nodes.size(), kNcclFloat64, (int)h.rank, e->comm, e->comm_stream));
+        }
+        NCK(g_nccl.GroupEnd());
+        CK(cudaEventRecord(e->ev_comm, e->comm_stream));
+        if ((rc = enqueue_steps(e, t, 1, false, 1))) return rc;       // overlaps the exchange
+        CK(cudaStreamWaitEvent(e->stream, e->ev_comm, 0));
+        if (frame_at_end && t == t_first + n_steps - 1) e->frame_next = true;
+        if ((rc = enqueue_steps(e, t, 1, false, 2))) return rc;
+    }
+    return 0;
+}
+#endif
+
 static int step_enqueue_impl(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     if (n_steps < 0 || t_first < 0 || t_first + n_steps >= (1ll << 31)) return fail(e, HK_ERR_ARG, "bad step range");
-    if (!e->halo.empty() && n_steps > 1) return fail(e, HK_ERR_ARG, "with halos, exchange and step one step at a time");
+#ifndef HK_EMU
+    if (!e->halo.empty() && e->comm) {                 // the engine exchanges the halos itself: any number of steps
+        if (e->prm.contact_flag >= 1 && !e->pairs.empty())
+            return fail(e, HK_ERR_UNSUPPORTED, "contact across ranks is exchanged by the host driver (hk_nodes_* / hk_contact_*), "
+                                               "one step at a time: use hk_halo_pack + hk_step_begin / hk_step_finish");
+        int rc = comm_steps(e, t_first, n_steps, frame_at_end);
+        if (rc) return rc;
+        CK(hkp::last_error());
+        return HK_OK;
+    }
+#endif
+    if (!e->halo.empty() && n_steps > 1)
+        return fail(e, HK_ERR_ARG, "with halos and no communicator (hk_comm_init), exchange and step one step at a time");
 
     int rc = enqueue_steps(e, t_first, n_steps, frame_at_end, 0);
     if (rc) return rc;
@@ -1527,13 +1666,68 @@ int HKAPI(halo_bind)(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_
 
 int HKAPI(halo_pack)(hk_engine* e) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
-    for (HaloNbr& h : e->halo) {
-        if (!h.send) return fail(e, HK_ERR_STATE, "hk_halo_bind not called for every neighbour");
-        hk_launch_halo_pack(e->d, h.d_nodes, (long long)h.nodes.size(), h.send, e->stream);
-        e->n_launch += 1;
-    }
+    int rc = halo_pack_all(e);
+    if (rc) return rc;
     CK(hkp::last_error());
     return HK_OK;
+}
+
+int HKAPI(set_halo_ranks)(hk_engine* e, int64_t my_rank, int64_t n_neighbors, const int64_t* ranks) {
+    if (!e) return HK_ERR_ARG;
+    if (n_neighbors != (int64_t)e->halo.size()) return fail(e, HK_ERR_ARG, "hk_set_halo_ranks: one rank per hk_set_halo neighbour");
+    if (my_rank < 0) return fail(e, HK_ERR_ARG, "bad rank");
+    for (int64_t i = 0; i < n_neighbors; ++i) {
+        if (!ranks || ranks[i] < 0 || ranks[i] == my_rank) return fail(e, HK_ERR_ARG, "bad neighbour rank");
+        e->halo[i].rank = ranks[i];
+    }
+    e->my_rank = my_rank;
+    return HK_OK;
+}
+
+int HKAPI(comm_unique_id)(void* id128) {
+#ifndef HK_EMU
+    if (!id128) return HK_ERR_ARG;
+    if (!nccl_load()) return fail(nullptr, HK_ERR_UNSUPPORTED, g_nccl.err);
+    HkNcclId id;
+    const int rn = g_nccl.GetUniqueId(&id);
+    if (rn) return fail(nullptr, HK_ERR_CUDA, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rn));
+    std::memcpy(id128, &id, sizeof(id));
+    return HK_OK;
+#else
+    (void)id128;
+    return fail(nullptr, HK_ERR_UNSUPPORTED, "host-compiled debugging build has no NCCL");
+#endif
+}
+
+int HKAPI(comm_init)(hk_engine* e, const void* id128, int32_t rank, int32_t world) {
+#ifndef HK_EMU
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(e, HK_ERR_ARG, "bad communicator arguments");
+    if (e->comm) return fail(e, HK_ERR_STATE, "communicator already created");
+    if (!e->halo.empty() && (e->my_rank != rank)) return fail(e, HK_ERR_STATE, "hk_set_halo_ranks must give this rank before hk_comm_init");
+    for (const HaloNbr& h : e->halo)
+        if (h.rank < 0 || h.rank >= world) return fail(e, HK_ERR_STATE, "hk_set_halo_ranks: neighbour rank outside the communicator");
+    if (!nccl_load()) return fail(e, HK_ERR_UNSUPPORTED, g_nccl.err);
+    CK(cudaSetDevice(e->prm.device));
+    HkNcclId id;
+    std::memcpy(&id, id128, sizeof(id));
+    NCK(g_nccl.CommInitRank(&e->comm, world, id, rank));
+    e->comm_world = world;
+    CK(cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_pack, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
+    for (HaloNbr& h : e->halo) {                      // the engine's own exchange buffers
+        if (h.send && h.recv) continue;
+        int rc;
+        if ((rc = dalloc(e, &h.send, 3 * h.nodes.size()))) return rc;
+        if ((rc = dalloc(e, &h.recv, 3 * h.nodes.size()))) return rc;
+        h.own_buffers = true;
+    }
+    return HK_OK;
+#else
+    (void)id128; (void)rank; (void)world;
+    return fail(e, HK_ERR_UNSUPPORTED, "host-compiled debugging build has no NCCL");
+#endif
 }
 
 int HKAPI(set_node_list)(hk_engine* e, int32_t which, int64_t n, const int64_t* nodes) {

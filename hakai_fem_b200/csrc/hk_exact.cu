@@ -156,10 +156,10 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
     bool has_bc[3] = {false, false, false};
     if (si >= 0) {
         const HkSpecialNode sp = d.spec[si];
-        if (sp.halo_slot >= 0) {                 // partial sums of the neighbour rank (multi-GPU)
-            q0 += d.halo_recv[3 * sp.halo_slot];
-            q1 += d.halo_recv[3 * sp.halo_slot + 1];
-            q2 += d.halo_recv[3 * sp.halo_slot + 2];
+        if (sp.halo_slot >= 0) {                 // interface node (multi-GPU): the complete sum over all holders, formed in
+            q0 = d.halo_recv[3 * sp.halo_slot];  // ascending global-rank order with this rank's own partial in its place
+            q1 = d.halo_recv[3 * sp.halo_slot + 1];   // (hk_engine.cu: halo_total) — the same bits on every holder
+            q2 = d.halo_recv[3 * sp.halo_slot + 2];
         }
         if (A.contact_on && sp.contact_slot >= 0) {     // external_force += c_force3, J2:536-538
             const unsigned long long* acc = d.cacc + (long long)sp.contact_slot * 6;
@@ -727,33 +727,47 @@ void hk_launch_gather_Q(const HkDev& dd, double* Q_out, cudaStream_t s) {
     });
 }
 
-// partial internal force of the listed (interface) nodes, same gather order as the nodal kernel
-void hk_launch_halo_pack(const HkDev& dd, const int* nodes, long long n, double* out, cudaStream_t s) {
+// partial internal force of the listed (interface) nodes, same gather order as the nodal kernel; Q0 != NULL: the
+// partial force was supplied through hk_upload_state
+void hk_launch_halo_pack(const HkDev& dd, const int* nodes, long long n, double* out, const double* Q0, cudaStream_t s) {
     const HkDev d = dd;
     hk_parallel_for(n, s, HK_LAMBDA(long long i) {
         const long long nd = nodes[i];
         double q0 = 0.0, q1 = 0.0, q2 = 0.0;
-        for (int w = 0; w < d.ell_width; ++w) {
-            const int ent = d.ell[(long long)w * d.nNode + nd];
-            if (ent < 0) break;
-            const long long e = ent >> 3;
-            const int a = ent & 7;
-            q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
-            q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
-            q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+        if (Q0) {
+            q0 = Q0[3 * nd]; q1 = Q0[3 * nd + 1]; q2 = Q0[3 * nd + 2];
+        } else {
+            for (int w = 0; w < d.ell_width; ++w) {
+                const int ent = d.ell[(long long)w * d.nNode + nd];
+                if (ent < 0) break;
+                const long long e = ent >> 3;
+                const int a = ent & 7;
+                q0 += d.Qe[(long long)(a * 3 + 0) * d.nEp + e];
+                q1 += d.Qe[(long long)(a * 3 + 1) * d.nEp + e];
+                q2 += d.Qe[(long long)(a * 3 + 2) * d.nEp + e];
+            }
         }
         out[3 * i] = q0; out[3 * i + 1] = q1; out[3 * i + 2] = q2;
     });
 }
 
-// halo_recv[slot] (=|+=) recv[i]: neighbours are accumulated in a fixed order -> reproducible
-void hk_launch_halo_accumulate(const HkDev& dd, const int* slots, long long n, const double* recv, int first, cudaStream_t s) {
+// send[i] = own[slots[i]]: the part of this rank's interface partials that neighbour shares
+void hk_launch_halo_gather(const double* own, const int* slots, long long n, double* send, cudaStream_t s) {
+    hk_parallel_for(n * 3, s, HK_LAMBDA(long long j) {
+        const long long i = j / 3;
+        send[j] = own[3ll * slots[i] + (j - 3 * i)];
+    });
+}
+
+// halo_recv[slot] += recv[i] (slots == NULL: dense, slot = i): contributions are added one holder at a time in
+// ascending global-rank order, so every holder of a node forms the same sum bit for bit
+void hk_launch_halo_accumulate(const HkDev& dd, const int* slots, long long n, const double* recv, cudaStream_t s) {
     const HkDev d = dd;
     hk_parallel_for(n * 3, s, HK_LAMBDA(long long j) {
         const long long i = j / 3;
         const int c = (int)(j - 3 * i);
-        const long long k = 3ll * slots[i] + c;
-        d.halo_recv[k] = first ? recv[j] : d.halo_recv[k] + recv[j];
+        const long long k = 3ll * (slots ? slots[i] : i) + c;
+        d.halo_recv[k] = d.halo_recv[k] + recv[j];
     });
 }
 

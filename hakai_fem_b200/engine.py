@@ -44,7 +44,7 @@ EXPORTS = [
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
     "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
-    "state_export", "state_import", "state_summary", "deleted_steps",
+    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init",
 ]
 
 
@@ -325,6 +325,23 @@ class EngineBase:
         """node_lists[i]: local 1-based ids of the nodes shared with neighbour i (call before finalize)."""
         ptr, flat = _csr(node_lists)
         self._chk(self._fn("set_halo")(self._h, c_i64(len(node_lists)), _pi(ptr), _pi(flat)))
+
+    def set_halo_ranks(self, my_rank: int, ranks):
+        """Global rank of this engine and of each set_halo neighbour: rank-ordered (holder-count independent) sums."""
+        a = _i64(ranks)
+        self._chk(self._fn("set_halo_ranks")(self._h, c_i64(my_rank), c_i64(len(a)), _pi(a)))
+
+    def comm_unique_id(self) -> bytes:
+        """128-byte ncclUniqueId (call on one rank, broadcast the bytes)."""
+        buf = C.create_string_buffer(128)
+        self._chk(self._fn("comm_unique_id")(buf), created=False)
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """The engine creates its own NCCL communicator; step_enqueue(t, n) then runs n multi-GPU steps by itself."""
+        if len(unique_id) != 128:
+            raise ValueError("unique_id: 128 bytes")
+        self._chk(self._fn("comm_init")(self._h, C.c_char_p(unique_id), C.c_int32(rank), C.c_int32(world)))
 
     def halo_bind(self, neighbor: int, send_ptr: int, recv_ptr: int):
         self._chk(self._fn("halo_bind")(self._h, c_i64(neighbor), C.c_void_p(send_ptr), C.c_void_p(recv_ptr)))

@@ -206,7 +206,7 @@ def slab_deck(deck, rank: int, world: int):
 
 
 def slab_parity_check(make_engine, torch_device, rank: int, world: int, n_steps: int = 32, nx: int = 24, ny: int = 24,
-                      nz_per_rank: int = 8, **params):
+                      nz_per_rank: int = 8, engine_comm: bool = False, **params):
     """Checks the z-slab / force-halo path against an unpartitioned run of the SAME mesh and the same kernels.
 
     A small GLOBAL deck (nx x ny x nz_per_rank*world ductile block, jitter seeded per global node layer, stretched fast
@@ -222,7 +222,8 @@ def slab_parity_check(make_engine, torch_device, rank: int, world: int, n_steps:
                                 strain_per_step=1.0e-3, jitter_by_layer=True)
     fields = ("disp", "integ_eq_plastic_strain", "integ_stress", "element_flag")
     deck, nbrs, halos = slab_deck(mk(nz_per_rank), rank, world)
-    runner = SlabRunner(make_engine, prepare(deck.build_model()), nbrs, halos, torch_device, sum_mass=True, **params)
+    runner = SlabRunner(make_engine, prepare(deck.build_model()), nbrs, halos, torch_device, sum_mass=True, rank=rank,
+                        engine_comm=engine_comm, **params)
     runner.run(1, n_steps)
     d = runner.engine.download(fields=fields)
     mine = dict(disp=d["disp"], eps=d["integ_eq_plastic_strain"], stress=np.ascontiguousarray(d["integ_stress"]),
@@ -253,19 +254,41 @@ def slab_parity_check(make_engine, torch_device, rank: int, world: int, n_steps:
     del_equal = bool(np.array_equal(np.sort(np.concatenate(got_del)), ref_del)) and flags_equal
     return {"n_ranks": world, "deck": f"{nx}x{ny}x{nz_per_rank * world} ductile block, {n_steps} steps, {world} slabs over "
                                       f"the halo exchange vs the same mesh unpartitioned on one engine",
+            "exchange": "engine-owned NCCL communicator (hk_comm_init), all steps enqueued in one call" if engine_comm
+                        else "host-driven (torch.distributed P2P per step)",
             "max_rel_err": float(err), "deleted_equal": del_equal, "n_deleted": int(len(ref_del)),
             "interface_bitwise": bool(bitwise),
             "ok": bool(err <= 1e-10 and del_equal and bitwise and 0 < len(ref_del))}
 
 
 class HaloExchanger:
-    """send/recv buffers (torch tensors on the engine's device) + one batch of P2P ops per step."""
+    """send/recv buffers (torch tensors on the engine's device) + one batch of P2P ops per step.
 
-    def __init__(self, engine, neighbors, halo_nodes, device):
+    engine_comm=True: the ENGINE owns an NCCL communicator (hk_comm_init; the 128-byte id is created by rank 0 through
+    the library and broadcast here) and its own exchange blocks; `hk_step_enqueue(t, n)` then packs, sends, receives
+    and steps n times without Python in the loop."""
+
+    def __init__(self, engine, neighbors, halo_nodes, device, rank=None, engine_comm=False):
         import torch
         self.torch = torch
         self.engine = engine
         self.neighbors = list(neighbors)
+        self.engine_comm = False
+        self._bytes = sum(3 * len(h) * 8 for h in halo_nodes) * 2
+        if rank is not None and self.neighbors:
+            engine.set_halo_ranks(rank, self.neighbors)          # rank-ordered sums: any number of holders per node
+        if engine_comm:
+            import torch.distributed as dist
+            world = dist.get_world_size()
+            me = dist.get_rank() if rank is None else rank
+            idt = torch.zeros(128, dtype=torch.uint8, device=device)
+            if me == 0:
+                idt.copy_(torch.frombuffer(bytearray(engine.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            engine.comm_init(bytes(idt.cpu().numpy().tobytes()), me, world)
+            self.engine_comm = True
+            self.send = self.recv = []
+            return
         self.send = [torch.zeros(3 * len(h), dtype=torch.float64, device=device) for h in halo_nodes]
         self.recv = [torch.zeros(3 * len(h), dtype=torch.float64, device=device) for h in halo_nodes]
         for i in range(len(self.neighbors)):
@@ -293,7 +316,7 @@ class HaloExchanger:
 
     @property
     def bytes_per_step(self):
-        return sum(t.numel() * 8 for t in self.send) * 2
+        return self._bytes
 
 
 def exchange_sum(values_per_nbr, neighbors, device):
@@ -404,7 +427,8 @@ class SlabRunner:
     host-compiled kernel build, whose "device" pointers are host pointers."""
 
     def __init__(self, engine_cls, setup: Setup, neighbors, halo_nodes, torch_device, sum_mass=False, contact=None,
-                 world=1, rank=None, node_l2g=None, elem_l2g=None, force_exchange="allreduce", **params):
+                 world=1, rank=None, node_l2g=None, elem_l2g=None, force_exchange="allreduce", engine_comm=False,
+                 **params):
         self.setup = setup
         if sum_mass and neighbors:
             # interface nodes: add the neighbour's partial lumped mass (J2:201-215 summed over ALL elements)
@@ -421,7 +445,9 @@ class SlabRunner:
                 eng.set_halo(halo_nodes)
             return eng
         self.engine = configure_engine(with_halo, setup, **params)
-        self.halo = HaloExchanger(self.engine, neighbors, halo_nodes, torch_device)
+        if engine_comm and contact is not None:
+            raise ValueError("engine_comm: decks with contact across ranks use the host-driven exchange")
+        self.halo = HaloExchanger(self.engine, neighbors, halo_nodes, torch_device, rank=rank, engine_comm=engine_comm)
         self.contact = (ContactExchanger(self.engine, contact, world, torch_device, rank, node_l2g, len(setup.CT),
                                          force_exchange)
                         if contact is not None else None)
@@ -460,6 +486,12 @@ class SlabRunner:
         import time as _time
         _t0 = _time.perf_counter()
         n_del = 0
+        if self.halo.engine_comm:                        # one call: the engine packs, exchanges (its own NCCL) and steps
+            if frame_at_end:
+                self.engine.mark_frame()
+            self.engine.step_enqueue(t_first, n_steps)
+            self.last_enqueue_s = _time.perf_counter() - _t0
+            return self.engine.sync()
         for t in range(t_first, t_first + n_steps):
             if frame_at_end and t == t_first + n_steps - 1:
                 self.engine.mark_frame()

@@ -225,6 +225,23 @@ int hk_set_stream(hk_engine* e, void* cuda_stream);
 int hk_set_halo(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr, const int64_t* nodes);
 int hk_halo_bind(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_dev);
 int hk_halo_pack(hk_engine* e);
+/* Global rank of this engine and of every hk_set_halo neighbour (same order).  With them the partial forces of an
+ * interface node are summed one holder at a time in ascending rank order, this rank's own partial in its place, so that
+ * EVERY holder forms the same bits even when a node is shared by three or more ranks; without them the own partial comes
+ * first (identical on both sides only for nodes with exactly two holders). */
+int hk_set_halo_ranks(hk_engine* e, int64_t my_rank, int64_t n_neighbors, const int64_t* ranks);
+
+/* NCCL inside the library: the engine owns its communicator (libnccl.so.2 is loaded at run time; the copy already in
+ * the process is shared when there is one).
+ *   hk_comm_unique_id  fills 128 bytes (an ncclUniqueId) on one rank; the host hands them to every rank by any means.
+ *   hk_comm_init       after hk_finalize and hk_set_halo_ranks: creates the communicator on the engine's device and
+ *                      allocates the engine's own send/recv blocks (hk_halo_bind is then not needed).
+ * With a communicator hk_step / hk_step_enqueue(t, n) run n >= 1 complete multi-GPU steps with no host involvement:
+ * pack -> ncclSend/ncclRecv with every neighbour on a side stream, overlapped with the nodal update of the non-interface
+ * nodes -> interface nodes -> element kernel.  (Decks with contact across ranks still use the host-driven exchange.) */
+int hk_comm_unique_id(void* id128);
+int hk_comm_init(hk_engine* e, const void* id128, int32_t rank, int32_t world);
+
 /* The asynchronous step calls imply no output frame, so they do not store integ_triax_stress (hk_download and
  * hk_node_output then derive it from the current stress).  hk_mark_frame announces that the last step of the NEXT
  * hk_step_enqueue / hk_step_finish call is followed by a frame: that step stores the triaxiality computed inside it

@@ -217,3 +217,50 @@ def test_ghost_partitions_are_bit_identical_to_one_gpu(kind):
         assert np.array_equal(a["disp"], ref["disp"].reshape(-1, 3)[a["nodes"]]), (kind, r)
         assert np.array_equal(a["eps"], ref["integ_eq_plastic_strain"][ip]), (kind, r)
         assert np.array_equal(a["flag"], ref["element_flag"][a["elems"]]), (kind, r)
+
+
+# ---- the engine's own NCCL communicator (hk_comm_init): all steps of a call enqueued by the library ------------------
+def _worker_engine_comm(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hakai_fem_b200.engine import Engine
+        from hakai_fem_b200.multi import slab_parity_check
+        stream = torch.cuda.current_stream()
+
+        def make(**p):
+            e = Engine(**p)
+            e.set_stream(stream.cuda_stream)
+            return e
+        res = {}
+        for mode in (True, False):        # engine-owned communicator vs host-driven torch.distributed P2P
+            res[mode] = slab_parity_check(make, torch.device("cuda", rank), rank, world, engine_comm=mode, device=rank)
+        q.put((rank, res))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_engine_owned_communicator_matches_unpartitioned_run():
+    """hk_comm_init + hk_step_enqueue(t, n): n multi-GPU steps (pack -> ncclSend/ncclRecv on a side stream -> split
+    step) enqueued by the library in ONE call, against the same mesh unpartitioned on one GPU: identical deleted set,
+    fields <= 1e-10, shared node layer bit-identical on both ranks; and the same verdict through the host-driven path."""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_engine_comm, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for mode in (True, False):
+        r0 = res[0][mode]
+        assert r0["ok"] and r0["interface_bitwise"] and r0["deleted_equal"] and r0["n_deleted"] > 0, (mode, r0)

@@ -680,3 +680,53 @@ def test_slab_jitter_is_a_function_of_the_global_layer():
     inner = whole[:, 3 * per:4 * per]                         # an interface plane: interior nodes ARE jittered
     base, _ = StretchDeck(5, 4, 3 * world).coord_elem()
     assert np.any(inner != base[:, 3 * per:4 * per])
+
+
+# ---- interface nodes held by three or more ranks: rank-ordered sums keep every copy bit-identical ----------
+def _worker_threeway(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hakai_fem_b200.model_setup import prepare
+        from hakai_fem_b200.multi import partition_model, SlabRunner
+        from hakai_fem_b200.mesh import StretchDeck
+        from tests.emu.emu_engine import EmuEngine
+        gsetup = prepare(StretchDeck(4, 3, 2, jitter=0.1, strain_per_step=3e-4).build_model())
+        dom = partition_model(gsetup, world)[rank]
+        run = SlabRunner.from_domain(EmuEngine, dom, "cpu", world)
+        run.run(1, 200)
+        d = run.engine.download(fields=("disp",))
+        n_own = len(np.unique(dom.setup.model.elementmat))
+        q.put((rank, dict(disp=d["disp"][:3 * n_own].reshape(-1, 3), node_l2g=dom.node_l2g[:n_own])))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nodes_shared_by_three_ranks_stay_bit_identical():
+    """Contiguous element blocks of a 4 x 3 x 2 mesh on 4 ranks give nodes held by 3 ranks.  With hk_set_halo_ranks the
+    partial forces are added in ascending global-rank order on every holder, so all copies of a node carry the same
+    bits after 200 steps (own-first order let them drift apart by ~1e-15 per step)."""
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 32500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_threeway, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    copies = {}
+    for r in range(world):
+        for g, u in zip(res[r]["node_l2g"], res[r]["disp"]):
+            copies.setdefault(int(g), []).append(u)
+    multi = {g: c for g, c in copies.items() if len(c) >= 3}
+    assert len(multi) >= 4, "mesh has no node held by three ranks: test is vacuous"
+    for g, c in copies.items():
+        for u in c[1:]:
+            assert np.array_equal(c[0], u), f"node {g} ({len(c)} holders) differs across ranks"
+    assert np.abs(np.concatenate([c[0] for c in copies.values()])).max() > 0
