@@ -148,6 +148,14 @@ struct hk_engine {
     std::vector<void*> allocs;
     double* staging = nullptr;     // device staging for layout transposes
     size_t staging_doubles = 0;
+    // double-buffered transfer of the Gauss-point state (hk_upload_state / hk_download): two staging blocks, a copy
+    // stream beside the engine's stream, events instead of host synchronisation per chunk
+    double* stage2[2] = {nullptr, nullptr};
+    size_t stage2_doubles = 0;
+#ifndef HK_EMU
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+#endif
     std::vector<int64_t> deleted_all;
     std::vector<int64_t> deleted_step;          // step t of every entry of deleted_all (0: replayed by hk_apply_deleted)
     size_t deleted_reported = 0;
@@ -819,6 +827,10 @@ int HKAPI(destroy)(hk_engine* e) {
         cudaEventDestroy(e->ev_pack);
         cudaEventDestroy(e->ev_comm);
     }
+    if (e->copy_stream) {
+        cudaStreamDestroy(e->copy_stream);
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(e->ev_ready[b]); cudaEventDestroy(e->ev_free[b]); }
+    }
     if (e->own_stream) cudaStreamDestroy(e->stream);
 #endif
     delete e;
@@ -1397,32 +1409,85 @@ static int ensure_staging(hk_engine* e, size_t doubles) {
     e->staging_doubles = doubles;
     return 0;
 }
-static const long long CHUNK_E = 1 << 18;   // elements per transposed chunk (<= 100 MB staging)
+static const long long CHUNK_E = 1 << 18;   // elements per transposed chunk (<= 100 MB per staging block)
 
+static int ensure_stage2(hk_engine* e, size_t doubles) {
+#ifndef HK_EMU
+    if (!e->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaEventCreateWithFlags(&e->ev_ready[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_free[b], cudaEventDisableTiming));
+        }
+    }
+#endif
+    if (e->stage2_doubles >= doubles) return 0;
+    for (int b = 0; b < 2; ++b) {
+        dfree(e, e->stage2[b]);
+        e->stage2[b] = nullptr;
+        int rc = dalloc(e, &e->stage2[b], doubles);
+        if (rc) return rc;
+    }
+    e->stage2_doubles = doubles;
+    return 0;
+}
+
+// Gauss-point fields between the reference's (ncomp, nip) arrays and the tile-blocked device rows, chunk by chunk
+// through two staging blocks: the PCIe copy of chunk i+1 (copy stream) overlaps the transpose of chunk i (engine
+// stream); events order them, the host never waits inside the loop.  The caller synchronises both streams once.
 static int download_ip(hk_engine* e, int row0, double* host, int ncomp) {   // row0 < 0: triax
     if (!host) return 0;
     const long long nE = e->nElement;
-    int rc = ensure_staging(e, (size_t)std::min<long long>(CHUNK_E, nE) * 8 * ncomp);
+    int rc = ensure_stage2(e, (size_t)std::min<long long>(CHUNK_E, nE) * 8 * 6);
     if (rc) return rc;
-    for (long long e0 = 0; e0 < nE; e0 += CHUNK_E) {
+    long long i = 0;
+    for (long long e0 = 0; e0 < nE; e0 += CHUNK_E, ++i) {
+        const int b = (int)(i & 1);
         const long long ne = std::min<long long>(CHUNK_E, nE - e0);
-        if (row0 < 0) hk_launch_triax_to_aos(e->d, e->staging, e0, ne, e->stream);
-        else hk_launch_ip_to_aos(e->d, e->staging, row0, ncomp, e0, ne, e->stream);
-        CK(hkp::d2h(host + e0 * 8 * ncomp, e->staging, (size_t)ne * 8 * ncomp * sizeof(double), e->stream));
+#ifndef HK_EMU
+        if (i >= 2) CK(cudaStreamWaitEvent(e->stream, e->ev_free[b], 0));        // its previous copy has left the block
+#endif
+        if (row0 < 0) hk_launch_triax_to_aos(e->d, e->stage2[b], e0, ne, e->stream);
+        else hk_launch_ip_to_aos(e->d, e->stage2[b], row0, ncomp, e0, ne, e->stream);
+#ifndef HK_EMU
+        CK(cudaEventRecord(e->ev_ready[b], e->stream));
+        CK(cudaStreamWaitEvent(e->copy_stream, e->ev_ready[b], 0));
+        CK(hkp::d2h_async(host + e0 * 8 * ncomp, e->stage2[b], (size_t)ne * 8 * ncomp * sizeof(double), e->copy_stream));
+        CK(cudaEventRecord(e->ev_free[b], e->copy_stream));
+#else
+        CK(hkp::d2h(host + e0 * 8 * ncomp, e->stage2[b], (size_t)ne * 8 * ncomp * sizeof(double), e->stream));
+#endif
     }
+#ifndef HK_EMU
+    CK(cudaStreamSynchronize(e->copy_stream));       // the next field reuses the blocks from chunk 0
+#endif
     return 0;
 }
 static int upload_ip(hk_engine* e, int row0, const double* host, int ncomp) {
     if (!host) return 0;
     const long long nE = e->nElement;
-    int rc = ensure_staging(e, (size_t)std::min<long long>(CHUNK_E, nE) * 8 * ncomp);
+    int rc = ensure_stage2(e, (size_t)std::min<long long>(CHUNK_E, nE) * 8 * 6);
     if (rc) return rc;
-    for (long long e0 = 0; e0 < nE; e0 += CHUNK_E) {
+    long long i = 0;
+    for (long long e0 = 0; e0 < nE; e0 += CHUNK_E, ++i) {
+        const int b = (int)(i & 1);
         const long long ne = std::min<long long>(CHUNK_E, nE - e0);
-        CK(hkp::h2d(e->staging, host + e0 * 8 * ncomp, (size_t)ne * 8 * ncomp * sizeof(double), e->stream));
-        hk_launch_ip_to_dev(e->staging, e->d, row0, ncomp, e0, ne, e->stream);
-        CK(hkp::sync(e->stream));
+#ifndef HK_EMU
+        if (i >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->ev_free[b], 0));   // its previous transpose has read the block
+        CK(hkp::h2d_async(e->stage2[b], host + e0 * 8 * ncomp, (size_t)ne * 8 * ncomp * sizeof(double), e->copy_stream));
+        CK(cudaEventRecord(e->ev_ready[b], e->copy_stream));
+        CK(cudaStreamWaitEvent(e->stream, e->ev_ready[b], 0));
+#else
+        CK(hkp::h2d(e->stage2[b], host + e0 * 8 * ncomp, (size_t)ne * 8 * ncomp * sizeof(double), e->stream));
+#endif
+        hk_launch_ip_to_dev(e->stage2[b], e->d, row0, ncomp, e0, ne, e->stream);
+#ifndef HK_EMU
+        CK(cudaEventRecord(e->ev_free[b], e->stream));
+#endif
     }
+#ifndef HK_EMU
+    CK(cudaStreamSynchronize(e->stream));            // the next field reuses the blocks from chunk 0
+#endif
     return 0;
 }
 
@@ -1432,10 +1497,10 @@ int HKAPI(download)(hk_engine* e, double* disp, double* velo, double* integ_stre
     const HkDev& d = e->d;
     const size_t fnb = sizeof(double) * 3 * e->nNode;
     int rc;
-    if (disp) CK(hkp::d2h(disp, d.u, fnb, e->stream));
+    if (disp) CK(hkp::d2h_async(disp, d.u, fnb, e->stream));          // one synchronisation at the end of the call
     if (velo) {
         if (!e->velo_current) { hk_launch_velo_from_rec(d, e->prm.d_time, e->stream); e->velo_current = true; }
-        CK(hkp::d2h(velo, d.velo, fnb, e->stream));
+        CK(hkp::d2h_async(velo, d.velo, fnb, e->stream));
     }
     if ((rc = download_ip(e, 0, integ_stress, 6))) return rc;
     if ((rc = download_ip(e, 6, integ_strain, 6))) return rc;
@@ -1449,6 +1514,7 @@ int HKAPI(download)(hk_engine* e, double* disp, double* velo, double* integ_stre
         CK(hkp::d2h(fl.data(), d.flag, fl.size(), e->stream));
         for (int64_t i = 0; i < e->nElement; ++i) element_flag[i] = fl[i] == 1 ? 1 : 0;
     }
+    CK(hkp::sync(e->stream));
     CK(hkp::last_error());
     return HK_OK;
 }
@@ -1469,12 +1535,12 @@ int HKAPI(node_output)(hk_engine* e, double* node_stress, double* node_strain, d
     e->n_launch += 2;
     const size_t nb = sizeof(double) * (size_t)d.nNode;
     int err = 0;
-    if (node_stress) err |= hkp::d2h(node_stress, out, 6 * nb, e->stream);
-    if (node_strain) err |= hkp::d2h(node_strain, out + 6 * d.nNode, 6 * nb, e->stream);
-    if (node_eq_plastic_strain) err |= hkp::d2h(node_eq_plastic_strain, out + 12 * d.nNode, nb, e->stream);
-    if (node_mises_stress && !raw) err |= hkp::d2h(node_mises_stress, out + 13 * d.nNode, nb, e->stream);
-    if (node_triax_stress) err |= hkp::d2h(node_triax_stress, out + 14 * d.nNode, nb, e->stream);
-    if (inc_num) err |= hkp::d2h(inc_num, out + 15 * d.nNode, nb, e->stream);
+    if (node_stress) err |= hkp::d2h_async(node_stress, out, 6 * nb, e->stream);
+    if (node_strain) err |= hkp::d2h_async(node_strain, out + 6 * d.nNode, 6 * nb, e->stream);
+    if (node_eq_plastic_strain) err |= hkp::d2h_async(node_eq_plastic_strain, out + 12 * d.nNode, nb, e->stream);
+    if (node_mises_stress && !raw) err |= hkp::d2h_async(node_mises_stress, out + 13 * d.nNode, nb, e->stream);
+    if (node_triax_stress) err |= hkp::d2h_async(node_triax_stress, out + 14 * d.nNode, nb, e->stream);
+    if (inc_num) err |= hkp::d2h_async(inc_num, out + 15 * d.nNode, nb, e->stream);
     err |= hkp::sync(e->stream);
     if (err) return fail(e, HK_ERR_CUDA, "hk_node_output: copy failed");
     CK(hkp::last_error());
@@ -1532,7 +1598,7 @@ int HKAPI(upload_state)(hk_engine* e, const double* disp, const double* disp_pre
     const size_t fnb = sizeof(double) * 3 * nN;
     int rc;
     if (disp) {
-        CK(hkp::h2d(d.u, disp, fnb, e->stream));
+        CK(hkp::h2d_async(d.u, disp, fnb, e->stream));                // synchronised once at the end of the call
         const HkDev dd = d;
         hk_parallel_for(nN * 3, e->stream, HK_LAMBDA(long long i) {      // position = coordmat + disp, J2:650-652
             const long long n = i / 3;
@@ -1540,9 +1606,9 @@ int HKAPI(upload_state)(hk_engine* e, const double* disp, const double* disp_pre
             dd.rec[6 * n + c] = dd.X[i] + dd.u[i];
         });
     }
-    if (disp_pre) CK(hkp::h2d(d.u_pre, disp_pre, fnb, e->stream));
-    if (velo) { CK(hkp::h2d(d.velo, velo, fnb, e->stream)); e->velo_current = true; }
-    if (Q) { CK(hkp::h2d(d.Q0, Q, fnb, e->stream)); e->use_Q0 = 1; }
+    if (disp_pre) CK(hkp::h2d_async(d.u_pre, disp_pre, fnb, e->stream));
+    if (velo) { CK(hkp::h2d_async(d.velo, velo, fnb, e->stream)); e->velo_current = true; }
+    if (Q) { CK(hkp::h2d_async(d.Q0, Q, fnb, e->stream)); e->use_Q0 = 1; }
     if ((rc = upload_ip(e, 0, integ_stress, 6))) return rc;
     if ((rc = upload_ip(e, 6, integ_strain, 6))) return rc;
     if ((rc = upload_ip(e, 12, integ_eq_plastic_strain, 1))) return rc;

@@ -37,6 +37,9 @@ inline int d2h(void* h, const void* d, size_t n, cudaStream_t s) {
     if (rc) return rc;
     return (int)cudaStreamSynchronize(s);
 }
+// asynchronous forms: the caller synchronises the stream before the host buffer is reused / read
+inline int h2d_async(void* d, const void* h, size_t n, cudaStream_t s) { return (int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s); }
+inline int d2h_async(void* h, const void* d, size_t n, cudaStream_t s) { return (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s); }
 inline int d2d(void* dst, const void* src, size_t n, cudaStream_t s) {
     return (int)cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s);
 }
@@ -49,6 +52,8 @@ inline int dev_malloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return 
 inline int dev_free(void* p) { std::free(p); return 0; }
 inline int h2d(void* d, const void* h, size_t n, cudaStream_t) { std::memcpy(d, h, n); return 0; }
 inline int d2h(void* h, const void* d, size_t n, cudaStream_t) { std::memcpy(h, d, n); return 0; }
+inline int h2d_async(void* d, const void* h, size_t n, cudaStream_t) { std::memcpy(d, h, n); return 0; }
+inline int d2h_async(void* h, const void* d, size_t n, cudaStream_t) { std::memcpy(h, d, n); return 0; }
 inline int d2d(void* dst, const void* src, size_t n, cudaStream_t) { std::memcpy(dst, src, n); return 0; }
 inline int dev_memset(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
 inline int sync(cudaStream_t) { return 0; }

@@ -92,6 +92,12 @@ struct hk_engine {
     std::vector<double> position, disp, disp_new, disp_pre, d_disp, velo, external_force, Q, Qe;
     std::vector<double> integ_stress, integ_strain, integ_eq_plastic_strain, integ_triax_stress,
         integ_yield_stress, elementVolume, d_disp_norm;
+    // evaluation order of the three StaticArrays products of cal_stress_hexa (J2:1204-1205, 1330), a THIRD-PARTY choice the
+    // reference tree does not pin (no Manifest): 0 = left-to-right sums of products (StaticArrays' unrolled `+` of `*`,
+    // no FMA: Julia never contracts by itself), 1 = a muladd chain (what newer StaticArrays kernels emit; fused on any
+    // CPU with FMA).  Set by the environment variable HKO_MATVEC=muladd at hko_create; scripts/oracle_matvec_orders.py
+    // reports what the choice changes.
+    int matvec_mode = 0;
     // v0.0.1 penetration-rate clamp (hk_params.contact_dmax_clamp): J1:413-415, 492, 513, 618
     std::vector<double> d_node, d_node_pre;
     double d_max = 0.0;
@@ -263,6 +269,7 @@ static void cal_stress_hexa(hk_engine* E) {
     const int integ_num = 8;
     const double W = 1.0;
     int64_t negJ = 0;
+    const bool fused = E->matvec_mode == 1;
 #pragma omp parallel for schedule(static) reduction(+ : negJ)
     for (int64_t e = 0; e < nElement; ++e) {
         if (E->element_flag[e] == 0) continue;
@@ -294,12 +301,14 @@ static void cal_stress_hexa(hk_engine* E) {
             double d_e_vec[6], d_o_vec[6];
             for (int r = 0; r < 6; ++r) {                 // d_e_vec = Bfinal * d_u      J2:1204
                 double s = Bfinal[r] * d_u[0];
-                for (int c = 1; c < 24; ++c) s += Bfinal[r + 6 * c] * d_u[c];
+                if (fused) for (int c = 1; c < 24; ++c) s = std::fma(Bfinal[r + 6 * c], d_u[c], s);
+                else for (int c = 1; c < 24; ++c) s += Bfinal[r + 6 * c] * d_u[c];
                 d_e_vec[r] = s;
             }
             for (int r = 0; r < 6; ++r) {                 // d_o_vec = Dmat * d_e_vec    J2:1205
                 double s = Dmat[r] * d_e_vec[0];
-                for (int c = 1; c < 6; ++c) s += Dmat[r + 6 * c] * d_e_vec[c];
+                if (fused) for (int c = 1; c < 6; ++c) s = std::fma(Dmat[r + 6 * c], d_e_vec[c], s);
+                else for (int c = 1; c < 6; ++c) s += Dmat[r + 6 * c] * d_e_vec[c];
                 d_o_vec[r] = s;
             }
             const int64_t index_i = e * integ_num + i;
@@ -340,7 +349,8 @@ static void cal_stress_hexa(hk_engine* E) {
             for (int r = 0; r < 6; ++r) E->integ_stress[r + 6 * index_i] = final_stress[r];
             for (int j = 0; j < 24; ++j) {                 // q_vec_i = Bfinal' * final_stress  J2:1330
                 double s = Bfinal[6 * j] * final_stress[0];
-                for (int r = 1; r < 6; ++r) s += Bfinal[r + 6 * j] * final_stress[r];
+                if (fused) for (int r = 1; r < 6; ++r) s = std::fma(Bfinal[r + 6 * j], final_stress[r], s);
+                else for (int r = 1; r < 6; ++r) s += Bfinal[r + 6 * j] * final_stress[r];
                 Qe[j] += W * W * W * detJ * s;
             }
         }
@@ -802,6 +812,7 @@ int hko_create(hk_engine** out, const hk_params* p) {
     if (p->struct_size != (int32_t)sizeof(hk_params)) return fail(nullptr, HK_ERR_ARG, "hk_params size mismatch");
     hk_engine* e = new hk_engine();
     e->prm = *p;
+    if (const char* m = std::getenv("HKO_MATVEC")) e->matvec_mode = std::strcmp(m, "muladd") == 0 ? 1 : 0;
     cal_Pusai_hexa(e->Pusai);
     *out = e;
     return HK_OK;
