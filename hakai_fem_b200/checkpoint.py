@@ -11,6 +11,8 @@ The contact surfaces grown by erosion are not stored: `hk_apply_deleted` replays
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 _FIELDS = ("disp", "disp_pre", "velo", "Q", "integ_stress", "integ_strain", "integ_eq_plastic_strain",
@@ -24,8 +26,15 @@ def save_checkpoint(engine, path: str, t: int) -> None:
                                 "element_flag"))
     x = engine.download_ex(fields=("disp_pre", "Q", "integ_yield_stress"))
     out = {k: (d[k] if k in d else x[k]) for k in _FIELDS}
-    np.savez(path, t=np.int64(t), format=np.int64(FORMAT), nNode=np.int64(engine.nNode),
-             nElement=np.int64(engine.nElement), deleted_ids=engine.deleted_ids(), **out)
+    # written to the EXACT path given (np.savez on a file name would append ".npz") through a temporary file that is
+    # renamed over it: a crash during the write leaves the previous restart point intact
+    tmp = "%s.tmp.%d" % (path, os.getpid())
+    with open(tmp, "wb") as f:
+        np.savez(f, t=np.int64(t), format=np.int64(FORMAT), nNode=np.int64(engine.nNode),
+                 nElement=np.int64(engine.nElement), deleted_ids=engine.deleted_ids(), **out)
+        f.flush()
+        os.fsync(f.fileno())
+    os.replace(tmp, path)
 
 
 def load_checkpoint(engine, path: str) -> int:

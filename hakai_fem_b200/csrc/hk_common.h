@@ -188,7 +188,7 @@ void hk_launch_element_means(const HkDev& d, double* emean, cudaStream_t s);    
 void hk_launch_node_means(const HkDev& d, const double* emean, double* out, int raw, cudaStream_t s);   // [16][nNode]
 void hk_launch_state_summary(const HkDev& d, unsigned long long* out4, cudaStream_t s);   // out4 preset {0,~0,0,0}
 double hk_decode_double(unsigned long long order_encoded);
-void hk_upload_pusai(const double* P);
+int hk_upload_pusai(const double* P);
 void hk_launch_element_exact(const HkDev& d, long long step, int write_triax, cudaStream_t s);
 int hk_element_variant_from_env();        // HK_ELEMENT_VARIANT / HK_ELEMENT_KERNEL (A/B switches), else the default
 long long hk_element_tile(int variant);   // nEp must be a multiple of this

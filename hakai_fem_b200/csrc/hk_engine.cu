@@ -169,6 +169,14 @@ struct hk_engine {
 
 static std::string g_create_err;
 
+// Engines on different devices may live in one process: every ABI entry that touches the device selects the
+// engine's device first (kernel attributes are set per launch, constant tables uploaded per engine at hk_finalize).
+#ifndef HK_EMU
+#define HK_DEVICE(e) do { cudaError_t rd_ = cudaSetDevice((e)->prm.device); if (rd_ != cudaSuccess) return cuda_fail(e, (int)rd_, "cudaSetDevice"); } while (0)
+#else
+#define HK_DEVICE(e) do { } while (0)
+#endif
+
 static int fail(hk_engine* e, int code, const std::string& msg) {
     if (e) e->err = msg; else g_create_err = msg;
     return code;
@@ -816,6 +824,9 @@ int HKAPI(create)(hk_engine** out, const hk_params* p) {
 
 int HKAPI(destroy)(hk_engine* e) {
     if (!e) return HK_OK;
+#ifndef HK_EMU
+    cudaSetDevice(e->prm.device);
+#endif
     prof_collect(e);
     hkp::sync(e->stream);
     for (void* p : e->allocs) hkp::dev_free(p);
@@ -873,6 +884,8 @@ int HKAPI(add_material)(hk_engine* e, double young, double poisson, double densi
     if (!e) return HK_ERR_ARG;
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
     if (npp == 1) return fail(e, HK_ERR_ARG, "*Plastic table needs >= 2 rows (the reference indexes Hd[1])");
+    if (npp < 0 || nd < 0 || (npp > 0 && (!plastic || !Hd)) || (nd > 0 && !ductile))
+        return fail(e, HK_ERR_ARG, "material table pointer is NULL (or a negative row count)");
     if (npp > HK_MAX_TABLE || nd > HK_MAX_TABLE) return fail(e, HK_ERR_UNSUPPORTED, "material table longer than HK_MAX_TABLE");
     for (int64_t r = 1; r < npp; ++r)
         if (!(plastic[npp + r] > plastic[npp + r - 1]))
@@ -889,8 +902,10 @@ int HKAPI(add_bc)(hk_engine* e, int64_t n_lists, const int64_t* dof_ptr, const i
                   int64_t n_amp, const double* amp_time, const double* amp_value) {
     if (!e) return HK_ERR_ARG;
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    if (n_lists < 0 || (n_lists > 0 && (!dof_ptr || !values))) return fail(e, HK_ERR_ARG, "hk_add_bc: null argument");
     BCH b;
     for (int64_t j = 0; j < n_lists; ++j) {
+        if (dof_ptr[j + 1] < dof_ptr[j] || (dof_ptr[j + 1] > dof_ptr[j] && !dofs)) return fail(e, HK_ERR_ARG, "hk_add_bc: bad dof_ptr");
         b.dof.emplace_back(dofs + dof_ptr[j], dofs + dof_ptr[j + 1]);
         b.value.push_back(values[j]);
     }
@@ -906,6 +921,7 @@ int HKAPI(add_bc)(hk_engine* e, int64_t n_lists, const int64_t* dof_ptr, const i
 int HKAPI(add_ic)(hk_engine* e, int64_t n_lists, const int64_t* dof_ptr, const int64_t* dofs, const double* values) {
     if (!e) return HK_ERR_ARG;
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    if (n_lists < 0 || (n_lists > 0 && (!dof_ptr || !values))) return fail(e, HK_ERR_ARG, "hk_add_ic: null argument");
     ICH b;
     for (int64_t j = 0; j < n_lists; ++j) {
         b.dof.emplace_back(dofs + dof_ptr[j], dofs + dof_ptr[j + 1]);
@@ -919,9 +935,14 @@ int HKAPI(add_instance)(hk_engine* e, int64_t node_offset, int64_t nNode, int64_
                         const int64_t* surfaces, const int64_t* surfaces_eleid) {
     if (!e) return HK_ERR_ARG;
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    if (node_offset < 0 || nNode < 0 || element_offset < 0 || nElement < 0) return fail(e, HK_ERR_ARG, "hk_add_instance: negative range");
     InstanceH I;
     I.node_offset = node_offset; I.nNode = nNode; I.element_offset = element_offset; I.nElement = nElement;
     if (surfaces && surfaces_eleid) {
+        for (int64_t k = 0; k < 24 * nElement; ++k)
+            if (surfaces[k] < 1 || surfaces[k] > nNode) return fail(e, HK_ERR_ARG, "hk_add_instance: face node outside the instance");
+        for (int64_t k = 0; k < 6 * nElement; ++k)
+            if (surfaces_eleid[k] < 1 || surfaces_eleid[k] > nElement) return fail(e, HK_ERR_ARG, "hk_add_instance: face element outside the instance");
         I.surfaces.assign(surfaces, surfaces + 24 * nElement);
         I.eleid.assign(surfaces_eleid, surfaces_eleid + 6 * nElement);
     }
@@ -934,6 +955,14 @@ int HKAPI(add_contact_pair)(hk_engine* e, int64_t i_instance, int64_t j_instance
                             const int64_t* c_triangles_eleid, double young) {
     if (!e) return HK_ERR_ARG;
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    if (e->nNode == 0) return fail(e, HK_ERR_STATE, "hk_set_mesh must precede hk_add_contact_pair");
+    if (nn_i < 0 || nn_j < 0 || nTri < 0 || (nn_i > 0 && !c_nodes_i) || (nn_j > 0 && !c_nodes_j) ||
+        (nTri > 0 && (!c_triangles || !c_triangles_eleid)))
+        return fail(e, HK_ERR_ARG, "hk_add_contact_pair: null argument");
+    for (int64_t k = 0; k < nn_i; ++k) if (c_nodes_i[k] < 1 || c_nodes_i[k] > e->nNode) return fail(e, HK_ERR_ARG, "c_nodes_i entry out of range");
+    for (int64_t k = 0; k < nn_j; ++k) if (c_nodes_j[k] < 1 || c_nodes_j[k] > e->nNode) return fail(e, HK_ERR_ARG, "c_nodes_j entry out of range");
+    for (int64_t k = 0; k < 3 * nTri; ++k) if (c_triangles[k] < 1 || c_triangles[k] > e->nNode) return fail(e, HK_ERR_ARG, "c_triangles entry out of range");
+    for (int64_t k = 0; k < nTri; ++k) if (c_triangles_eleid[k] < 1 || c_triangles_eleid[k] > e->nElement) return fail(e, HK_ERR_ARG, "c_triangles_eleid entry out of range");
     PairH p;
     p.i_instance = i_instance; p.j_instance = j_instance; p.young = young;
     std::memset(&p.dev, 0, sizeof(p.dev));
@@ -953,6 +982,7 @@ int HKAPI(finalize)(hk_engine* e) {
     if (!e) return HK_ERR_ARG;
     if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
     if (e->nNode == 0) return fail(e, HK_ERR_STATE, "hk_set_mesh not called");
+    HK_DEVICE(e);
     const int64_t nN = e->nNode, nE = e->nElement;
     HkDev& d = e->d;
     d.variant = hk_element_variant_from_env();
@@ -995,7 +1025,7 @@ int HKAPI(finalize)(hk_engine* e) {
     {
         double P[8][3][8];
         cal_Pusai_hexa(P);
-        hk_upload_pusai(&P[0][0][0]);
+        CK(hk_upload_pusai(&P[0][0][0]));
     }
 
     // ---- nodes
@@ -1356,12 +1386,14 @@ int HKAPI(step_enqueue)(hk_engine* e, int64_t t_first, int64_t n_steps) {
 // i.e. before the fracture pass zeroes the stress of the elements it deletes (what a frame of the reference shows).
 int HKAPI(mark_frame)(hk_engine* e) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     e->frame_next = true;
     return HK_OK;
 }
 
 int HKAPI(step_begin)(hk_engine* e, int64_t t) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     if (e->begun_t >= 0) return fail(e, HK_ERR_STATE, "hk_step_begin called twice without hk_step_finish");
     int rc = enqueue_steps(e, t, 1, false, 1);
     if (rc) return rc;
@@ -1372,6 +1404,7 @@ int HKAPI(step_begin)(hk_engine* e, int64_t t) {
 
 int HKAPI(step_finish)(hk_engine* e, int64_t t) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     if (e->begun_t != t) return fail(e, HK_ERR_STATE, "hk_step_finish without matching hk_step_begin");
     e->begun_t = -1;
     int rc = enqueue_steps(e, t, 1, false, 2);
@@ -1382,6 +1415,7 @@ int HKAPI(step_finish)(hk_engine* e, int64_t t) {
 
 int HKAPI(sync)(hk_engine* e, int64_t* n_deleted_out) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     const size_t before = e->deleted_reported;
     int rc = fetch_deleted(e, nullptr);
     if (rc) return rc;
@@ -1494,6 +1528,7 @@ static int upload_ip(hk_engine* e, int row0, const double* host, int ncomp) {
 int HKAPI(download)(hk_engine* e, double* disp, double* velo, double* integ_stress, double* integ_strain,
                     double* integ_eq_plastic_strain, double* integ_triax_stress, int64_t* element_flag) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     const HkDev& d = e->d;
     const size_t fnb = sizeof(double) * 3 * e->nNode;
     int rc;
@@ -1522,6 +1557,7 @@ int HKAPI(download)(hk_engine* e, double* disp, double* velo, double* integ_stre
 int HKAPI(node_output)(hk_engine* e, double* node_stress, double* node_strain, double* node_eq_plastic_strain,
                        double* node_mises_stress, double* node_triax_stress, double* inc_num, int32_t raw) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     const HkDev& d = e->d;
     if (!e->triax_current) { hk_launch_triax(d, e->stream); e->triax_current = true; }
     int rc = 0;
@@ -1550,6 +1586,7 @@ int HKAPI(node_output)(hk_engine* e, double* node_stress, double* node_strain, d
 int HKAPI(download_ex)(hk_engine* e, double* disp_pre, double* Q, double* external_force, double* position,
                        double* integ_yield_stress, double* elementVolume) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     const HkDev& d = e->d;
     const int64_t nN = e->nNode;
     const size_t fnb = sizeof(double) * 3 * nN;
@@ -1593,6 +1630,7 @@ int HKAPI(upload_state)(hk_engine* e, const double* disp, const double* disp_pre
                         const double* integ_stress, const double* integ_strain, const double* integ_eq_plastic_strain,
                         const double* integ_yield_stress, const int64_t* element_flag) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     HkDev& d = e->d;
     const int64_t nN = e->nNode;
     const size_t fnb = sizeof(double) * 3 * nN;
@@ -1664,6 +1702,7 @@ int HKAPI(contact_pair_info)(hk_engine* e, int64_t c, int64_t* nn_i, int64_t* nn
 
 int HKAPI(counters)(hk_engine* e, int64_t out[8]) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     unsigned long long c[8];
     CK(hkp::d2h(c, e->d.counters, sizeof(c), e->stream));
     out[0] = (int64_t)c[0];
@@ -1679,6 +1718,7 @@ int HKAPI(counters)(hk_engine* e, int64_t out[8]) {
 
 int HKAPI(state_summary)(hk_engine* e, double out[8]) {
     if (!e || !e->finalized || !out) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     if (!e->d_summary) { int rc = dalloc(e, &e->d_summary, (size_t)4); if (rc) return rc; }
     const unsigned long long init[4] = {0ull, ~0ull, 0ull, 0ull};
     unsigned long long got[4];
@@ -1724,6 +1764,7 @@ int HKAPI(set_halo)(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr, c
 
 int HKAPI(halo_bind)(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_dev) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     if (neighbor < 0 || neighbor >= (int64_t)e->halo.size()) return fail(e, HK_ERR_ARG, "bad neighbour index");
     e->halo[neighbor].send = (double*)send_dev;
     e->halo[neighbor].recv = (double*)recv_dev;
@@ -1732,6 +1773,7 @@ int HKAPI(halo_bind)(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_
 
 int HKAPI(halo_pack)(hk_engine* e) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     int rc = halo_pack_all(e);
     if (rc) return rc;
     CK(hkp::last_error());
@@ -1798,6 +1840,7 @@ int HKAPI(comm_init)(hk_engine* e, const void* id128, int32_t rank, int32_t worl
 
 int HKAPI(set_node_list)(hk_engine* e, int32_t which, int64_t n, const int64_t* nodes) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     if (which < 0 || which > 4) return fail(e, HK_ERR_ARG, "bad list id");
     { int rc = contact_refresh_host(e); if (rc) return rc; }
     std::vector<int>& L = e->node_list[which];
@@ -1817,6 +1860,7 @@ int HKAPI(set_node_list)(hk_engine* e, int32_t which, int64_t n, const int64_t* 
 
 int HKAPI(nodes_export)(hk_engine* e, void* out_dev) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     if (!e->velo_current) { hk_launch_velo_from_rec(e->d, e->prm.d_time, e->stream); e->velo_current = true; }
     hk_launch_nodes_export(e->d, e->d_node_list[0], (long long)e->node_list[0].size(), (double*)out_dev, e->stream);
     e->n_launch += 1;
@@ -1826,6 +1870,7 @@ int HKAPI(nodes_export)(hk_engine* e, void* out_dev) {
 
 int HKAPI(nodes_import)(hk_engine* e, const void* in_dev, const int64_t* src_index) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     const size_t n = e->node_list[1].size();
     if (src_index) {               // (re)register where each ghost's record sits in the gathered buffer
         std::vector<long long> src(src_index, src_index + n);
@@ -1845,6 +1890,7 @@ int HKAPI(nodes_import)(hk_engine* e, const void* in_dev, const int64_t* src_ind
 // ghost-element partitions (bit-identical results for any number of ranks): displacement state of listed nodes
 int HKAPI(state_export)(hk_engine* e, void* out_dev) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     hk_launch_state_export(e->d, e->d_node_list[3], (long long)e->node_list[3].size(), (double*)out_dev, e->stream);
     e->n_launch += 1;
     CK(hkp::last_error());
@@ -1853,6 +1899,7 @@ int HKAPI(state_export)(hk_engine* e, void* out_dev) {
 
 int HKAPI(state_import)(hk_engine* e, const void* in_dev) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     hk_launch_state_import(e->d, e->d_node_list[4], (long long)e->node_list[4].size(), (const double*)in_dev,
                            e->prm.d_time, e->stream);
     e->n_launch += 1;
@@ -1863,6 +1910,7 @@ int HKAPI(state_import)(hk_engine* e, const void* in_dev) {
 int HKAPI(set_global_maps)(hk_engine* e, int64_t n_global_nodes, const int64_t* node_map, int64_t n_global_elements,
                            const int64_t* elem_map, const int64_t* element_instance) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     if (!node_map || !elem_map || !element_instance) return fail(e, HK_ERR_ARG, "null argument");
     e->g_node_map.resize(n_global_nodes);
     for (int64_t i = 0; i < n_global_nodes; ++i) {
@@ -1880,6 +1928,7 @@ int HKAPI(set_global_maps)(hk_engine* e, int64_t n_global_nodes, const int64_t* 
 
 int HKAPI(apply_deleted)(hk_engine* e, int64_t n, const int64_t* global_ids) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     const bool global = !e->g_node_map.empty();
     const int64_t limit = global ? (int64_t)e->g_elem_map.size() : e->nElement;
     std::vector<int64_t> ids(global_ids, global_ids + n);
@@ -1901,6 +1950,7 @@ int HKAPI(apply_deleted)(hk_engine* e, int64_t n, const int64_t* global_ids) {
 
 int HKAPI(contact_enqueue)(hk_engine* e) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     if (!contact_on) return HK_OK;
     { int rc = ensure_erosion(e); if (rc) return rc; }
@@ -1912,6 +1962,7 @@ int HKAPI(contact_enqueue)(hk_engine* e) {
 
 int HKAPI(contact_export)(hk_engine* e, void* out_dev) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     hk_launch_cacc_export(e->d, e->d_node_list[2], (long long)e->node_list[2].size(), (unsigned long long*)out_dev, e->stream);
     e->n_launch += 1;
     CK(hkp::last_error());
@@ -1920,6 +1971,7 @@ int HKAPI(contact_export)(hk_engine* e, void* out_dev) {
 
 int HKAPI(contact_import)(hk_engine* e, const void* in_dev, int64_t n_ranks) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     hk_launch_cacc_import(e->d, e->d_node_list[2], (long long)e->node_list[2].size(), (const unsigned long long*)in_dev,
                           (long long)n_ranks, e->stream);
     e->n_launch += 1;
@@ -1929,6 +1981,7 @@ int HKAPI(contact_import)(hk_engine* e, const void* in_dev, int64_t n_ranks) {
 
 int HKAPI(contact_export_limbs)(hk_engine* e, void* out_dev) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     hk_launch_cacc_export_limbs(e->d, e->d_node_list[2], (long long)e->node_list[2].size(), (long long*)out_dev, e->stream);
     e->n_launch += 1;
     CK(hkp::last_error());
@@ -1937,6 +1990,7 @@ int HKAPI(contact_export_limbs)(hk_engine* e, void* out_dev) {
 
 int HKAPI(contact_import_limbs)(hk_engine* e, const void* in_dev) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
     hk_launch_cacc_import_limbs(e->d, e->d_node_list[2], (long long)e->node_list[2].size(), (const long long*)in_dev, e->stream);
     e->n_launch += 1;
     CK(hkp::last_error());

@@ -1041,11 +1041,12 @@ __device__ double x_P[8][3][8];
 static double x_P[8][3][8];
 #endif
 
-void hk_upload_pusai(const double* P) {
+int hk_upload_pusai(const double* P) {          // per device: called by every engine at hk_finalize
 #ifndef HK_EMU
-    cudaMemcpyToSymbol(x_P, P, sizeof(double) * 192);
+    return (int)cudaMemcpyToSymbol(x_P, P, sizeof(double) * 192);
 #else
     memcpy(x_P, P, sizeof(double) * 192);
+    return 0;
 #endif
 }
 

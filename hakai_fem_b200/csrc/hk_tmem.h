@@ -1,11 +1,12 @@
-// hk_tmem.h — Blackwell tensor memory (TMEM) used as a per-thread scratchpad.  GENERATED by scripts.
+// hk_tmem.h — Blackwell tensor memory (TMEM) used as a per-thread scratchpad.
 //
 // TMEM is 512 columns x 128 lanes x 32 bit per SM and is normally the accumulator store of tcgen05.mma.  The
-// element kernel has no matrix product to offer the tensor cores, but its real limiter is register pressure
-// (78 doubles of per-element state that must survive the Gauss-point loop).  With the 32x32b access shape every
-// thread of a warp owns one TMEM lane (warp w of the CTA reaches lanes 32*(w%4)..+31), so a thread can park N
-// consecutive 32-bit columns there with tcgen05.st and fetch them back with tcgen05.ld (LDTM/STTM in SASS) —
-// a second register file of 2 KB per lane that costs neither shared memory nor occupancy.
+// element kernel has no matrix product to offer the tensor cores, but it has 78 doubles of per-element state that must
+// survive the Gauss-point loop.  With the 32x32b access shape every thread of a warp owns one TMEM lane (warp w of the
+// CTA reaches lanes 32*(w%4)..+31), so a thread can park N consecutive 32-bit columns there with tcgen05.st and fetch
+// them back with tcgen05.ld (LDTM/STTM in SASS) — a second register file of 2 KB per lane that costs neither shared
+// memory nor occupancy.  Measured (profiles/r2_tmem_bw_probe.json): 67 B/clk per warp with .x8 loads, scaling
+// linearly with the number of warps (487 B/clk/SM at 8 warps), i.e. faster than shared memory (128 B/clk/SM).
 #pragma once
 #include <cstdint>
 
@@ -15,27 +16,9 @@ __device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t* v) {
                  : "r"(taddr)
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-                 : "r"(taddr)
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr)
                  : "memory");
 }
@@ -45,55 +28,22 @@ __device__ __forceinline__ void tmem_st_x2(uint32_t taddr, const uint32_t* v) {
                  : "r"(taddr), "r"(v[0]), "r"(v[1])
                  : "memory");
 }
-__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 :
-                 : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  :
                  : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
-__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-                 :
-                 : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-                 :
-                 : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-                 : "memory");
-}
-
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// ND doubles <-> 2*ND columns, ND in {1,2,4,8,16}
-template <int ND>
-__device__ __forceinline__ void tmem_ld_doubles(uint32_t taddr, double* out) {
-    uint32_t v[2 * ND];
-    if (ND == 1) tmem_ld_x2(taddr, v);
-    if (ND == 2) tmem_ld_x4(taddr, v);
-    if (ND == 4) tmem_ld_x8(taddr, v);
-    if (ND == 8) tmem_ld_x16(taddr, v);
-    if (ND == 16) tmem_ld_x32(taddr, v);
-    tmem_wait_ld();
-#pragma unroll
-    for (int i = 0; i < ND; ++i) out[i] = __hiloint2double((int)v[2 * i + 1], (int)v[2 * i]);
-}
+// ND doubles -> 2*ND columns, ND in {1, 4}
 template <int ND>
 __device__ __forceinline__ void tmem_st_doubles(uint32_t taddr, const double* in) {
+    static_assert(ND == 1 || ND == 4, "tmem_st_doubles: 1 or 4 doubles");
     uint32_t v[2 * ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) { v[2 * i] = (uint32_t)__double2loint(in[i]); v[2 * i + 1] = (uint32_t)__double2hiint(in[i]); }
     if (ND == 1) tmem_st_x2(taddr, v);
-    if (ND == 2) tmem_st_x4(taddr, v);
     if (ND == 4) tmem_st_x8(taddr, v);
-    if (ND == 8) tmem_st_x16(taddr, v);
-    if (ND == 16) tmem_st_x32(taddr, v);
 }

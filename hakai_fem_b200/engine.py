@@ -141,6 +141,8 @@ class EngineBase:
                                            c_i64(npp), _pf(pl), _pf(hd), c_i64(nd), _pf(du)))
 
     def add_bc(self, dof_lists, values, amp_time=None, amp_value=None):
+        if len(values) != len(dof_lists):            # the reference raises BoundsError here (e.g. numbered lines + ENCASTRE)
+            raise HakaiError(f"add_bc: {len(dof_lists)} dof lists but {len(values)} values")
         ptr, flat = _csr(dof_lists)
         vals = _f64(values)
         n_amp = 0 if amp_time is None else len(amp_time)
@@ -150,6 +152,8 @@ class EngineBase:
                                      c_i64(n_amp), _pf(at), _pf(av)))
 
     def add_ic(self, dof_lists, values):
+        if len(values) != len(dof_lists):
+            raise HakaiError(f"add_ic: {len(dof_lists)} dof lists but {len(values)} values")
         ptr, flat = _csr(dof_lists)
         vals = _f64(values)
         self._chk(self._fn("add_ic")(self._h, c_i64(len(dof_lists)), _pi(ptr), _pi(flat), _pf(vals)))

@@ -182,9 +182,10 @@ def hakai(fname, outdir="temp", engine_cls=None, output_num=100, write_frames=Tr
         if ndel:
             flags = eng.download(fields=("element_flag",))["element_flag"]
             log("Element deleted:", int(flags.sum()), "/", model.nElement)       # J2:736
-        if write_frames and d_out > 0 and t % d_out == 0:       # rem(t, d_out) == 0, J2:932
-            frame(i_out)
-            if checkpoint is not None and i_out % checkpoint_frames == 0:
+        if d_out > 0 and t % d_out == 0:                         # rem(t, d_out) == 0, J2:932
+            if write_frames:
+                frame(i_out)
+            if checkpoint is not None and i_out % checkpoint_frames == 0:     # also when no frames are written
                 from .checkpoint import save_checkpoint
                 save_checkpoint(eng, checkpoint, t)
             i_out += 1

@@ -102,3 +102,36 @@ def test_restart_and_multi_domain_hooks_are_checked():
     e.mark_frame()
     e.step_enqueue(1, 1)
     assert e.sync() == 0
+
+
+def test_lengths_ids_and_null_tables_are_validated():
+    """the ABI must not trust lengths and ids.  A *Boundary block mixing numbered lines with ENCASTRE yields
+    more dof lists than values (the reference raises BoundsError there): refused before anything is read past the end;
+    contact node / element ids and instance face tables are range-checked; material tables may not be NULL."""
+    import ctypes as C
+    st = prepare(StretchDeck(2, 2, 2).build_model())
+    e = EmuEngine(d_time=st.d_time)
+    m = st.model
+    e.set_mesh(m.coordmat, m.elementmat, m.element_material, m.element_instance, st.diag_M)
+    with pytest.raises(HakaiError):
+        e.add_bc([np.array([1, 2]), np.array([3])], [0.0])                  # 2 lists, 1 value
+    with pytest.raises(HakaiError):
+        e.add_ic([np.array([1, 2]), np.array([3])], [0.0])
+    nN, nE = m.nNode, m.nElement
+    tri = np.array([[1, 2, 3]])
+    with pytest.raises(HakaiError):
+        e.add_contact_pair(1, 1, [1, nN + 1], [1], tri, [1], 1.0)           # slave node beyond the mesh
+    with pytest.raises(HakaiError):
+        e.add_contact_pair(1, 1, [1], [1], np.array([[1, 2, 0]]), [1], 1.0)  # triangle node 0
+    with pytest.raises(HakaiError):
+        e.add_contact_pair(1, 1, [1], [1], tri, [nE + 1], 1.0)              # triangle element beyond the mesh
+    faces = np.ones((6 * nE, 4), np.int64)
+    bad = faces.copy()
+    bad[3, 2] = nN + 5
+    with pytest.raises(HakaiError):
+        e.add_instance(0, nN, 0, nE, bad, np.repeat(np.arange(1, nE + 1), 6))
+    with pytest.raises(HakaiError):
+        e.add_instance(0, nN, 0, nE, faces, np.full(6 * nE, nE + 1))
+    fn = e._fn("add_material")                                              # npp = 2 with NULL tables, straight at the ABI
+    rc = fn(e._h, C.c_double(1.0), C.c_double(0.3), C.c_double(1.0), C.c_int64(2), None, None, C.c_int64(0), None)
+    assert rc != 0 and b"NULL" in e._fn("last_error")(e._h)

@@ -37,3 +37,27 @@ def test_checkpoint_rejects_other_mesh_and_used_engine(tmp_path):
         load_checkpoint(configure_engine(OracleEngine, _erosion_setup()), path)
     with pytest.raises(ValueError):
         load_checkpoint(a, path)                                  # not fresh: it already has a deletion history
+
+
+def test_checkpoint_is_written_to_the_exact_path_atomically(tmp_path):
+    """`checkpoint='run.ckpt'` must create run.ckpt (np.savez on a name would write run.ckpt.npz and resume
+    would not find it); the file is replaced in one rename, no temporary is left behind; and the host driver writes
+    checkpoints even when it writes no frames."""
+    import os
+    a = configure_engine(OracleEngine, _fracture_setup())
+    a.step(1, 10)
+    path = str(tmp_path / "run.ckpt")
+    save_checkpoint(a, path, 10)
+    save_checkpoint(a, path, 10)                                   # overwrite in place
+    assert sorted(os.listdir(tmp_path)) == ["run.ckpt"]
+    b = configure_engine(OracleEngine, _fracture_setup())
+    assert load_checkpoint(b, path) == 10
+    assert np.array_equal(a.download()["disp"], b.download()["disp"])
+    from hakai_fem_b200.host import hakai
+    from hakai_fem_b200.mesh import StretchDeck
+    deck_path = str(tmp_path / "d.inp")
+    StretchDeck(3, 3, 4, jitter=0.05, n_steps=40).write_inp(deck_path)
+    ck = str(tmp_path / "frames_off.ckpt")
+    hakai(deck_path, str(tmp_path / "out"), engine_cls=OracleEngine, output_num=4, write_frames=False, verbose=False,
+          checkpoint=ck, checkpoint_frames=1)
+    assert os.path.exists(ck)
