@@ -25,7 +25,9 @@ mutable struct Params
     contact_ddiv_other::Float64
     contact_ddiv_self::Float64
     deterministic::Int32
-    reserved::Int32
+    element_mode::Int32           # 0 fast element kernel, 1 reference-order kernel (bit-identical to the CPU oracle)
+    contact_dmax_clamp::Int32     # 1: v0.0.1's penetration-rate clamp (HAKAI-v0.0.1 HAKAI_j.jl:2756)
+    reserved0::Int32
     Params() = new()
 end
 
@@ -125,5 +127,42 @@ node_output!(e, nd) =          # nd::NodeDataType (HAKAI_j.jl:43-50)
           (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32),
           e.ptr, nd.node_stress, nd.node_strain, nd.node_eq_plastic_strain, nd.node_mises_stress, nd.node_triax_stress,
           C_NULL, 0))
+
+# state summary reduced on the device: (live elements, min / max eq. plastic strain of live Gauss points, yielded points)
+function state_summary(e)
+    out = zeros(Float64, 8)
+    check(e.ptr, ccall((:hk_state_summary, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), e.ptr, out))
+    return (live_elements = Int(out[1]), eps_min = out[2], eps_max = out[3], yielded_points = Int(out[4]))
+end
+
+function deleted_ids(e)
+    n = Ref{Int64}(0)
+    check(e.ptr, ccall((:hk_deleted_ids, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ref{Int64}), e.ptr, C_NULL, 0, n))
+    ids = zeros(Int64, n[]); steps = zeros(Int64, n[])
+    check(e.ptr, ccall((:hk_deleted_ids, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ref{Int64}), e.ptr, ids, n[], n))
+    check(e.ptr, ccall((:hk_deleted_steps, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ref{Int64}), e.ptr, steps, n[], n))
+    return ids, steps
+end
+
+# ---- multi-GPU: one Julia process (or task) per GPU, element-block partition ------------------------------------------
+# The engine owns the NCCL communicator, so the Julia side needs NO NCCL binding: rank 0 asks the library for the
+# 128-byte id, the host hands it to the other ranks by whatever it already has (MPI.Bcast!, a file, a socket), and from
+# then on `step!(e, t, n)` runs n complete multi-GPU steps (pack -> ncclSend/ncclRecv -> split step) inside the library.
+#   halo_nodes[i]: local 1-based ids of the nodes shared with neighbour i, ascending global id (before finalize!)
+#   ranks[i]:      global rank of neighbour i
+set_halo(e, halo_nodes::Vector{Vector{Int}}) = begin
+    ptr, flat = csr(halo_nodes)
+    check(e.ptr, ccall((:hk_set_halo, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}), e.ptr, length(halo_nodes), ptr, flat))
+end
+set_halo_ranks(e, my_rank::Integer, ranks::Vector{Int}) =
+    check(e.ptr, ccall((:hk_set_halo_ranks, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}), e.ptr, my_rank, length(ranks), ranks))
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    rc = ccall((:hk_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)
+    rc == 0 || check(C_NULL, rc)
+    return id
+end
+comm_init(e, id::Vector{UInt8}, rank::Integer, world::Integer) =
+    check(e.ptr, ccall((:hk_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), e.ptr, id, rank, world))
 
 end # module
