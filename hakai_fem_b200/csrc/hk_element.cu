@@ -563,23 +563,16 @@ static int launch_ring(const ElemArgs& A, int n_sm, cudaStream_t s) {
 }
 #endif
 
-// element-kernel variant table (A/B history: profiles/r2_element_kernel_variants.md).  variant = groups, warps per
-// group, ring stages per group, connectivity prefetch
+// element-kernel variant table: the configurations kept for A/B (profiles/r2_element_kernel_variants.md has the
+// measurements of these and of the ones that were tried and dropped).  variant = groups, warps per group, ring stages
+// per group, prefetch (0 none, 1 connectivity, 2 connectivity + material ids + flags)
 struct RingVariant { int id, ng, wg, stages, cp; };
 static const RingVariant kVariants[] = {
-    {11, 1, 11, 4, 0},      // round-1 kernel: one group of 11 warps (tile 352)
+    {11, 1, 11, 4, 0},      // round-1 configuration: one group of 11 warps (tile 352), no prefetch
     {12, 1, 11, 4, 1},
-    {20, 2, 5, 4, 1},
-    {21, 2, 5, 5, 1},
-    {22, 2, 5, 6, 0},
-    {23, 2, 5, 5, 0},
-    {24, 2, 5, 3, 1},
-    {25, 2, 5, 4, 2},       // + material ids / flags prefetched with the connectivity
-    {26, 2, 5, 3, 2},
     {13, 1, 11, 4, 2},      // default
-    {27, 3, 3, 4, 2},       // three groups of 3 warps (tile 96)
-    {28, 2, 6, 4, 2},       // 12 consumer warps at 144 registers
-    {29, 2, 6, 3, 2},
+    {20, 2, 5, 4, 1},       // two phase-shifted groups of 5 warps (tile 160)
+    {25, 2, 5, 4, 2},
 };
 #define HK_DEFAULT_VARIANT 13
 
@@ -604,15 +597,7 @@ int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStrea
         case 11: return launch_ring<1, 11, 4, 0>(A, d.n_sm, s);
         case 12: return launch_ring<1, 11, 4, 1>(A, d.n_sm, s);
         case 20: return launch_ring<2, 5, 4, 1>(A, d.n_sm, s);
-        case 22: return launch_ring<2, 5, 6, 0>(A, d.n_sm, s);
-        case 23: return launch_ring<2, 5, 5, 0>(A, d.n_sm, s);
-        case 24: return launch_ring<2, 5, 3, 1>(A, d.n_sm, s);
         case 25: return launch_ring<2, 5, 4, 2>(A, d.n_sm, s);
-        case 26: return launch_ring<2, 5, 3, 2>(A, d.n_sm, s);
-        case 27: return launch_ring<3, 3, 4, 2>(A, d.n_sm, s);
-        case 28: return launch_ring<2, 6, 4, 2>(A, d.n_sm, s);
-        case 29: return launch_ring<2, 6, 3, 2>(A, d.n_sm, s);
-        case 21: return launch_ring<2, 5, 5, 1>(A, d.n_sm, s);
         default: return launch_ring<1, 11, 4, 2>(A, d.n_sm, s);
     }
 #else
