@@ -163,8 +163,8 @@ struct hk_engine {
     int64_t n_launch = 0, n_steps = 0;
     bool profiling = false;
     std::vector<TimedEvent> events;
-    double prof_ms[4] = {0, 0, 0, 0};
-    int64_t prof_n[4] = {0, 0, 0, 0};
+    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // kinds 0-3 as hk_profile_read; 4 halo exchange; 5 deletion pass
+    int64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static std::string g_create_err;
@@ -209,31 +209,32 @@ static int upload(hk_engine* e, T* dst, const std::vector<T>& src) {
 }
 
 // --------------------------------------------------------------------------------- profiling helpers
-static void prof_begin(hk_engine* e, int kind) {
+static void prof_begin(hk_engine* e, int kind, cudaStream_t on = nullptr, bool other_stream = false) {
 #ifndef HK_EMU
     if (!e->profiling) return;
     TimedEvent t;
     t.kind = kind;
     cudaEventCreate(&t.a);
     cudaEventCreate(&t.b);
-    cudaEventRecord(t.a, e->stream);
+    cudaEventRecord(t.a, other_stream ? on : e->stream);
     e->events.push_back(t);
 #else
-    (void)e; (void)kind;
+    (void)e; (void)kind; (void)on; (void)other_stream;
 #endif
 }
-static void prof_end(hk_engine* e) {
+static void prof_end(hk_engine* e, cudaStream_t on = nullptr, bool other_stream = false) {
 #ifndef HK_EMU
     if (!e->profiling) return;
-    cudaEventRecord(e->events.back().b, e->stream);
+    cudaEventRecord(e->events.back().b, other_stream ? on : e->stream);
 #else
-    (void)e;
+    (void)e; (void)on; (void)other_stream;
 #endif
 }
 static void prof_collect(hk_engine* e) {
 #ifndef HK_EMU
     if (e->events.empty()) return;
     cudaStreamSynchronize(e->stream);
+    if (e->comm_stream) cudaStreamSynchronize(e->comm_stream);
     for (auto& t : e->events) {
         float ms = 0;
         cudaEventElapsedTime(&ms, t.a, t.b);
@@ -1305,7 +1306,7 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
         if (e->any_ductile) {
             // marked elements: stress/strain zeroed; with contact their exposed faces join the surfaces ON THE DEVICE
             // (multi-GPU engines: the host driver replays the all-gathered ids through hk_apply_deleted instead)
-            prof_begin(e, 3);
+            prof_begin(e, 5);
             long long nl = 0;
             hk_launch_deletion_pass(d, e->dev_erosion ? &e->er : nullptr, e->stream, &nl);
             e->n_launch += nl;
@@ -1334,12 +1335,14 @@ static int comm_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame
         if (rc) return rc;
         CK(cudaEventRecord(e->ev_pack, e->stream));
         CK(cudaStreamWaitEvent(e->comm_stream, e->ev_pack, 0));
+        prof_begin(e, 4, e->comm_stream, true);
         NCK(g_nccl.GroupStart());
         for (HaloNbr& h : e->halo) {
             NCK(g_nccl.Send(h.send, 3 * h.nodes.size(), kNcclFloat64, (int)h.rank, e->comm, e->comm_stream));
             NCK(g_nccl.Recv(h.recv, 3 * h.nodes.size(), kNcclFloat64, (int)h.rank, e->comm, e->comm_stream));
         }
         NCK(g_nccl.GroupEnd());
+        prof_end(e, e->comm_stream, true);
         CK(cudaEventRecord(e->ev_comm, e->comm_stream));
         if ((rc = enqueue_steps(e, t, 1, false, 1))) return rc;       // overlaps the exchange
         CK(cudaStreamWaitEvent(e->stream, e->ev_comm, 0));
@@ -1738,7 +1741,7 @@ int HKAPI(state_summary)(hk_engine* e, double out[8]) {
 int HKAPI(profile)(hk_engine* e, int32_t enable) {
     if (!e) return HK_ERR_ARG;
     prof_collect(e);
-    for (int i = 0; i < 4; ++i) { e->prof_ms[i] = 0; e->prof_n[i] = 0; }
+    for (int i = 0; i < 8; ++i) { e->prof_ms[i] = 0; e->prof_n[i] = 0; }
     e->profiling = enable != 0;
     return HK_OK;
 }
@@ -1747,6 +1750,13 @@ int HKAPI(profile_read)(hk_engine* e, double ms[4], int64_t launches[4]) {
     if (!e) return HK_ERR_ARG;
     prof_collect(e);
     for (int i = 0; i < 4; ++i) { ms[i] = e->prof_ms[i]; launches[i] = e->prof_n[i]; }
+    return HK_OK;
+}
+
+int HKAPI(profile_read_ex)(hk_engine* e, double ms[8], int64_t launches[8]) {
+    if (!e) return HK_ERR_ARG;
+    prof_collect(e);
+    for (int i = 0; i < 8; ++i) { ms[i] = e->prof_ms[i]; launches[i] = e->prof_n[i]; }
     return HK_OK;
 }
 

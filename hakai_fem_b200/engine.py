@@ -44,7 +44,7 @@ EXPORTS = [
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
     "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
-    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init",
+    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init", "profile_read_ex",
 ]
 
 
@@ -322,6 +322,13 @@ class EngineBase:
         ms = np.zeros(4)
         n = np.zeros(4, np.int64)
         self._chk(self._fn("profile_read")(self._h, _pf(ms), _pi(n)))
+        return ms, n
+
+    def profile_read_ex(self):
+        """profile_read plus kinds 4 (halo exchange on the engine's side stream) and 5 (deletion pass)."""
+        ms = np.zeros(8)
+        n = np.zeros(8, np.int64)
+        self._chk(self._fn("profile_read_ex")(self._h, _pf(ms), _pi(n)))
         return ms, n
 
     # -- multi-GPU halo ---------------------------------------------------------------

@@ -203,6 +203,10 @@ int hk_state_summary(hk_engine* e, double out[8]);
  * hk_profile(e, 1) enables/reset; hk_profile_read returns total ms and launch count per kind. */
 int hk_profile(hk_engine* e, int32_t enable);
 int hk_profile_read(hk_engine* e, double ms[4], int64_t launches[4]);
+/* The same with the kinds a multi-GPU / fracture run adds: 4 halo exchange (the ncclSend/ncclRecv group of the engine's
+ * own communicator, timed on its side stream — it overlaps kind 1), 5 deletion pass (ordered list, zeroing, exposed
+ * faces); 6-7 reserved. */
+int hk_profile_read_ex(hk_engine* e, double ms[8], int64_t launches[8]);
 
 /* Run all work on the caller's CUDA stream (cudaStream_t as void*).  NULL is the CUDA legacy default stream (what
  * torch.cuda.current_stream().cuda_stream returns by default), so that NCCL ops enqueued by the host framework are

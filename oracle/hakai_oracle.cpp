@@ -1117,6 +1117,10 @@ int hko_profile_read(hk_engine*, double ms[4], int64_t launches[4]) {
     for (int i = 0; i < 4; ++i) { ms[i] = 0; launches[i] = 0; }
     return HK_OK;
 }
+int hko_profile_read_ex(hk_engine*, double ms[8], int64_t launches[8]) {
+    for (int i = 0; i < 8; ++i) { ms[i] = 0; launches[i] = 0; }
+    return HK_OK;
+}
 int hko_set_stream(hk_engine*, void*) { return HK_OK; }
 // the oracle is single-domain (the reference has no distributed code): halo calls are rejected
 int hko_set_halo(hk_engine* e, int64_t, const int64_t*, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
