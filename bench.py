@@ -255,10 +255,13 @@ def main():
                         engine_comm=world > 1, device=local_rank, **prm)
     eng = runner.engine
 
-    def run_steps(t0, n):
+    def run_steps(t0, n, sync=True):
+        """sync=False: only enqueue (the timed region ends with a CUDA event on the stream, BEFORE hk_sync's host work —
+        copying and recording the deletion log of the steps)."""
         if world > 1:
-            return runner.run(t0, n)          # hk_step_enqueue(t0, n): pack -> ncclSend/Recv -> split step, n times, in the engine
-        return eng.step(t0, n)
+            return runner.run(t0, n, sync=sync)   # hk_step_enqueue(t0, n): pack -> ncclSend/Recv -> split step, n times, in the engine
+        eng.step_enqueue(t0, n)
+        return eng.sync() if sync else 0
 
     def barrier():
         if world > 1:
@@ -304,8 +307,9 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    run_steps(t_next, args.steps)
+    run_steps(t_next, args.steps, sync=False)
     ev1.record(stream)
+    eng.sync()
     barrier()
     # live element-steps: elements alive at the start of each timed step.  The steps were enqueued in ONE call; the step
     # of every deletion comes from the engine's deletion log afterwards (hk_deleted_steps)

@@ -78,7 +78,9 @@ struct HkDev {
     double* triax;        // [8][nEp]   integ_triax_stress (written on request)
     double* Qe;           // [24][nEp]
     // deletion log
-    int* del_count;
+    int* del_count;       // entries in del_list (all steps so far)
+    int* del_block;       // deletion pass: marks per block of 1024 elements
+    int* del_fresh;       // deletion pass: elements deleted in the step that just ran
     long long* del_list;  // (step << 32 | element) entries
     int del_cap;
     unsigned long long* counters;  // [0] negative jacobians [1] contact hits [2] contact tests [3] fixed-point overflow
@@ -131,9 +133,6 @@ struct HkErodeDev {              // everything hk_erode_kernel needs
     HkInstDev* inst;
     HkPairDev* pairs;            // device copy of the pair descriptors
     unsigned short* einst;       // [nElement] 1-based instance of every element (0: none)
-    int* fresh;                  // elements deleted in the step that just ran, ascending id
-    int* fresh_count;
-    int* block_count;            // per 1024-element block: elements marked for deletion in this step
     int* n_spec;                 // special-node table length / capacity, contact slots / capacity
     int* n_slots;
     int spec_cap, slot_cap;
@@ -158,9 +157,10 @@ void hk_launch_nodal(const HkDev& d, double current_time, double d_time, double 
                      unsigned long long* dmax_out, cudaStream_t s);   // dmax_out: NULL or max |d_disp| accumulator
 int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s);   // 0 or a CUDA error code
 void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams& cp, cudaStream_t s);
-// deletion pass of a step: elements the element kernel marked (flag 3) are listed in ascending id order (er != NULL),
-// their stress/strain zeroed (J2:742-756), and the faces they expose join the contact surfaces (er != NULL)
-void hk_launch_deletion_pass(const HkDev& d, const HkErodeDev* er, cudaStream_t s, long long* n_launch);
+// deletion pass of a step: elements the element kernel marked (flag 3) are appended to the deletion log in ascending
+// id order (the reference's order, J2:701-735), their stress/strain zeroed (J2:742-756), and the faces they expose join
+// the contact surfaces (er != NULL)
+void hk_launch_deletion_pass(const HkDev& d, const HkErodeDev* er, long long step, cudaStream_t s, long long* n_launch);
 void hk_launch_cacc_zero(const HkDev& d, const int* n_slots, int slot_cap, cudaStream_t s);
 void hk_launch_velo_from_rec(const HkDev& d, double d_time, cudaStream_t s);
 void hk_launch_gather_Q(const HkDev& d, double* Q_out, cudaStream_t s);

@@ -19,6 +19,9 @@ struct ElemArgs {
     long long step;
     int write_triax;
     int fast;          // MatLite::fast
+    int n_tiles;       // ring kernels: nEp / tile (host-computed so the tile loop needs no 64-bit division and no
+                       // register that survives the Gauss-point loop: round 2's ncu showed the spilled trip count
+                       // costing a DRAM-latency reload per tile)
 };
 HK_HD MatLite mat_lite(const HkMaterialDev* m) {
     MatLite l;
@@ -114,15 +117,10 @@ HK_D void element_finish(const ElemArgs& A, long long e, const HexModes& X, cons
     if (acc.negj) hk_atomic_add_u64(&d.counters[0], (unsigned long long)acc.negj);
 }
 
-// deletion (J2:733-756): the element is only MARKED here (flag 3) and logged; hk_launch_deletion_pass, which follows
-// every element kernel in stream order, zeroes its stress/strain (in the ring kernels the rows are still in flight in
-// bulk stores at this point), lists the step's deletions in ascending order and updates the contact surfaces
-HK_D void element_delete(const ElemArgs& A, long long e) {
-    const HkDev& d = A.d;
-    d.flag[e] = 3;
-    const int slot = hk_atomic_add_i32(d.del_count, 1);
-    if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
-}
+// deletion (J2:733-756): the element is only MARKED here (flag 3); hk_launch_deletion_pass, which follows every element
+// kernel in stream order, logs the step's deletions in ascending element order, zeroes their stress/strain (in the ring
+// kernels the rows are still in flight in bulk stores at this point) and updates the contact surfaces
+HK_D void element_delete(const ElemArgs& A, long long e) { A.d.flag[e] = 3; }
 
 // ---- simple kernel: thread per element, state straight from global memory ---------------------------------
 HK_D void element_body_simple(const ElemArgs& A, long long e) {
@@ -311,7 +309,7 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
     uint32_t* tbase_s = reinterpret_cast<uint32_t*>(flag_buf + (CP >= 2 ? NG * 2 * TLD * 2 : 0));
     const HkDev& d = A.d;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const long long n_tiles = d.nEp / TLD;
+    const int n_tiles = A.n_tiles;
 
     if (tid == 0) {
         for (int s = 0; s < NG * S; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], WG); }
@@ -335,10 +333,8 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
 
     // group of this warp, its virtual CTA id and its share of the tiles (round-robin over all groups of the grid)
     const int g = warp < NG * WG ? warp / WG : warp - NG * WG;
-    const long long n_v = (long long)gridDim.x * NG;
-    const long long vcta = (long long)blockIdx.x * NG + g;
-    const long long my_tiles = vcta < n_tiles ? (n_tiles - vcta + n_v - 1) / n_v : 0;
-    const long long total_q = my_tiles * 8;                 // (tile, Gauss point) work items of this group
+    const int n_v = (int)gridDim.x * NG;
+    const int vcta = (int)blockIdx.x * NG + g;
     double* gstage = stage_buf + (long long)g * S * STAGE;
     unsigned long long* gfull = full + g * S;
     unsigned long long* gdone = done + g * S;
@@ -350,9 +346,11 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
     if (warp >= NG * WG) {
         // ===== producer warp of group g =====
         if ((tid & 31) == 0) {
+            const long long my_tiles = vcta < n_tiles ? (n_tiles - vcta + n_v - 1) / n_v : 0;
+            const long long total_q = my_tiles * 8;             // (tile, Gauss point) work items of this group
             auto issue_conn = [&](long long it) {             // connectivity of this group's tile number `it`
                 if (!CP || it >= my_tiles) return;
-                const long long e0 = (vcta + it * n_v) * TLD;
+                const long long e0 = ((long long)vcta + it * n_v) * TLD;
                 unsigned long long* bar = &gcfull[it & 1];
                 mbar_expect_tx(bar, 8 * TLD * 4 + (CP >= 2 ? TLD * 3 : 0));
 #pragma unroll
@@ -365,7 +363,7 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
             };
             auto issue_load = [&](long long q) {
                 const int st = (int)(q % S);
-                const long long e0 = (vcta + (q >> 3) * n_v) * TLD;
+                const long long e0 = ((long long)vcta + (q >> 3) * n_v) * TLD;
                 mbar_expect_tx(&gfull[st], STAGE * 8);
                 tma_load_1d(gstage + st * STAGE, stage_base(d, (int)(q & 7), e0), STAGE * 8, &gfull[st]);
             };
@@ -374,7 +372,7 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
             for (long long q = 0; q < total_q; ++q) {
                 const int st = (int)(q % S);
                 mbar_wait(&gdone[st], (unsigned)((q / S) & 1));      // every warp of the group finished item q
-                const long long e0 = (vcta + (q >> 3) * n_v) * TLD;
+                const long long e0 = ((long long)vcta + (q >> 3) * n_v) * TLD;
                 tma_store_1d(stage_base(d, (int)(q & 7), e0), gstage + st * STAGE, STAGE * 8);
                 tma_commit();
                 // the group is past the prologue of tile q/8: the buffer of tile q/8 - 1 is free for tile q/8 + 1
@@ -395,13 +393,14 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
         const uint32_t tX = tcol, tU = tcol + 48, tM = tcol + 96;
         // phase shift: group g > 0 starts when group 0 has finished g*8/NG Gauss points of its first tile
         if (NG > 1 && g > 0) {
-            const long long tiles0 = (long long)blockIdx.x * NG < n_tiles ? 1 : 0;
+            const int tiles0 = (int)blockIdx.x * NG < n_tiles ? 1 : 0;
             const int item = g * 8 / NG - 1;                    // group 0's work item whose completion releases group g
             if (tiles0) mbar_wait(&done[item % S], (unsigned)((item / S) & 1));
         }
-        long long q = 0;
-        for (long long it = 0; it < my_tiles; ++it) {
-            const long long e0 = (vcta + it * n_v) * TLD;
+        unsigned q = 0;                                        // work item = 8 * (tile number of this group) + Gauss point
+        unsigned it = 0;
+        for (int tile = vcta; tile < A.n_tiles; tile += n_v, ++it) {      // trip bound from the constant bank
+            const long long e0 = (long long)tile * TLD;
             const long long e = e0 + gt;
             if (CP) mbar_wait(&gcfull[it & 1], (unsigned)((it >> 1) & 1));
             const bool live = !element_dead(d, e, CP >= 2 ? (int)gflag[(it & 1) * TLD + gt] : -1);
@@ -538,7 +537,10 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
             tmem_load_modes(tX, X);
             if (live) {
                 element_finish(A, e, X, acc, V);
-                if (ductile_check(*Mt, acc.v_e, acc.t_e)) element_delete(A, e);
+                // the material id is read again (shared memory / L1) rather than kept in a register across the Gauss-point
+                // loop: it used to be spilled, and its reload was a DRAM-latency stall per tile (ncu, round 2)
+                const HkMaterialDev& Md = d.mats[CP >= 2 ? (int)gmat[(it & 1) * TLD + gt] : (int)d.mat[e]];
+                if (ductile_check(Md, acc.v_e, acc.t_e)) element_delete(A, e);
             }
         }
     }
@@ -558,7 +560,9 @@ static int launch_ring(const ElemArgs& A, int n_sm, cudaStream_t s) {
     const long long n_tiles = A.d.nEp / Cfg::TLD;
     long long grid = n_sm;
     if (grid * NG > n_tiles) grid = (n_tiles + NG - 1) / NG;
-    hk_element_ring_kernel<NG, WG, S, CP><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, s>>>(A);
+    ElemArgs B = A;
+    B.n_tiles = (int)n_tiles;
+    hk_element_ring_kernel<NG, WG, S, CP><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, s>>>(B);
     return 0;
 }
 #endif
@@ -586,7 +590,7 @@ int hk_element_variant_from_env() {
 
 int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStream_t s) {
     if (d.element_mode == 1) { hk_launch_element_exact(d, step, write_triax, s); return 0; }
-    ElemArgs A{d, step, write_triax, 1};
+    ElemArgs A{d, step, write_triax, 1, 0};
 #ifndef HK_EMU
     switch (d.variant) {
         case 1: {

@@ -596,14 +596,10 @@ static int ensure_erosion(hk_engine* e) {
         if ((rc = dalloc(e, &E.einst, ei.size()))) return rc;
         if ((rc = upload(e, E.einst, ei))) return rc;
     }
-    if ((rc = dalloc(e, &E.fresh, (size_t)e->nElement))) return rc;
-    if ((rc = dalloc(e, &E.fresh_count, (size_t)1))) return rc;
-    if ((rc = dalloc(e, &E.block_count, (size_t)((e->nElement + 1023) / 1024)))) return rc;
     if ((rc = dalloc(e, &E.n_spec, (size_t)1))) return rc;
     if ((rc = dalloc(e, &E.n_slots, (size_t)1))) return rc;
     if ((rc = dalloc(e, &E.overflow, (size_t)1))) return rc;
     if ((rc = dalloc(e, &E.pairs, e->pairs.size()))) return rc;
-    CK(hkp::dev_memset(E.fresh_count, 0, sizeof(int), e->stream));
     CK(hkp::dev_memset(E.overflow, 0, sizeof(int), e->stream));
     // special-node table and accumulators at worst-case capacity, lengths on the device from now on
     e->dev_erosion = true;
@@ -680,7 +676,7 @@ static int fetch_deleted(hk_engine* e, std::vector<int64_t>* fresh) {
     if (count <= e->del_seen) return 0;
     std::vector<long long> ent(count - e->del_seen);
     CK(hkp::d2h(ent.data(), e->d.del_list + e->del_seen, ent.size() * sizeof(long long), e->stream));
-    std::sort(ent.begin(), ent.end());
+    // already in the reference's order: the deletion pass appends ascending ids, steps are stream-ordered
     for (long long v : ent) {
         int64_t id = (int64_t)(v & 0xffffffffll) + 1;
         e->deleted_all.push_back(id);
@@ -1150,6 +1146,9 @@ int HKAPI(finalize)(hk_engine* e) {
     d.del_cap = (int)nE;
     if ((rc = dalloc(e, &d.del_count, (size_t)1))) return rc;
     if ((rc = dalloc(e, &d.del_list, (size_t)nE))) return rc;
+    if ((rc = dalloc(e, &d.del_block, (size_t)((nE + 1023) / 1024)))) return rc;
+    if ((rc = dalloc(e, &d.del_fresh, (size_t)1))) return rc;
+    CK(hkp::dev_memset(d.del_fresh, 0, sizeof(int), e->stream));
     if ((rc = dalloc(e, &d.counters, (size_t)8))) return rc;
     CK(hkp::dev_memset(d.del_count, 0, sizeof(int), e->stream));
     CK(hkp::dev_memset(d.counters, 0, 8 * sizeof(unsigned long long), e->stream));
@@ -1308,7 +1307,7 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
             // (multi-GPU engines: the host driver replays the all-gathered ids through hk_apply_deleted instead)
             prof_begin(e, 5);
             long long nl = 0;
-            hk_launch_deletion_pass(d, e->dev_erosion ? &e->er : nullptr, e->stream, &nl);
+            hk_launch_deletion_pass(d, e->dev_erosion ? &e->er : nullptr, t, e->stream, &nl);
             e->n_launch += nl;
             prof_end(e);
             if (e->dev_erosion) e->contact_host_stale = true;

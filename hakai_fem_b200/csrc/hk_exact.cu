@@ -527,14 +527,17 @@ void hk_launch_cacc_zero(const HkDev& dd, const int* n_slots, int slot_cap, cuda
 }
 
 // ------------------------------------------------------------------ deletion pass + exposed faces on the device (A9/A10)
-// Step 1 (count): per block of HK_DEL_BLOCK elements, how many the element kernel marked for deletion (flag 3).
-// Step 2 (emit):  blocks holding marks write their elements to `fresh` in ASCENDING id order (offset = sum of the
-//                 counts of the blocks before: read only by the few blocks that have marks), zero stress/strain
-//                 (J2:742-756) and set flag 0.
-// Step 3 (erode): ONE thread replays the reference's serial loop J2:767-804 over `fresh`: for each face of a deleted
-//                 element the twin face (precomputed at hk_finalize) becomes two master triangles of every pair whose
-//                 j instance is the element's instance, and its nodes join c_nodes_i / c_nodes_j, in the reference's
-//                 order.  Deletions per step are few, the replay is inherently ordered, and nothing leaves the device.
+// Step 1 (count):  per block of HK_DEL_BLOCK elements, how many the element kernel marked for deletion (flag 3).
+// Step 2 (emit):   blocks holding marks append their elements to the deletion log in ASCENDING id order (offset = log
+//                  length before this step + the counts of the blocks before: read only by the few blocks that have
+//                  marks), zero stress/strain (J2:742-756) and set flag 0.  The log is therefore in the reference's
+//                  deletion order (ascending step, ascending id within a step, J2:701-735) without any sort, and the
+//                  element kernel needs no atomic.
+// Step 3 (finish): ONE thread; with contact it replays the reference's serial loop J2:767-804 over the step's entries:
+//                  for each face of a deleted element the twin face (precomputed at the first step) becomes two
+//                  master triangles of every pair whose j instance is the element's instance, and its nodes join
+//                  c_nodes_i / c_nodes_j, in the reference's order; then it advances the log length.  Deletions per
+//                  step are few, the replay is inherently ordered, and nothing leaves the device.
 #define HK_DEL_BLOCK 1024
 
 HK_HD void flush_element(const HkDev& d, long long e) {
@@ -619,7 +622,7 @@ HK_HD void erode_element(const HkDev& d, const HkErodeDev& E, int e) {
 }
 
 #ifndef HK_EMU
-__global__ void __launch_bounds__(256) hk_delete_count_kernel(HkDev d, HkErodeDev E) {
+__global__ void __launch_bounds__(256) hk_delete_count_kernel(HkDev d) {
     __shared__ int cnt;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
@@ -631,23 +634,23 @@ __global__ void __launch_bounds__(256) hk_delete_count_kernel(HkDev d, HkErodeDe
     }
     if (mine) atomicAdd(&cnt, mine);
     __syncthreads();
-    if (threadIdx.x == 0) E.block_count[blockIdx.x] = cnt;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *E.fresh_count = 0;
+    if (threadIdx.x == 0) d.del_block[blockIdx.x] = cnt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d.del_fresh = 0;
 }
-__global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, HkErodeDev E) {
-    const int mycount = E.block_count[blockIdx.x];
+__global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, long long step) {
+    const int mycount = d.del_block[blockIdx.x];
     if (mycount == 0) return;
     __shared__ int base, warp_tot[8];
     __shared__ int red[256];
     int part = 0;                                     // offset: marks in all blocks before this one
-    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 256) part += E.block_count[b];
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 256) part += d.del_block[b];
     red[threadIdx.x] = part;
     __syncthreads();
     for (int off = 128; off; off >>= 1) {
         if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
         __syncthreads();
     }
-    if (threadIdx.x == 0) base = red[0];
+    if (threadIdx.x == 0) base = *d.del_count + red[0];             // the log length is advanced by the finish kernel
     __syncthreads();
     const long long e0 = (long long)blockIdx.x * HK_DEL_BLOCK;
     int run = base;
@@ -661,41 +664,47 @@ __global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, HkErodeDev
         int before = 0, total = 0;
         for (int i = 0; i < 8; ++i) { if (i < w) before += warp_tot[i]; total += warp_tot[i]; }
         if (m) {
-            E.fresh[run + before + __popc(bal & ((1u << lane) - 1u))] = (int)e;
+            const int slot = run + before + __popc(bal & ((1u << lane) - 1u));
+            if (slot < d.del_cap) d.del_list[slot] = (step << 32) | e;
             flush_element(d, e);
         }
         run += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) atomicAdd(E.fresh_count, mycount);
+    if (threadIdx.x == 0) atomicAdd(d.del_fresh, mycount);
 }
-__global__ void hk_erode_kernel(HkDev d, HkErodeDev E) {
-    const int n = *E.fresh_count;
-    for (int i = 0; i < n; ++i) erode_element(d, E, E.fresh[i]);
+__global__ void hk_delete_finish_kernel(HkDev d, HkErodeDev E, int erode) {
+    const int n = *d.del_fresh, first = *d.del_count;
+    if (erode)
+        for (int i = 0; i < n && first + i < d.del_cap; ++i) erode_element(d, E, (int)(d.del_list[first + i] & 0xffffffffll));
+    *d.del_count = first + n;
 }
 #endif
 
-void hk_launch_deletion_pass(const HkDev& dd, const HkErodeDev* er, cudaStream_t s, long long* n_launch) {
+void hk_launch_deletion_pass(const HkDev& dd, const HkErodeDev* er, long long step, cudaStream_t s, long long* n_launch) {
     const HkDev d = dd;
-    if (!er) {                                       // no contact surface to update: zero the marked elements, any order
-        hk_parallel_for(d.nElement, s, HK_LAMBDA(long long e) { if (d.flag[e] == 3) flush_element(d, e); });
-        if (n_launch) *n_launch += 1;
-        return;
-    }
-    const HkErodeDev E = *er;
+    HkErodeDev E;
+    memset(&E, 0, sizeof(E));
+    if (er) E = *er;
 #ifndef HK_EMU
     const unsigned nb = (unsigned)((d.nElement + HK_DEL_BLOCK - 1) / HK_DEL_BLOCK);
-    hk_delete_count_kernel<<<nb, 256, 0, s>>>(d, E);
-    hk_delete_emit_kernel<<<nb, 256, 0, s>>>(d, E);
-    hk_erode_kernel<<<1, 1, 0, s>>>(d, E);
+    hk_delete_count_kernel<<<nb, 256, 0, s>>>(d);
+    hk_delete_emit_kernel<<<nb, 256, 0, s>>>(d, step);
+    hk_delete_finish_kernel<<<1, 1, 0, s>>>(d, E, er ? 1 : 0);
     if (n_launch) *n_launch += 3;
 #else
     (void)s; (void)n_launch;
+    const int first = *d.del_count;
     int n = 0;
     for (long long e = 0; e < d.nElement; ++e)
-        if (d.flag[e] == 3) { E.fresh[n++] = (int)e; flush_element(d, e); }
-    *E.fresh_count = n;
-    for (int i = 0; i < n; ++i) erode_element(d, E, E.fresh[i]);
+        if (d.flag[e] == 3) {
+            if (first + n < d.del_cap) d.del_list[first + n] = (step << 32) | e;
+            ++n;
+            flush_element(d, e);
+        }
+    if (er)
+        for (int i = 0; i < n && first + i < d.del_cap; ++i) erode_element(d, E, (int)(d.del_list[first + i] & 0xffffffffll));
+    *d.del_count = first + n;
 #endif
 }
 
@@ -1230,9 +1239,7 @@ HK_D void element_body_exact(const ExactArgs& A, long long e) {
                     break;
                 }
             if (v_e >= fr_e) {
-                d.flag[e] = 3;                     // zeroed by hk_launch_deletion_pass (stream order)
-                const int slot = hk_atomic_add_i32(d.del_count, 1);
-                if (slot < d.del_cap) d.del_list[slot] = (A.step << 32) | e;
+                d.flag[e] = 3;                     // logged and zeroed by hk_launch_deletion_pass (stream order)
             }
         }
     }

@@ -480,9 +480,10 @@ class SlabRunner:
                                           else np.zeros(0, np.int64))
         return n
 
-    def run(self, t_first: int, n_steps: int, frame_at_end: bool = False) -> int:
+    def run(self, t_first: int, n_steps: int, frame_at_end: bool = False, sync: bool = True) -> int:
         """Enqueues pack -> exchange -> step for every step without blocking the host, then synchronises once.
-        frame_at_end: an output frame follows (the last step stores integ_triax_stress, hk_mark_frame)."""
+        frame_at_end: an output frame follows (the last step stores integ_triax_stress, hk_mark_frame).
+        sync=False (no contact erosion across ranks): only enqueue; the caller calls engine.sync() itself."""
         import time as _time
         _t0 = _time.perf_counter()
         n_del = 0
@@ -491,7 +492,7 @@ class SlabRunner:
                 self.engine.mark_frame()
             self.engine.step_enqueue(t_first, n_steps)
             self.last_enqueue_s = _time.perf_counter() - _t0
-            return self.engine.sync()
+            return self.engine.sync() if sync else 0
         for t in range(t_first, t_first + n_steps):
             if frame_at_end and t == t_first + n_steps - 1:
                 self.engine.mark_frame()
@@ -507,7 +508,7 @@ class SlabRunner:
             if self.erosion:
                 n_del += self._after_step()
         self.last_enqueue_s = _time.perf_counter() - _t0      # host time to enqueue (diagnostic)
-        return n_del + self.engine.sync()
+        return n_del + (self.engine.sync() if sync else 0)
 
 
 # ------------------------------------------------------------------ ghost-element partitions (partition-independent bits)
