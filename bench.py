@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--workload", default="W16")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", default=None)
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=40, help="timed steps of the CPU baseline sample (~10 s at 16 threads)")
     ap.add_argument("--strain-per-step", type=float, default=None,
                     help="override the deck's stretch rate (1e-6: purely elastic run, SURVEY §8d; disables the regime gate)")
     ap.add_argument("--no-cpu", action="store_true")

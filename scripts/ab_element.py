@@ -3,7 +3,7 @@ the deck is built once, every configuration gets its own engine, configurations 
 times, each visit = warm-up into the plastic regime + `--steps` timed steps with CUDA events around every launch.
 
   python scripts/ab_element.py --configs "20,1,;12,1,;20,0,;20,1,red" [--workload W16] [--steps 30] [--rounds 2]
-A configuration is variant,blocked,experiment.  Prints one JSON line per visit and a summary."""
+A configuration is variant,rec_soa,experiment (HK_ELEMENT_VARIANT, HK_REC_SOA, HK_EXPERIMENT).  Prints one JSON line per visit and a summary."""
 import argparse
 import json
 import os
@@ -34,7 +34,7 @@ def main():
     for rnd in range(args.rounds):
         for v, blocked, exp in cfgs:
             os.environ["HK_ELEMENT_VARIANT"] = v
-            os.environ["HK_LAYOUT_BLOCKED"] = blocked
+            os.environ["HK_REC_SOA"] = blocked
             os.environ["HK_EXPERIMENT"] = exp
             g = configure_engine(Engine, st)
             g.step(1, args.warmup)
@@ -44,7 +44,7 @@ def main():
             ms, n = g.profile_read()
             g.close()
             el, nd = ms[2] / max(n[2], 1), ms[1] / max(n[1], 1)
-            key = f"v{v} blocked={blocked} {exp}".strip()
+            key = f"v{v} rec_soa={blocked} {exp}".strip()
             res.setdefault(key, []).append((el, nd))
             print(json.dumps({"config": key, "round": rnd, "element_ms": el, "nodal_ms": nd,
                               "frac": 1904 * nE / (el * 1e-3) / 1e9 / 6448.4,
