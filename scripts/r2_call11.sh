@@ -24,4 +24,4 @@ for w in ("W16","F16D","I8"):
     r=j["roofline"]; c=j["config"]; e=j.get("e2e") or {}
     print(w, round(j["value"]/1e9,3),"G", round(j["ms_per_step"],3),"ms el",round(r["avg_launch_ms"],3),"frac",round(r["frac"],3),"step frac",round(r["whole_step"]["frac"],3),"nodal",round(r["nodal_kernel"]["ms_per_step"],3),c["regime"],c["untimed_steps_before_timing"],"live",c["live_elements_start"],c["live_elements_end"],"e2e",e.get("value"),e.get("seconds"),(e.get("frame_loop") or {}).get("value"), j.get("contact",{}).get("ms_per_step") if j.get("contact") else None, (j.get("cpu_baseline") or {}).get("value"))
 PY
-tail -2 gpurun_out/r2_bench_n1_*.err
+for f in gpurun_out/r2_bench_n1_*.err; do tail -n 2 $f; done
