@@ -235,11 +235,18 @@ static void prof_collect(hk_engine* e) {
     if (e->events.empty()) return;
     cudaStreamSynchronize(e->stream);
     if (e->comm_stream) cudaStreamSynchronize(e->comm_stream);
-    for (auto& t : e->events) {
+    for (size_t i = 0; i < e->events.size(); ++i) {
+        TimedEvent& t = e->events[i];
         float ms = 0;
         cudaEventElapsedTime(&ms, t.a, t.b);
         e->prof_ms[t.kind] += ms;
         e->prof_n[t.kind] += 1;
+        if (i + 1 < e->events.size() && t.kind != 4 && e->events[i + 1].kind != 4) {   // kind 6: idle time between the
+            float gap = 0;                                                                // profiled launches of the main stream
+            if (cudaEventElapsedTime(&gap, t.b, e->events[i + 1].a) == cudaSuccess && gap > 0) { e->prof_ms[6] += gap; e->prof_n[6] += 1; }
+        }
+    }
+    for (auto& t : e->events) {
         cudaEventDestroy(t.a);
         cudaEventDestroy(t.b);
     }

@@ -205,7 +205,8 @@ int hk_profile(hk_engine* e, int32_t enable);
 int hk_profile_read(hk_engine* e, double ms[4], int64_t launches[4]);
 /* The same with the kinds a multi-GPU / fracture run adds: 4 halo exchange (the ncclSend/ncclRecv group of the engine's
  * own communicator, timed on its side stream — it overlaps kind 1), 5 deletion pass (ordered list, zeroing, exposed
- * faces); 6-7 reserved. */
+ * faces), 6 time between the end of one profiled launch and the start of the next on the engine's stream (launch gaps;
+ * its count is the number of gaps); 7 reserved. */
 int hk_profile_read_ex(hk_engine* e, double ms[8], int64_t launches[8]);
 
 /* Run all work on the caller's CUDA stream (cudaStream_t as void*).  NULL is the CUDA legacy default stream (what
