@@ -101,6 +101,11 @@ struct hk_engine {
     // NCCL inside the library (hk_comm_init): communicator, side stream for the exchange, ordering events
     void* comm = nullptr;
     int comm_world = 0;
+    // contact exchange inside the library (hk_comm_contact): padded export block, gathered blocks of all ranks, limbs
+    int64_t cx_maxlen = 0;
+    double* cx_send = nullptr;
+    double* cx_all = nullptr;
+    long long* cx_limbs = nullptr;
 #ifndef HK_EMU
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_pack = nullptr, ev_comm = nullptr;
@@ -708,6 +713,8 @@ struct NcclApi {
     int (*CommDestroy)(void*) = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -715,6 +722,8 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 const int kNcclFloat64 = 8;          // ncclFloat64 (nccl.h)
+const int kNcclInt64 = 4;            // ncclInt64
+const int kNcclSum = 0;              // ncclSum
 
 bool nccl_load() {
     if (g_nccl.lib) return true;
@@ -728,10 +737,13 @@ bool nccl_load() {
     g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
     g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
     g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
     g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
     g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
     g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.Send || !g_nccl.Recv ||
+        !g_nccl.AllGather || !g_nccl.AllReduce ||
         !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.GetErrorString)
         return false;
     g_nccl.lib = h;
@@ -1334,11 +1346,37 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
 //     pack (main stream) -> ncclSend/ncclRecv with every neighbour (side stream) || nodal update of the non-interface
 //     nodes (main stream) -> interface nodes, element kernel (main stream, after the exchange)
 // all enqueued for n_steps steps without the host looking at anything in between.
+// contact across ranks, all on the engine's stream (every stage needs the previous one): surface-node states of the
+// nodes this rank owns -> ncclAllGather -> ghost copies -> contact pass on the local master triangles -> the 128-bit
+// force accumulators as 43-bit limbs -> ncclAllReduce(int64, sum), exact -> accumulators identical on every rank
+static int comm_contact_exchange(hk_engine* e) {
+    if (!e->velo_current) { hk_launch_velo_from_rec(e->d, e->prm.d_time, e->stream); e->velo_current = true; }
+    hk_launch_nodes_export(e->d, e->d_node_list[0], (long long)e->node_list[0].size(), e->cx_send, e->stream);
+    NCK(g_nccl.AllGather(e->cx_send, e->cx_all, (size_t)e->cx_maxlen * 6, kNcclFloat64, e->comm, e->stream));
+    hk_launch_nodes_import(e->d, e->d_node_list[1], e->d_import_src, (long long)e->node_list[1].size(), e->cx_all, e->stream);
+    int rc = contact_pass(e);
+    if (rc) return rc;
+    e->contact_done = true;
+    const long long ns = (long long)e->node_list[2].size();
+    hk_launch_cacc_export_limbs(e->d, e->d_node_list[2], ns, e->cx_limbs, e->stream);
+    NCK(g_nccl.AllReduce(e->cx_limbs, e->cx_limbs, (size_t)ns * 9, kNcclInt64, kNcclSum, e->comm, e->stream));
+    hk_launch_cacc_import_limbs(e->d, e->d_node_list[2], ns, e->cx_limbs, e->stream);
+    e->n_launch += 4;
+    return 0;
+}
+
 static int comm_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end) {
     if (e->frame_next && n_steps > 0) { frame_at_end = true; e->frame_next = false; }      // hk_mark_frame: LAST step
+    const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
-        int rc = halo_pack_all(e);
-        if (rc) return rc;
+        int rc;
+        if (contact_on && !e->contact_done) { if ((rc = comm_contact_exchange(e))) return rc; }
+        if (e->halo.empty()) {                            // a rank with no interface node (does not occur with blocks)
+            if (frame_at_end && t == t_first + n_steps - 1) e->frame_next = true;
+            if ((rc = enqueue_steps(e, t, 1, false, 0))) return rc;
+            continue;
+        }
+        if ((rc = halo_pack_all(e))) return rc;
         CK(cudaEventRecord(e->ev_pack, e->stream));
         CK(cudaStreamWaitEvent(e->comm_stream, e->ev_pack, 0));
         prof_begin(e, 4, e->comm_stream, true);
@@ -1363,10 +1401,15 @@ static int step_enqueue_impl(hk_engine* e, int64_t t_first, int64_t n_steps, boo
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
     if (n_steps < 0 || t_first < 0 || t_first + n_steps >= (1ll << 31)) return fail(e, HK_ERR_ARG, "bad step range");
 #ifndef HK_EMU
-    if (!e->halo.empty() && e->comm) {                 // the engine exchanges the halos itself: any number of steps
-        if (e->prm.contact_flag >= 1 && !e->pairs.empty())
-            return fail(e, HK_ERR_UNSUPPORTED, "contact across ranks is exchanged by the host driver (hk_nodes_* / hk_contact_*), "
-                                               "one step at a time: use hk_halo_pack + hk_step_begin / hk_step_finish");
+    if (e->comm && (!e->halo.empty() || e->cx_maxlen > 0)) {   // the engine exchanges by itself: any number of steps
+        if (e->prm.contact_flag >= 1 && !e->pairs.empty()) {
+            if (e->cx_maxlen <= 0)
+                return fail(e, HK_ERR_STATE, "contact across ranks: call hk_comm_contact after hk_set_node_list (or drive the "
+                                             "exchange from the host: hk_nodes_* / hk_contact_* + hk_step_begin / hk_step_finish)");
+            if (n_steps > 1 && e->any_ductile && !e->g_node_map.empty())
+                return fail(e, HK_ERR_UNSUPPORTED, "contact surfaces that erode across ranks: the host replays the all-gathered "
+                                                   "deletions (hk_apply_deleted) after every step, so enqueue one step at a time");
+        }
         int rc = comm_steps(e, t_first, n_steps, frame_at_end);
         if (rc) return rc;
         CK(hkp::last_error());
@@ -1776,6 +1819,35 @@ int HKAPI(set_halo)(hk_engine* e, int64_t n_neighbors, const int64_t* nbr_ptr, c
         e->halo.push_back(std::move(h));
     }
     return HK_OK;
+}
+
+int HKAPI(comm_contact)(hk_engine* e, int64_t maxlen, const int64_t* src_index) {
+#ifndef HK_EMU
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
+    if (!e->comm) return fail(e, HK_ERR_STATE, "hk_comm_init first");
+    if (maxlen < 1 || (int64_t)e->node_list[0].size() > maxlen) return fail(e, HK_ERR_ARG, "maxlen smaller than this rank's export list");
+    const size_t n_ghost = e->node_list[1].size();
+    if (n_ghost && !src_index) return fail(e, HK_ERR_ARG, "src_index missing");
+    for (size_t i = 0; i < n_ghost; ++i)
+        if (src_index[i] < 0 || src_index[i] >= maxlen * e->comm_world) return fail(e, HK_ERR_ARG, "src_index out of range");
+    CK(hkp::sync(e->stream));
+    dfree(e, e->cx_send); dfree(e, e->cx_all); dfree(e, e->cx_limbs); dfree(e, e->d_import_src);
+    e->cx_send = nullptr; e->cx_all = nullptr; e->cx_limbs = nullptr; e->d_import_src = nullptr;
+    int rc;
+    if ((rc = dalloc(e, &e->cx_send, (size_t)maxlen * 6))) return rc;
+    if ((rc = dalloc(e, &e->cx_all, (size_t)maxlen * 6 * e->comm_world))) return rc;
+    if ((rc = dalloc(e, &e->cx_limbs, std::max<size_t>(1, e->node_list[2].size() * 9)))) return rc;
+    CK(hkp::dev_memset(e->cx_send, 0, (size_t)maxlen * 6 * sizeof(double), e->stream));
+    std::vector<long long> src(src_index, src_index + n_ghost);
+    if ((rc = dalloc(e, &e->d_import_src, std::max<size_t>(1, n_ghost)))) return rc;
+    if ((rc = upload(e, e->d_import_src, src))) return rc;
+    e->cx_maxlen = maxlen;
+    return HK_OK;
+#else
+    (void)maxlen; (void)src_index;
+    return fail(e, HK_ERR_UNSUPPORTED, "host-compiled debugging build has no NCCL");
+#endif
 }
 
 int HKAPI(halo_bind)(hk_engine* e, int64_t neighbor, void* send_dev, void* recv_dev) {

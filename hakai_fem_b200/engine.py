@@ -44,7 +44,7 @@ EXPORTS = [
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
     "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
-    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init", "profile_read_ex",
+    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init", "profile_read_ex", "comm_contact",
 ]
 
 
@@ -353,6 +353,12 @@ class EngineBase:
         if len(unique_id) != 128:
             raise ValueError("unique_id: 128 bytes")
         self._chk(self._fn("comm_init")(self._h, C.c_char_p(unique_id), C.c_int32(rank), C.c_int32(world)))
+
+    def comm_contact(self, maxlen: int, src_index):
+        """The engine runs the contact exchange of every step itself (all-gather of surface-node states, exact all-reduce
+        of the force accumulators) — after set_node_list(0/1/2) and comm_init."""
+        a = _i64(src_index)
+        self._chk(self._fn("comm_contact")(self._h, c_i64(maxlen), _pi(a)))
 
     def halo_bind(self, neighbor: int, send_ptr: int, recv_ptr: int):
         self._chk(self._fn("halo_bind")(self._h, c_i64(neighbor), C.c_void_p(send_ptr), C.c_void_p(recv_ptr)))

@@ -339,12 +339,13 @@ class ContactExchanger:
     """All-gather of contact-surface node {position, velocity} and of the fixed-point force accumulators."""
 
     def __init__(self, engine, lists: ContactLists, world: int, device, rank=None, node_l2g=None, n_pairs=0,
-                 force_exchange="allreduce"):
+                 force_exchange="allreduce", engine_comm=False):
         """force_exchange: "allgather" (6 x u64 per surface node from every rank, summed on import) or "allreduce"
         (three 43-bit limbs per accumulator in int64 lanes, one SUM all-reduce: world/1.5 times fewer bytes)."""
         if force_exchange not in ("allgather", "allreduce"):
             raise ValueError("force_exchange: allgather | allreduce")
         self.force_exchange = force_exchange
+        self.engine_comm = engine_comm       # the engine's own communicator runs the exchange inside hk_step_enqueue
         self.engine, self.world, self.device = engine, world, device
         self.rank, self.node_l2g, self.n_pairs = rank, node_l2g, n_pairs
         self.erosion = lists.erosion
@@ -361,6 +362,12 @@ class ContactExchanger:
         import torch
         engine, world, device = self.engine, self.world, self.device
         self.lists = lists
+        if self.engine_comm:
+            engine.set_node_list(0, lists.export_nodes)
+            engine.set_node_list(1, lists.import_nodes)
+            engine.set_node_list(2, lists.surface_nodes)
+            engine.comm_contact(lists.maxlen, lists.import_src)
+            return
         self.send_nodes = torch.zeros(lists.maxlen * 6, dtype=torch.float64, device=device)
         self.all_nodes = torch.zeros(world * lists.maxlen * 6, dtype=torch.float64, device=device)
         n_surf = len(lists.surface_nodes)
@@ -407,6 +414,8 @@ class ContactExchanger:
         """positions -> ghosts, contact pass on the local triangles, exact sum of the forces over ranks."""
         import torch.distributed as dist
         eng = self.engine
+        if self.engine_comm:
+            return                          # done by the engine at the start of the step it is about to run
         eng.nodes_export(self.send_nodes.data_ptr())
         dist.all_gather(list(self.all_nodes.chunk(self.world)), self.send_nodes)
         eng.nodes_import(self.all_nodes.data_ptr(), self.lists.import_src if self._first else None)
@@ -445,11 +454,9 @@ class SlabRunner:
                 eng.set_halo(halo_nodes)
             return eng
         self.engine = configure_engine(with_halo, setup, **params)
-        if engine_comm and contact is not None:
-            raise ValueError("engine_comm: decks with contact across ranks use the host-driven exchange")
         self.halo = HaloExchanger(self.engine, neighbors, halo_nodes, torch_device, rank=rank, engine_comm=engine_comm)
         self.contact = (ContactExchanger(self.engine, contact, world, torch_device, rank, node_l2g, len(setup.CT),
-                                         force_exchange)
+                                         force_exchange, engine_comm=engine_comm)
                         if contact is not None else None)
         self.erosion = self.contact is not None and self.contact.erosion is not None
         if self.erosion and elem_l2g is None:
@@ -471,6 +478,8 @@ class SlabRunner:
         return n
 
     def step(self, t: int) -> int:
+        if self.halo.engine_comm:
+            return self.run(t, 1)
         if self.contact is not None:
             self.contact.run()
         self.halo.exchange()
@@ -487,12 +496,19 @@ class SlabRunner:
         import time as _time
         _t0 = _time.perf_counter()
         n_del = 0
-        if self.halo.engine_comm:                        # one call: the engine packs, exchanges (its own NCCL) and steps
+        if self.halo.engine_comm and not self.erosion:   # one call: the engine packs, exchanges (its own NCCL) and steps
             if frame_at_end:
                 self.engine.mark_frame()
             self.engine.step_enqueue(t_first, n_steps)
             self.last_enqueue_s = _time.perf_counter() - _t0
             return self.engine.sync() if sync else 0
+        if self.halo.engine_comm:                        # eroding contact surfaces: the host replays deletions every step
+            for t in range(t_first, t_first + n_steps):
+                if frame_at_end and t == t_first + n_steps - 1:
+                    self.engine.mark_frame()
+                self.engine.step_enqueue(t, 1)
+                n_del += self._after_step()
+            return n_del
         for t in range(t_first, t_first + n_steps):
             if frame_at_end and t == t_first + n_steps - 1:
                 self.engine.mark_frame()

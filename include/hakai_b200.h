@@ -243,9 +243,17 @@ int hk_set_halo_ranks(hk_engine* e, int64_t my_rank, int64_t n_neighbors, const 
  *                      allocates the engine's own send/recv blocks (hk_halo_bind is then not needed).
  * With a communicator hk_step / hk_step_enqueue(t, n) run n >= 1 complete multi-GPU steps with no host involvement:
  * pack -> ncclSend/ncclRecv with every neighbour on a side stream, overlapped with the nodal update of the non-interface
- * nodes -> interface nodes -> element kernel.  (Decks with contact across ranks still use the host-driven exchange.) */
+ * nodes -> interface nodes -> element kernel. */
 int hk_comm_unique_id(void* id128);
 int hk_comm_init(hk_engine* e, const void* id128, int32_t rank, int32_t world);
+/* Contact across ranks exchanged by the engine too.  After hk_set_node_list(0 / 1 / 2) (own surface nodes, ghost copies,
+ * all surface nodes — see "multi-GPU contact" below): maxlen = the longest own-export list of any rank (every rank's
+ * block of the all-gather is padded to it), src_index[i] = rank * maxlen + position of ghost i's owner record.  From
+ * then on every step of hk_step / hk_step_enqueue first runs, on the engine's stream: export of the own surface nodes ->
+ * ncclAllGather -> ghost copies -> contact pass on the local master triangles -> 43-bit limbs of the 128-bit force
+ * accumulators -> ncclAllReduce(int64, sum) (exact) -> the halo step.  Call again whenever the lists change.  Surfaces
+ * that erode across ranks (hk_set_global_maps) still need the host's replay after every step: then n_steps = 1. */
+int hk_comm_contact(hk_engine* e, int64_t maxlen, const int64_t* src_index);
 
 /* The asynchronous step calls imply no output frame, so they do not store integ_triax_stress (hk_download and
  * hk_node_output then derive it from the current stress).  hk_mark_frame announces that the last step of the NEXT

@@ -28,7 +28,7 @@ def _global_setup(mode):
     return prepare(deck.build_model()), {}, 90
 
 
-def _worker(rank, world, port, mode, q):
+def _worker(rank, world, port, mode, q, engine_comm=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -45,7 +45,8 @@ def _worker(rank, world, port, mode, q):
             e = Engine(**p)
             e.set_stream(stream.cuda_stream)
             return e
-        run = SlabRunner.from_domain(make, dom, torch.device("cuda", rank), world, device=rank, **prm)
+        run = SlabRunner.from_domain(make, dom, torch.device("cuda", rank), world, device=rank, engine_comm=engine_comm,
+                                     **prm)
         nd = run.run(1, n_steps)
         d = run.engine.download()
         n_own = len(np.unique(dom.setup.model.elementmat))          # held nodes come first, ghosts after
@@ -59,18 +60,21 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,world", [("fracture", 2), ("contact", 2), ("erosion", 2), ("erosion", 1)])
-def test_ranks_match_single_domain_oracle(mode, world):
+@pytest.mark.parametrize("mode,world,engine_comm", [("fracture", 2, False), ("contact", 2, False), ("erosion", 2, False),
+                                                    ("erosion", 1, False), ("fracture", 2, True), ("contact", 2, True),
+                                                    ("erosion", 2, True), ("erosion", 1, True)])
+def test_ranks_match_single_domain_oracle(mode, world, engine_comm):
     """world == 1 runs the whole domain-runner path (global maps, hk_apply_deleted, list rebuild, NCCL calls) on a
-    single-GPU box, where the 2-rank cases are skipped."""
+    single-GPU box, where the 2-rank cases are skipped.  engine_comm: the ENGINE's communicator runs every exchange
+    (hk_comm_init / hk_comm_contact: halo send/recv, surface all-gather, limb all-reduce) inside hk_step_enqueue."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     from hakai_fem_b200.model_setup import configure_engine
     from oracle.oracle_engine import OracleEngine
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29200 + (os.getpid() % 2000) + ("fracture", "contact", "erosion").index(mode) + 10 * world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    port = 29200 + (os.getpid() % 2000) + ("fracture", "contact", "erosion").index(mode) + 10 * world + (40 if engine_comm else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q, engine_comm)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(world)]
