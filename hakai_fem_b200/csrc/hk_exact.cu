@@ -528,9 +528,9 @@ void hk_launch_cacc_zero(const HkDev& dd, const int* n_slots, int slot_cap, cuda
 
 // ------------------------------------------------------------------ deletion pass + exposed faces on the device (A9/A10)
 // Step 1 (count):  per block of HK_DEL_BLOCK elements, how many the element kernel marked for deletion (flag 3).
-// Step 2 (emit):   blocks holding marks append their elements to the deletion log in ASCENDING id order (offset = log
-//                  length before this step + the counts of the blocks before: read only by the few blocks that have
-//                  marks), zero stress/strain (J2:742-756) and set flag 0.  The log is therefore in the reference's
+// Step 2 (scan + emit): an exclusive scan of the block counts (one CTA), then blocks holding marks append their elements
+//                  to the deletion log in ASCENDING id order (offset = log length before this step + the block's scan
+//                  value), zero stress/strain (J2:742-756) and set flag 0.  The log is therefore in the reference's
 //                  deletion order (ascending step, ascending id within a step, J2:701-735) without any sort, and the
 //                  element kernel needs no atomic.
 // Step 3 (finish): ONE thread; with contact it replays the reference's serial loop J2:767-804 over the step's entries:
@@ -635,25 +635,45 @@ __global__ void __launch_bounds__(256) hk_delete_count_kernel(HkDev d) {
     if (mine) atomicAdd(&cnt, mine);
     __syncthreads();
     if (threadIdx.x == 0) d.del_block[blockIdx.x] = cnt;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *d.del_fresh = 0;
 }
-__global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, long long step) {
-    const int mycount = d.del_block[blockIdx.x];
-    if (mycount == 0) return;
-    __shared__ int base, warp_tot[8];
-    __shared__ int red[256];
-    int part = 0;                                     // offset: marks in all blocks before this one
-    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 256) part += d.del_block[b];
-    red[threadIdx.x] = part;
+// exclusive scan of the per-block counts (one CTA; the mesh has nElement / 1024 blocks) -> del_block[b] becomes the
+// offset of block b inside this step's entries, *del_fresh the step's total
+__global__ void __launch_bounds__(1024) hk_delete_scan_kernel(HkDev d, int nb) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int off = 128; off; off >>= 1) {
-        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? d.del_block[i] : 0;
+        int x = v;
+        for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+        if (lane == 31) warp_sum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int s = warp_sum[lane];
+            for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, off); if (lane >= off) s += y; }
+            warp_sum[lane] = s;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int incl = x + (w ? warp_sum[w - 1] : 0);
+        if (i < nb) d.del_block[i] = carry + incl - v;          // exclusive offset; the count is recovered by the emit kernel
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) base = *d.del_count + red[0];             // the log length is advanced by the finish kernel
-    __syncthreads();
+    if (threadIdx.x == 0) *d.del_fresh = carry_s;
+}
+__global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, long long step, int nb) {
+    if (*d.del_fresh == 0) return;                             // nothing was deleted in this step (the common case)
+    const int off0 = d.del_block[blockIdx.x];
+    const int off1 = (int)blockIdx.x + 1 < nb ? d.del_block[blockIdx.x + 1] : *d.del_fresh;
+    if (off1 == off0) return;
+    __shared__ int warp_tot[8];
     const long long e0 = (long long)blockIdx.x * HK_DEL_BLOCK;
-    int run = base;
+    int run = *d.del_count + off0;                            // the log length is advanced by the finish kernel
     for (int chunk = 0; chunk < HK_DEL_BLOCK; chunk += 256) {      // ordered compaction, 256 elements at a time
         const long long e = e0 + chunk + threadIdx.x;
         const bool m = e < d.nElement && d.flag[e] == 3;
@@ -671,7 +691,6 @@ __global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, long long 
         run += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) atomicAdd(d.del_fresh, mycount);
 }
 __global__ void hk_delete_finish_kernel(HkDev d, HkErodeDev E, int erode) {
     const int n = *d.del_fresh, first = *d.del_count;
@@ -689,9 +708,10 @@ void hk_launch_deletion_pass(const HkDev& dd, const HkErodeDev* er, long long st
 #ifndef HK_EMU
     const unsigned nb = (unsigned)((d.nElement + HK_DEL_BLOCK - 1) / HK_DEL_BLOCK);
     hk_delete_count_kernel<<<nb, 256, 0, s>>>(d);
-    hk_delete_emit_kernel<<<nb, 256, 0, s>>>(d, step);
+    hk_delete_scan_kernel<<<1, 1024, 0, s>>>(d, (int)nb);
+    hk_delete_emit_kernel<<<nb, 256, 0, s>>>(d, step, (int)nb);
     hk_delete_finish_kernel<<<1, 1, 0, s>>>(d, E, er ? 1 : 0);
-    if (n_launch) *n_launch += 3;
+    if (n_launch) *n_launch += 4;
 #else
     (void)s; (void)n_launch;
     const int first = *d.del_count;
