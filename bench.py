@@ -62,13 +62,14 @@ def make_deck(workload, strain_per_step=None):
             "ductile" if ductile else "stretch")
 
 
-def prepare_setup(deck):
+def prepare_setup(deck, contact="host"):
+    """contact="device": the contact tables are built by hk_build_contact on the GPU (CUDA engine only)."""
     from hakai_fem_b200.model_setup import prepare
     model = deck.build_model()
     vol = None
     if getattr(deck, "jitter", None) == 0.0:
         vol = np.full(model.nElement, deck.h ** 3)
-    return prepare(model, elementVolume=vol)
+    return prepare(model, elementVolume=vol, contact=contact)
 
 
 def deck_text(deck, kind):
@@ -242,7 +243,9 @@ def main():
         deck, nbrs, halos = slab_deck(deck, rank, world)
     else:
         nbrs, halos = [], []
-    st = prepare_setup(deck)
+    t_setup = time.perf_counter()
+    st = prepare_setup(deck, contact="device" if kind == "impact" else "host")
+    t_setup = time.perf_counter() - t_setup
     nE, nN = st.model.nElement, st.model.nNode
     prm = dict(contact_myu=0.0) if kind == "impact" else {}        # north star: frictionless
 
@@ -251,9 +254,11 @@ def main():
         e_.set_stream(stream.cuda_stream)
         return e_
     # N > 1: the engine owns the NCCL communicator and runs pack -> send/recv -> step for all steps of a call by itself
+    t_setup0 = time.perf_counter()
     runner = SlabRunner(make_engine, st, nbrs, halos, torch.device("cuda", local_rank), sum_mass=True, rank=rank,
                         engine_comm=world > 1, device=local_rank, **prm)
     eng = runner.engine
+    t_engine = time.perf_counter() - t_setup0
 
     def run_steps(t0, n, sync=True):
         """sync=False: only enqueue (the timed region ends with a CUDA event on the stream, BEFORE hk_sync's host work —
@@ -397,9 +402,12 @@ def main():
                             "source": "profiles/r1_fp64_ops.json (ncu instruction counts, same Gauss-point math)"}
     contact = None
     if kind == "impact":
+        pinfo = [eng.contact_pair(c) for c in range(2)]
         contact = {"ms_per_step": ct_ms, "hits_per_step": float(c1[1] - c0[1]) / args.steps,
                    "tests_per_step": float(c1[2] - c0[2]) / args.steps,
-                   "pairs": [dict(nn_i=len(c.c_nodes_i), nn_j=len(c.c_nodes_j), nTri=len(c.c_triangles)) for c in st.CT],
+                   "pairs": [dict(nn_i=len(p["c_nodes_i"]), nn_j=len(p["c_nodes_j"]), nTri=len(p["c_triangles_eleid"])) for p in pinfo],
+                   "setup": "hk_build_contact: faces, orientation, exterior faces and exposed-face twins by radix sort on the GPU "
+                            "(engine_setup_s includes it)",
                    "fixed_point_overflows": int(c1[5]),
                    "kernels": "hk_contact_{reset,bbox,cells,narrow}_kernel per ordered pair + accumulator memset"}
 
@@ -501,6 +509,7 @@ def main():
                "regime": regime, "untimed_steps_before_timing": args.warmup + extra,
                "eps_at_start": [s_start["eps_min"], s_start["eps_max"]],
                "live_elements_start": s_start["live_elements"], "live_elements_end": s_end["live_elements"],
+               "host_setup_s": round(t_setup, 2), "engine_setup_s": round(t_engine, 2),
                "l2": "state >> L2 (inputs larger than L2), no flush", "parallelism": f"z-slab x{world}",
                "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step}
         if per_step_deleted:

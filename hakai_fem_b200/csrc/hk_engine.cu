@@ -41,6 +41,7 @@ struct ICH {
 struct InstanceH {
     int64_t node_offset, nNode, element_offset, nElement;
     std::vector<int64_t> surfaces, eleid;        // (F,4) column-major part-local 1-based; (F)
+    std::vector<int> twin;                       // (F) from hk_build_contact (else built at the first step)
     bool table_built = false;
     std::vector<std::array<int64_t, 4>> key;     // sorted 4-tuples
     std::vector<int64_t> order;                  // face ids sorted by (key, id)
@@ -393,6 +394,9 @@ static int spec_upload(hk_engine* e, const std::vector<int>* touched_nodes) {
 }
 
 static int erosion_upload_descriptors(hk_engine* e);
+int hk_setup_instance_faces(const int* d_conn, long long nEp, const double* d_X, long long node_offset, long long element_offset,
+                            long long nElement, cudaStream_t s, std::vector<int>& surf, std::vector<int>& twin,
+                            std::vector<int>& exterior_ids);
 
 // --------------------------------------------------------------------------------- exposed faces (A10)
 static void build_face_table(InstanceH& I) {
@@ -576,7 +580,7 @@ static int ensure_erosion(hk_engine* e) {
             return fail(e, HK_ERR_ARG, "instance range outside the mesh");
         const int64_t F = 6 * I.nElement;
         std::vector<int> twin, surf((size_t)4 * F), fele(F);
-        build_twin_table(I, twin);
+        if ((int64_t)I.twin.size() == F) twin = I.twin; else build_twin_table(I, twin);
         for (int64_t j = 0; j < 4 * F; ++j) {
             const int64_t v = I.surfaces[j];
             if (v < 1 || v > I.nNode) return fail(e, HK_ERR_ARG, "instance face node out of range");
@@ -991,6 +995,122 @@ int HKAPI(add_contact_pair)(hk_engine* e, int64_t i_instance, int64_t j_instance
         p.tele.push_back((int)(c_triangles_eleid[k] - 1));
     }
     e->pairs.push_back(std::move(p));
+    return HK_OK;
+}
+
+// Contact set-up on the device (A12; hk_setup.cu): replaces the host's get_element_face / get_surface_triangle and the
+// hk_add_instance / hk_add_contact_pair calls built from them.
+int HKAPI(build_contact)(hk_engine* e, int64_t n_inst, const int64_t* node_offset, const int64_t* nNode,
+                         const int64_t* element_offset, const int64_t* nElement, const double* young, int64_t n_cp,
+                         const int64_t* cp_inst1, const int64_t* cp_inst2, const int64_t* cp_ptr1, const int64_t* cp_elems1,
+                         const int64_t* cp_ptr2, const int64_t* cp_elems2) {
+    if (!e) return HK_ERR_ARG;
+    if (e->finalized) return fail(e, HK_ERR_STATE, "already finalised");
+    if (e->nNode == 0) return fail(e, HK_ERR_STATE, "hk_set_mesh must precede hk_build_contact");
+    if (!e->instances.empty() || !e->pairs.empty()) return fail(e, HK_ERR_STATE, "hk_build_contact replaces hk_add_instance / hk_add_contact_pair");
+    if (n_inst < 1 || !node_offset || !nNode || !element_offset || !nElement || !young) return fail(e, HK_ERR_ARG, "null argument");
+    if (n_cp < 0 || (n_cp > 0 && (!cp_inst1 || !cp_inst2))) return fail(e, HK_ERR_ARG, "null argument");
+    for (int64_t i = 0; i < n_inst; ++i)
+        if (node_offset[i] < 0 || nNode[i] < 0 || node_offset[i] + nNode[i] > e->nNode || element_offset[i] < 0 || nElement[i] < 0 ||
+            element_offset[i] + nElement[i] > e->nElement)
+            return fail(e, HK_ERR_ARG, "instance range outside the mesh");
+    HK_DEVICE(e);
+    // the pair list (J2:272-314 for *Contact Inclusions, ALL EXTERIOR; else the given *Contact Pair list)
+    struct CPH { int64_t i1, i2; std::vector<int64_t> el1, el2; };
+    std::vector<CPH> cps;
+    if (n_cp == 0) {
+        if (n_inst > 1) {
+            for (int64_t i = 1; i <= n_inst; ++i)
+                for (int64_t j = (e->prm.contact_flag == 2 ? i : i + 1); j <= n_inst; ++j) cps.push_back({i, j, {}, {}});
+        } else {
+            cps.push_back({1, 1, {}, {}});
+        }
+    } else {
+        for (int64_t k = 0; k < n_cp; ++k) {
+            if (cp_inst1[k] < 1 || cp_inst1[k] > n_inst || cp_inst2[k] < 1 || cp_inst2[k] > n_inst) return fail(e, HK_ERR_ARG, "contact pair instance out of range");
+            CPH c{cp_inst1[k], cp_inst2[k], {}, {}};
+            if (cp_ptr1 && cp_elems1) c.el1.assign(cp_elems1 + cp_ptr1[k], cp_elems1 + cp_ptr1[k + 1]);
+            if (cp_ptr2 && cp_elems2) c.el2.assign(cp_elems2 + cp_ptr2[k], cp_elems2 + cp_ptr2[k + 1]);
+            cps.push_back(std::move(c));
+        }
+    }
+    // temporary device copies of the mesh (hk_finalize builds the resident ones)
+    const int64_t nE = e->nElement, nN = e->nNode;
+    int* d_conn = nullptr;
+    double* d_X = nullptr;
+    {
+        std::vector<int> soa((size_t)8 * nE);
+        for (int64_t el = 0; el < nE; ++el)
+            for (int a = 0; a < 8; ++a) soa[(size_t)a * nE + el] = e->conn[8 * el + a];
+        int rc;
+        if ((rc = dalloc(e, &d_conn, soa.size()))) return rc;
+        if ((rc = dalloc(e, &d_X, (size_t)3 * nN))) return rc;
+        if ((rc = upload(e, d_conn, soa))) return rc;
+        if ((rc = upload(e, d_X, e->coordmat))) return rc;
+    }
+    std::vector<std::vector<int>> exterior(n_inst);
+    e->instances.clear();
+    for (int64_t i = 0; i < n_inst; ++i) {
+        InstanceH I;
+        I.node_offset = node_offset[i]; I.nNode = nNode[i]; I.element_offset = element_offset[i]; I.nElement = nElement[i];
+        std::vector<int> surf;
+        const int rc = hk_setup_instance_faces(d_conn, nE, d_X, I.node_offset, I.element_offset, I.nElement, e->stream, surf,
+                                               I.twin, exterior[i]);
+        if (rc) { dfree(e, d_conn); dfree(e, d_X); return cuda_fail(e, rc, "hk_setup_instance_faces"); }
+        I.surfaces.assign(surf.begin(), surf.end());
+        I.eleid.resize((size_t)6 * I.nElement);
+        for (int64_t f = 0; f < 6 * I.nElement; ++f) I.eleid[f] = f / 6 + 1;
+        e->instances.push_back(std::move(I));
+    }
+    dfree(e, d_conn);
+    dfree(e, d_X);
+    // get_surface_triangle's tail (J2:2094-2159) on the exterior faces: optional *Surface element filter, two triangles
+    // per face, sorted unique nodes — all part-local 1-based
+    struct Surf { std::vector<int64_t> tri, te, nodes; };
+    auto surface_of = [&](int64_t inst, const std::vector<int64_t>& subset, Surf& out) {
+        const InstanceH& I = e->instances[inst - 1];
+        const int64_t F = 6 * I.nElement;
+        std::vector<char> keep;
+        if (!subset.empty() && (int64_t)subset.size() != I.nElement) {
+            keep.assign(I.nElement + 1, 0);
+            for (int64_t el : subset) if (el >= 1 && el <= I.nElement) keep[el] = 1;
+        }
+        for (int f : exterior[inst - 1]) {
+            const int64_t el = f / 6 + 1;
+            if (!keep.empty() && !keep[el]) continue;
+            const int64_t s0 = I.surfaces[f], s1 = I.surfaces[f + F], s2 = I.surfaces[f + 2 * F], s3 = I.surfaces[f + 3 * F];
+            out.tri.insert(out.tri.end(), {s0, s1, s2, s2, s3, s0});
+            out.te.push_back(el); out.te.push_back(el);
+        }
+        out.nodes = out.tri;
+        std::sort(out.nodes.begin(), out.nodes.end());
+        out.nodes.erase(std::unique(out.nodes.begin(), out.nodes.end()), out.nodes.end());
+    };
+    for (const CPH& c : cps) {
+        Surf s1, s2;
+        surface_of(c.i1, c.el1, s1);
+        surface_of(c.i2, c.el2, s2);
+        const int n_dir = c.i1 == c.i2 ? 1 : 2;                   // J2:339-354
+        for (int dir = 0; dir < n_dir; ++dir) {
+            const int64_t ii = dir == 0 ? c.i1 : c.i2, jj = dir == 0 ? c.i2 : c.i1;
+            const Surf& si = dir == 0 ? s1 : s2;
+            const Surf& sj = dir == 0 ? s2 : s1;
+            const InstanceH& Ii = e->instances[ii - 1];
+            const InstanceH& Ij = e->instances[jj - 1];
+            PairH p;
+            p.i_instance = ii; p.j_instance = jj; p.young = young[jj - 1];          // J2:372
+            std::memset(&p.dev, 0, sizeof(p.dev));
+            for (int64_t n : si.nodes) { const int g = (int)(n + Ii.node_offset - 1); p.nodes_i.push_back(g); p.set_i.insert(g); }
+            for (int64_t n : sj.nodes) { const int g = (int)(n + Ij.node_offset - 1); p.nodes_j.push_back(g); p.set_j.insert(g); }
+            for (size_t t = 0; t < sj.te.size(); ++t) {
+                p.t0.push_back((int)(sj.tri[3 * t] + Ij.node_offset - 1));
+                p.t1.push_back((int)(sj.tri[3 * t + 1] + Ij.node_offset - 1));
+                p.t2.push_back((int)(sj.tri[3 * t + 2] + Ij.node_offset - 1));
+                p.tele.push_back((int)(sj.te[t] + Ij.element_offset - 1));
+            }
+            e->pairs.push_back(std::move(p));
+        }
+    }
     return HK_OK;
 }
 

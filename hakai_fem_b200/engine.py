@@ -44,7 +44,7 @@ EXPORTS = [
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
     "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
-    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init", "profile_read_ex", "comm_contact",
+    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init", "profile_read_ex", "comm_contact", "build_contact",
 ]
 
 
@@ -171,6 +171,24 @@ class EngineBase:
         self._chk(self._fn("add_contact_pair")(self._h, c_i64(i_instance), c_i64(j_instance), c_i64(len(ni)), _pi(ni),
                                                c_i64(len(nj)), _pi(nj), c_i64(len(te)), _pi(tri), _pi(te),
                                                c_f64(young)))
+
+    def build_contact(self, instances, young, pairs=None):
+        """Contact set-up on the device instead of add_instance / add_contact_pair.
+        instances: (node_offset, nNode, element_offset, nElement) per instance; young: Young's modulus of each instance's
+        material; pairs: None (ALL EXTERIOR) or a list of (inst1, inst2, elements1, elements2) with 1-based instance ids
+        and part-local 1-based element ids of the *Surface sets (None / empty: all elements)."""
+        a = _i64(np.asarray(instances, np.int64).reshape(-1, 4))
+        cols = [np.ascontiguousarray(a[:, k]) for k in range(4)]
+        yg = _f64(young)
+        if pairs:
+            i1, i2 = _i64([p[0] for p in pairs]), _i64([p[1] for p in pairs])
+            p1, e1 = _csr([np.zeros(0, np.int64) if p[2] is None else p[2] for p in pairs])
+            p2, e2 = _csr([np.zeros(0, np.int64) if p[3] is None else p[3] for p in pairs])
+            args = (c_i64(len(pairs)), _pi(i1), _pi(i2), _pi(p1), _pi(e1), _pi(p2), _pi(e2))
+        else:
+            args = (c_i64(0), None, None, None, None, None, None)
+        self._chk(self._fn("build_contact")(self._h, c_i64(len(a)), _pi(cols[0]), _pi(cols[1]), _pi(cols[2]), _pi(cols[3]),
+                                             _pf(yg), *args))
 
     def finalize(self):
         self._chk(self._fn("finalize")(self._h))

@@ -164,6 +164,7 @@ class Setup:
     CT: List[ContactTriangle] = field(default_factory=list)
     instance_pair: List[List[int]] = field(default_factory=list)
     all_exterior_flag: int = 0
+    contact_on_device: bool = False   # prepare(contact="device"): hk_build_contact builds the tables on the GPU
 
 
 def build_contact(model: Model, setup: Setup):
@@ -221,8 +222,11 @@ def build_contact(model: Model, setup: Setup):
     setup.instance_pair = instance_pair
 
 
-def prepare(model: Model, elementVolume: Optional[np.ndarray] = None) -> Setup:
-    """Everything hakai() computes before `for t = 1 : time_num` (J2:100-465)."""
+def prepare(model: Model, elementVolume: Optional[np.ndarray] = None, contact: str = "host") -> Setup:
+    """Everything hakai() computes before `for t = 1 : time_num` (J2:100-465).
+    contact="device": the contact tables (get_element_face, get_surface_triangle, pair lists: J2:250-398) are NOT built
+    here; configure_engine hands the instance ranges and the *Contact Pair list to hk_build_contact, which builds them
+    on the GPU."""
     d_time = model.d_time * np.sqrt(model.mass_scaling)          # J2:114
     time_num = model.end_time / d_time
     for m in model.MATERIAL:                                     # J2:143-172 (Dmat is rebuilt in the engine)
@@ -232,7 +236,10 @@ def prepare(model: Model, elementVolume: Optional[np.ndarray] = None) -> Setup:
     diag_M = lumped_mass(model, elementVolume)
     emin, emax = element_sizes(model.coordmat, model.elementmat)
     st = Setup(model, float(d_time), float(time_num), elementVolume, diag_M, emin, emax)
-    if model.contact_flag >= 1:
+    if contact not in ("host", "device"):
+        raise ValueError("contact: host | device")
+    st.contact_on_device = contact == "device"
+    if model.contact_flag >= 1 and not st.contact_on_device:
         build_contact(model, st)
     return st
 
@@ -255,7 +262,12 @@ def configure_engine(engine_cls, setup: Setup, **param_overrides):
                    bc.amplitude.value if has_amp else None)
     for ic in model.IC:
         eng.add_ic(ic.dof, ic.value)
-    if model.contact_flag >= 1:
+    if model.contact_flag >= 1 and setup.contact_on_device:
+        inst = [(i.node_offset, i.nNode, i.element_offset, i.nElement) for i in model.INSTANCE]
+        young = [model.MATERIAL[i.material_id - 1].young for i in model.INSTANCE]
+        pairs = [(cp.instance_id_1, cp.instance_id_2, cp.elements_1, cp.elements_2) for cp in model.CP] or None
+        eng.build_contact(inst, young, pairs)
+    elif model.contact_flag >= 1:
         for ins in model.INSTANCE:
             eng.add_instance(ins.node_offset, ins.nNode, ins.element_offset, ins.nElement,
                              ins.surfaces, ins.surfaces_eleid)

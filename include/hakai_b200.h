@@ -122,6 +122,23 @@ int hk_add_contact_pair(hk_engine* e, int64_t i_instance, int64_t j_instance,
                         int64_t nTri, const int64_t* c_triangles /* (nTri,3) col-major */,
                         const int64_t* c_triangles_eleid, double young);
 
+/* Contact set-up on the device, instead of hk_add_instance + hk_add_contact_pair (A12: get_element_face J2:1946-1992,
+ * get_surface_triangle J2:1996-2164, pair list J2:272-398).  The faces of every instance are oriented, sorted by their
+ * node set and matched on the GPU (radix sort, O(F log F); the reference's face matching is O(F^2)), with the
+ * reference's quirks (odd groups emit their last member; the very last face is never emitted, J2:2040); the face each
+ * deletion would expose (add_surface_triangle, J2:2167-2245) comes out of the same sort.  Call after hk_set_mesh.
+ *   instances: node_offset / nNode / element_offset / nElement as InstanceType (readInpFile_j.jl:59-76), young[i] =
+ *              MATERIAL[INSTANCE[i].material_id].young (J2:372)
+ *   n_cp = 0:  *Contact Inclusions, ALL EXTERIOR — pairs as J2:272-314 (params.contact_flag == 2 adds the self pairs)
+ *   n_cp > 0:  MODEL.CP: instance ids (1-based) of both sides and, per side, the *Surface element set as CSR lists of
+ *              part-local 1-based element ids (cp_ptrX / cp_elemsX may be NULL or a list empty: all elements)
+ * Orientation uses the global undeformed coordinates (the reference uses the part's: identical up to the rigid
+ * instance transform). */
+int hk_build_contact(hk_engine* e, int64_t n_inst, const int64_t* node_offset, const int64_t* nNode,
+                     const int64_t* element_offset, const int64_t* nElement, const double* young, int64_t n_cp,
+                     const int64_t* cp_inst1, const int64_t* cp_inst2, const int64_t* cp_ptr1, const int64_t* cp_elems1,
+                     const int64_t* cp_ptr2, const int64_t* cp_elems2);
+
 /* Freezes the set-up: builds device layouts (SoA state, node->element gather table, BC table,
  * contact buckets), initialises state as J2:220-230, 447-465 (zero state, yield = plastic[1,1],
  * element_flag = 1).  Must be called once before hk_step/hk_upload_state/hk_download. */

@@ -1129,6 +1129,10 @@ int hko_halo_pack(hk_engine* e) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is 
 int hko_set_halo_ranks(hk_engine* e, int64_t, int64_t, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_comm_unique_id(void*) { return HK_ERR_UNSUPPORTED; }
 int hko_comm_init(hk_engine* e, const void*, int32_t, int32_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_build_contact(hk_engine* e, int64_t, const int64_t*, const int64_t*, const int64_t*, const int64_t*, const double*, int64_t,
+                      const int64_t*, const int64_t*, const int64_t*, const int64_t*, const int64_t*, const int64_t*) {
+    return fail(e, HK_ERR_UNSUPPORTED, "the oracle takes the host-built contact tables (hko_add_instance / hko_add_contact_pair)");
+}
 int hko_comm_contact(hk_engine* e, int64_t, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_set_node_list(hk_engine* e, int32_t, int64_t, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_nodes_export(hk_engine* e, void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }

@@ -62,8 +62,16 @@ def setup_to_arrays(st):
 def main():
     out = os.path.join(ROOT, "tests", "golden")
     for name, rel in DECKS.items():
-        st = prepare(read_inp_file(os.path.join("/root/reference", rel)))
+        model = read_inp_file(os.path.join("/root/reference", rel))
+        cps = [(cp.instance_id_1, cp.instance_id_2, np.asarray(cp.elements_1, np.int64), np.asarray(cp.elements_2, np.int64))
+               for cp in model.CP]                      # the deck's *Contact Pair list (empty: ALL EXTERIOR), before prepare()
+        st = prepare(model)
         arrs = setup_to_arrays(st)
+        arrs["cp_n"] = np.array([len(cps)], np.int64)   # what hk_build_contact (contact set-up on the device) is given
+        for k, (i1, i2, e1, e2) in enumerate(cps):
+            arrs[f"cp{k}_s"] = np.array([i1, i2], np.int64)
+            arrs[f"cp{k}_e1"] = e1
+            arrs[f"cp{k}_e2"] = e2
         np.savez_compressed(os.path.join(out, f"deck_{name}.npz"), **arrs)
         print(name, st.model.nNode, st.model.nElement, os.path.getsize(os.path.join(out, f"deck_{name}.npz")))
 

@@ -300,6 +300,33 @@ def case_contact_pair_surfaces(engine_cls, tmp_path):
             assert np.array_equal(po[k], pg[k]), (c, k)
 
 
+def case_build_contact(engine_cls, name, n_steps):
+    """hk_build_contact (contact set-up on the device: faces, orientation, exterior faces by radix sort, pair lists; A12,
+    SURVEY 8f.1) against the host mirror of get_element_face / get_surface_triangle: identical node lists, triangles
+    and element ids for every ordered pair of the reference's deck, and — the exposed-face table coming out of the same
+    sort — identical erosion: a run on the device-built tables is bit-identical to the run on the host-built ones."""
+    import copy
+    st_h = util.deck_setup(name)
+    st_d = copy.copy(st_h)
+    st_d.contact_on_device = True
+    gh, gd = configure_engine(engine_cls, st_h), configure_engine(engine_cls, st_d)
+    assert len(st_h.CT) > 0
+    for c in range(len(st_h.CT)):
+        a, b = gh.contact_pair(c), gd.contact_pair(c)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (name, c, k)
+    nh, nd = gh.step(1, n_steps), gd.step(1, n_steps)
+    assert nh == nd and np.array_equal(gh.deleted_ids(), gd.deleted_ids())
+    a, b = util.full_state(gh), util.full_state(gd)
+    for k in ("disp", "integ_stress", "integ_eq_plastic_strain", "element_flag", "external_force"):
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (name, k)
+    for c in range(len(st_h.CT)):
+        pa, pb = gh.contact_pair(c), gd.contact_pair(c)
+        for k in pa:
+            assert np.array_equal(pa[k], pb[k]), (name, "after erosion", c, k)
+    return nh
+
+
 def case_bc_edge_cases(engine_cls):
     """Boundary-condition corners of J2:585-617: a multi-segment amplitude table, times outside every segment (the
     search falls back to segment 1 and extrapolates it), a BC without amplitude, later BCs overriding earlier ones on

@@ -41,6 +41,12 @@ def test_contact_pair_surfaces(tmp_path):
     pc.case_contact_pair_surfaces(EmuEngine, tmp_path)
 
 
+@pytest.mark.parametrize("name,n_steps,min_deleted", [("bullet_impact", 2500, 5), ("charpy", 300, 0), ("crash_tube", 200, 0),
+                                                     ("metal_cutting", 1500, 1)])
+def test_contact_built_on_device(name, n_steps, min_deleted):
+    assert pc.case_build_contact(EmuEngine, name, n_steps) >= min_deleted
+
+
 def test_bc_edge_cases():
     pc.case_bc_edge_cases(EmuEngine)
 

@@ -159,6 +159,9 @@ def deck_setup(name):
                     element_material=z["element_material"], element_instance=z["element_instance"], d_time=d_time,
                     end_time=d_time * time_num, mass_scaling=1.0, contact_flag=cflag)
     st = Setup(model, d_time, time_num, None, z["diag_M"], emin, emax)
+    # the deck's own *Contact Pair list (empty: ALL EXTERIOR), for hk_build_contact
+    model.CP = [I.CP(instance_id_1=int(z[f"cp{k}_s"][0]), instance_id_2=int(z[f"cp{k}_s"][1]), elements_1=z[f"cp{k}_e1"],
+                     elements_2=z[f"cp{k}_e2"]) for k in range(int(z["cp_n"][0]))] if "cp_n" in z else []
     for c in range(n_ct):
         a, b, young = z[f"ct{c}_s"]
         st.CT.append(ContactTriangle(int(a), int(b), z[f"ct{c}_ni"], z[f"ct{c}_nj"], z[f"ct{c}_tri"], z[f"ct{c}_te"], float(young)))
