@@ -107,6 +107,20 @@ add_contact_pair(e, i_instance, j_instance, ct) =   # ct::ContactTriangle (HAKAI
           e.ptr, i_instance, j_instance, length(ct.c_nodes_i), ct.c_nodes_i, length(ct.c_nodes_j), ct.c_nodes_j,
           size(ct.c_triangles, 1), ct.c_triangles, ct.c_triangles_eleid, ct.young))
 
+# Contact set-up on the GPU instead of get_element_face / get_surface_triangle / the CT loop (HAKAI_j.jl:250-398):
+# replaces the add_instance / add_contact_pair calls.  INSTANCE, MATERIAL, CP = MODEL's arrays (CP empty: ALL EXTERIOR).
+function build_contact(e, INSTANCE, MATERIAL, CP)
+    no = Int64[i.node_offset for i in INSTANCE]; nn = Int64[i.nNode for i in INSTANCE]
+    eo = Int64[i.element_offset for i in INSTANCE]; ne = Int64[i.nElement for i in INSTANCE]
+    yg = Float64[MATERIAL[i.material_id].young for i in INSTANCE]
+    i1 = Int64[c.instance_id_1 for c in CP]; i2 = Int64[c.instance_id_2 for c in CP]
+    p1, e1 = csr([c.elements_1 for c in CP]); p2, e2 = csr([c.elements_2 for c in CP])
+    check(e.ptr, ccall((:hk_build_contact, LIB), Cint,
+          (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int64},
+           Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+          e.ptr, length(INSTANCE), no, nn, eo, ne, yg, length(CP), i1, i2, p1, e1, p2, e2))
+end
+
 finalize!(e) = check(e.ptr, ccall((:hk_finalize, LIB), Cint, (Ptr{Cvoid},), e.ptr))
 
 function step!(e, t_first::Integer, n_steps::Integer)
