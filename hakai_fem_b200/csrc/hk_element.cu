@@ -377,10 +377,13 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
                 tma_commit();
                 // the group is past the prologue of tile q/8: the buffer of tile q/8 - 1 is free for tile q/8 + 1
                 if ((q & 7) == 0) issue_conn((q >> 3) + 1);
-                // refill the stage whose store group was committed one round ago (it has been read by now)
-                const long long qn = q - 1 + S;
-                if (q >= 1 && qn < total_q) {
-                    tma_wait_read<1>();
+                // early refill: wait until THIS store has left the stage (a few hundred ns; the next `done` is a whole item
+                // time away, the producer has nothing else to do) and reuse the stage at once.  Round 1 refilled the stage
+                // of the PREVIOUS item here (wait_group.read 1, no blocking): one block fewer in flight — measured 3 %
+                // slower, and 3 stages with the early refill equal 4 stages with the lagged one
+                const long long qn = q + S;
+                if (qn < total_q) {
+                    tma_wait_read<0>();
                     issue_load(qn);
                 }
             }
