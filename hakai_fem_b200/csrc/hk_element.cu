@@ -226,6 +226,25 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, u
                  "r"(bytes)
                  : "memory");
 }
+// the same with an L2 cache policy (createpolicy): the Gauss-point state is a pure stream — marked evict-first it stops
+// pushing the node records (re-read by the z-neighbour tile ~180 tiles later) and its own write-backs out of L2
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar,
+                                                 unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_1d_hint(void* gdst, const void* smem_src, unsigned bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -293,7 +312,7 @@ struct RingCfg {
                                 (CP ? NG * 2 * 8 * TLD * 4 : 0) + (CP >= 2 ? NG * 2 * TLD * 4 : 0) + 64;
 };
 
-template <int NG, int WG, int S, int CP>
+template <int NG, int WG, int S, int CP, int EF = 0>
 __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel(ElemArgs A) {
     using Cfg = RingCfg<NG, WG, S, CP>;
     constexpr int TLD = Cfg::TLD, STAGE = Cfg::STAGE;
@@ -361,11 +380,13 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
                     tma_load_1d(gflag + (it & 1) * TLD, d.flag + e0, TLD, bar);
                 }
             };
+            const unsigned long long pol = EF ? l2_policy_evict_first() : 0ull;
             auto issue_load = [&](long long q) {
                 const int st = (int)(q % S);
                 const long long e0 = ((long long)vcta + (q >> 3) * n_v) * TLD;
                 mbar_expect_tx(&gfull[st], STAGE * 8);
-                tma_load_1d(gstage + st * STAGE, stage_base(d, (int)(q & 7), e0), STAGE * 8, &gfull[st]);
+                if (EF) tma_load_1d_hint(gstage + st * STAGE, stage_base(d, (int)(q & 7), e0), STAGE * 8, &gfull[st], pol);
+                else tma_load_1d(gstage + st * STAGE, stage_base(d, (int)(q & 7), e0), STAGE * 8, &gfull[st]);
             };
             issue_conn(0);
             for (long long q = 0; q < S && q < total_q; ++q) issue_load(q);
@@ -373,7 +394,8 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
                 const int st = (int)(q % S);
                 mbar_wait(&gdone[st], (unsigned)((q / S) & 1));      // every warp of the group finished item q
                 const long long e0 = ((long long)vcta + (q >> 3) * n_v) * TLD;
-                tma_store_1d(stage_base(d, (int)(q & 7), e0), gstage + st * STAGE, STAGE * 8);
+                if (EF) tma_store_1d_hint(stage_base(d, (int)(q & 7), e0), gstage + st * STAGE, STAGE * 8, pol);
+                else tma_store_1d(stage_base(d, (int)(q & 7), e0), gstage + st * STAGE, STAGE * 8);
                 tma_commit();
                 // the group is past the prologue of tile q/8: the buffer of tile q/8 - 1 is free for tile q/8 + 1
                 if ((q & 7) == 0) issue_conn((q >> 3) + 1);
@@ -552,12 +574,12 @@ __global__ void __launch_bounds__((NG * WG + NG) * 32, 1) hk_element_ring_kernel
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
 }
 
-template <int NG, int WG, int S, int CP>
+template <int NG, int WG, int S, int CP, int EF = 0>
 static int launch_ring(const ElemArgs& A, int n_sm, cudaStream_t s) {
     using Cfg = RingCfg<NG, WG, S, CP>;
     static_assert(Cfg::SMEM <= 227 * 1024, "ring does not fit in shared memory");
     static_assert(((NG * WG + 3) / 4) * HK_TCOLS <= 512, "TMEM columns");
-    cudaError_t rc = cudaFuncSetAttribute(hk_element_ring_kernel<NG, WG, S, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t rc = cudaFuncSetAttribute(hk_element_ring_kernel<NG, WG, S, CP, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::SMEM);               // per device: cheap, so set on every launch
     if (rc != cudaSuccess) return (int)rc;
     const long long n_tiles = A.d.nEp / Cfg::TLD;
@@ -565,9 +587,10 @@ static int launch_ring(const ElemArgs& A, int n_sm, cudaStream_t s) {
     if (grid * NG > n_tiles) grid = (n_tiles + NG - 1) / NG;
     ElemArgs B = A;
     B.n_tiles = (int)n_tiles;
-    hk_element_ring_kernel<NG, WG, S, CP><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, s>>>(B);
+    hk_element_ring_kernel<NG, WG, S, CP, EF><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, s>>>(B);
     return 0;
 }
+
 #endif
 
 // element-kernel variant table: the configurations kept for A/B (profiles/r2_element_kernel_variants.md has the
@@ -575,9 +598,10 @@ static int launch_ring(const ElemArgs& A, int n_sm, cudaStream_t s) {
 // per group, prefetch (0 none, 1 connectivity, 2 connectivity + material ids + flags)
 struct RingVariant { int id, ng, wg, stages, cp; };
 static const RingVariant kVariants[] = {
-    {11, 1, 11, 4, 0},      // round-1 configuration: one group of 11 warps (tile 352), no prefetch
+    {11, 1, 11, 4, 0},      // one group of 11 warps (tile 352), no prefetch
     {12, 1, 11, 4, 1},
-    {13, 1, 11, 4, 2},      // default
+    {13, 1, 11, 4, 2},      // default: + evict-first L2 policy on the state stream
+    {14, 1, 11, 4, 2},      //   the same without the policy
     {20, 2, 5, 4, 1},       // two phase-shifted groups of 5 warps (tile 160)
     {25, 2, 5, 4, 2},
 };
@@ -603,9 +627,10 @@ int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStrea
         }
         case 11: return launch_ring<1, 11, 4, 0>(A, d.n_sm, s);
         case 12: return launch_ring<1, 11, 4, 1>(A, d.n_sm, s);
+        case 14: return launch_ring<1, 11, 4, 2>(A, d.n_sm, s);
         case 20: return launch_ring<2, 5, 4, 1>(A, d.n_sm, s);
         case 25: return launch_ring<2, 5, 4, 2>(A, d.n_sm, s);
-        default: return launch_ring<1, 11, 4, 2>(A, d.n_sm, s);
+        default: return launch_ring<1, 11, 4, 2, 1>(A, d.n_sm, s);
     }
 #else
     for (long long e = 0; e < d.nElement; ++e) element_body_simple(A, e);
