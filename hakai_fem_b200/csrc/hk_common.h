@@ -137,6 +137,11 @@ struct HkErodeDev {              // everything hk_erode_kernel needs
     int* n_slots;
     int spec_cap, slot_cap;
     int* overflow;               // set when a capacity would be exceeded (checked at hk_sync)
+    // partitioned meshes (hk_comm_erosion): the instance tables cover the GLOBAL mesh — `surf` holds engine-local node ids
+    // (every node of an instance in contact is held or ghosted), `feleid` the engine-local element or -1 when another
+    // rank owns it (that rank adds the triangle), `einst` is indexed by the global element; node_key[local node] = its
+    // global id, the order in which `unique(sort(tri))` (J2:2242) lists an element's exposed nodes.  NULL: single domain
+    const int* node_key;
 };
 
 struct HkContactParams {
@@ -160,7 +165,11 @@ void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams
 // deletion pass of a step: elements the element kernel marked (flag 3) are appended to the deletion log in ascending
 // id order (the reference's order, J2:701-735), their stress/strain zeroed (J2:742-756), and the faces they expose join
 // the contact surfaces (er != NULL)
-void hk_launch_deletion_pass(const HkDev& d, const HkErodeDev* er, long long step, cudaStream_t s, long long* n_launch);
+void hk_launch_deletion_pass(const HkDev& d, const HkErodeDev* er, long long step, cudaStream_t s, long long* n_launch,
+                             long long* send = nullptr, const int* e_l2g = nullptr, int cap = 0);
+// partitioned meshes: replays the deletions of ALL ranks of one step, `gathered` = [world][cap + 1] = {n, global 0-based
+// element ids ascending} per rank in rank order (= ascending global id: ranks own contiguous element blocks)
+void hk_launch_erode_replay(const HkDev& d, const HkErodeDev& E, const long long* gathered, int world, int cap, cudaStream_t s);
 void hk_launch_cacc_zero(const HkDev& d, const int* n_slots, int slot_cap, cudaStream_t s);
 void hk_launch_velo_from_rec(const HkDev& d, double d_time, cudaStream_t s);
 void hk_launch_gather_Q(const HkDev& d, double* Q_out, cudaStream_t s);

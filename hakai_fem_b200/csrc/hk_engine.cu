@@ -132,6 +132,13 @@ struct hk_engine {
     bool frame_next = false;       // hk_mark_frame: the next asynchronous step stores integ_triax_stress
     // multi-GPU erosion: instance tables are GLOBAL; these map global (1-based) ids to engine-local 0-based ids or -1
     std::vector<int> g_node_map, g_elem_map;
+    // hk_comm_erosion: deletions of all ranks replayed on the device (static exchange lists over every candidate node)
+    bool xerode = false;
+    int xe_cap = 0;                // deletions per rank and step the all-gather carries
+    long long* xe_send = nullptr;  // [xe_cap + 1]: n, global 0-based ids of this rank's deletions of the step
+    long long* xe_all = nullptr;   // [world][xe_cap + 1]
+    int* d_e_l2g = nullptr;        // engine element -> global 0-based id
+    int* d_node_key = nullptr;     // engine node -> global 0-based id
     std::vector<int64_t> g_einst;  // instance of every GLOBAL element
     // hk_node_output work buffers, allocated at the first call and kept (cudaMalloc/cudaFree of ~4 GB per frame costs
     // more than the averaging itself)
@@ -544,9 +551,11 @@ static int ensure_erosion(hk_engine* e) {
     if (e->erosion_checked) return 0;
     e->erosion_checked = true;
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
-    if (!contact_on || !e->any_ductile || !e->g_node_map.empty()) return 0;
+    const bool global = !e->g_node_map.empty();       // partitioned mesh: GLOBAL instance tables (hk_set_global_maps)
+    if (!contact_on || !e->any_ductile) return 0;
+    if (global && !e->xerode) return 0;               // the host driver replays deletions through hk_apply_deleted
     const size_t nI = e->instances.size();
-    if (nI == 0 || nI >= 65535) return 0;
+    if (nI == 0 || nI >= 65535) return global ? fail(e, HK_ERR_STATE, "hk_comm_erosion: no instance tables") : 0;
     std::vector<char> used(nI, 0);
     for (const PairH& p : e->pairs) {
         if (p.i_instance >= 1 && p.i_instance <= (int64_t)nI) used[p.i_instance - 1] = 1;
@@ -554,12 +563,19 @@ static int ensure_erosion(hk_engine* e) {
     }
     e->inst_erodes.assign(nI, 0);
     bool any = false;
-    for (int64_t el = 0; el < e->nElement; ++el) {
-        const int64_t inst = e->einst[el];
-        if (inst < 1 || inst > (int64_t)nI || !used[inst - 1] || e->instances[inst - 1].surfaces.empty()) continue;
-        if (e->materials[e->emat[el]].nd > 0) { e->inst_erodes[inst - 1] = 1; any = true; }
+    if (global) {                 // a rank sees the materials of its own elements only: any instance in contact may erode
+        for (size_t i = 0; i < nI; ++i)
+            if (used[i] && !e->instances[i].surfaces.empty()) { e->inst_erodes[i] = 1; any = true; }
+    } else {
+        for (int64_t el = 0; el < e->nElement; ++el) {
+            const int64_t inst = e->einst[el];
+            if (inst < 1 || inst > (int64_t)nI || !used[inst - 1] || e->instances[inst - 1].surfaces.empty()) continue;
+            if (e->materials[e->emat[el]].nd > 0) { e->inst_erodes[inst - 1] = 1; any = true; }
+        }
     }
-    if (!any) return 0;
+    if (!any) { e->xerode = false; return 0; }
+    const int64_t nE_all = global ? (int64_t)e->g_elem_map.size() : e->nElement;
+    const int64_t nN_all = global ? (int64_t)e->g_node_map.size() : e->nNode;
     int rc;
     HkErodeDev& E = e->er;
     std::memset(&E, 0, sizeof(E));
@@ -575,8 +591,8 @@ static int ensure_erosion(hk_engine* e) {
         D.element_offset = I.element_offset;
         D.nElement = I.nElement;
         if (!e->inst_erodes[i]) continue;
-        if (I.element_offset < 0 || I.element_offset + I.nElement > e->nElement || I.node_offset < 0 ||
-            I.node_offset + I.nNode > e->nNode)
+        if (I.element_offset < 0 || I.element_offset + I.nElement > nE_all || I.node_offset < 0 ||
+            I.node_offset + I.nNode > nN_all)
             return fail(e, HK_ERR_ARG, "instance range outside the mesh");
         const int64_t F = 6 * I.nElement;
         std::vector<int> twin, surf((size_t)4 * F), fele(F);
@@ -584,12 +600,15 @@ static int ensure_erosion(hk_engine* e) {
         for (int64_t j = 0; j < 4 * F; ++j) {
             const int64_t v = I.surfaces[j];
             if (v < 1 || v > I.nNode) return fail(e, HK_ERR_ARG, "instance face node out of range");
-            surf[j] = (int)(v + I.node_offset - 1);
+            const int64_t g = v + I.node_offset - 1;
+            surf[j] = global ? e->g_node_map[g] : (int)g;
+            if (surf[j] < 0) return fail(e, HK_ERR_STATE, "node of an instance in contact is not present on this rank (ghost set too small)");
         }
         for (int64_t j = 0; j < F; ++j) {
             const int64_t v = I.eleid[j];
             if (v < 1 || v > I.nElement) return fail(e, HK_ERR_ARG, "instance face element out of range");
-            fele[j] = (int)(v + I.element_offset - 1);
+            const int64_t g = v + I.element_offset - 1;
+            fele[j] = global ? e->g_elem_map[g] : (int)g;       // -1: another rank owns the element
         }
         InstDevH& H = e->inst_dev[i];
         if ((rc = dalloc(e, &H.surf, surf.size()))) return rc;
@@ -604,13 +623,27 @@ static int ensure_erosion(hk_engine* e) {
     if ((rc = dalloc(e, &E.inst, nI))) return rc;
     if ((rc = upload(e, E.inst, idv))) return rc;
     {
-        std::vector<unsigned short> ei(e->nElement);
-        for (int64_t el = 0; el < e->nElement; ++el) {
-            const int64_t v = e->einst[el];
+        std::vector<unsigned short> ei(nE_all);
+        for (int64_t el = 0; el < nE_all; ++el) {
+            const int64_t v = global ? e->g_einst[el] : e->einst[el];
             ei[el] = (unsigned short)((v >= 1 && v <= (int64_t)nI) ? v : 0);
         }
         if ((rc = dalloc(e, &E.einst, ei.size()))) return rc;
         if ((rc = upload(e, E.einst, ei))) return rc;
+    }
+    if (global) {
+        std::vector<int> l2g(e->nElement, 0), key(e->nNode, 0);
+        for (int64_t g = 0; g < nE_all; ++g) if (e->g_elem_map[g] >= 0) l2g[e->g_elem_map[g]] = (int)g;
+        for (int64_t g = 0; g < nN_all; ++g) if (e->g_node_map[g] >= 0) key[e->g_node_map[g]] = (int)g;
+        if ((rc = dalloc(e, &e->d_e_l2g, l2g.size()))) return rc;
+        if ((rc = upload(e, e->d_e_l2g, l2g))) return rc;
+        if ((rc = dalloc(e, &e->d_node_key, key.size()))) return rc;
+        if ((rc = upload(e, e->d_node_key, key))) return rc;
+        E.node_key = e->d_node_key;
+        const int world = e->comm ? e->comm_world : 1;
+        if ((rc = dalloc(e, &e->xe_send, (size_t)e->xe_cap + 1))) return rc;
+        if ((rc = dalloc(e, &e->xe_all, (size_t)world * (e->xe_cap + 1)))) return rc;
+        CK(hkp::dev_memset(e->xe_send, 0, ((size_t)e->xe_cap + 1) * sizeof(long long), e->stream));
     }
     if ((rc = dalloc(e, &E.n_spec, (size_t)1))) return rc;
     if ((rc = dalloc(e, &E.n_slots, (size_t)1))) return rc;
@@ -1446,7 +1479,10 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
             // (multi-GPU engines: the host driver replays the all-gathered ids through hk_apply_deleted instead)
             prof_begin(e, 5);
             long long nl = 0;
-            hk_launch_deletion_pass(d, e->dev_erosion ? &e->er : nullptr, t, e->stream, &nl);
+            if (e->dev_erosion && e->xerode)     // partitioned mesh: log + pack this rank's ids; every rank's are replayed below
+                hk_launch_deletion_pass(d, nullptr, t, e->stream, &nl, e->xe_send, e->d_e_l2g, e->xe_cap);
+            else
+                hk_launch_deletion_pass(d, e->dev_erosion ? &e->er : nullptr, t, e->stream, &nl);
             e->n_launch += nl;
             prof_end(e);
             if (e->dev_erosion) e->contact_host_stale = true;
@@ -1485,6 +1521,20 @@ static int comm_contact_exchange(hk_engine* e) {
     return 0;
 }
 
+// contact surfaces that erode across ranks (hk_comm_erosion): the step's deletions of every rank, as global ids, in one
+// fixed-size all-gather; one thread replays them in ascending global order on every rank (add_surface_triangle,
+// J2:767-804 + 2167-2245), so the pair lists of the next contact pass are in place without the host
+static int comm_erosion_replay(hk_engine* e) {
+    if (!e->dev_erosion || !e->xerode) return 0;
+    prof_begin(e, 5);
+    NCK(g_nccl.AllGather(e->xe_send, e->xe_all, (size_t)e->xe_cap + 1, kNcclInt64, e->comm, e->stream));
+    hk_launch_erode_replay(e->d, e->er, e->xe_all, e->comm_world, e->xe_cap, e->stream);
+    prof_end(e);
+    e->n_launch += 1;
+    e->contact_host_stale = true;
+    return 0;
+}
+
 static int comm_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end) {
     if (e->frame_next && n_steps > 0) { frame_at_end = true; e->frame_next = false; }      // hk_mark_frame: LAST step
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
@@ -1494,6 +1544,7 @@ static int comm_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame
         if (e->halo.empty()) {                            // a rank with no interface node (does not occur with blocks)
             if (frame_at_end && t == t_first + n_steps - 1) e->frame_next = true;
             if ((rc = enqueue_steps(e, t, 1, false, 0))) return rc;
+            if ((rc = comm_erosion_replay(e))) return rc;
             continue;
         }
         if ((rc = halo_pack_all(e))) return rc;
@@ -1512,6 +1563,7 @@ static int comm_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame
         CK(cudaStreamWaitEvent(e->stream, e->ev_comm, 0));
         if (frame_at_end && t == t_first + n_steps - 1) e->frame_next = true;
         if ((rc = enqueue_steps(e, t, 1, false, 2))) return rc;
+        if ((rc = comm_erosion_replay(e))) return rc;
     }
     return 0;
 }
@@ -1526,9 +1578,10 @@ static int step_enqueue_impl(hk_engine* e, int64_t t_first, int64_t n_steps, boo
             if (e->cx_maxlen <= 0)
                 return fail(e, HK_ERR_STATE, "contact across ranks: call hk_comm_contact after hk_set_node_list (or drive the "
                                              "exchange from the host: hk_nodes_* / hk_contact_* + hk_step_begin / hk_step_finish)");
-            if (n_steps > 1 && e->any_ductile && !e->g_node_map.empty())
-                return fail(e, HK_ERR_UNSUPPORTED, "contact surfaces that erode across ranks: the host replays the all-gathered "
-                                                   "deletions (hk_apply_deleted) after every step, so enqueue one step at a time");
+            if (n_steps > 0) { int rc = ensure_erosion(e); if (rc) return rc; }
+            if (n_steps > 1 && e->any_ductile && !e->g_node_map.empty() && !(e->dev_erosion && e->xerode))
+                return fail(e, HK_ERR_UNSUPPORTED, "contact surfaces that erode across ranks: without hk_comm_erosion the host replays "
+                                                   "the all-gathered deletions (hk_apply_deleted) after every step, so enqueue one step at a time");
         }
         int rc = comm_steps(e, t_first, n_steps, frame_at_end);
         if (rc) return rc;
@@ -2056,7 +2109,7 @@ int HKAPI(set_node_list)(hk_engine* e, int32_t which, int64_t n, const int64_t* 
     for (int64_t i = 0; i < n; ++i) {
         if (nodes[i] < 1 || nodes[i] > e->nNode) return fail(e, HK_ERR_ARG, "node id out of range");
         L[i] = (int)(nodes[i] - 1);
-        if (which == 2 && (e->spec_idx_h[L[i]] < 0 || e->spec_h[e->spec_idx_h[L[i]]].contact_slot < 0))
+        if (which == 2 && !e->xerode && (e->spec_idx_h[L[i]] < 0 || e->spec_h[e->spec_idx_h[L[i]]].contact_slot < 0))
             return fail(e, HK_ERR_ARG, "surface list holds a node that is in no contact pair");
     }
     dfree(e, e->d_node_list[which]);
@@ -2115,6 +2168,17 @@ int HKAPI(state_import)(hk_engine* e, const void* in_dev) {
     return HK_OK;
 }
 
+int HKAPI(comm_erosion)(hk_engine* e, int32_t max_deleted_per_step) {
+    if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
+    HK_DEVICE(e);
+    if (e->g_node_map.empty()) return fail(e, HK_ERR_STATE, "hk_comm_erosion: call hk_set_global_maps first");
+    if (e->erosion_checked) return fail(e, HK_ERR_STATE, "hk_comm_erosion: call before the first step");
+    if (max_deleted_per_step < 1 || max_deleted_per_step > (1 << 24)) return fail(e, HK_ERR_ARG, "bad capacity");
+    e->xerode = true;
+    e->xe_cap = max_deleted_per_step;
+    return HK_OK;
+}
+
 int HKAPI(set_global_maps)(hk_engine* e, int64_t n_global_nodes, const int64_t* node_map, int64_t n_global_elements,
                            const int64_t* elem_map, const int64_t* element_instance) {
     if (!e || !e->finalized) return fail(e, HK_ERR_STATE, "engine not finalised");
@@ -2142,8 +2206,25 @@ int HKAPI(apply_deleted)(hk_engine* e, int64_t n, const int64_t* global_ids) {
     std::vector<int64_t> ids(global_ids, global_ids + n);
     for (int64_t g : ids)
         if (g < 1 || g > limit) return fail(e, HK_ERR_ARG, "element id out of range");
-    int rc = global ? 0 : ensure_erosion(e);          // restart hook: the replay and later steps share one set of lists
+    int rc = (global && !e->xerode) ? 0 : ensure_erosion(e);   // restart hook: the replay and later steps share one set of lists
     if (rc) return rc;
+    if (global && e->dev_erosion && e->xerode) {      // host-driven exchange, device-side lists: replay the ids on the device
+        if (e->comm) return fail(e, HK_ERR_STATE, "hk_comm_erosion with a communicator: the engine replays deletions itself");
+        std::vector<long long> buf((size_t)e->xe_cap + 1);
+        for (int64_t done = 0; done < n;) {
+            const int64_t m = std::min<int64_t>(n - done, e->xe_cap);
+            buf[0] = m;
+            for (int64_t i = 0; i < m; ++i) buf[1 + i] = ids[done + i] - 1;
+            CK(hkp::h2d(e->xe_all, buf.data(), (size_t)(m + 1) * sizeof(long long), e->stream));
+            hk_launch_erode_replay(e->d, e->er, e->xe_all, 1, e->xe_cap, e->stream);
+            CK(hkp::sync(e->stream));
+            done += m;
+        }
+        e->n_launch += 1;
+        e->contact_host_stale = true;
+        CK(hkp::last_error());
+        return HK_OK;
+    }
     if ((rc = contact_refresh_host(e))) return rc;
     rc = update_surfaces(e, ids);
     if (rc) return rc;

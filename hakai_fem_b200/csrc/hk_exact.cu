@@ -579,9 +579,10 @@ HK_HD void erode_element(const HkDev& d, const HkErodeDev& E, int e) {
         tri[3 * nt] = s0; tri[3 * nt + 1] = s1; tri[3 * nt + 2] = s2; tele[nt++] = I.feleid[k];
         tri[3 * nt] = s2; tri[3 * nt + 1] = s3; tri[3 * nt + 2] = s0; tele[nt++] = I.feleid[k];
         const int q[4] = {s0, s1, s2, s3};
-        for (int a = 0; a < 4; ++a) {                 // sorted unique insert (`nodes = unique(sort(tri))`)
+        for (int a = 0; a < 4; ++a) {                 // sorted unique insert (`nodes = unique(sort(tri))`), global-id order
             int pos = 0;
-            while (pos < nn && nodes[pos] < q[a]) ++pos;
+            const int kq = E.node_key ? E.node_key[q[a]] : q[a];
+            while (pos < nn && (E.node_key ? E.node_key[nodes[pos]] : nodes[pos]) < kq) ++pos;
             if (pos < nn && nodes[pos] == q[a]) continue;
             for (int m = nn; m > pos; --m) nodes[m] = nodes[m - 1];
             nodes[pos] = q[a];
@@ -613,6 +614,7 @@ HK_HD void erode_element(const HkDev& d, const HkErodeDev& E, int e) {
                 erode_contact_slot(d, E, g);
             }
             for (int r = 0; r < nt; ++r) {
+                if (tele[r] < 0) continue;            // the rank that owns that element adds this triangle
                 if (D.nTri >= p.cap_tri) { *E.overflow = 1; break; }
                 const int o = D.nTri++;
                 p.t0[o] = tri[3 * r]; p.t1[o] = tri[3 * r + 1]; p.t2[o] = tri[3 * r + 2]; p.tele[o] = tele[r];
@@ -692,15 +694,42 @@ __global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, long long 
         __syncthreads();
     }
 }
-__global__ void hk_delete_finish_kernel(HkDev d, HkErodeDev E, int erode) {
+__global__ void hk_delete_finish_kernel(HkDev d, HkErodeDev E, int erode, long long* send, const int* e_l2g, int cap) {
     const int n = *d.del_fresh, first = *d.del_count;
     if (erode)
         for (int i = 0; i < n && first + i < d.del_cap; ++i) erode_element(d, E, (int)(d.del_list[first + i] & 0xffffffffll));
+    if (send) {                                               // this step's deletions as global ids, for the all-gather
+        send[0] = n;
+        for (int i = 0; i < n && i < cap && first + i < d.del_cap; ++i) send[1 + i] = e_l2g[d.del_list[first + i] & 0xffffffffll];
+    }
     *d.del_count = first + n;
+}
+__global__ void hk_erode_replay_kernel(HkDev d, HkErodeDev E, const long long* gathered, int world, int cap) {
+    for (int r = 0; r < world; ++r) {
+        const long long* g = gathered + (long long)r * (cap + 1);
+        const long long n = g[0];
+        if (n > cap) { *E.overflow = 1; }
+        for (long long i = 0; i < n && i < cap; ++i) erode_element(d, E, (int)g[1 + i]);
+    }
 }
 #endif
 
-void hk_launch_deletion_pass(const HkDev& dd, const HkErodeDev* er, long long step, cudaStream_t s, long long* n_launch) {
+void hk_launch_erode_replay(const HkDev& dd, const HkErodeDev& E, const long long* gathered, int world, int cap, cudaStream_t s) {
+#ifndef HK_EMU
+    hk_erode_replay_kernel<<<1, 1, 0, s>>>(dd, E, gathered, world, cap);
+#else
+    (void)s;
+    for (int r = 0; r < world; ++r) {
+        const long long* g = gathered + (long long)r * (cap + 1);
+        const long long n = g[0];
+        if (n > cap) *E.overflow = 1;
+        for (long long i = 0; i < n && i < cap; ++i) erode_element(dd, E, (int)g[1 + i]);
+    }
+#endif
+}
+
+void hk_launch_deletion_pass(const HkDev& dd, const HkErodeDev* er, long long step, cudaStream_t s, long long* n_launch,
+                             long long* send, const int* e_l2g, int cap) {
     const HkDev d = dd;
     HkErodeDev E;
     memset(&E, 0, sizeof(E));
@@ -710,7 +739,7 @@ void hk_launch_deletion_pass(const HkDev& dd, const HkErodeDev* er, long long st
     hk_delete_count_kernel<<<nb, 256, 0, s>>>(d);
     hk_delete_scan_kernel<<<1, 1024, 0, s>>>(d, (int)nb);
     hk_delete_emit_kernel<<<nb, 256, 0, s>>>(d, step, (int)nb);
-    hk_delete_finish_kernel<<<1, 1, 0, s>>>(d, E, er ? 1 : 0);
+    hk_delete_finish_kernel<<<1, 1, 0, s>>>(d, E, er ? 1 : 0, send, e_l2g, cap);
     if (n_launch) *n_launch += 4;
 #else
     (void)s; (void)n_launch;
@@ -724,6 +753,10 @@ void hk_launch_deletion_pass(const HkDev& dd, const HkErodeDev* er, long long st
         }
     if (er)
         for (int i = 0; i < n && first + i < d.del_cap; ++i) erode_element(d, E, (int)(d.del_list[first + i] & 0xffffffffll));
+    if (send) {
+        send[0] = n;
+        for (int i = 0; i < n && i < cap && first + i < d.del_cap; ++i) send[1 + i] = e_l2g[d.del_list[first + i] & 0xffffffffll];
+    }
     *d.del_count = first + n;
 #endif
 }
@@ -855,8 +888,9 @@ void hk_launch_cacc_export(const HkDev& dd, const int* nodes, long long n, unsig
     hk_parallel_for(n * 6, s, HK_LAMBDA(long long j) {
         const long long i = j / 6;
         const int w = (int)(j - 6 * i);
-        const int slot = d.spec[d.spec_idx[nodes[i]]].contact_slot;
-        out[j] = d.cacc[6ll * slot + w];
+        const int si = d.spec_idx[nodes[i]];
+        const int slot = si < 0 ? -1 : d.spec[si].contact_slot;
+        out[j] = slot < 0 ? 0ull : d.cacc[6ll * slot + w];
     });
 }
 void hk_launch_cacc_import(const HkDev& dd, const int* nodes, long long n, const unsigned long long* in, long long n_ranks,
@@ -872,7 +906,9 @@ void hk_launch_cacc_import(const HkDev& dd, const int* nodes, long long n, const
             hi += p[1] + (nlo < lo ? 1ull : 0ull);
             lo = nlo;
         }
-        const int slot = d.spec[d.spec_idx[nodes[i]]].contact_slot;
+        const int si = d.spec_idx[nodes[i]];
+        const int slot = si < 0 ? -1 : d.spec[si].contact_slot;
+        if (slot < 0) return;
         d.cacc[6ll * slot + 2 * c] = lo;
         d.cacc[6ll * slot + 2 * c + 1] = hi;
     });
@@ -886,8 +922,9 @@ void hk_launch_cacc_export_limbs(const HkDev& dd, const int* nodes, long long n,
     hk_parallel_for(n * 3, s, HK_LAMBDA(long long j) {
         const long long i = j / 3;
         const int c = (int)(j - 3 * i);
-        const int slot = d.spec[d.spec_idx[nodes[i]]].contact_slot;
-        const unsigned long long lo = d.cacc[6ll * slot + 2 * c], hi = d.cacc[6ll * slot + 2 * c + 1];
+        const int si = d.spec_idx[nodes[i]];
+        const int slot = si < 0 ? -1 : d.spec[si].contact_slot;      // candidate node not (yet) on a contact surface: zero
+        const unsigned long long lo = slot < 0 ? 0ull : d.cacc[6ll * slot + 2 * c], hi = slot < 0 ? 0ull : d.cacc[6ll * slot + 2 * c + 1];
         const unsigned long long m43 = (1ull << 43) - 1;
         out[9 * i + 3 * c + 0] = (long long)(lo & m43);
         out[9 * i + 3 * c + 1] = (long long)(((lo >> 43) | (hi << 21)) & m43);      // bits 43..85
@@ -909,7 +946,9 @@ void hk_launch_cacc_import_limbs(const HkDev& dd, const int* nodes, long long n,
         hi += a_hi + (nlo < lo ? 1ull : 0ull);
         lo = nlo;
         hi += s2 << 22;
-        const int slot = d.spec[d.spec_idx[nodes[i]]].contact_slot;
+        const int si = d.spec_idx[nodes[i]];
+        const int slot = si < 0 ? -1 : d.spec[si].contact_slot;
+        if (slot < 0) return;
         d.cacc[6ll * slot + 2 * c] = lo;
         d.cacc[6ll * slot + 2 * c + 1] = hi;
     });

@@ -44,7 +44,7 @@ EXPORTS = [
     "set_halo", "halo_bind", "halo_pack", "step_enqueue", "sync", "step_begin", "step_finish",
     "set_node_list", "nodes_export", "nodes_import", "contact_enqueue", "contact_export", "contact_import",
     "set_global_maps", "apply_deleted", "node_output", "mark_frame", "contact_export_limbs", "contact_import_limbs",
-    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init", "profile_read_ex", "comm_contact", "build_contact",
+    "state_export", "state_import", "state_summary", "deleted_steps", "set_halo_ranks", "comm_unique_id", "comm_init", "profile_read_ex", "comm_contact", "build_contact", "comm_erosion",
 ]
 
 
@@ -371,6 +371,11 @@ class EngineBase:
         if len(unique_id) != 128:
             raise ValueError("unique_id: 128 bytes")
         self._chk(self._fn("comm_init")(self._h, C.c_char_p(unique_id), C.c_int32(rank), C.c_int32(world)))
+
+    def comm_erosion(self, max_deleted_per_step: int = 4096):
+        """Deletions of all ranks replayed on the device (hk_comm_erosion): after set_global_maps, before the first step;
+        the node lists 0 / 1 / 2 must then cover every candidate surface node and never change."""
+        self._chk(self._fn("comm_erosion")(self._h, C.c_int32(max_deleted_per_step)))
 
     def comm_contact(self, maxlen: int, src_index):
         """The engine runs the contact exchange of every step itself (all-gather of surface-node states, exact all-reduce

@@ -236,8 +236,9 @@ def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, 
         dom = partition_model(setup, world, only_rank=rank)[rank]
         # over NCCL the engine runs every exchange with its own communicator (hk_comm_init / hk_comm_contact); over gloo
         # (CPU ranks with the host-compiled kernels) the host drives them through torch.distributed
-        runner = SlabRunner.from_domain(engine_cls, dom, torch_device, world,
-                                        engine_comm=dist.get_backend() == "nccl", **params)
+        on_nccl = dist.get_backend() == "nccl"      # the engine exchanges by itself and keeps eroding surfaces current
+        runner = SlabRunner.from_domain(engine_cls, dom, torch_device, world, engine_comm=on_nccl,
+                                        device_erosion=on_nccl, **params)
         n_held = len(np.unique(dom.setup.model.elementmat))     # local ids 1..n_held are nodes of own elements
         sel_n, sel_e = np.arange(n_held), np.arange(dom.setup.model.nElement)
     eng = runner.engine

@@ -179,4 +179,16 @@ end
 comm_init(e, id::Vector{UInt8}, rank::Integer, world::Integer) =
     check(e.ptr, ccall((:hk_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), e.ptr, id, rank, world))
 
+# contact across ranks (INTEGRATION.md "Decks with contact"): node lists 0 own surface nodes / 1 ghost copies / 2 all
+# surface nodes (1-based local ids), then the engine exchanges by itself; with failure: global maps + device-side replay
+set_node_list(e, which::Integer, nodes::Vector{Int64}) =
+    check(e.ptr, ccall((:hk_set_node_list, LIB), Cint, (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}), e.ptr, which, length(nodes), nodes))
+comm_contact(e, maxlen::Integer, src_index::Vector{Int64}) =
+    check(e.ptr, ccall((:hk_comm_contact, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}), e.ptr, maxlen, src_index))
+set_global_maps(e, node_map::Vector{Int64}, elem_map::Vector{Int64}, element_instance::Vector{Int64}) =
+    check(e.ptr, ccall((:hk_set_global_maps, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}),
+                       e.ptr, length(node_map), node_map, length(elem_map), elem_map, element_instance))
+comm_erosion(e, max_deleted_per_step::Integer = 4096) =
+    check(e.ptr, ccall((:hk_comm_erosion, LIB), Cint, (Ptr{Cvoid}, Int32), e.ptr, max_deleted_per_step))
+
 end # module

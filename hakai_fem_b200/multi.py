@@ -35,6 +35,7 @@ class LocalDomain:
     neighbors: List[int] = field(default_factory=list)
     halo_nodes: List[np.ndarray] = field(default_factory=list)     # local 1-based ids per neighbour
     contact: object = None             # ContactLists when the model has contact
+    contact_all: object = None         # ContactLists over every node that may ever join a surface (device-side erosion)
 
 
 def _restrict_dofs(dof_lists, values, g2l):
@@ -175,6 +176,8 @@ def partition_model(setup: Setup, n_ranks: int, only_rank: int = None) -> List[L
                 lst.CT.append(ContactTriangle(ct.i_instance, ct.j_instance, g2l[ct.c_nodes_i], g2l[ct.c_nodes_j],
                                               g2l[ct.c_triangles[mine]], e_g2l[ct.c_triangles_eleid[mine]], ct.young))
             dom.contact = build_contact_lists(surf, first_holder, g2l, len(nodes_own), r, n_ranks, maps)
+            if erosion:
+                dom.contact_all = build_contact_lists(candidates, first_holder, g2l, len(nodes_own), r, n_ranks, maps)
         for q in range(n_ranks):
             if q == r:
                 continue
@@ -339,9 +342,13 @@ class ContactExchanger:
     """All-gather of contact-surface node {position, velocity} and of the fixed-point force accumulators."""
 
     def __init__(self, engine, lists: ContactLists, world: int, device, rank=None, node_l2g=None, n_pairs=0,
-                 force_exchange="allreduce", engine_comm=False):
+                 force_exchange="allreduce", engine_comm=False, static_lists: ContactLists = None,
+                 max_deleted_per_step: int = 4096):
         """force_exchange: "allgather" (6 x u64 per surface node from every rank, summed on import) or "allreduce"
-        (three 43-bit limbs per accumulator in int64 lanes, one SUM all-reduce: world/1.5 times fewer bytes)."""
+        (three 43-bit limbs per accumulator in int64 lanes, one SUM all-reduce: world/1.5 times fewer bytes).
+        static_lists (surfaces that erode): exchange lists over EVERY candidate surface node, never rebuilt — the engine
+        then replays the deletions of all ranks on the device (hk_comm_erosion); with engine_comm it also gathers them,
+        so run() needs no host between steps."""
         if force_exchange not in ("allgather", "allreduce"):
             raise ValueError("force_exchange: allgather | allreduce")
         self.force_exchange = force_exchange
@@ -349,6 +356,7 @@ class ContactExchanger:
         self.engine, self.world, self.device = engine, world, device
         self.rank, self.node_l2g, self.n_pairs = rank, node_l2g, n_pairs
         self.erosion = lists.erosion
+        self.device_erosion = self.erosion is not None and static_lists is not None
         if self.erosion is not None:
             if rank is None or node_l2g is None:
                 raise ValueError("erosion across ranks needs rank and node_l2g")
@@ -356,6 +364,9 @@ class ContactExchanger:
             engine.set_global_maps(er.node_map, er.elem_map, er.element_instance)
             self._g2l = np.concatenate([[0], er.node_map])
             self._surf0 = np.asarray(node_l2g)[lists.surface_nodes - 1]
+            if self.device_erosion:
+                engine.comm_erosion(max_deleted_per_step)
+                lists = static_lists
         self.set_lists(lists)
 
     def set_lists(self, lists: ContactLists):
@@ -399,6 +410,8 @@ class ContactExchanger:
         dist.all_gather(got, mine)
         ids = np.sort(np.concatenate([g[:c].cpu().numpy() for g, c in zip(got, counts)]))
         self.engine.apply_deleted(ids)
+        if self.device_erosion:              # lists cover every candidate node: nothing to rebuild
+            return len(ids)
         l2g = np.asarray(self.node_l2g)
         parts = [self._surf0]
         for c in range(self.n_pairs):
@@ -437,7 +450,7 @@ class SlabRunner:
 
     def __init__(self, engine_cls, setup: Setup, neighbors, halo_nodes, torch_device, sum_mass=False, contact=None,
                  world=1, rank=None, node_l2g=None, elem_l2g=None, force_exchange="allreduce", engine_comm=False,
-                 **params):
+                 contact_all=None, **params):
         self.setup = setup
         if sum_mass and neighbors:
             # interface nodes: add the neighbour's partial lumped mass (J2:201-215 summed over ALL elements)
@@ -456,19 +469,24 @@ class SlabRunner:
         self.engine = configure_engine(with_halo, setup, **params)
         self.halo = HaloExchanger(self.engine, neighbors, halo_nodes, torch_device, rank=rank, engine_comm=engine_comm)
         self.contact = (ContactExchanger(self.engine, contact, world, torch_device, rank, node_l2g, len(setup.CT),
-                                         force_exchange, engine_comm=engine_comm)
+                                         force_exchange, engine_comm=engine_comm, static_lists=contact_all)
                         if contact is not None else None)
         self.erosion = self.contact is not None and self.contact.erosion is not None
+        # the engine gathers and replays the deletions of all ranks itself: no host between steps
+        self.erosion_on_device = self.erosion and engine_comm and self.contact.device_erosion
         if self.erosion and elem_l2g is None:
             raise ValueError("erosion across ranks needs elem_l2g")
         self.elem_l2g = None if elem_l2g is None else np.asarray(elem_l2g, np.int64)
         self.nElement = model.nElement
 
     @classmethod
-    def from_domain(cls, engine_cls, dom: LocalDomain, torch_device, world, force_exchange="allreduce", **params):
+    def from_domain(cls, engine_cls, dom: LocalDomain, torch_device, world, force_exchange="allreduce",
+                    device_erosion=False, **params):
+        """device_erosion: surfaces that erode across ranks are kept current on the device (static exchange lists over all
+        candidate nodes, hk_comm_erosion) instead of by a host replay + list rebuild after every step."""
         return cls(engine_cls, dom.setup, dom.neighbors, dom.halo_nodes, torch_device, contact=dom.contact,
                    world=world, rank=dom.rank, node_l2g=dom.node_l2g, elem_l2g=dom.elem_l2g,
-                   force_exchange=force_exchange, **params)
+                   force_exchange=force_exchange, contact_all=dom.contact_all if device_erosion else None, **params)
 
     def _after_step(self) -> int:
         """Erosion across ranks: one host sync per step (the deleted set decides the next step's contact surface)."""
@@ -496,7 +514,8 @@ class SlabRunner:
         import time as _time
         _t0 = _time.perf_counter()
         n_del = 0
-        if self.halo.engine_comm and not self.erosion:   # one call: the engine packs, exchanges (its own NCCL) and steps
+        if self.halo.engine_comm and (not self.erosion or self.erosion_on_device):
+            # one call: the engine packs, exchanges (its own NCCL), steps and keeps eroding surfaces current
             if frame_at_end:
                 self.engine.mark_frame()
             self.engine.step_enqueue(t_first, n_steps)

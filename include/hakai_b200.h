@@ -269,7 +269,8 @@ int hk_comm_init(hk_engine* e, const void* id128, int32_t rank, int32_t world);
  * then on every step of hk_step / hk_step_enqueue first runs, on the engine's stream: export of the own surface nodes ->
  * ncclAllGather -> ghost copies -> contact pass on the local master triangles -> 43-bit limbs of the 128-bit force
  * accumulators -> ncclAllReduce(int64, sum) (exact) -> the halo step.  Call again whenever the lists change.  Surfaces
- * that erode across ranks (hk_set_global_maps) still need the host's replay after every step: then n_steps = 1. */
+ * that erode across ranks (hk_set_global_maps) need the host's replay after every step (then n_steps = 1) unless
+ * hk_comm_erosion moved that replay onto the device. */
 int hk_comm_contact(hk_engine* e, int64_t maxlen, const int64_t* src_index);
 
 /* The asynchronous step calls imply no output frame, so they do not store integ_triax_stress (hk_download and
@@ -327,6 +328,16 @@ int hk_contact_import_limbs(hk_engine* e, const void* in_dev); /* lane-wise sums
 int hk_set_global_maps(hk_engine* e, int64_t n_global_nodes, const int64_t* node_map,
                        int64_t n_global_elements, const int64_t* elem_map, const int64_t* element_instance);
 int hk_apply_deleted(hk_engine* e, int64_t n, const int64_t* global_ids);
+/* The same replay ON THE DEVICE (call after hk_set_global_maps, before the first step).  The exchange lists of
+ * hk_set_node_list(0 / 1 / 2) must then be STATIC and cover every node that can ever join a surface — all nodes of the
+ * instances in contact — because nothing rebuilds them (nodes without a contact slot export zeros and ignore imports).
+ * Every step the engine logs its own deletions as global ids; with a communicator (hk_comm_init) it all-gathers
+ * {count, ids[max_deleted_per_step]} of every rank on its stream and one thread replays them in ascending global order
+ * (ranks own contiguous ascending element blocks) — pair lists, contact slots and special-node table grow on the
+ * device, and hk_step_enqueue(t, n > 1) needs no host in between.  Without a communicator the host still gathers the
+ * ids and calls hk_apply_deleted, which then replays them on the device.  A step that deletes more than
+ * max_deleted_per_step elements on one rank is reported by hk_sync as an error (HK_ERR_STATE). */
+int hk_comm_erosion(hk_engine* e, int32_t max_deleted_per_step);
 /* Without hk_set_global_maps (single-domain engine) hk_apply_deleted is the RESTART hook: ids are the engine's own
  * 1-based element ids in their original deletion order (hk_deleted_ids of the checkpointed run); the exposed-face
  * updates are replayed and the ids are recorded as already deleted.  State itself comes back through

@@ -1134,6 +1134,7 @@ int hko_build_contact(hk_engine* e, int64_t, const int64_t*, const int64_t*, con
     return fail(e, HK_ERR_UNSUPPORTED, "the oracle takes the host-built contact tables (hko_add_instance / hko_add_contact_pair)");
 }
 int hko_comm_contact(hk_engine* e, int64_t, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
+int hko_comm_erosion(hk_engine* e, int32_t) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_set_node_list(hk_engine* e, int32_t, int64_t, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_nodes_export(hk_engine* e, void*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }
 int hko_nodes_import(hk_engine* e, const void*, const int64_t*) { return fail(e, HK_ERR_UNSUPPORTED, "oracle is single-domain"); }

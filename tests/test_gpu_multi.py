@@ -28,7 +28,7 @@ def _global_setup(mode):
     return prepare(deck.build_model()), {}, 90
 
 
-def _worker(rank, world, port, mode, q, engine_comm=False):
+def _worker(rank, world, port, mode, q, engine_comm=False, device_erosion=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -46,7 +46,9 @@ def _worker(rank, world, port, mode, q, engine_comm=False):
             e.set_stream(stream.cuda_stream)
             return e
         run = SlabRunner.from_domain(make, dom, torch.device("cuda", rank), world, device=rank, engine_comm=engine_comm,
-                                     **prm)
+                                     device_erosion=device_erosion, **prm)
+        if device_erosion:
+            assert run.erosion_on_device == engine_comm
         nd = run.run(1, n_steps)
         d = run.engine.download()
         n_own = len(np.unique(dom.setup.model.elementmat))          # held nodes come first, ghosts after
@@ -60,21 +62,26 @@ def _worker(rank, world, port, mode, q, engine_comm=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,world,engine_comm", [("fracture", 2, False), ("contact", 2, False), ("erosion", 2, False),
-                                                    ("erosion", 1, False), ("fracture", 2, True), ("contact", 2, True),
-                                                    ("erosion", 2, True), ("erosion", 1, True)])
-def test_ranks_match_single_domain_oracle(mode, world, engine_comm):
+@pytest.mark.parametrize("mode,world,engine_comm,device_erosion",
+                         [("fracture", 2, False, False), ("contact", 2, False, False), ("erosion", 2, False, False),
+                          ("erosion", 1, False, False), ("fracture", 2, True, False), ("contact", 2, True, False),
+                          ("erosion", 2, True, False), ("erosion", 1, True, False),
+                          ("erosion", 2, True, True), ("erosion", 1, True, True), ("erosion", 2, False, True)])
+def test_ranks_match_single_domain_oracle(mode, world, engine_comm, device_erosion):
     """world == 1 runs the whole domain-runner path (global maps, hk_apply_deleted, list rebuild, NCCL calls) on a
     single-GPU box, where the 2-rank cases are skipped.  engine_comm: the ENGINE's communicator runs every exchange
-    (hk_comm_init / hk_comm_contact: halo send/recv, surface all-gather, limb all-reduce) inside hk_step_enqueue."""
+    (hk_comm_init / hk_comm_contact: halo send/recv, surface all-gather, limb all-reduce) inside hk_step_enqueue.
+    device_erosion: exposed faces of elements deleted on ANY rank join the surfaces on the device (hk_comm_erosion); with
+    engine_comm the whole run is ONE hk_step_enqueue(1, n_steps) per rank — no host between steps."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     from hakai_fem_b200.model_setup import configure_engine
     from oracle.oracle_engine import OracleEngine
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29200 + (os.getpid() % 2000) + ("fracture", "contact", "erosion").index(mode) + 10 * world + (40 if engine_comm else 0)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q, engine_comm)) for r in range(world)]
+    port = (29200 + (os.getpid() % 2000) + ("fracture", "contact", "erosion").index(mode) + 10 * world + (40 if engine_comm else 0)
+            + (80 if device_erosion else 0))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q, engine_comm, device_erosion)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(world)]
@@ -99,7 +106,8 @@ def test_ranks_match_single_domain_oracle(mode, world, engine_comm):
     elif mode == "erosion":
         got = np.sort(np.concatenate([r["deleted"] for _, r in res]))
         assert len(got) > 0 and np.array_equal(got, np.sort(o.deleted_ids())), "deleted-element set differs"
-        assert any(r["n_surf"] > r["n_surf0"] for _, r in res), "contact surface never grew"
+        if not device_erosion:                                  # (static candidate lists never change)
+            assert any(r["n_surf"] > r["n_surf0"] for _, r in res), "contact surface never grew"
     else:
         assert sum(r["nd"] for _, r in res) == nd_ref > 0
 
@@ -268,3 +276,47 @@ def test_engine_owned_communicator_matches_unpartitioned_run():
     for mode in (True, False):
         r0 = res[0][mode]
         assert r0["ok"] and r0["interface_bitwise"] and r0["deleted_equal"] and r0["n_deleted"] > 0, (mode, r0)
+
+
+# ---- SURVEY 8f.1 across ranks: the reference's eroding decks, ONE hk_step_enqueue(1, n) per rank, no host in between
+def _worker_reference_deck(rank, world, port, name, n_steps, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hakai_fem_b200.engine import Engine
+        from tests.test_multi_gloo import reference_deck_rank
+        stream = torch.cuda.current_stream()
+
+        def make(**p):
+            e = Engine(device=rank, **p)
+            e.set_stream(stream.cuda_stream)
+            return e
+        q.put((rank, reference_deck_rank(name, n_steps, rank, world, make, torch.device("cuda", rank), True)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,n_steps,expect_deleted,world", [("bullet_impact", 3000, 13, 1), ("bullet_impact", 3000, 13, 2),
+                                                               ("metal_cutting", 3000, 30, 2)])
+def test_reference_deck_erodes_across_ranks_on_the_device(name, n_steps, expect_deleted, world):
+    """bullet-impact.inp / metal-cutting.inp in element blocks over `world` GPUs: every rank logs its deletions, the
+    engines all-gather them (NCCL, hk_comm_erosion) and replay them on the device — surfaces, deleted set, hit count and
+    fields equal the oracle's unpartitioned run, and the whole run is one hk_step_enqueue(1, n_steps) per rank."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from tests.test_multi_gloo import check_reference_deck_ranks
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30300 + (os.getpid() % 2000) + 3 * world + (1 if name == "metal_cutting" else 0)
+    procs = [ctx.Process(target=_worker_reference_deck, args=(r, world, port, name, n_steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=900) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    check_reference_deck_ranks(name, n_steps, expect_deleted, res)

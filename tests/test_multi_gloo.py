@@ -225,8 +225,9 @@ def _erosion_setup():
     return prepare(model)
 
 
-def _worker_erosion(rank, world, port, q):
-    """Brittle plate split over ranks: faces exposed by deletions on one rank join the contact surface on all."""
+def _worker_erosion(rank, world, port, q, device_erosion=False):
+    """Brittle plate split over ranks: faces exposed by deletions on one rank join the contact surface on all.
+    device_erosion: the gathered ids are replayed on the "device" (hk_comm_erosion, static exchange lists)."""
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -236,7 +237,8 @@ def _worker_erosion(rank, world, port, q):
         from tests.emu.emu_engine import EmuEngine
         dom = partition_model(_erosion_setup(), world)[rank]
         assert dom.contact.erosion is not None
-        run = SlabRunner.from_domain(EmuEngine, dom, "cpu", world)
+        run = SlabRunner.from_domain(EmuEngine, dom, "cpu", world, device_erosion=device_erosion)
+        assert run.contact.device_erosion == device_erosion
         n_del = run.run(1, 400)
         d = run.engine.download()
         n_own = dom.contact.erosion.n_held
@@ -254,14 +256,14 @@ def _worker_erosion(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_erosion_across_ranks_matches_single_domain(world):
+@pytest.mark.parametrize("world,device_erosion", [(2, False), (3, False), (2, True), (3, True)])
+def test_erosion_across_ranks_matches_single_domain(world, device_erosion):
     from hakai_fem_b200.model_setup import configure_engine
     from oracle.oracle_engine import OracleEngine
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world
-    procs = [ctx.Process(target=_worker_erosion, args=(r, world, port, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + world + (10 if device_erosion else 0)
+    procs = [ctx.Process(target=_worker_erosion, args=(r, world, port, q, device_erosion)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in range(world))
@@ -276,7 +278,8 @@ def test_erosion_across_ranks_matches_single_domain(world):
     got = np.concatenate([res[r]["deleted"] for r in range(world)])
     assert np.array_equal(np.sort(got), np.sort(ids)), "deleted-element set differs"
     assert sum(res[r]["n_del"] for r in range(world)) == len(ids)
-    assert any(res[r]["n_surf"] > res[r]["n_surf0"] for r in range(world)), "surface never grew"
+    if not device_erosion:                                        # (static candidate lists never change)
+        assert any(res[r]["n_surf"] > res[r]["n_surf0"] for r in range(world)), "surface never grew"
     for c in range(2):
         po = o.contact_pair(c)
         for r in range(world):                                   # node lists: identical, same order, on every rank
@@ -730,3 +733,87 @@ def test_nodes_shared_by_three_ranks_stay_bit_identical():
         for u in c[1:]:
             assert np.array_equal(c[0], u), f"node {g} ({len(c)} holders) differs across ranks"
     assert np.abs(np.concatenate([c[0] for c in copies.values()])).max() > 0
+
+
+# ---- the reference's eroding example decks, partitioned, surfaces kept current on the device (hk_comm_erosion) --------
+def reference_deck_rank(name, n_steps, rank, world, make_engine, device, engine_comm):
+    """One rank of a reference deck split into element blocks with device-side erosion; returns what the checker needs
+    (global ids).  Shared with tests/test_gpu_multi.py (CUDA engine, NCCL, engine_comm=True: ONE hk_step_enqueue)."""
+    from hakai_fem_b200.multi import partition_model, SlabRunner
+    from tests import util
+    dom = partition_model(util.deck_setup(name), world, only_rank=rank)[rank]
+    run = SlabRunner.from_domain(make_engine, dom, device, world, engine_comm=engine_comm, device_erosion=True)
+    assert run.contact.device_erosion and run.erosion_on_device == engine_comm
+    n_del = run.run(1, n_steps)
+    d = run.engine.download()
+    n_own = dom.contact.erosion.n_held
+    pairs = []
+    for c in range(len(dom.setup.CT)):
+        info = run.engine.contact_pair(c)
+        pairs.append(dict(nodes_i=dom.node_l2g[info["c_nodes_i"] - 1], nodes_j=dom.node_l2g[info["c_nodes_j"] - 1],
+                          tri=dom.node_l2g[info["c_triangles"] - 1], tele=dom.elem_l2g[info["c_triangles_eleid"] - 1]))
+    return dict(disp=d["disp"][:3 * n_own], flag=d["element_flag"], node_l2g=dom.node_l2g[:n_own], elem_l2g=dom.elem_l2g,
+                n_del=n_del, deleted=dom.elem_l2g[run.engine.deleted_ids() - 1], pairs=pairs,
+                hits=int(run.engine.counters()[1]))
+
+
+def check_reference_deck_ranks(name, n_steps, expect_deleted, res, tol=1e-7):
+    """res[rank] = reference_deck_rank(...) of every rank, against ONE oracle run of the unpartitioned deck."""
+    from hakai_fem_b200.model_setup import configure_engine
+    from oracle.oracle_engine import OracleEngine
+    from tests import util
+    world = len(res)
+    o = configure_engine(OracleEngine, util.deck_setup(name))
+    o.step(1, n_steps)
+    ref = o.download()
+    ids = o.deleted_ids()
+    assert len(ids) == expect_deleted
+    got = np.concatenate([res[r]["deleted"] for r in range(world)])
+    assert np.array_equal(np.sort(got), np.sort(ids)), "deleted-element set differs"
+    assert sum(res[r]["n_del"] for r in range(world)) == len(ids)
+    assert sum(res[r]["hits"] for r in range(world)) == o.counters()[1] > 0, "contact hit counts differ"
+    for c in range(len(res[0]["pairs"])):
+        po = o.contact_pair(c)
+        for r in range(world):                                   # node lists: identical, same order, on every rank
+            assert np.array_equal(res[r]["pairs"][c]["nodes_i"], po["c_nodes_i"]), (c, r)
+            assert np.array_equal(res[r]["pairs"][c]["nodes_j"], po["c_nodes_j"]), (c, r)
+        tri = np.concatenate([np.column_stack([res[r]["pairs"][c]["tri"], res[r]["pairs"][c]["tele"]]) for r in range(world)])
+        want = np.column_stack([po["c_triangles"], po["c_triangles_eleid"]])
+        assert len(tri) == len(want)                             # every triangle lives on exactly one rank
+        assert np.array_equal(tri[np.lexsort(tri.T[::-1])], want[np.lexsort(want.T[::-1])])
+    scale = np.abs(ref["disp"]).max()
+    for r in range(world):
+        n, e = res[r]["node_l2g"] - 1, res[r]["elem_l2g"] - 1
+        assert np.abs(res[r]["disp"] - ref["disp"].reshape(-1, 3)[n].reshape(-1)).max() <= tol * scale, r
+        assert np.array_equal(res[r]["flag"], ref["element_flag"][e])
+
+
+def _worker_reference_deck(rank, world, port, name, n_steps, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.emu.emu_engine import EmuEngine
+        q.put((rank, reference_deck_rank(name, n_steps, rank, world, EmuEngine, "cpu", False)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,n_steps,expect_deleted", [("bullet_impact", 3000, 13)])
+def test_reference_deck_erodes_across_ranks_with_device_side_lists(name, n_steps, expect_deleted):
+    """bullet-impact.inp on 2 ranks: the 13 deletions expose faces on both; the pair lists every rank holds on the
+    "device" equal the oracle's, in its order (host gathers the ids here; over NCCL the engine does: test_gpu_multi)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_reference_deck, args=(r, world, port, name, n_steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=1500) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    check_reference_deck_ranks(name, n_steps, expect_deleted, res)
