@@ -77,6 +77,7 @@ def _csr(lists: Sequence[np.ndarray]):
 
 
 class EngineBase:
+    builds_contact = True      # hk_build_contact: contact tables built by the engine (the CPU oracle takes host-built ones)
     """Thin, stateful wrapper: one instance = one hk_engine*."""
 
     def __init__(self, lib: C.CDLL, prefix: str, **params):

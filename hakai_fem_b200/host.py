@@ -134,20 +134,29 @@ def _write_vtk_binary(outdir, index, coordmat, elementmat, element_flag, disp, v
 
 
 def hakai(fname, outdir="temp", engine_cls=None, output_num=100, write_frames=True, verbose=True,
-          node_output="device", vtk_format="ascii", checkpoint=None, checkpoint_frames=10, resume=None, **params):
+          node_output="device", vtk_format="ascii", checkpoint=None, checkpoint_frames=10, resume=None,
+          contact_setup=None, **params):
     """hakai(fname), J2:81.  Returns the engine (state on the GPU) and the list of frame files.
     checkpoint: file rewritten every `checkpoint_frames` frames (checkpoint.py); resume: checkpoint to continue
-    from (frames already written are kept; numbering continues)."""
+    from (frames already written are kept; numbering continues).
+    contact_setup: "device" — faces, exterior faces, pair lists and exposed-face twins are built by hk_build_contact
+    (radix sort on the GPU; the reference's all-pairs face match, J2:1996-2084, is what keeps it from large decks) —
+    or "host" (the NumPy mirror in model_setup.py; same tables, tests/parity_cases.py::case_build_contact).  Default:
+    "device" when the engine class can (`builds_contact`: the CUDA engine), else "host" (the CPU oracle)."""
     if node_output not in ("device", "host") or vtk_format not in ("ascii", "binary"):
         raise ValueError("node_output: device|host, vtk_format: ascii|binary")
     if engine_cls is None:
         from .engine import Engine as engine_cls               # the CUDA engine; raises without a GPU
+    if contact_setup is None:
+        contact_setup = "device" if getattr(engine_cls, "builds_contact", False) else "host"
+    if contact_setup not in ("device", "host"):
+        raise ValueError("contact_setup: device|host")
     log = print if verbose else (lambda *a, **k: None)
     model = read_inp_file(fname)
     log("nNode:", model.nNode)
     log("nElement:", model.nElement)
     log("contact_flag:", model.contact_flag)
-    setup = prepare(model)
+    setup = prepare(model, contact=contact_setup)
     log("mass_scaling:", model.mass_scaling)
     log("time_num:", setup.time_num)
     log("elementMinSize:", setup.elementMinSize)

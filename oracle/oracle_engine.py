@@ -32,6 +32,7 @@ def load() -> C.CDLL:
 
 
 class OracleEngine(EngineBase):
+    builds_contact = False
     """CPU restatement of the reference step (HAKAI_j.jl:487-951)."""
 
     def __init__(self, **params):

@@ -95,3 +95,34 @@ def test_reference_deck(name, n_steps, expect_deleted):
 def test_exact_mode_bitwise():
     """On the B200: element_mode=1 reproduces the CPU oracle bit for bit (IEEE FP64, -fmad=false)."""
     pc.case_exact_mode_bitwise(Engine)
+
+
+def test_host_driver_with_device_built_contact_writes_the_oracle_frames(tmp_path):
+    """hakai(deck) with the CUDA engine — contact tables built by hk_build_contact (the default there), exposed faces
+    and frames' nodal averages on the device — against the same driver on the CPU oracle with host-built tables."""
+    import os
+    from hakai_fem_b200.host import hakai
+    from hakai_fem_b200.mesh import ImpactDeck
+    from oracle.oracle_engine import OracleEngine
+    from .test_multi_gloo import _vtk_sections
+    deck_path = str(tmp_path / "deck.inp")
+    ImpactDeck(plate=(8, 8, 2), proj=(3, 3, 3), v0=-900.0, n_steps=120,
+               plate_ductile=[[0.02, 0.0, 30.0], [0.015, 0.4, 30.0]]).write_inp(deck_path)
+    g, got = hakai(deck_path, str(tmp_path / "gpu"), output_num=6, verbose=False)
+    o, ref = hakai(deck_path, str(tmp_path / "cpu"), engine_cls=OracleEngine, output_num=6, verbose=False)
+    assert len(o.deleted_ids()) > 0 and np.array_equal(o.deleted_ids(), g.deleted_ids())
+    assert len(got) == len(ref) == 7
+    for c in range(2):
+        po, pg = o.contact_pair(c), g.contact_pair(c)
+        for k in po:
+            assert np.array_equal(po[k], pg[k]), (c, k)
+    for fa, fb in zip(ref, got):
+        a, b = _vtk_sections(fa), _vtk_sections(fb)
+        assert list(a) == list(b)
+        for k in a:
+            assert a[k].shape == b[k].shape, (os.path.basename(fa), k)
+            if k in ("CELLS", "CELL_TYPES", "POINTS"):
+                assert np.array_equal(a[k], b[k]), (os.path.basename(fa), k)
+            elif k != "TRIAX_STRESS":                            # a ratio that is rounding noise while the plate is at rest
+                scale = max(np.abs(a[k]).max(), 1e-300)
+                assert np.allclose(a[k], b[k], rtol=0, atol=1e-5 * scale), (os.path.basename(fa), k, scale)
