@@ -72,10 +72,11 @@ def prepare_setup(deck, contact="host"):
     return prepare(model, elementVolume=vol, contact=contact)
 
 
-def deck_text(deck, kind):
+def deck_text(deck, kind, myu=0.0):
     if kind == "impact":
         return (f"impact: plate {deck.plate[0]}x{deck.plate[1]}x{deck.plate[2]} (alum, elastoplastic + ductile) + projectile "
-                f"{deck.proj[0]}x{deck.proj[1]}x{deck.proj[2]} (lead) at {deck.v0:g} m/s, frictionless penalty contact")
+                f"{deck.proj[0]}x{deck.proj[1]}x{deck.proj[2]} (lead) at {deck.v0:g} m/s, "
+                f"{'frictionless penalty contact' if myu == 0.0 else f'penalty contact with friction mu = {myu:g}'}")
     return (f"{deck.nx}x{deck.ny}x{deck.nz} hex8, steel {'elastoplastic + ductile damage' if kind == 'ductile' else 'elastoplastic'}"
             f", uniform stretch {deck.strain_per_step:g}/step, jitter {deck.jitter}")
 
@@ -128,7 +129,7 @@ def cpu_sample_for(workload):
     return "S1D" if workload.endswith("D") else "S1"
 
 
-def cpu_oracle_rate(sample_workload, warmup, steps, threads=None):
+def cpu_oracle_rate(sample_workload, warmup, steps, threads=None, contact_myu=0.0):
     """Times the CPU oracle (C++ restatement of HAKAI_j.jl's loop, OpenMP) on a bounded sample."""
     from hakai_fem_b200.model_setup import configure_engine
     from oracle.oracle_engine import OracleEngine
@@ -136,7 +137,7 @@ def cpu_oracle_rate(sample_workload, warmup, steps, threads=None):
         os.environ["OMP_NUM_THREADS"] = str(threads)
     deck, kind = make_deck(sample_workload)
     st = prepare_setup(deck)
-    prm = dict(contact_myu=0.0) if kind == "impact" else {}
+    prm = dict(contact_myu=contact_myu) if kind == "impact" else {}
     eng = configure_engine(OracleEngine, st, **prm)
     if threads:                 # torchrun exports OMP_NUM_THREADS=1 and libgomp may have read it already: set it directly
         try:
@@ -162,7 +163,7 @@ def run_reference(args, emit):
         return
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or cpu_sample_for(args.workload)
-    rate, nE, dt = cpu_oracle_rate(sample, args.warmup, args.steps, threads=cores)
+    rate, nE, dt = cpu_oracle_rate(sample, args.warmup, args.steps, threads=cores, contact_myu=args.contact_myu)
     line = {
         "impl": "reference", "metric": "element-steps/sec (hex8 elastoplastic)", "value": rate,
         "unit": "element-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -221,6 +222,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40, help="timed steps of the CPU baseline sample (~10 s at 16 threads)")
     ap.add_argument("--strain-per-step", type=float, default=None,
                     help="override the deck's stretch rate (1e-6: purely elastic run, SURVEY §8d; disables the regime gate)")
+    ap.add_argument("--contact-myu", type=float, default=0.0,
+                    help="I8: friction coefficient (north star: frictionless; 0.25 = the reference's v0.0.2 default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the partition parity check")
@@ -272,7 +275,7 @@ def main():
     st = prepare_setup(deck, contact="device" if kind == "impact" else "host")
     t_setup = time.perf_counter() - t_setup
     nE, nN = st.model.nElement, st.model.nNode
-    prm = dict(contact_myu=0.0) if kind == "impact" else {}        # north star: frictionless
+    prm = dict(contact_myu=args.contact_myu) if kind == "impact" else {}        # north star: frictionless
 
     def make_engine(**p):
         e_ = Engine(**p)
@@ -524,15 +527,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         sample = args.cpu_sample or cpu_sample_for(args.workload)
-        rate, nEs, dtc = cpu_oracle_rate(sample, 2, args.cpu_steps, threads=cores)
-        rate1, _, dt1 = cpu_oracle_rate(sample, 1, 2, threads=1)      # also OMP_NUM_THREADS=1
+        rate, nEs, dtc = cpu_oracle_rate(sample, 2, args.cpu_steps, threads=cores, contact_myu=args.contact_myu)
+        rate1, _, dt1 = cpu_oracle_rate(sample, 1, 2, threads=1, contact_myu=args.contact_myu)      # also OMP_NUM_THREADS=1
         cpu = {"value": rate, "unit": "element-steps/s", "cores": cores, "kind": "port",
                "sample": f"{sample}: {nEs} elements of the same deck recipe, 2 warm-up + {args.cpu_steps} timed "
                          f"steps ({dtc:.1f} s), OpenMP C++ oracle (our restatement of HAKAI_j.jl, not Julia), {cores} threads",
                "single_thread": {"value": rate1, "cores": 1, "sample": f"same sample, 1 warm-up + 2 timed steps ({dt1:.1f} s)"}}
 
     if rank == 0:
-        cfg = {"workload": args.workload, "elements_per_gpu": nE, "nodes_per_gpu": nN, "deck": deck_text(deck, kind),
+        cfg = {"workload": args.workload, "elements_per_gpu": nE, "nodes_per_gpu": nN, "deck": deck_text(deck, kind, args.contact_myu),
                "regime": regime, "untimed_steps_before_timing": args.warmup + extra,
                "eps_at_start": [s_start["eps_min"], s_start["eps_max"]],
                "live_elements_start": s_start["live_elements"], "live_elements_end": s_end["live_elements"],
