@@ -99,6 +99,7 @@ HK_HD long long hk_ip(const HkDev& d, int row, int k, long long e) {
 struct HkPairDyn {               // current sizes of a pair's lists: device-resident, because exposed faces are
     int nn_i, nn_j, nTri;        // appended on the device (hk_erode_kernel) without the host knowing
     int n_bucket;                // power of two >= 2*nn_i (<= cap_bucket)
+    int n_cand;                  // per step: master triangles that survived the culls (hk_contact_cull_kernel)
 };
 
 struct HkPairDev {               // one ordered contact pair (ContactTriangle, J2:72-78)
@@ -118,6 +119,7 @@ struct HkPairDev {               // one ordered contact pair (ContactTriangle, J
     int* cell_i;                 // [3][cap_i] cell coordinates of the i nodes
     int* head;                   // [cap_bucket] bucket heads (linked lists), -1 = empty
     int* next;                   // [cap_i]
+    int* cand;                   // [cap_tri] ids of the step's surviving master triangles
 };
 
 // exposed-face update on the device (A10, J2:767-804 + add_surface_triangle J2:2167-2245): static per-instance tables

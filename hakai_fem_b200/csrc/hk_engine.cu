@@ -296,7 +296,7 @@ static int pair_upload(hk_engine* e, PairH& p) {
     HkPairDev& D = p.dev;
     if (p.dev_valid) {
         dfree(e, D.nodes_i); dfree(e, D.nodes_j); dfree(e, D.t0); dfree(e, D.t1); dfree(e, D.t2); dfree(e, D.tele);
-        dfree(e, D.bbox); dfree(e, D.cell_i); dfree(e, D.head); dfree(e, D.next); dfree(e, D.dyn);
+        dfree(e, D.bbox); dfree(e, D.cell_i); dfree(e, D.head); dfree(e, D.next); dfree(e, D.dyn); dfree(e, D.cand);
         dfree(e, D.in_i); dfree(e, D.in_j);
         p.dev_valid = false;
     }
@@ -324,6 +324,7 @@ static int pair_upload(hk_engine* e, PairH& p) {
     if ((rc = dalloc(e, &D.cell_i, (size_t)3 * D.cap_i))) return rc;
     if ((rc = dalloc(e, &D.head, (size_t)D.cap_bucket))) return rc;
     if ((rc = dalloc(e, &D.next, (size_t)D.cap_i))) return rc;
+    if ((rc = dalloc(e, &D.cand, (size_t)D.cap_tri))) return rc;
     if ((rc = dalloc(e, &D.dyn, (size_t)1))) return rc;
     if ((rc = upload(e, D.nodes_i, p.nodes_i))) return rc;
     if ((rc = upload(e, D.nodes_j, p.nodes_j))) return rc;
@@ -331,7 +332,7 @@ static int pair_upload(hk_engine* e, PairH& p) {
     if ((rc = upload(e, D.t1, p.t1))) return rc;
     if ((rc = upload(e, D.t2, p.t2))) return rc;
     if ((rc = upload(e, D.tele, p.tele))) return rc;
-    const HkPairDyn dyn = {nn_i, nn_j, nTri, pow2(nn_i)};
+    const HkPairDyn dyn = {nn_i, nn_j, nTri, pow2(nn_i), 0};
     CK(hkp::h2d(D.dyn, &dyn, sizeof(dyn), e->stream));
     if (ei || ej) {                                   // membership bytes for the device-side `unique!` (J2:786, 791)
         std::vector<unsigned char> in(e->nNode, 0);

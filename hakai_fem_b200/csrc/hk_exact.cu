@@ -303,137 +303,162 @@ HK_D void contact_cells_body(const ContactArgs& A, long long k) {
     p.next[k] = hk_atomic_exch_i32(&p.head[h], (int)k);
 }
 
-// one master triangle against the slave nodes of the 27 neighbouring cells (J2:2370-2692)
-HK_D void contact_tri_body(const ContactArgs& A, long long j) {
+// one master triangle against the slave nodes of the 27 neighbouring cells (J2:2370-2692), in two parts: everything
+// that depends on the triangle only (flag, culls against the overlap box, normal, area, the node-independent half of
+// my3SolveAb, the cell of vertex j0) and the walk through ONE of the 27 cells.  The serial form does both for all cells;
+// on the GPU one thread per triangle culls and a warp per surviving triangle walks its cells in parallel — the force sums
+// are exact integers, so the order of the hits does not matter.
+struct TriCtx {
+    int eleid, j0, j1, j2;
+    double q0x, q0y, q0z, cx, cy, cz, Rmax, Lmax, S, nx, ny, nz, detA;
+    double im11, im12, im13, im21, im22, im23, im31, im32, im33;
+    int cj[3];
+    PairBox b;
+};
+
+HK_D bool contact_tri_prepare(const ContactArgs& A, long long j, TriCtx& T) {
     const HkDev& d = A.d;
     const HkPairDev& p = A.p;
-    const HkContactParams& cp = A.cp;
-    const int eleid = p.tele[j];
-    if (d.flag[eleid] != 1) return;                               // J2:2373-2376
-    const PairBox b = pair_box(p);
-    if (b.skip) return;
-    const double kc = p.self ? cp.kc_s : cp.kc_o;
-    const double Cr = p.self ? cp.cr_s : cp.cr_o;
-    const double ddiv = p.self ? cp.ddiv_s : cp.ddiv_o;
+    T.eleid = p.tele[j];
+    if (d.flag[T.eleid] != 1) return false;                       // J2:2373-2376
+    T.b = pair_box(p);
+    const PairBox& b = T.b;
+    if (b.skip) return false;
+    const double ddiv = p.self ? A.cp.ddiv_s : A.cp.ddiv_o;
     const int j0 = p.t0[j], j1 = p.t1[j], j2 = p.t2[j];
+    T.j0 = j0; T.j1 = j1; T.j2 = j2;
     const double q0x = d.rec[6ll * j0], q0y = d.rec[6ll * j0 + 1], q0z = d.rec[6ll * j0 + 2];
     const double q1x = d.rec[6ll * j1], q1y = d.rec[6ll * j1 + 1], q1z = d.rec[6ll * j1 + 2];
     const double q2x = d.rec[6ll * j2], q2y = d.rec[6ll * j2 + 1], q2z = d.rec[6ll * j2 + 2];
-    if (q0x < b.range_min[0] && q1x < b.range_min[0] && q2x < b.range_min[0]) return;
-    if (q0y < b.range_min[1] && q1y < b.range_min[1] && q2y < b.range_min[1]) return;
-    if (q0z < b.range_min[2] && q1z < b.range_min[2] && q2z < b.range_min[2]) return;
-    if (q0x > b.range_max[0] && q1x > b.range_max[0] && q2x > b.range_max[0]) return;
-    if (q0y > b.range_max[1] && q1y > b.range_max[1] && q2y > b.range_max[1]) return;
-    if (q0z > b.range_max[2] && q1z > b.range_max[2] && q2z > b.range_max[2]) return;
-
+    if (q0x < b.range_min[0] && q1x < b.range_min[0] && q2x < b.range_min[0]) return false;
+    if (q0y < b.range_min[1] && q1y < b.range_min[1] && q2y < b.range_min[1]) return false;
+    if (q0z < b.range_min[2] && q1z < b.range_min[2] && q2z < b.range_min[2]) return false;
+    if (q0x > b.range_max[0] && q1x > b.range_max[0] && q2x > b.range_max[0]) return false;
+    if (q0y > b.range_max[1] && q1y > b.range_max[1] && q2y > b.range_max[1]) return false;
+    if (q0z > b.range_max[2] && q1z > b.range_max[2] && q2z > b.range_max[2]) return false;
+    T.q0x = q0x; T.q0y = q0y; T.q0z = q0z;
     const double cx = (q0x + q1x + q2x) / 3.0, cy = (q0y + q1y + q2y) / 3.0, cz = (q0z + q1z + q2z) / 3.0;
+    T.cx = cx; T.cy = cy; T.cz = cz;
     const double R0 = my3norm(q0x - cx, q0y - cy, q0z - cz);
     const double R1 = my3norm(q1x - cx, q1y - cy, q1z - cz);
     const double R2 = my3norm(q2x - cx, q2y - cy, q2z - cz);
-    const double Rmax = fmax(fmax(R0, R1), R2);
+    T.Rmax = fmax(fmax(R0, R1), R2);
     const double v1x = q1x - q0x, v1y = q1y - q0y, v1z = q1z - q0z;
     const double v2x = q2x - q0x, v2y = q2y - q0y, v2z = q2z - q0z;
     const double L1 = my3norm(v1x, v1y, v1z), L2 = my3norm(v2x, v2y, v2z);
-    const double Lmax = fmax(L1, L2);
+    T.Lmax = fmax(L1, L2);
     double nx = v1y * v2z - v1z * v2y;                            // my3crossNNz, J2:3209
     double ny = v1z * v2x - v1x * v2z;
     double nz = v1x * v2y - v1y * v2x;
     const double mag_n = sqrt(nx * nx + ny * ny + nz * nz);
     nx = nx / mag_n; ny = ny / mag_n; nz = nz / mag_n;
+    T.nx = nx; T.ny = ny; T.nz = nz;
     const double d12 = v1x * v2x + v1y * v2y + v1z * v2z;
-    const double S = 0.5 * sqrt(L1 * L1 * L2 * L2 - d12 * d12);
+    T.S = 0.5 * sqrt(L1 * L1 * L2 * L2 - d12 * d12);
     const double A11 = v1x, A21 = v1y, A31 = v1z, A12 = v2x, A22 = v2y, A32 = v2z;
     const double A13 = -nx, A23 = -ny, A33 = -nz;
     // my3SolveAb, J2:3342: the parts that do not depend on the node
-    const double detA = (A11 * A22 * A33 + A12 * A23 * A31 + A13 * A21 * A32 - A11 * A23 * A32 - A12 * A21 * A33 -
-                         A13 * A22 * A31);
-    const double im11 = A22 * A33 - A23 * A32, im21 = A23 * A31 - A21 * A33, im31 = A21 * A32 - A22 * A31;
-    const double im12 = A13 * A32 - A12 * A33, im22 = A11 * A33 - A13 * A31, im32 = A12 * A31 - A11 * A32;
-    const double im13 = A12 * A23 - A13 * A22, im23 = A13 * A21 - A11 * A23, im33 = A11 * A22 - A12 * A21;
-
+    T.detA = (A11 * A22 * A33 + A12 * A23 * A31 + A13 * A21 * A32 - A11 * A23 * A32 - A12 * A21 * A33 -
+              A13 * A22 * A31);
+    T.im11 = A22 * A33 - A23 * A32; T.im21 = A23 * A31 - A21 * A33; T.im31 = A21 * A32 - A22 * A31;
+    T.im12 = A13 * A32 - A12 * A33; T.im22 = A11 * A33 - A13 * A31; T.im32 = A12 * A31 - A11 * A32;
+    T.im13 = A12 * A23 - A13 * A22; T.im23 = A13 * A21 - A11 * A23; T.im33 = A11 * A22 - A12 * A21;
     // cell of vertex j0 (J2:2351-2363, 2462-2472): same formula, evaluated directly on j0's position
-    int cj[3];
-    cj[0] = (int)ceil((q0x - b.all_min[0]) / ddiv);
-    cj[1] = (int)ceil((q0y - b.all_min[1]) / ddiv);
-    cj[2] = (int)ceil((q0z - b.all_min[2]) / ddiv);
+    T.cj[0] = (int)ceil((q0x - b.all_min[0]) / ddiv);
+    T.cj[1] = (int)ceil((q0y - b.all_min[1]) / ddiv);
+    T.cj[2] = (int)ceil((q0z - b.all_min[2]) / ddiv);
+    return true;
+}
 
-    int en[8];
-    if (p.self)
-        for (int q = 0; q < 8; ++q) en[q] = d.conn[(long long)q * d.nEp + eleid];
-
-    unsigned long long n_tests = 0, n_hits = 0;
+// slave nodes of cell (cj + (dx, dy, dz)) against the prepared triangle
+HK_D void contact_tri_cell(const ContactArgs& A, const TriCtx& T, int dx, int dy, int dz, unsigned long long& n_tests,
+                           unsigned long long& n_hits) {
+    const HkDev& d = A.d;
+    const HkPairDev& p = A.p;
+    const HkContactParams& cp = A.cp;
+    const PairBox& b = T.b;
+    const double kc = p.self ? cp.kc_s : cp.kc_o;
+    const double Cr = p.self ? cp.cr_s : cp.cr_o;
+    const int j0 = T.j0;
+    const double nx = T.nx, ny = T.ny, nz = T.nz;
     const unsigned bucket_mask = (unsigned)(p.dyn->n_bucket - 1);
+    const int ccx = T.cj[0] + dx, ccy = T.cj[1] + dy, ccz = T.cj[2] + dz;
+    const unsigned h = cell_hash(ccx, ccy, ccz) & bucket_mask;
+    for (int k = p.head[h]; k >= 0; k = p.next[k]) {
+        if (p.cell_i[k] != ccx || p.cell_i[p.cap_i + k] != ccy || p.cell_i[2ll * p.cap_i + k] != ccz) continue;
+        const int i = p.nodes_i[k];
+        if (p.self) {
+            bool own = false;
+            for (int q = 0; q < 8; ++q) own = own || (i == d.conn[(long long)q * d.nEp + T.eleid]);
+            if (own) continue;
+        }
+        const double px = d.rec[6ll * i], py = d.rec[6ll * i + 1], pz = d.rec[6ll * i + 2];
+        if (px < b.range_min[0] || py < b.range_min[1] || pz < b.range_min[2]) continue;
+        if (px > b.range_max[0] || py > b.range_max[1] || pz > b.range_max[2]) continue;
+        const double dpc = my3norm(px - T.cx, py - T.cy, pz - T.cz);
+        if (dpc >= T.Rmax) continue;
+        const double bx = px - T.q0x, by = py - T.q0y, bz = pz - T.q0z;
+        ++n_tests;
+        const double x1 = (T.im11 * bx + T.im12 * by + T.im13 * bz) / T.detA;
+        const double x2 = (T.im21 * bx + T.im22 * by + T.im23 * bz) / T.detA;
+        const double dd = (T.im31 * bx + T.im32 * by + T.im33 * bz) / T.detA;
+        if (0.0 <= x1 && 0.0 <= x2 && x1 + x2 <= 1.0 && dd > 0.0 && dd <= cp.d_lim) {
+            ++n_hits;
+            const int slot_i = d.spec[d.spec_idx[i]].contact_slot;
+            double dcl = dd;
+            if (cp.clamp) {                           // J1:2756-2758
+                double dmax;
+                const unsigned long long mb = *cp.dmax;
+                memcpy(&dmax, &mb, 8);
+                const double pre = cp.dnode_pre[slot_i];
+                if (dcl - pre > dmax) dcl = pre + dmax;
+            }
+            const double vx = d.velo[3ll * i] - d.velo[3ll * j0];
+            const double vy = d.velo[3ll * i + 1] - d.velo[3ll * j0 + 1];
+            const double vz = d.velo[3ll * i + 2] - d.velo[3ll * j0 + 2];
+            const double mag_v = my3norm(vx, vy, vz);
+            double vex = 0.0, vey = 0.0, vez = 0.0;
+            if (mag_v > 0.0) { vex = vx / mag_v; vey = vy / mag_v; vez = vz / mag_v; }
+            const double k_ = p.young * T.S / T.Lmax * kc;
+            const double F = k_ * dcl;
+            double fx = F * nx, fy = F * ny, fz = F * nz;
+            // damping: diag_M[i] is indexed with the NODE id in the reference (J2:2593)
+            const double C = 2 * sqrt(d.mass[i / 3] * k_) * Cr;
+            const double fc_x = -C * vx, fc_y = -C * vy, fc_z = -C * vz;
+            const double dot_ve_n = vex * nx + vey * ny + vez * nz;
+            const double vsx = vex - dot_ve_n * nx, vsy = vey - dot_ve_n * ny, vsz = vez - dot_ve_n * nz;
+            const double fric_x = -cp.myu * F * vsx, fric_y = -cp.myu * F * vsy, fric_z = -cp.myu * F * vsz;
+            fx += fric_x + fc_x;
+            fy += fric_y + fc_y;
+            fz += fric_z + fc_z;
+            const double f[3] = {fx, fy, fz};
+            const double f3[3] = {-fx / 3.0, -fy / 3.0, -fz / 3.0};
+            unsigned long long* ovf = &d.counters[3];
+            for (int c = 0; c < 3; ++c) fx_atomic_add(d.cacc + 6ll * slot_i + 2 * c, f[c], cp.lsb_exp, ovf);
+            if (cp.clamp) {                           // d_node[i] = max(d_node[i], d), J1:2898-2900
+                unsigned long long bits;
+                memcpy(&bits, &dcl, 8);
+                hk_atomic_max_u64(reinterpret_cast<unsigned long long*>(cp.dnode + slot_i), bits);
+            }
+            const int jn[3] = {j0, T.j1, T.j2};
+            for (int q = 0; q < 3; ++q) {
+                const int slot = d.spec[d.spec_idx[jn[q]]].contact_slot;
+                for (int c = 0; c < 3; ++c) fx_atomic_add(d.cacc + 6ll * slot + 2 * c, f3[c], cp.lsb_exp, ovf);
+            }
+        }
+    }
+}
+
+// serial form: one triangle, all 27 cells (the host-compiled build; the order the reference visits them in)
+HK_D void contact_tri_body(const ContactArgs& A, long long j) {
+    TriCtx T;
+    if (!contact_tri_prepare(A, j, T)) return;
+    unsigned long long n_tests = 0, n_hits = 0;
     for (int dz = -1; dz <= 1; ++dz)
         for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int ccx = cj[0] + dx, ccy = cj[1] + dy, ccz = cj[2] + dz;
-                const unsigned h = cell_hash(ccx, ccy, ccz) & bucket_mask;
-                for (int k = p.head[h]; k >= 0; k = p.next[k]) {
-                    if (p.cell_i[k] != ccx || p.cell_i[p.cap_i + k] != ccy || p.cell_i[2ll * p.cap_i + k] != ccz) continue;
-                    const int i = p.nodes_i[k];
-                    if (p.self) {
-                        bool own = false;
-                        for (int q = 0; q < 8; ++q) own = own || (i == en[q]);
-                        if (own) continue;
-                    }
-                    const double px = d.rec[6ll * i], py = d.rec[6ll * i + 1], pz = d.rec[6ll * i + 2];
-                    if (px < b.range_min[0] || py < b.range_min[1] || pz < b.range_min[2]) continue;
-                    if (px > b.range_max[0] || py > b.range_max[1] || pz > b.range_max[2]) continue;
-                    const double dpc = my3norm(px - cx, py - cy, pz - cz);
-                    if (dpc >= Rmax) continue;
-                    const double bx = px - q0x, by = py - q0y, bz = pz - q0z;
-                    ++n_tests;
-                    const double x1 = (im11 * bx + im12 * by + im13 * bz) / detA;
-                    const double x2 = (im21 * bx + im22 * by + im23 * bz) / detA;
-                    const double dd = (im31 * bx + im32 * by + im33 * bz) / detA;
-                    if (0.0 <= x1 && 0.0 <= x2 && x1 + x2 <= 1.0 && dd > 0.0 && dd <= cp.d_lim) {
-                        ++n_hits;
-                        const int slot_i = d.spec[d.spec_idx[i]].contact_slot;
-                        double dcl = dd;
-                        if (cp.clamp) {                           // J1:2756-2758
-                            double dmax;
-                            const unsigned long long mb = *cp.dmax;
-                            memcpy(&dmax, &mb, 8);
-                            const double pre = cp.dnode_pre[slot_i];
-                            if (dcl - pre > dmax) dcl = pre + dmax;
-                        }
-                        const double vx = d.velo[3ll * i] - d.velo[3ll * j0];
-                        const double vy = d.velo[3ll * i + 1] - d.velo[3ll * j0 + 1];
-                        const double vz = d.velo[3ll * i + 2] - d.velo[3ll * j0 + 2];
-                        const double mag_v = my3norm(vx, vy, vz);
-                        double vex = 0.0, vey = 0.0, vez = 0.0;
-                        if (mag_v > 0.0) { vex = vx / mag_v; vey = vy / mag_v; vez = vz / mag_v; }
-                        const double k_ = p.young * S / Lmax * kc;
-                        const double F = k_ * dcl;
-                        double fx = F * nx, fy = F * ny, fz = F * nz;
-                        // damping: diag_M[i] is indexed with the NODE id in the reference (J2:2593)
-                        const double C = 2 * sqrt(d.mass[i / 3] * k_) * Cr;
-                        const double fc_x = -C * vx, fc_y = -C * vy, fc_z = -C * vz;
-                        const double dot_ve_n = vex * nx + vey * ny + vez * nz;
-                        const double vsx = vex - dot_ve_n * nx, vsy = vey - dot_ve_n * ny, vsz = vez - dot_ve_n * nz;
-                        const double fric_x = -cp.myu * F * vsx, fric_y = -cp.myu * F * vsy, fric_z = -cp.myu * F * vsz;
-                        fx += fric_x + fc_x;
-                        fy += fric_y + fc_y;
-                        fz += fric_z + fc_z;
-                        const double f[3] = {fx, fy, fz};
-                        const double f3[3] = {-fx / 3.0, -fy / 3.0, -fz / 3.0};
-                        unsigned long long* ovf = &d.counters[3];
-                        for (int c = 0; c < 3; ++c) fx_atomic_add(d.cacc + 6ll * slot_i + 2 * c, f[c], cp.lsb_exp, ovf);
-                        if (cp.clamp) {                           // d_node[i] = max(d_node[i], d), J1:2898-2900
-                            unsigned long long bits;
-                            memcpy(&bits, &dcl, 8);
-                            hk_atomic_max_u64(reinterpret_cast<unsigned long long*>(cp.dnode + slot_i), bits);
-                        }
-                        const int jn[3] = {j0, j1, j2};
-                        for (int q = 0; q < 3; ++q) {
-                            const int slot = d.spec[d.spec_idx[jn[q]]].contact_slot;
-                            for (int c = 0; c < 3; ++c) fx_atomic_add(d.cacc + 6ll * slot + 2 * c, f3[c], cp.lsb_exp, ovf);
-                        }
-                    }
-                }
-            }
-    if (n_tests) hk_atomic_add_u64(&d.counters[2], n_tests);
-    if (n_hits) hk_atomic_add_u64(&d.counters[1], n_hits);
+            for (int dx = -1; dx <= 1; ++dx) contact_tri_cell(A, T, dx, dy, dz, n_tests, n_hits);
+    if (n_tests) hk_atomic_add_u64(&A.d.counters[2], n_tests);
+    if (n_hits) hk_atomic_add_u64(&A.d.counters[1], n_hits);
 }
 
 #ifndef HK_EMU
@@ -475,14 +500,47 @@ __global__ void hk_contact_cells_kernel(ContactArgs A) {
     const long long n = A.p.dyn->nn_i, stride = (long long)gridDim.x * blockDim.x;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += stride) contact_cells_body(A, k);
 }
-__global__ void __launch_bounds__(128) hk_contact_narrow_kernel(ContactArgs A) {
+// narrow phase in two kernels.  cull: one thread per master triangle — dead element, overlap-box culls (J2:2373-2440);
+// the survivors (the triangles of the contact zone: thousands out of a million) are compacted into p.cand.
+// narrow: one WARP per surviving triangle, lane c < 27 walks cell c's bucket chain.  One thread walking 27 chains of
+// dependent loads per triangle took 100-200 us per pair at 4 warps active per SM (ncu, round 2): the few triangles in
+// the contact zone set the kernel's time.
+__global__ void __launch_bounds__(256) hk_contact_cull_kernel(ContactArgs A) {
     const long long n = A.p.dyn->nTri, stride = (long long)gridDim.x * blockDim.x;
-    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += stride) contact_tri_body(A, j);
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += stride) {
+        const HkDev& d = A.d;
+        const HkPairDev& p = A.p;
+        if (d.flag[p.tele[j]] != 1) continue;
+        const PairBox b = pair_box(p);
+        if (b.skip) continue;
+        const int j0 = p.t0[j], j1 = p.t1[j], j2 = p.t2[j];
+        bool out = false;
+        for (int a = 0; a < 3; ++a) {
+            const double q0 = d.rec[6ll * j0 + a], q1 = d.rec[6ll * j1 + a], q2 = d.rec[6ll * j2 + a];
+            out = out || (q0 < b.range_min[a] && q1 < b.range_min[a] && q2 < b.range_min[a]) ||
+                  (q0 > b.range_max[a] && q1 > b.range_max[a] && q2 > b.range_max[a]);
+        }
+        if (!out) p.cand[atomicAdd(&p.dyn->n_cand, 1)] = (int)j;
+    }
+}
+__global__ void __launch_bounds__(128) hk_contact_narrow_kernel(ContactArgs A) {
+    const int n = A.p.dyn->n_cand;
+    const int lane = threadIdx.x & 31;
+    const int warps = (int)(gridDim.x * (blockDim.x >> 5));
+    for (int w = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); w < n; w += warps) {
+        TriCtx T;
+        if (!contact_tri_prepare(A, A.p.cand[w], T)) continue;       // (never: the cull kernel applied the same tests)
+        unsigned long long n_tests = 0, n_hits = 0;
+        if (lane < 27) contact_tri_cell(A, T, lane % 3 - 1, (lane / 3) % 3 - 1, lane / 9 - 1, n_tests, n_hits);
+        if (n_tests) hk_atomic_add_u64(&A.d.counters[2], n_tests);
+        if (n_hits) hk_atomic_add_u64(&A.d.counters[1], n_hits);
+    }
 }
 __global__ void hk_contact_reset_kernel(HkPairDev p) {
     const long long n = p.dyn->n_bucket, stride = (long long)gridDim.x * blockDim.x;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += stride) p.head[t] = -1;
     if (blockIdx.x == 0 && threadIdx.x < 12) p.bbox[threadIdx.x] = ((threadIdx.x % 6) < 3) ? ~0ull : 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 12) p.dyn->n_cand = 0;
 }
 static unsigned contact_grid(long long cap, int block, int n_sm) {
     long long g = (cap + block - 1) / block, mx = (long long)(n_sm > 0 ? n_sm : 148) * 32;
@@ -496,9 +554,14 @@ void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams
     ContactArgs A{d, p, cp};
 #ifndef HK_EMU
     hk_contact_reset_kernel<<<contact_grid(p.cap_bucket, 256, d.n_sm), 256, 0, s>>>(p);
-    hk_contact_bbox_kernel<<<contact_grid((long long)p.cap_i + p.cap_j, 256, d.n_sm), 256, 0, s>>>(A);
+    {   // few blocks, several nodes per thread: the warp reduction (120 shuffles) and the 12 atomics are per warp
+        unsigned g = contact_grid((long long)p.cap_i + p.cap_j, 256, d.n_sm);
+        const unsigned cap = (unsigned)(d.n_sm > 0 ? d.n_sm : 148) * 2;
+        hk_contact_bbox_kernel<<<g < cap ? g : cap, 256, 0, s>>>(A);
+    }
     hk_contact_cells_kernel<<<contact_grid(p.cap_i, 256, d.n_sm), 256, 0, s>>>(A);
-    hk_contact_narrow_kernel<<<contact_grid(p.cap_tri, 128, d.n_sm), 128, 0, s>>>(A);
+    hk_contact_cull_kernel<<<contact_grid(p.cap_tri, 256, d.n_sm), 256, 0, s>>>(A);
+    hk_contact_narrow_kernel<<<contact_grid((long long)p.cap_tri * 32, 128, d.n_sm) / 4 + 1, 128, 0, s>>>(A);      // candidates are few: <= 8 blocks per SM
 #else
     for (int t = 0; t < p.dyn->n_bucket; ++t) p.head[t] = -1;
     for (int t = 0; t < 12; ++t) p.bbox[t] = ((t % 6) < 3) ? ~0ull : 0ull;
