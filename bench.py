@@ -439,7 +439,7 @@ def main():
                    "setup": "hk_build_contact: faces, orientation, exterior faces and exposed-face twins by radix sort on the GPU "
                             "(engine_setup_s includes it)",
                    "fixed_point_overflows": int(c1[5]),
-                   "kernels": "hk_contact_{reset,bbox,cells,narrow}_kernel per ordered pair + accumulator memset"}
+                   "kernels": "hk_contact_{reset,bbox,cells,cull,narrow}_kernel per ordered pair + accumulator zeroing"}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
     e2e = None

@@ -1420,7 +1420,7 @@ static int contact_pass(hk_engine* e) {
         e->cp.dmax = e->d_dmax + cur;
         CK(hkp::dev_memset(e->cp.dnode, 0, e->dnode_cap * sizeof(double), e->stream));
     }
-    for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 4; }
+    for (PairH& p : e->pairs) { hk_launch_contact(d, p.dev, e->cp, e->stream); e->n_launch += 5; }   // reset, bbox, cells, cull, narrow
     prof_end(e);
     return 0;
 }
