@@ -598,12 +598,14 @@ static int launch_ring(const ElemArgs& A, int n_sm, cudaStream_t s) {
 // per group, prefetch (0 none, 1 connectivity, 2 connectivity + material ids + flags)
 struct RingVariant { int id, ng, wg, stages, cp; };
 static const RingVariant kVariants[] = {
-    {11, 1, 11, 4, 0},      // one group of 11 warps (tile 352), no prefetch
+    {13, 1, 11, 4, 2},      // default: one group of 11 warps (tile 352), conn + mat + flag prefetched, evict-first L2 policy
+#ifdef HK_AB_VARIANTS       // `make ab`: the comparison kernels of scripts/ab_element.py; not in the shipped library
+    {11, 1, 11, 4, 0},      // no prefetch
     {12, 1, 11, 4, 1},
-    {13, 1, 11, 4, 2},      // default: + evict-first L2 policy on the state stream
-    {14, 1, 11, 4, 2},      //   the same without the policy
+    {14, 1, 11, 4, 2},      // default without the L2 policy
     {20, 2, 5, 4, 1},       // two phase-shifted groups of 5 warps (tile 160)
     {25, 2, 5, 4, 2},
+#endif
 };
 #define HK_DEFAULT_VARIANT 13
 
@@ -625,11 +627,13 @@ int hk_launch_element(const HkDev& d, long long step, int write_triax, cudaStrea
             hk_element_simple_kernel<<<(unsigned)((d.nElement + block - 1) / block), block, 0, s>>>(A);
             return 0;
         }
+#ifdef HK_AB_VARIANTS
         case 11: return launch_ring<1, 11, 4, 0>(A, d.n_sm, s);
         case 12: return launch_ring<1, 11, 4, 1>(A, d.n_sm, s);
         case 14: return launch_ring<1, 11, 4, 2>(A, d.n_sm, s);
         case 20: return launch_ring<2, 5, 4, 1>(A, d.n_sm, s);
         case 25: return launch_ring<2, 5, 4, 2>(A, d.n_sm, s);
+#endif
         default: return launch_ring<1, 11, 4, 2, 1>(A, d.n_sm, s);
     }
 #else

@@ -3,6 +3,7 @@ the deck is built once, every configuration gets its own engine, configurations 
 times, each visit = warm-up into the plastic regime + `--steps` timed steps with CUDA events around every launch.
 
   python scripts/ab_element.py --configs "20,1,;12,1,;20,0,;20,1,red" [--workload W16] [--steps 30] [--rounds 2]
+Build the comparison kernels first: make -C hakai_fem_b200/csrc ab (the shipped library holds the default only).
 A configuration is variant,rec_soa,experiment (HK_ELEMENT_VARIANT, HK_REC_SOA, HK_EXPERIMENT).  Prints one JSON line per visit and a summary."""
 import argparse
 import json
