@@ -9,7 +9,7 @@ cd "$ROOT/hakai_fem_b200/csrc" || exit 1
 ASAN_LIB="$(/usr/bin/g++ -print-file-name=libasan.so)"
 /usr/bin/g++ -x c++ -DHK_EMU -O1 -g -std=c++17 -fPIC -ffp-contract=off -fsanitize=address,undefined \
     -fno-omit-frame-pointer -Wno-unknown-pragmas -shared -o ../../tests/emu/libhakai_emu.so \
-    hk_exact.cu hk_element.cu hk_engine.cu || exit 1
+    hk_exact.cu hk_element.cu hk_engine.cu hk_setup.cu || exit 1
 cd "$ROOT" || exit 1
 ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 LD_PRELOAD="$ASAN_LIB" \
     python -m pytest tests/test_emu_parity.py tests/test_abi_errors.py tests/test_checkpoint.py tests/test_multi_gloo.py \
