@@ -97,7 +97,7 @@ HK_HD long long hk_ip(const HkDev& d, int row, int k, long long e) {
 }
 
 struct HkPairDyn {               // current sizes of a pair's lists: device-resident, because exposed faces are
-    int nn_i, nn_j, nTri;        // appended on the device (hk_erode_kernel) without the host knowing
+    int nn_i, nn_j, nTri;        // appended on the device (erode_element) without the host knowing
     int n_bucket;                // power of two >= 2*nn_i (<= cap_bucket)
     int n_cand;                  // per step: master triangles that survived the culls (hk_contact_cull_kernel)
 };
@@ -130,7 +130,7 @@ struct HkInstDev {
     int* twin;                   // [F] first face (in face-id order) of ANOTHER element with the same node set, or -1
 };
 
-struct HkErodeDev {              // everything hk_erode_kernel needs
+struct HkErodeDev {              // everything erode_element needs
     int n_inst, n_pair;
     HkInstDev* inst;
     HkPairDev* pairs;            // device copy of the pair descriptors

@@ -54,7 +54,7 @@ struct PairH {
     HkPairDev dev;
     bool dev_valid = false;
 };
-struct InstDevH {                   // device tables of one instance for hk_erode_kernel
+struct InstDevH {                   // device tables of one instance for erode_element
     int* surf = nullptr;
     int* feleid = nullptr;
     int* twin = nullptr;
@@ -117,7 +117,7 @@ struct hk_engine {
     int* d_node_list[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     long long* d_import_src = nullptr;
     // exposed-face update on the device (single-domain engines whose contact surfaces can erode)
-    bool dev_erosion = false;      // tables built, hk_erode_kernel runs after every step
+    bool dev_erosion = false;      // tables built, erode_element runs after every step
     bool erosion_checked = false;  // decided at the first step (multi-GPU drivers call hk_set_global_maps after finalize)
     bool contact_host_stale = false;   // device lists may have grown since the host mirrors were read
     std::vector<char> inst_erodes; // per instance: has surfaces and an element whose material can fail
@@ -291,7 +291,7 @@ static bool inst_can_erode(const hk_engine* e, int64_t inst) {
 
 // (re)creates the device arrays of a pair from the host mirrors.  With device-side erosion the lists are allocated at
 // their worst-case length (every node of an eroding instance exposed, two triangles per face of its elements), so
-// hk_erode_kernel can append without the host.
+// erode_element can append without the host.
 static int pair_upload(hk_engine* e, PairH& p) {
     HkPairDev& D = p.dev;
     if (p.dev_valid) {
@@ -675,7 +675,7 @@ static int ensure_erosion(hk_engine* e) {
     return erosion_upload_descriptors(e);
 }
 
-// Host mirrors of everything hk_erode_kernel may have grown: pair lists, special-node table, slot count.
+// Host mirrors of everything erode_element may have grown: pair lists, special-node table, slot count.
 static int contact_refresh_host(hk_engine* e) {
     if (!e->dev_erosion || !e->contact_host_stale) return 0;
     CK(hkp::sync(e->stream));

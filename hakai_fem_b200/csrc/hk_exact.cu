@@ -463,7 +463,7 @@ HK_D void contact_tri_body(const ContactArgs& A, long long j) {
 
 #ifndef HK_EMU
 // All contact kernels are grid-stride over list lengths that live on the device (HkPairDyn): the lists grow when
-// deleted elements expose new faces (hk_erode_kernel), and the host never has to know by how much.
+// deleted elements expose new faces (erode_element), and the host never has to know by how much.
 __global__ void hk_contact_bbox_kernel(ContactArgs A) {
     const long long nn_i = A.p.dyn->nn_i;
     const long long n = nn_i + A.p.dyn->nn_j;
