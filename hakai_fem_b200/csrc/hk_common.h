@@ -72,6 +72,7 @@ struct HkDev {
                           // 12 eps (integ_eq_plastic_strain), 13 yield (integ_yield_stress): the 14 rows x TL
                           // elements of one Gauss point of one tile are ONE contiguous burst (14*TL*8 bytes)
     int element_mode;     // hk_params.element_mode (1: reference-order kernel)
+    const long long* t_dev;   // step replay by CUDA graph: the step number t lives on the device (NULL: passed by value)
     int variant;          // element-kernel variant (hk_element.cu: kVariants; 1 = simple kernel)
     int n_sm;             // multiprocessors of the engine's device (grid of the persistent kernels)
     int TL;               // layout tile = elements per tile of the element kernel in use; nEp % TL == 0
@@ -167,6 +168,8 @@ void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams
 // deletion pass of a step: elements the element kernel marked (flag 3) are appended to the deletion log in ascending
 // id order (the reference's order, J2:701-735), their stress/strain zeroed (J2:742-756), and the faces they expose join
 // the contact surfaces (er != NULL)
+void hk_launch_step_set(long long* t_dev, long long t, cudaStream_t s);      // *t_dev = t
+void hk_launch_step_advance(long long* t_dev, cudaStream_t s);               // ++*t_dev (last node of a captured step)
 void hk_launch_deletion_pass(const HkDev& d, const HkErodeDev* er, long long step, cudaStream_t s, long long* n_launch,
                              long long* send = nullptr, const int* e_l2g = nullptr, int cap = 0);
 // partitioned meshes: replays the deletions of ALL ranks of one step, `gathered` = [world][cap + 1] = {n, global 0-based

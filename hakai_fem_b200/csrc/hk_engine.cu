@@ -132,6 +132,17 @@ struct hk_engine {
     bool frame_next = false;       // hk_mark_frame: the next asynchronous step stores integ_triax_stress
     // multi-GPU erosion: instance tables are GLOBAL; these map global (1-based) ids to engine-local 0-based ids or -1
     std::vector<int> g_node_map, g_elem_map;
+    // step replay by CUDA graph (single-domain engines on their own stream): the launches of ONE step captured once and
+    // replayed for every further step; the step number lives on the device (d.t_dev).  Small decks are bound by the
+    // host's launch rate (the reference's example decks: 16 launches and 190 us of host time per step of 25 us of kernels).
+    long long* d_step = nullptr;
+#ifndef HK_EMU
+    cudaGraphExec_t step_graph = nullptr;
+#endif
+    bool capturing = false;
+    bool graph_dirty = true;       // set by every device (re)allocation and by anything else a captured launch depends on
+    bool graph_off = false;        // HK_STEP_GRAPH=0, or a capture failed: plain launches from then on
+    long long graph_launches = 0;  // kernel launches inside one replay
     // hk_comm_erosion: deletions of all ranks replayed on the device (static exchange lists over every candidate node)
     bool xerode = false;
     int xe_cap = 0;                // deletions per rank and step the all-gather carries
@@ -205,10 +216,12 @@ static int dalloc(hk_engine* e, T** p, size_t count) {
     int rc = hkp::dev_malloc(&q, count * sizeof(T));
     if (rc) return cuda_fail(e, rc, "device allocation");
     e->allocs.push_back(q);
+    e->graph_dirty = true;
     *p = (T*)q;
     return 0;
 }
 static void dfree(hk_engine* e, void* p) {
+    e->graph_dirty = true;
     if (!p) return;
     auto it = std::find(e->allocs.begin(), e->allocs.end(), p);
     if (it != e->allocs.end()) e->allocs.erase(it);
@@ -871,6 +884,7 @@ int HKAPI(create)(hk_engine** out, const hk_params* p) {
     rc = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (rc != cudaSuccess) { delete e; return fail(nullptr, HK_ERR_CUDA, cudaGetErrorString(rc)); }
     e->own_stream = true;
+    if (const char* g = getenv("HK_STEP_GRAPH")) e->graph_off = atoi(g) == 0;      // HK_STEP_GRAPH=0: plain launches only
 #endif
     *out = e;
     return HK_OK;
@@ -885,6 +899,7 @@ int HKAPI(destroy)(hk_engine* e) {
     hkp::sync(e->stream);
     for (void* p : e->allocs) hkp::dev_free(p);
 #ifndef HK_EMU
+    if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
     if (e->comm) {
         cudaStreamSynchronize(e->comm_stream);
         g_nccl.CommDestroy(e->comm);
@@ -1429,12 +1444,70 @@ static int contact_pass(hk_engine* e) {
 // unless contact surfaces may change: exposed faces must be in place before the next contact pass).
 // phase 0: whole step; phase 1: everything that does not need the halo (contact + nodal update of non-interface
 // nodes); phase 2: the rest (received partials, interface nodes, element kernel).
+static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end, int phase);
+
+#ifndef HK_EMU
+// Captures the launches of one ordinary step (whatever enqueue_steps issues for it: contact pass, nodal update, element
+// kernel, deletion pass) into a graph whose kernels read the step number from *d_step, plus a last node that advances it.
+static int step_graph_capture(hk_engine* e) {
+    if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+    if (!e->d_step) { int rc = dalloc(e, &e->d_step, (size_t)1); if (rc) return rc; }
+    const long long launches0 = e->n_launch, steps0 = e->n_steps;
+    const bool velo0 = e->velo_current, triax0 = e->triax_current, stale0 = e->contact_host_stale;
+    e->d.t_dev = e->d_step;
+    cudaGraph_t g = nullptr;
+    int rc = 0;
+    cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+        e->capturing = true;
+        rc = enqueue_steps(e, 0, 1, false, 0);
+        e->capturing = false;
+        hk_launch_step_advance(e->d_step, e->stream);
+        ce = cudaStreamEndCapture(e->stream, &g);
+    }
+    e->d.t_dev = nullptr;
+    e->graph_launches = e->n_launch - launches0 + 1;
+    e->n_launch = launches0; e->n_steps = steps0;                  // nothing ran
+    e->velo_current = velo0; e->triax_current = triax0; e->contact_host_stale = stale0;
+    if (rc == 0 && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&e->step_graph, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (rc || ce != cudaSuccess || !e->step_graph) {                // keep running with plain launches (a real error
+        cudaGetLastError();                                         // will show up again there, with its message)
+        e->step_graph = nullptr;
+        e->graph_off = true;
+        return 0;
+    }
+    e->graph_dirty = false;
+    return 0;
+}
+#endif
+
 static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool frame_at_end, int phase) {
     if (phase != 1 && e->frame_next && n_steps > 0) { frame_at_end = true; e->frame_next = false; }
     const bool contact_on = e->prm.contact_flag >= 1 && !e->pairs.empty();
     if (e->prm.contact_dmax_clamp && (!e->halo.empty() || !e->g_node_map.empty()))
         return fail(e, HK_ERR_UNSUPPORTED, "contact_dmax_clamp: d_max is a global maximum; single-domain engines only");
     if (n_steps > 0) { int rc = ensure_erosion(e); if (rc) return rc; }
+    const int64_t n_requested = n_steps;
+#ifndef HK_EMU
+    // replay: steps after the engine's first, without profiling events, clamp ping-pong, halos or a pending special case;
+    // a frame's last step (it stores integ_triax_stress) and the remainder go through the plain loop below
+    if (phase == 0 && !e->capturing && !e->graph_off && e->stream != nullptr && e->n_steps > 0 && !e->profiling &&
+        e->halo.empty() && !e->comm && e->g_node_map.empty() && !e->prm.contact_dmax_clamp && !e->use_Q0 &&
+        !e->contact_done && n_steps - (frame_at_end ? 1 : 0) >= 2) {
+        if (e->graph_dirty || !e->step_graph) { int rc = step_graph_capture(e); if (rc) return rc; }
+        if (e->step_graph) {
+            const int64_t n_replay = n_steps - (frame_at_end ? 1 : 0);
+            hk_launch_step_set(e->d_step, (long long)t_first, e->stream);
+            for (int64_t i = 0; i < n_replay; ++i) CK(cudaGraphLaunch(e->step_graph, e->stream));
+            e->n_launch += 1 + n_replay * e->graph_launches;
+            e->n_steps += n_replay;
+            if (e->any_ductile && e->dev_erosion) e->contact_host_stale = true;
+            t_first += n_replay;
+            n_steps -= n_replay;
+        }
+    }
+#endif
     const HkDev& d = e->d;
     for (int64_t t = t_first; t < t_first + n_steps; ++t) {
         if (phase != 2 && contact_on && e->contact_done) {
@@ -1491,7 +1564,7 @@ static int enqueue_steps(hk_engine* e, int64_t t_first, int64_t n_steps, bool fr
         e->n_steps += 1;
         if (contact_on && e->prm.contact_dmax_clamp) e->clamp_cur = 1 - e->clamp_cur;
     }
-    if (n_steps > 0 && phase != 1) {
+    if (n_requested > 0 && phase != 1) {
         e->velo_current = contact_on;
         e->triax_current = frame_at_end;      // otherwise hk_download recomputes it from the current stress
     }
@@ -2293,6 +2366,7 @@ int HKAPI(set_stream)(hk_engine* e, void* cuda_stream) {
     hkp::sync(e->stream);
     if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
     e->stream = (cudaStream_t)cuda_stream;      // NULL is a valid handle: the CUDA legacy default stream
+    e->graph_dirty = true;                      // (the legacy stream cannot be captured: steps on it are plain launches)
 #else
     (void)cuda_stream;
 #endif

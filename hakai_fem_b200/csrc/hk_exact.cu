@@ -172,7 +172,8 @@ HK_HD void nodal_body(const NodalArgs& A, long long n) {
             if (be >= 0) {
                 double amp = 1.0;
                 int aid = d.bc_amp[be];
-                if (aid >= 0) amp = eval_amp(d, aid, A.current_time);
+                // a step replayed from a CUDA graph reads its number from the device: same product as the host's (double)t * dt
+                if (aid >= 0) amp = eval_amp(d, aid, d.t_dev ? (double)(*d.t_dev) * A.d_time : A.current_time);
                 bcv[c] = d.bc_value[be] * amp;    // disp_new[dof] .= v * amp, J2:612
                 has_bc[c] = true;
             }
@@ -740,6 +741,7 @@ __global__ void __launch_bounds__(1024) hk_delete_scan_kernel(HkDev d, int nb) {
 }
 __global__ void __launch_bounds__(256) hk_delete_emit_kernel(HkDev d, long long step, int nb) {
     if (*d.del_fresh == 0) return;                             // nothing was deleted in this step (the common case)
+    if (d.t_dev) step = *d.t_dev;
     const int off0 = d.del_block[blockIdx.x];
     const int off1 = (int)blockIdx.x + 1 < nb ? d.del_block[blockIdx.x + 1] : *d.del_fresh;
     if (off1 == off0) return;
@@ -783,6 +785,25 @@ __global__ void hk_erode_replay_kernel(HkDev d, HkErodeDev E, const long long* g
     }
 }
 #endif
+
+#ifndef HK_EMU
+__global__ void hk_step_set_kernel(long long* t_dev, long long t) { *t_dev = t; }
+__global__ void hk_step_advance_kernel(long long* t_dev) { *t_dev = *t_dev + 1; }
+#endif
+void hk_launch_step_set(long long* t_dev, long long t, cudaStream_t s) {
+#ifndef HK_EMU
+    hk_step_set_kernel<<<1, 1, 0, s>>>(t_dev, t);
+#else
+    (void)s; *t_dev = t;
+#endif
+}
+void hk_launch_step_advance(long long* t_dev, cudaStream_t s) {
+#ifndef HK_EMU
+    hk_step_advance_kernel<<<1, 1, 0, s>>>(t_dev);
+#else
+    (void)s; *t_dev = *t_dev + 1;
+#endif
+}
 
 void hk_launch_erode_replay(const HkDev& dd, const HkErodeDev& E, const long long* gathered, int world, int cap, cudaStream_t s) {
 #ifndef HK_EMU
