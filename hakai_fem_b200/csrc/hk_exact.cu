@@ -562,7 +562,9 @@ void hk_launch_contact(const HkDev& d, const HkPairDev& p, const HkContactParams
     }
     hk_contact_cells_kernel<<<contact_grid(p.cap_i, 256, d.n_sm), 256, 0, s>>>(A);
     hk_contact_cull_kernel<<<contact_grid(p.cap_tri, 256, d.n_sm), 256, 0, s>>>(A);
-    hk_contact_narrow_kernel<<<contact_grid((long long)p.cap_tri * 32, 128, d.n_sm) / 4 + 1, 128, 0, s>>>(A);      // candidates are few: <= 8 blocks per SM
+    // a warp per candidate; the grid covers every triangle the pair could hold (warps without a candidate exit at once),
+    // so that a small deck's few dozen candidates all walk their cells at the same time
+    hk_contact_narrow_kernel<<<contact_grid((long long)p.cap_tri * 32, 128, d.n_sm), 128, 0, s>>>(A);
 #else
     for (int t = 0; t < p.dyn->n_bucket; ++t) p.head[t] = -1;
     for (int t = 0; t < 12; ++t) p.bbox[t] = ((t % 6) < 3) ? ~0ull : 0ull;
