@@ -245,9 +245,13 @@ def hakai_distributed(fname, outdir="temp", engine_cls=None, torch_device=None, 
         dom = partition_model(setup, world, only_rank=rank)[rank]
         # over NCCL the engine runs every exchange with its own communicator (hk_comm_init / hk_comm_contact); over gloo
         # (CPU ranks with the host-compiled kernels) the host drives them through torch.distributed
-        on_nccl = dist.get_backend() == "nccl"      # the engine exchanges by itself and keeps eroding surfaces current
+        on_nccl = dist.get_backend() == "nccl"      # the engine exchanges by itself ...
+        # ... and keeps eroding surfaces current on the device, unless that would make every step exchange far more
+        # nodes than the surfaces hold: the static lists of hk_comm_erosion cover ALL nodes of the instances in contact
+        dev_er = on_nccl and dom.contact_all is not None and (
+            len(dom.contact_all.surface_nodes) <= max(4 * len(dom.contact.surface_nodes), 200_000))
         runner = SlabRunner.from_domain(engine_cls, dom, torch_device, world, engine_comm=on_nccl,
-                                        device_erosion=on_nccl, **params)
+                                        device_erosion=dev_er, **params)
         n_held = len(np.unique(dom.setup.model.elementmat))     # local ids 1..n_held are nodes of own elements
         sel_n, sel_e = np.arange(n_held), np.arange(dom.setup.model.nElement)
     eng = runner.engine
