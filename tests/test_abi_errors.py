@@ -135,3 +135,36 @@ def test_lengths_ids_and_null_tables_are_validated():
     fn = e._fn("add_material")                                              # npp = 2 with NULL tables, straight at the ABI
     rc = fn(e._h, C.c_double(1.0), C.c_double(0.3), C.c_double(1.0), C.c_int64(2), None, None, C.c_int64(0), None)
     assert rc != 0 and b"NULL" in e._fn("last_error")(e._h)
+
+
+def test_comm_erosion_call_order_and_capacity_are_checked():
+    """hk_comm_erosion: after hk_set_global_maps, before the first step, with a sane capacity; and a deck that cannot erode
+    (no contact, no failing material) simply keeps the plain path."""
+    st = prepare(StretchDeck(2, 2, 2).build_model())
+    e = EmuEngine(d_time=st.d_time)
+    with pytest.raises(HakaiError):
+        e.comm_erosion(16)                                       # not finalised
+    e = configure_engine(EmuEngine, st)
+    nE, nN = st.model.nElement, st.model.nNode
+    with pytest.raises(HakaiError) as ei:
+        e.comm_erosion(16)                                       # no global maps yet
+    assert "hk_set_global_maps" in str(ei.value)
+    e.set_global_maps(np.arange(1, nN + 1), np.arange(1, nE + 1), np.ones(nE))
+    for bad in (0, -3, 1 << 25):
+        with pytest.raises(HakaiError):
+            e.comm_erosion(bad)
+    e.comm_erosion(16)
+    e.step_enqueue(1, 2)                                         # nothing to erode: steps run, no device lists are built
+    assert e.sync() == 0
+    with pytest.raises(HakaiError) as ei:
+        e.comm_erosion(16)                                       # too late
+    assert "first step" in str(ei.value)
+    e.apply_deleted([1])                                         # the host replay still works on such an engine
+
+
+def test_host_driver_rejects_unknown_contact_setup(tmp_path):
+    from hakai_fem_b200.host import hakai
+    path = tmp_path / "d.inp"
+    StretchDeck(2, 2, 2, n_steps=4).write_inp(str(path))
+    with pytest.raises(ValueError):
+        hakai(str(path), str(tmp_path / "o"), engine_cls=EmuEngine, contact_setup="gpu", verbose=False)
